@@ -1,0 +1,52 @@
+"""xerus_b200 — B200-native (sm_100a) implementation of xerus's tensor-train hot path behind a C ABI.
+
+Host-side mirror of the reference interface for that path; all arithmetic runs in libxb200.so (hand-written CUDA).
+"""
+from ._lib import XerusError, lib, declared_symbols, LIB_PATH      # noqa: F401
+from . import blas_wrapper as blasWrapper                          # noqa: F401
+from .blas_wrapper import contract, reshuffle, calculate_svd, EPSILON   # noqa: F401
+from .tt import TTTensor, TTOperator, TTNetwork, round_batched, reduce_to_maximal_ranks   # noqa: F401
+from .als import ALSVariant, ALS, ALS_SPD, DMRG, DMRG_SPD          # noqa: F401
+
+
+def init(device=0):
+    """Selects the CUDA device and creates the library stream (idempotent)."""
+    from ._lib import call
+    call("xb_init", int(device))
+
+
+def synchronize():
+    from ._lib import call
+    call("xb_synchronize")
+
+
+def kernel_launch_count():
+    import ctypes as C
+    from ._lib import call
+    n = C.c_uint64()
+    call("xb_kernel_launch_count", C.byref(n))
+    return n.value
+
+
+def stream_handle():
+    """cudaStream_t (as int) on which all xb200 work is enqueued — for CUDA-event timing on that stream."""
+    import ctypes as C
+    from ._lib import call
+    s = C.c_void_p()
+    call("xb_get_stream", C.byref(s))
+    return s.value
+
+
+def profile_enable(on=True):
+    """CUDA-event timing per kernel class inside the library (bench/roofline only)."""
+    from ._lib import call
+    call("xb_profile_enable", int(bool(on)))
+
+
+def profile_get(kernel_class):
+    """(scopes, launches, milliseconds) accumulated for a kernel class since profile_enable(True)."""
+    import ctypes as C
+    from ._lib import call
+    s, l, ms = C.c_uint64(), C.c_uint64(), C.c_double()
+    call("xb_profile_get", kernel_class.encode(), C.byref(s), C.byref(l), C.byref(ms))
+    return s.value, l.value, ms.value

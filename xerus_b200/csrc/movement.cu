@@ -1,0 +1,245 @@
+// Memory-bound kernels of the TT hot path: copies, fills, transposes, general mode permutation (xerus::reshuffle,
+// reference: src/xerus/indexedTensor_tensor_evaluate.cpp:55-137), diagonal scalings (the sparse-diagonal S * Vt
+// product of round_edge, src/xerus/tensorNetwork.cpp:769), axpy/scal (misc/basicArraySupport.h:53-111) and the
+// level-1 reductions (cblas_dnrm2/ddot/dasum behind blasLapackWrapper.cpp:76-112).  All HBM/L2-bound: coalesced,
+// grid-stride, grids sized in multiples of the SM count; reductions are deterministic (fixed two-stage tree).
+#include "xb_internal.cuh"
+
+namespace xb {
+
+static inline unsigned grid_for(size_t n, unsigned threads, unsigned per_sm = 8) {
+	size_t blocks = (n + threads - 1) / threads;
+	const size_t cap = size_t(ctx().num_sms) * per_sm;
+	if (blocks > cap) blocks = cap;
+	if (blocks == 0) blocks = 1;
+	return unsigned(blocks);
+}
+
+__global__ void copy_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void copy2d_kernel(double* __restrict__ dst, size_t ldd, const double* __restrict__ src, size_t lds, size_t rows, size_t cols) {
+	const size_t n = rows * cols;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const size_t r = i / cols, c = i % cols;
+		dst[r * ldd + c] = src[r * lds + c];
+	}
+}
+__global__ void fill_kernel(double* __restrict__ dst, double v, size_t n) {
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+__global__ void identity_kernel(double* __restrict__ dst, size_t rows, size_t cols, size_t ld) {
+	const size_t n = rows * cols;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const size_t r = i / cols, c = i % cols;
+		dst[r * ld + c] = (r == c) ? 1.0 : 0.0;
+	}
+}
+__global__ void scale_kernel(double* __restrict__ x, double a, size_t n) {
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= a;
+}
+__global__ void axpy_kernel(double* __restrict__ y, double a, const double* __restrict__ x, size_t n) {
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] += a * x[i];
+}
+__global__ void scale_rows_kernel(double* __restrict__ A, const double* __restrict__ s, size_t rows, size_t cols, size_t ld) {
+	const size_t n = rows * cols;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const size_t r = i / cols, c = i % cols;
+		A[r * ld + c] *= s[r];
+	}
+}
+__global__ void scale_cols_kernel(double* __restrict__ A, const double* __restrict__ s, size_t rows, size_t cols, size_t ld) {
+	const size_t n = rows * cols;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		const size_t r = i / cols, c = i % cols;
+		A[r * ld + c] *= s[c];
+	}
+}
+
+// out (cols x rows) = in^T ; 32x32 tiles through shared memory, both sides coalesced.  REVERSE additionally flips
+// both index ranges (used to express RQ through QR: out(j,i) = in(rows-1-i, cols-1-j)).
+template <bool REVERSE>
+__global__ void transpose_kernel(double* __restrict__ out, const double* __restrict__ in, size_t rows, size_t cols) {
+	__shared__ double tile[32][33];
+	const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
+	for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+		const size_t r = r0 + dy, c = c0 + threadIdx.x;
+		if (r < rows && c < cols) tile[dy][threadIdx.x] = in[r * cols + c];
+	}
+	__syncthreads();
+	for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+		const size_t c = c0 + dy, r = r0 + threadIdx.x;   // out element (c, r)
+		if (r < rows && c < cols) {
+			if (REVERSE) out[(cols - 1 - c) * rows + (rows - 1 - r)] = tile[threadIdx.x][dy];
+			else out[c * rows + r] = tile[threadIdx.x][dy];
+		}
+	}
+}
+
+struct PermuteArgs {
+	int degree;
+	unsigned long long out_dims[16];     // dimensions of the output tensor
+	unsigned long long in_strides[16];   // stride in the input of the mode that became output mode i
+};
+// General mode permutation as a gather: consecutive threads write consecutive output elements.
+__global__ void permute_kernel(double* __restrict__ out, const double* __restrict__ in, const PermuteArgs a, size_t n) {
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		size_t rem = i, off = 0;
+#pragma unroll 1
+		for (int d = a.degree - 1; d >= 0; --d) {
+			const size_t idx = rem % a.out_dims[d];
+			rem /= a.out_dims[d];
+			off += idx * a.in_strides[d];
+		}
+		out[i] = in[off];
+	}
+}
+
+// ---- deterministic reductions -----------------------------------------------------------------------------------
+constexpr int RED_THREADS = 256;
+constexpr int RED_MAX_BLOCKS = 296;
+
+template <int MODE>   // 0: sum x*y   1: sum |x|
+__global__ void reduce_stage1(double* __restrict__ partial, const double* __restrict__ x, const double* __restrict__ y, size_t n) {
+	__shared__ double sh[RED_THREADS / 32];
+	double acc = 0.0;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		acc += (MODE == 0) ? x[i] * y[i] : fabs(x[i]);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double s = 0.0;
+		for (int w = 0; w < RED_THREADS / 32; ++w) s += sh[w];
+		partial[blockIdx.x] = s;
+	}
+}
+__global__ void reduce_stage2(double* __restrict__ result, const double* __restrict__ partial, int nblocks) {
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
+		double s = 0.0;
+		for (int i = 0; i < nblocks; ++i) s += partial[i];
+		*result = s;
+	}
+}
+
+static void reduce(double* d_result, const double* x, const double* y, size_t n, int mode) {
+	static double* partial = nullptr;
+	if (!partial) partial = dalloc(RED_MAX_BLOCKS);
+	unsigned blocks = unsigned(std::min<size_t>(RED_MAX_BLOCKS, std::max<size_t>(1, (n + RED_THREADS * 4 - 1) / (RED_THREADS * 4))));
+	if (mode == 0) reduce_stage1<0><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);
+	else reduce_stage1<1><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);
+	XB_LAUNCH_CHECK();
+	reduce_stage2<<<1, 32, 0, ctx().stream>>>(d_result, partial, int(blocks));
+	XB_LAUNCH_CHECK();
+}
+
+// ---- host wrappers ----------------------------------------------------------------------------------------------
+void copy(double* dst, const double* src, size_t n) {
+	if (!n || dst == src) return;
+	XB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+}
+void copy2d(double* dst, size_t ldd, const double* src, size_t lds, size_t rows, size_t cols) {
+	if (!rows || !cols) return;
+	copy2d_kernel<<<grid_for(rows * cols, 256), 256, 0, ctx().stream>>>(dst, ldd, src, lds, rows, cols);
+	XB_LAUNCH_CHECK();
+}
+void fill(double* dst, double v, size_t n) {
+	if (!n) return;
+	fill_kernel<<<grid_for(n, 256), 256, 0, ctx().stream>>>(dst, v, n);
+	XB_LAUNCH_CHECK();
+}
+void set_identity(double* dst, size_t rows, size_t cols, size_t ld) {
+	if (!rows || !cols) return;
+	identity_kernel<<<grid_for(rows * cols, 256), 256, 0, ctx().stream>>>(dst, rows, cols, ld);
+	XB_LAUNCH_CHECK();
+}
+void scale(double* x, double a, size_t n) {
+	if (!n || a == 1.0) return;
+	scale_kernel<<<grid_for(n, 256), 256, 0, ctx().stream>>>(x, a, n);
+	XB_LAUNCH_CHECK();
+}
+void axpy(double* y, double a, const double* x, size_t n) {
+	if (!n) return;
+	axpy_kernel<<<grid_for(n, 256), 256, 0, ctx().stream>>>(y, a, x, n);
+	XB_LAUNCH_CHECK();
+}
+void scale_rows(double* A, const double* s, size_t rows, size_t cols, size_t ld) {
+	if (!rows || !cols) return;
+	scale_rows_kernel<<<grid_for(rows * cols, 256), 256, 0, ctx().stream>>>(A, s, rows, cols, ld);
+	XB_LAUNCH_CHECK();
+}
+void scale_cols(double* A, const double* s, size_t rows, size_t cols, size_t ld) {
+	if (!rows || !cols) return;
+	scale_cols_kernel<<<grid_for(rows * cols, 256), 256, 0, ctx().stream>>>(A, s, rows, cols, ld);
+	XB_LAUNCH_CHECK();
+}
+void transpose(double* out, const double* in, size_t rows, size_t cols) {
+	if (!rows || !cols) return;
+	if (rows == 1 || cols == 1) { copy(out, in, rows * cols); return; }
+	dim3 grid(unsigned((cols + 31) / 32), unsigned((rows + 31) / 32)), block(32, 8);
+	XB_REQUIRE(grid.y <= 65535, "matrix too tall for the transpose grid");
+	transpose_kernel<false><<<grid, block, 0, ctx().stream>>>(out, in, rows, cols);
+	XB_LAUNCH_CHECK();
+}
+void transpose_reverse(double* out, const double* in, size_t rows, size_t cols) {
+	if (!rows || !cols) return;
+	dim3 grid(unsigned((cols + 31) / 32), unsigned((rows + 31) / 32)), block(32, 8);
+	XB_REQUIRE(grid.y <= 65535, "matrix too tall for the transpose grid");
+	transpose_kernel<true><<<grid, block, 0, ctx().stream>>>(out, in, rows, cols);
+	XB_LAUNCH_CHECK();
+}
+
+void permute(double* out, const double* in, const size_t* dims, const size_t* shuffle, size_t degree) {
+	XB_REQUIRE(out != in, "in-place reshuffle is not supported at this level");
+	// validate: shuffle must be a permutation (reference: indexedTensor_tensor_evaluate.cpp:57-71)
+	std::vector<char> seen(degree, 0);
+	size_t n = 1;
+	for (size_t i = 0; i < degree; ++i) {
+		XB_REQUIRE(shuffle[i] < degree && !seen[shuffle[i]], "shuffle is not a permutation");
+		seen[shuffle[i]] = 1;
+		n *= dims[i];
+	}
+	if (n == 0) return;
+	// merge modes that stay adjacent (in order) so that e.g. (a,b,c)->(a,c,b) with many modes still fits 8 slots
+	std::vector<size_t> in_stride(degree), inv(degree);
+	for (size_t i = 0, s = 1; i < degree; ++i) { in_stride[degree - 1 - i] = s; s *= dims[degree - 1 - i]; }
+	for (size_t i = 0; i < degree; ++i) inv[shuffle[i]] = i;        // output mode o came from input mode inv[o]
+	std::vector<unsigned long long> od, os;
+	for (size_t o = 0; o < degree; ++o) {
+		const size_t im = inv[o];
+		if (dims[im] == 1) continue;
+		if (!od.empty() && o > 0 && inv[o - 1] + 1 == im && dims[inv[o - 1]] != 1 && os.back() == in_stride[inv[o - 1]]) {
+			od.back() *= dims[im]; os.back() = in_stride[im];
+		} else {
+			od.push_back(dims[im]); os.push_back(in_stride[im]);
+		}
+	}
+	// identity (possibly after dropping size-1 modes): plain copy (reference :74-77)
+	bool identity = true;
+	{
+		unsigned long long expect = 1;
+		for (size_t i = od.size(); i-- > 0;) { if (os[i] != expect) { identity = false; break; } expect *= od[i]; }
+	}
+	if (identity) { copy(out, in, n); return; }
+	if (od.size() == 2 && os[1] == od[0] && os[0] == 1) { transpose(out, in, od[1], od[0]); return; }
+	XB_REQUIRE(od.size() <= 16, "reshuffle supports at most 16 non-mergeable modes");
+	PermuteArgs a;
+	a.degree = int(od.size());
+	for (size_t i = 0; i < od.size(); ++i) { a.out_dims[i] = od[i]; a.in_strides[i] = os[i]; }
+	permute_kernel<<<grid_for(n, 256), 256, 0, ctx().stream>>>(out, in, a, n);
+	XB_LAUNCH_CHECK();
+}
+
+void dot_dev(double* d_result, const double* x, const double* y, size_t n) { reduce(d_result, x, y, n, 0); }
+void asum_dev(double* d_result, const double* x, size_t n) { reduce(d_result, x, x, n, 1); }
+
+double dot(const double* x, const double* y, size_t n) {
+	DBuf r(1);
+	dot_dev(r, x, y, n);
+	return read_scalar(r);
+}
+double two_norm(const double* x, size_t n) { return std::sqrt(std::max(0.0, dot(x, x, n))); }
+
+} // namespace xb

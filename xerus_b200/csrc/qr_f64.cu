@@ -1,0 +1,316 @@
+// Blocked Householder QR for sm_100a (FP64), plus LQ / RQ / rank-revealing QC / CQ on top of it.
+//
+// Replaces LAPACKE_dgeqrf + dorgqr (blasWrapper::qr, reference: src/xerus/blasLapackWrapper.cpp:388-438),
+// dgerqf + dorgrq (:455-498) and dgeqp3 + dorgqr (qc/cq, :243-371).
+//
+// Structure (compact WY, panel width 32):
+//   qr_panel_kernel   one CTA, panel resident in shared memory (lane = panel column, warps stride the rows).
+//                     Per column ONE fused pass computes g_c = x^T a_c for all remaining columns c (c = j gives
+//                     ||x||^2), from which beta, tau and w = v^T A follow algebraically — no separate norm pass —
+//                     and one pass applies the rank-1 update.  T (compact WY) is built at the end from V^T V.
+//   qr_vtc_kernel     partial W_p = V^T C over row chunks (grid: column blocks x row chunks, deterministic)
+//   qr_update_kernel  sums the partials, W2 = op(T) W, C -= V W2
+// The trailing update and the formation of the explicit thin Q use the same two kernels (op(T) = T^T resp. T).
+#include "xb_internal.cuh"
+
+namespace xb {
+
+constexpr int QR_NB = 32;          // panel width == warp width
+constexpr int QR_PANEL_WARPS = 32; // 1024 threads
+constexpr int QR_CHUNK = 64;       // rows per CTA in the trailing kernels
+
+template <bool SMEM>
+__global__ void __launch_bounds__(QR_PANEL_WARPS * 32) qr_panel_kernel(double* __restrict__ W, const long long ldw, const int mp,
+                                                                      const int nbe, double* __restrict__ Vbuf, double* __restrict__ Tout) {
+	extern __shared__ double sm[];
+	double* red = sm;                         // [32][33]
+	double* GV = red + 32 * 33;               // [32][33]
+	double* Ts = GV + 32 * 33;                // [32][33]
+	double* s_wv = Ts + 32 * 33;              // [32]
+	double* s_tau = s_wv + 32;                // [32]
+	double* s_misc = s_tau + 32;              // [4]
+	double* Ps = s_misc + 4;                  // [mp][32] when SMEM
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int NW = blockDim.x >> 5;
+	const bool active = lane < nbe;
+	auto pe = [&](int i, int c) -> double& { return SMEM ? Ps[i * QR_NB + c] : W[(long long)i * ldw + c]; };
+
+	if (SMEM) {
+		for (int i = warp; i < mp; i += NW) Ps[i * QR_NB + lane] = active ? W[(long long)i * ldw + lane] : 0.0;
+	}
+	for (int i = threadIdx.x; i < 32 * 33; i += blockDim.x) { Ts[i] = 0.0; GV[i] = 0.0; }
+	if (threadIdx.x < 32) s_tau[threadIdx.x] = 0.0;
+	__syncthreads();
+
+	const int kmax = min(nbe, mp);
+	for (int j = 0; j < kmax; ++j) {
+		// pass 1: g_c = sum_{i >= j} P[i][j] * P[i][c]
+		double g = 0.0;
+		if (active && lane >= j) {
+			for (int i = j + warp; i < mp; i += NW) g += pe(i, j) * pe(i, lane);
+		}
+		red[warp * 33 + lane] = g;
+		__syncthreads();
+		if (warp == 0) {
+			double G = 0.0;
+			for (int w = 0; w < NW; ++w) G += red[w * 33 + lane];
+			const double sigma = __shfl_sync(0xffffffffu, G, j);
+			const double alpha = pe(j, j);
+			const double tail = sigma - alpha * alpha;
+			double beta = alpha, tau = 0.0, scl = 0.0;
+			if (tail > 0.0 && j + 1 < mp) {
+				beta = -copysign(sqrt(sigma), alpha);
+				tau = (beta - alpha) / beta;
+				scl = 1.0 / (alpha - beta);
+			}
+			double wv = 0.0;
+			if (active && lane > j && tau != 0.0) wv = tau * (G - beta * pe(j, lane)) * scl;
+			s_wv[lane] = wv;
+			if (lane == 0) { s_tau[j] = tau; s_misc[0] = beta; s_misc[1] = scl; }
+		}
+		__syncthreads();
+		const double tau = s_tau[j], beta = s_misc[0], scl = s_misc[1];
+		// pass 2: A[:, c] -= tau * w_c * v for c > j ; store v below the diagonal of column j, beta on it
+		for (int i = j + warp; i < mp; i += NW) {
+			const double vi = (i == j) ? 1.0 : pe(i, j) * scl;
+			__syncwarp();
+			if (active) {
+				if (lane > j) { if (tau != 0.0) pe(i, lane) -= s_wv[lane] * vi; }
+				else if (lane == j) pe(i, j) = (i == j) ? beta : ((tau != 0.0) ? vi : 0.0);
+			}
+		}
+		__syncthreads();
+	}
+
+	// explicit V (unit lower trapezoidal, zero padded to 32 columns)
+	auto vval = [&](int i, int c) -> double {
+		if (c >= kmax || i < c) return 0.0;
+		return (i == c) ? 1.0 : pe(i, c);
+	};
+	for (int i = warp; i < mp; i += NW) Vbuf[(long long)i * QR_NB + lane] = vval(i, lane);
+	// GV = V^T V : warp w owns row w
+	if (warp < kmax) {
+		double acc = 0.0;
+		for (int i = warp; i < mp; ++i) acc += vval(i, warp) * vval(i, lane);
+		GV[warp * 33 + lane] = acc;
+	}
+	__syncthreads();
+	// T(0:j, j) = -tau_j * T(0:j, 0:j) * GV(0:j, j) ; T(j, j) = tau_j
+	if (warp == 0) {
+		for (int j = 0; j < kmax; ++j) {
+			double t = 0.0;
+			if (lane < j) for (int c = lane; c < j; ++c) t += Ts[lane * 33 + c] * GV[c * 33 + j];
+			__syncwarp();
+			if (lane < j) Ts[lane * 33 + j] = -s_tau[j] * t;
+			else if (lane == j) Ts[j * 33 + j] = s_tau[j];
+			__syncwarp();
+		}
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) Tout[i] = Ts[(i >> 5) * 33 + (i & 31)];
+	if (SMEM) {
+		for (int i = warp; i < mp; i += NW) if (active) W[(long long)i * ldw + lane] = Ps[i * QR_NB + lane];
+	}
+}
+
+// Wp[chunk][kk][c] = sum_{rows of chunk} V[row][kk] * C[row][c]     block: 32 x 32 threads (warp = kk, lane = c)
+__global__ void __launch_bounds__(1024) qr_vtc_kernel(const double* __restrict__ Vbuf, const double* __restrict__ C, const long long ldc,
+                                                     const int mp, const int nc, double* __restrict__ Wp, const int ncpad) {
+	__shared__ double Vs[QR_CHUNK][32];
+	__shared__ double Cs[QR_CHUNK][33];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int r0 = blockIdx.y * QR_CHUNK;
+	const int c = blockIdx.x * 32 + lane;
+	for (int ii = warp; ii < QR_CHUNK; ii += 32) {
+		const int row = r0 + ii;
+		const bool ok = row < mp;
+		Vs[ii][lane] = ok ? Vbuf[(long long)row * QR_NB + lane] : 0.0;
+		Cs[ii][lane] = (ok && c < nc) ? C[(long long)row * ldc + c] : 0.0;
+	}
+	__syncthreads();
+	double acc = 0.0;
+#pragma unroll 8
+	for (int ii = 0; ii < QR_CHUNK; ++ii) acc += Vs[ii][warp] * Cs[ii][lane];
+	Wp[((long long)blockIdx.y * 32 + warp) * ncpad + c] = acc;
+}
+
+// C[rows of chunk][col block] -= V * (op(T) * sum_p Wp)
+__global__ void __launch_bounds__(1024) qr_update_kernel(double* __restrict__ C, const long long ldc, const int mp, const int nc,
+                                                        const double* __restrict__ Vbuf, const double* __restrict__ T, const int transT,
+                                                        const double* __restrict__ Wp, const int nchunks, const int ncpad) {
+	__shared__ double Tsm[32][33];
+	__shared__ double Ws[32][33];
+	__shared__ double W2[32][33];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int c = blockIdx.x * 32 + lane;
+	Tsm[warp][lane] = T[warp * 32 + lane];
+	double s = 0.0;
+	for (int p = 0; p < nchunks; ++p) s += Wp[((long long)p * 32 + warp) * ncpad + c];
+	Ws[warp][lane] = s;
+	__syncthreads();
+	double acc = 0.0;
+#pragma unroll 8
+	for (int l = 0; l < 32; ++l) acc += (transT ? Tsm[l][warp] : Tsm[warp][l]) * Ws[l][lane];
+	W2[warp][lane] = acc;
+	__syncthreads();
+	const int r0 = blockIdx.y * QR_CHUNK, r1 = min(mp, r0 + QR_CHUNK);
+	if (c < nc) {
+		for (int row = r0 + warp; row < r1; row += 32) {
+			const double* v = Vbuf + (long long)row * QR_NB;
+			double d = 0.0;
+#pragma unroll 8
+			for (int kk = 0; kk < 32; ++kk) d += v[kk] * W2[kk][lane];
+			C[(long long)row * ldc + c] -= d;
+		}
+	}
+}
+
+__global__ void qr_extract_r_kernel(double* __restrict__ R, const double* __restrict__ W, const size_t k, const size_t n) {
+	const size_t total = k * n;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+		const size_t r = i / n, c = i % n;
+		R[i] = (c >= r) ? W[i] : 0.0;
+	}
+}
+
+// min / max of |diag| of a (rows x cols, ld) matrix -> out[0] = min, out[1] = max      (single warp)
+__global__ void diag_minmax_kernel(const double* __restrict__ A, const size_t k, const size_t ld, double* __restrict__ out) {
+	double mn = HUGE_VAL, mx = 0.0;
+	for (size_t i = threadIdx.x; i < k; i += 32) { const double v = fabs(A[i * ld + i]); mn = fmin(mn, v); mx = fmax(mx, v); }
+	for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+	if (threadIdx.x == 0) { out[0] = mn; out[1] = mx; }
+}
+
+static void apply_block_reflector(double* C, size_t ldc, size_t mp, size_t nc, const double* Vbuf, const double* T, bool transT, double* Wp) {
+	if (nc == 0 || mp == 0) return;
+	const unsigned ncb = unsigned((nc + 31) / 32), nch = unsigned((mp + QR_CHUNK - 1) / QR_CHUNK);
+	const int ncpad = int(ncb * 32);
+	dim3 grid(ncb, nch);
+	qr_vtc_kernel<<<grid, 1024, 0, ctx().stream>>>(Vbuf, C, (long long)ldc, int(mp), int(nc), Wp, ncpad);
+	XB_LAUNCH_CHECK();
+	qr_update_kernel<<<grid, 1024, 0, ctx().stream>>>(C, (long long)ldc, int(mp), int(nc), Vbuf, T, transT ? 1 : 0, Wp, int(nch), ncpad);
+	XB_LAUNCH_CHECK();
+}
+
+void qr(double* Q, double* R, const double* A, size_t m, size_t n) {
+	XB_REQUIRE(m > 0 && n > 0, "Dimension m and n must be larger than zero");    // blasLapackWrapper.cpp:392-393
+	XB_REQUIRE(m <= 0x7fffffffULL && n <= 0x7fffffffULL, "Dimension to large for QR");
+	ProfScope prof("qr");
+	const size_t k = std::min(m, n);
+	const size_t npanels = (k + QR_NB - 1) / QR_NB;
+	DBuf W(m * n), Vall(npanels * m * QR_NB), Tall(npanels * QR_NB * QR_NB);
+	const size_t nch_max = (m + QR_CHUNK - 1) / QR_CHUNK;
+	const size_t ncpad_max = ((std::max(n, k) + 31) / 32) * 32;
+	DBuf Wp(nch_max * 32 * ncpad_max);
+	copy(W, A, m * n);
+
+	static bool attr_set = false;
+	const size_t fixed_smem = (3 * 32 * 33 + 32 + 32 + 4) * sizeof(double);
+	const size_t smem_cap = std::min<size_t>(ctx().max_smem_optin, 227 * 1024);
+	if (!attr_set) {
+		XB_CUDA(cudaFuncSetAttribute(qr_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+		attr_set = true;
+	}
+	for (size_t p = 0; p < npanels; ++p) {
+		const size_t j0 = p * QR_NB, nbe = std::min<size_t>(QR_NB, k - j0), mp = m - j0;
+		double* Wpanel = W.p + j0 * n + j0;
+		double* Vp = Vall.p + p * m * QR_NB;
+		double* Tp = Tall.p + p * QR_NB * QR_NB;
+		const size_t need = fixed_smem + mp * QR_NB * sizeof(double);
+		if (need <= smem_cap) {
+			qr_panel_kernel<true><<<1, QR_PANEL_WARPS * 32, need, ctx().stream>>>(Wpanel, (long long)n, int(mp), int(nbe), Vp, Tp);
+		} else {
+			qr_panel_kernel<false><<<1, QR_PANEL_WARPS * 32, fixed_smem, ctx().stream>>>(Wpanel, (long long)n, int(mp), int(nbe), Vp, Tp);
+		}
+		XB_LAUNCH_CHECK();
+		const size_t nc = n - (j0 + nbe);
+		apply_block_reflector(Wpanel + nbe, n, mp, nc, Vp, Tp, true, Wp);
+	}
+	// R = upper trapezoid of the first k rows
+	{
+		const size_t total = k * n;
+		const unsigned blocks = unsigned(std::min<size_t>((total + 255) / 256, size_t(ctx().num_sms) * 8));
+		qr_extract_r_kernel<<<blocks, 256, 0, ctx().stream>>>(R, W, k, n);
+		XB_LAUNCH_CHECK();
+	}
+	// Q = H_1 ... H_k [I; 0] : apply the block reflectors in reverse order to the identity
+	set_identity(Q, m, k, k);
+	for (size_t p = npanels; p-- > 0;) {
+		const size_t j0 = p * QR_NB, mp = m - j0;
+		apply_block_reflector(Q + j0 * k + j0, k, mp, k - j0, Vall.p + p * m * QR_NB, Tall.p + p * QR_NB * QR_NB, false, Wp);
+	}
+}
+
+void lq(double* L, double* Q, const double* A, size_t m, size_t n) {
+	const size_t k = std::min(m, n);
+	DBuf At(m * n), Qt(n * k), Rt(k * m);
+	transpose(At, A, m, n);            // n x m
+	qr(Qt, Rt, At, n, m);              // A^T = Qt * Rt
+	transpose(Q, Qt, n, k);            // k x n
+	transpose(L, Rt, k, m);            // m x k
+}
+
+void rq(double* R, double* Q, const double* A, size_t m, size_t n) {
+	// RQ in LAPACK's convention through the QR of the doubly reversed transpose: with Ar(j,i) = A(m-1-i, n-1-j) = Qr Rr,
+	// R(i,l) = Rr(k-1-l, m-1-i) is upper trapezoidal (bottom-right aligned) and Q(l,j) = Qr(n-1-j, k-1-l).
+	const size_t k = std::min(m, n);
+	DBuf Ar(m * n), Qr(n * k), Rr(k * m);
+	transpose_reverse(Ar, A, m, n);
+	qr(Qr, Rr, Ar, n, m);
+	transpose_reverse(Q, Qr, n, k);
+	transpose_reverse(R, Rr, k, m);
+}
+
+// ---- rank revealing variants ------------------------------------------------------------------------------------
+static bool diag_is_full_rank(const double* M, size_t k, size_t ld) {
+	DBuf mm(2);
+	diag_minmax_kernel<<<1, 32, 0, ctx().stream>>>(M, k, ld, mm);
+	XB_LAUNCH_CHECK();
+	Context& c = ctx();
+	XB_CUDA(cudaMemcpyAsync(c.h_scratch, mm.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaStreamSynchronize(c.stream));
+	const double mn = c.h_scratch[0], mx = c.h_scratch[1];
+	return mx > 0.0 && mn >= 16.0 * 2.220446049250313e-16 * mx;
+}
+
+static size_t numerical_rank(const std::vector<double>& S) {
+	size_t rank = 1;
+	for (size_t j = 1; j < S.size(); ++j) if (S[j] >= 16.0 * 2.220446049250313e-16 * S[0] && S[j] > 0.0) rank = j + 1; else break;
+	return rank;
+}
+
+size_t qc(double* Q, double* C, const double* A, size_t m, size_t n) {
+	const size_t k = std::min(m, n);
+	qr(Q, C, A, m, n);
+	if (diag_is_full_rank(C, k, n)) return k;
+	// (near) rank deficient: reveal the rank through the SVD of the triangular factor, R = U S Vt:
+	//   A = (Q U_r) (S_r Vt_r)
+	Svd s;
+	s.factor(C, k, n);
+	const size_t rank = numerical_rank(s.S);
+	DBuf U(k * rank), Cn(rank * n), Qn(m * rank);
+	s.extract(U, Cn, rank, false, true, nullptr);
+	gemm(Qn, rank, m, rank, 1.0, Q, k, false, k, U, rank, false, 0.0);
+	copy(Q, Qn, m * rank);
+	copy(C, Cn, rank * n);
+	return rank;
+}
+
+size_t cq(double* C, double* Q, const double* A, size_t m, size_t n) {
+	const size_t k = std::min(m, n);
+	lq(C, Q, A, m, n);
+	if (diag_is_full_rank(C, k, k)) return k;
+	// L = U S Vt  ->  A = (U_r S_r) (Vt_r Q)
+	Svd s;
+	s.factor(C, m, k);
+	const size_t rank = numerical_rank(s.S);
+	DBuf Cn(m * rank), Vt(rank * k), Qn(rank * n);
+	s.extract(Cn, Vt, rank, true, false, nullptr);
+	gemm(Qn, n, rank, n, 1.0, Vt, k, false, k, Q, n, false, 0.0);
+	copy(C, Cn, m * rank);
+	copy(Q, Qn, rank * n);
+	return rank;
+}
+
+} // namespace xb

@@ -1,0 +1,196 @@
+// xb200 runtime: device context, stream, stream-ordered memory pool, error state, memory hooks of the C ABI.
+#include "xb_internal.cuh"
+#include <mutex>
+
+namespace xb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+static Context g_ctx;
+static std::mutex g_ctx_mutex;
+Context& ctx() { return g_ctx; }
+
+static void init_locked(int device) {
+	if (g_ctx.initialised) return;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) {
+		throw Error(XB_ERR_NO_DEVICE, std::string("xb200: no usable CUDA device (") + cudaGetErrorString(e) +
+		            "); there is no CPU fallback for this library");
+	}
+	if (device < 0 || device >= count) throw Error(XB_ERR_INVALID, "xb_init: device index out of range");
+	XB_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	XB_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) {
+		throw Error(XB_ERR_NO_DEVICE, std::string("xb200 is built for sm_100a only; found ") + prop.name);
+	}
+	g_ctx.device = device;
+	g_ctx.num_sms = prop.multiProcessorCount;
+	g_ctx.max_smem_optin = prop.sharedMemPerBlockOptin;
+	XB_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+	XB_CUDA(cudaDeviceGetDefaultMemPool(&g_ctx.pool, device));
+	uint64_t threshold = UINT64_MAX;   // keep freed blocks cached: sweeps must not hit cudaMalloc
+	XB_CUDA(cudaMemPoolSetAttribute(g_ctx.pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+	XB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&g_ctx.h_scratch), g_ctx.h_scratch_len * sizeof(double)));
+	g_ctx.initialised = true;
+}
+
+void ensure_init() {
+	if (g_ctx.initialised) {
+		// the caller may be a different host thread (ctypes); make the library device current
+		cudaSetDevice(g_ctx.device);
+		return;
+	}
+	std::lock_guard<std::mutex> lock(g_ctx_mutex);
+	init_locked(0);
+}
+
+void* dalloc_bytes(size_t bytes) {
+	void* p = nullptr;
+	if (bytes == 0) bytes = 8;
+	XB_CUDA(cudaMallocAsync(&p, bytes, ctx().stream));
+	return p;
+}
+double* dalloc(size_t n) { return static_cast<double*>(dalloc_bytes(n * sizeof(double))); }
+void dfree(void* p) { if (p) cudaFreeAsync(p, ctx().stream); }
+
+double read_scalar(const double* d_value) {
+	Context& c = ctx();
+	XB_CUDA(cudaMemcpyAsync(c.h_scratch, d_value, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaStreamSynchronize(c.stream));
+	return c.h_scratch[0];
+}
+
+// ---- profiling ----------------------------------------------------------------------------------------------------
+struct ProfRecord { std::string name; cudaEvent_t e0, e1; uint64_t launches0, launches1; };
+static std::vector<ProfRecord> g_prof_pending;
+struct ProfTotal { uint64_t scopes = 0, launches = 0; double ms = 0.0; };
+static std::vector<std::pair<std::string, ProfTotal>> g_prof_totals;
+
+ProfScope::ProfScope(const char* kernel_class) {
+	Context& c = ctx();
+	if (!c.profile) return;
+	ProfRecord r;
+	r.name = kernel_class;
+	cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+	r.launches0 = c.launches; r.launches1 = 0;
+	cudaEventRecord(r.e0, c.stream);
+	slot = int(g_prof_pending.size());
+	g_prof_pending.push_back(r);
+}
+ProfScope::~ProfScope() {
+	if (slot < 0) return;
+	Context& c = ctx();
+	if (size_t(slot) >= g_prof_pending.size()) return;
+	cudaEventRecord(g_prof_pending[slot].e1, c.stream);
+	g_prof_pending[slot].launches1 = c.launches;
+}
+
+static void prof_collect() {
+	Context& c = ctx();
+	if (g_prof_pending.empty()) return;
+	cudaStreamSynchronize(c.stream);
+	for (ProfRecord& r : g_prof_pending) {
+		float ms = 0.f;
+		if (r.launches1 >= r.launches0 && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+			ProfTotal* t = nullptr;
+			for (auto& kv : g_prof_totals) if (kv.first == r.name) t = &kv.second;
+			if (!t) { g_prof_totals.emplace_back(r.name, ProfTotal()); t = &g_prof_totals.back().second; }
+			t->scopes += 1; t->launches += r.launches1 - r.launches0; t->ms += ms;
+		}
+		cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+	}
+	g_prof_pending.clear();
+}
+
+} // namespace xb
+
+using namespace xb;
+
+extern "C" {
+
+xb_status xb_init(int device) {
+	return guard([&] {
+		std::lock_guard<std::mutex> lock(g_ctx_mutex);
+		if (g_ctx.initialised) {
+			XB_REQUIRE(device == g_ctx.device, "xb_init: already initialised on another device");
+			return;
+		}
+		init_locked(device);
+	});
+}
+
+xb_status xb_shutdown(void) {
+	return guard([&] {
+		std::lock_guard<std::mutex> lock(g_ctx_mutex);
+		if (!g_ctx.initialised) return;
+		cudaStreamSynchronize(g_ctx.stream);
+		cudaFreeHost(g_ctx.h_scratch);
+		cudaStreamDestroy(g_ctx.stream);
+		g_ctx = Context();
+	});
+}
+
+const char* xb_last_error(void) { return g_last_error.c_str(); }
+int xb_version(void) { return 100; }
+
+xb_status xb_synchronize(void) { return guard([&] { ensure_init(); XB_CUDA(cudaStreamSynchronize(ctx().stream)); }); }
+
+xb_status xb_get_stream(void** s) { return guard([&] { ensure_init(); XB_REQUIRE(s, "null"); *s = ctx().stream; }); }
+
+xb_status xb_kernel_launch_count(uint64_t* n) { return guard([&] { XB_REQUIRE(n, "null"); *n = ctx().launches; }); }
+
+xb_status xb_set_option(const char* key, double value) {
+	return guard([&] {
+		XB_REQUIRE(key, "null key");
+		const std::string k(key);
+		if (k == "svd_max_sweeps") ctx().svd_max_sweeps = int(value);
+		else if (k == "gemm_force_small") ctx().gemm_force_small = int(value);
+		else throw Error(XB_ERR_INVALID, "xb_set_option: unknown key " + k);
+	});
+}
+
+xb_status xb_profile_enable(int on) {
+	return guard([&] {
+		ensure_init();
+		prof_collect();
+		g_prof_totals.clear();
+		ctx().profile = on != 0;
+	});
+}
+
+xb_status xb_profile_get(const char* kernel_class, uint64_t* scopes, uint64_t* launches, double* milliseconds) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(kernel_class, "null");
+		prof_collect();
+		ProfTotal t;
+		for (auto& kv : g_prof_totals) if (kv.first == kernel_class) t = kv.second;
+		if (scopes) *scopes = t.scopes;
+		if (launches) *launches = t.launches;
+		if (milliseconds) *milliseconds = t.ms;
+	});
+}
+
+xb_status xb_alloc(void** dptr, size_t bytes) {
+	return guard([&] { ensure_init(); XB_REQUIRE(dptr, "null"); *dptr = dalloc_bytes(bytes); });
+}
+xb_status xb_free(void* dptr) { return guard([&] { ensure_init(); dfree(dptr); }); }
+xb_status xb_alloc_host(void** hptr, size_t bytes) {
+	return guard([&] { ensure_init(); XB_REQUIRE(hptr, "null"); XB_CUDA(cudaMallocHost(hptr, bytes ? bytes : 8)); });
+}
+xb_status xb_free_host(void* hptr) { return guard([&] { if (hptr) XB_CUDA(cudaFreeHost(hptr)); }); }
+xb_status xb_upload(void* dst, const void* src, size_t bytes) {
+	return guard([&] { ensure_init(); if (bytes) XB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx().stream)); });
+}
+xb_status xb_download(void* dst, const void* src, size_t bytes) {
+	return guard([&] {
+		ensure_init();
+		if (bytes) XB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx().stream));
+		XB_CUDA(cudaStreamSynchronize(ctx().stream));
+	});
+}
+
+} // extern "C"

@@ -1,0 +1,186 @@
+// Dense direct solvers behind blasWrapper::solve (reference: src/xerus/blasLapackWrapper.cpp:542-651):
+// Cholesky (dpotrf2 + dpotrs, :593-610) for symmetric matrices with a definite diagonal, LU with partial pivoting
+// (dgesv, :570) otherwise.  These serve the per-call drop-in layer at the small/medium sizes the reference's tests
+// use; the ALS hot path never densifies its local operator (it is solved matrix-free, see als.cu), so these kernels
+// are deliberately simple: one CTA, right-looking, operating in L2-resident global memory.
+#include "xb_internal.cuh"
+
+namespace xb {
+
+// out[0] = max entry (signed, as the reference's is_symmetric :501-505), out[1] = max |A - A^T|,
+// out[2] = 1 if the diagonal is all > eps or all < -eps (pos_neg_definite_diagonal :519-537) else 0, out[3] = A[0][0]
+__global__ void sym_probe_kernel(const double* __restrict__ A, const int n, double* __restrict__ out) {
+	__shared__ double s_max[32], s_asym[32];
+	__shared__ int s_bad[32];
+	double mx = -HUGE_VAL, asym = 0.0;
+	int bad = 0;
+	const bool positive = A[0] > 0.0;
+	const double eps = 2.220446049250313e-16;
+	for (size_t e = threadIdx.x; e < (size_t)n * n; e += blockDim.x) {
+		const int i = int(e / n), j = int(e % n);
+		const double v = A[e];
+		mx = fmax(mx, v);
+		if (j > i) asym = fmax(asym, fabs(v - A[(size_t)j * n + i]));
+		if (i == j && i > 0) { if (positive ? (v < eps) : (v > -eps)) bad = 1; }
+	}
+	for (int o = 16; o > 0; o >>= 1) {
+		mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+		asym = fmax(asym, __shfl_xor_sync(0xffffffffu, asym, o));
+		bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+	}
+	if ((threadIdx.x & 31) == 0) { s_max[threadIdx.x >> 5] = mx; s_asym[threadIdx.x >> 5] = asym; s_bad[threadIdx.x >> 5] = bad; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < int(blockDim.x >> 5); ++w) { mx = fmax(mx, s_max[w]); asym = fmax(asym, s_asym[w]); bad |= s_bad[w]; }
+		out[0] = mx; out[1] = asym; out[2] = bad ? 0.0 : 1.0; out[3] = A[0];
+	}
+}
+
+// In-place upper Cholesky A = U^T U (row-major, upper triangle), then solves U^T U X = B in place.
+// status[0] = 0 on success, j+1 if the leading minor of order j+1 is not positive definite.
+__global__ void __launch_bounds__(1024) cholesky_solve_kernel(double* __restrict__ A, double* __restrict__ B, const int n, const int nrhs,
+                                                             const double sign, int* __restrict__ status) {
+	__shared__ double s_d;
+	__shared__ int s_fail;
+	if (threadIdx.x == 0) s_fail = 0;
+	__syncthreads();
+	for (int j = 0; j < n; ++j) {
+		if (threadIdx.x == 0) {
+			const double a = sign * A[(size_t)j * n + j];
+			if (!(a > 0.0)) s_fail = j + 1;
+			s_d = sqrt(a);
+		}
+		__syncthreads();
+		if (s_fail) { if (threadIdx.x == 0) status[0] = s_fail; return; }
+		const double d = s_d;
+		for (int c = j + threadIdx.x; c < n; c += blockDim.x) A[(size_t)j * n + c] = (c == j) ? d : sign * A[(size_t)j * n + c] / d;
+		__syncthreads();
+		// trailing update of the upper triangle: A[i][c] -= sign * U[j][i] * U[j][c]  (i > j, c >= i), in the signed matrix
+		const int rem = n - j - 1;
+		for (size_t e = threadIdx.x; e < (size_t)rem * rem; e += blockDim.x) {
+			const int i = j + 1 + int(e / rem), c = j + 1 + int(e % rem);
+			if (c >= i) A[(size_t)i * n + c] -= sign * A[(size_t)j * n + i] * A[(size_t)j * n + c];
+		}
+		__syncthreads();
+	}
+	// forward substitution U^T Y = sign * B, then back substitution U X = Y ; threads own rhs columns / row sweeps
+	for (int j = 0; j < n; ++j) {
+		for (int r = threadIdx.x; r < nrhs; r += blockDim.x) B[(size_t)j * nrhs + r] = sign * B[(size_t)j * nrhs + r] / A[(size_t)j * n + j];
+		__syncthreads();
+		for (size_t e = threadIdx.x; e < (size_t)(n - j - 1) * nrhs; e += blockDim.x) {
+			const int i = j + 1 + int(e / nrhs), r = int(e % nrhs);
+			B[(size_t)i * nrhs + r] -= sign * A[(size_t)j * n + i] * B[(size_t)j * nrhs + r] * sign;
+		}
+		__syncthreads();
+	}
+	for (int j = n - 1; j >= 0; --j) {
+		for (int r = threadIdx.x; r < nrhs; r += blockDim.x) B[(size_t)j * nrhs + r] /= A[(size_t)j * n + j];
+		__syncthreads();
+		for (size_t e = threadIdx.x; e < (size_t)j * nrhs; e += blockDim.x) {
+			const int i = int(e / nrhs), r = int(e % nrhs);
+			B[(size_t)i * nrhs + r] -= A[(size_t)i * n + j] * B[(size_t)j * nrhs + r];
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) status[0] = 0;
+}
+
+// LU with partial (row) pivoting in place, then solves for B in place.  status[0] = j+1 if a zero pivot was met.
+__global__ void __launch_bounds__(1024) lu_solve_kernel(double* __restrict__ A, double* __restrict__ B, const int n, const int nrhs,
+                                                       int* __restrict__ status) {
+	__shared__ double s_val[32];
+	__shared__ int s_idx[32];
+	__shared__ int s_piv;
+	__shared__ int s_fail;
+	if (threadIdx.x == 0) s_fail = 0;
+	__syncthreads();
+	for (int j = 0; j < n; ++j) {
+		double best = -1.0; int bi = j;
+		for (int i = j + threadIdx.x; i < n; i += blockDim.x) { const double v = fabs(A[(size_t)i * n + j]); if (v > best) { best = v; bi = i; } }
+		for (int o = 16; o > 0; o >>= 1) {
+			const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+			const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+			if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+		}
+		if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = bi; }
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			for (int w = 1; w < int(blockDim.x >> 5); ++w) if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
+			s_piv = bi;
+			if (!(best > 0.0)) s_fail = j + 1;
+		}
+		__syncthreads();
+		if (s_fail) { if (threadIdx.x == 0) status[0] = s_fail; return; }
+		const int p = s_piv;
+		if (p != j) {
+			for (int c = threadIdx.x; c < n; c += blockDim.x) { const double t = A[(size_t)j * n + c]; A[(size_t)j * n + c] = A[(size_t)p * n + c]; A[(size_t)p * n + c] = t; }
+			for (int r = threadIdx.x; r < nrhs; r += blockDim.x) { const double t = B[(size_t)j * nrhs + r]; B[(size_t)j * nrhs + r] = B[(size_t)p * nrhs + r]; B[(size_t)p * nrhs + r] = t; }
+		}
+		__syncthreads();
+		const double piv = A[(size_t)j * n + j];
+		for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) A[(size_t)i * n + j] /= piv;
+		__syncthreads();
+		const int rem = n - j - 1;
+		for (size_t e = threadIdx.x; e < (size_t)rem * rem; e += blockDim.x) {
+			const int i = j + 1 + int(e / rem), c = j + 1 + int(e % rem);
+			A[(size_t)i * n + c] -= A[(size_t)i * n + j] * A[(size_t)j * n + c];
+		}
+		for (size_t e = threadIdx.x; e < (size_t)rem * nrhs; e += blockDim.x) {
+			const int i = j + 1 + int(e / nrhs), r = int(e % nrhs);
+			B[(size_t)i * nrhs + r] -= A[(size_t)i * n + j] * B[(size_t)j * nrhs + r];
+		}
+		__syncthreads();
+	}
+	for (int j = n - 1; j >= 0; --j) {
+		for (int r = threadIdx.x; r < nrhs; r += blockDim.x) B[(size_t)j * nrhs + r] /= A[(size_t)j * n + j];
+		__syncthreads();
+		for (size_t e = threadIdx.x; e < (size_t)j * nrhs; e += blockDim.x) {
+			const int i = int(e / nrhs), r = int(e % nrhs);
+			B[(size_t)i * nrhs + r] -= A[(size_t)i * n + j] * B[(size_t)j * nrhs + r];
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) status[0] = 0;
+}
+
+static int read_status(int* d_status) {
+	Context& c = ctx();
+	int* h = reinterpret_cast<int*>(c.h_scratch);
+	XB_CUDA(cudaMemcpyAsync(h, d_status, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaStreamSynchronize(c.stream));
+	return h[0];
+}
+
+// sign = +1 for a positive, -1 for a negative diagonal (the reference's dpotrf2 only succeeds for +1)
+bool cholesky_solve(double* A, double* B, size_t n, size_t nrhs) {
+	int* d_status = static_cast<int*>(dalloc_bytes(sizeof(int)));
+	cholesky_solve_kernel<<<1, 1024, 0, ctx().stream>>>(A, B, int(n), int(nrhs), 1.0, d_status);
+	XB_LAUNCH_CHECK();
+	const int st = read_status(d_status);
+	dfree(d_status);
+	return st == 0;
+}
+
+void lu_solve(double* A, double* B, size_t n, size_t nrhs) {
+	int* d_status = static_cast<int*>(dalloc_bytes(sizeof(int)));
+	lu_solve_kernel<<<1, 1024, 0, ctx().stream>>>(A, B, int(n), int(nrhs), d_status);
+	XB_LAUNCH_CHECK();
+	const int st = read_status(d_status);
+	dfree(d_status);
+	if (st != 0) throw Error(XB_ERR_NUMERIC, "Unable to solve Ax = b (PLU solver): zero pivot in column " + std::to_string(st - 1));
+}
+
+// returns {symmetric, definite diagonal}
+void probe_symmetry(const double* A, size_t n, bool& symmetric, bool& definite_diag) {
+	DBuf out(4);
+	sym_probe_kernel<<<1, 1024, 0, ctx().stream>>>(A, int(n), out);
+	XB_LAUNCH_CHECK();
+	Context& c = ctx();
+	XB_CUDA(cudaMemcpyAsync(c.h_scratch, out.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaStreamSynchronize(c.stream));
+	const double mx = std::max(0.0, c.h_scratch[0]);
+	symmetric = (n == 1) || (c.h_scratch[1] < 4.0 * mx * 2.220446049250313e-16);   // blasLapackWrapper.cpp:509
+	definite_diag = c.h_scratch[2] != 0.0;
+}
+
+} // namespace xb

@@ -1,0 +1,292 @@
+// One-sided (Hestenes) block-Jacobi SVD for sm_100a, FP64 — replaces LAPACKE_dgesdd behind blasWrapper::svd
+// (reference: src/xerus/blasLapackWrapper.cpp:201-232) and carries the truncation of calculate_svd
+// (src/xerus/tensor.cpp:1464-1489: rank cap, eps rule, crop of U / Vt, optional Sigma fold-in of round_edge,
+// src/xerus/tensorNetwork.cpp:769) in its epilogue, so cropped factors are never materialised at full size.
+//
+// Layout: the working matrix is kept TRANSPOSED in HBM, GT[j] = [ x_j (mdot entries) ; v_j (nw entries) ], one
+// contiguous row per column of [X; V], so that a block of columns is a contiguous slab.  A CTA owns one pair of
+// column blocks, keeps the slab in shared memory (2*bw rows of mt doubles, up to ~200 KB), and runs the inner
+// rotations with one warp per column pair: three fused dot products (warp-shuffle reduction), one rotation of the
+// stacked vector.  Every pair is met exactly once per sweep: the first round of the outer tournament runs the full
+// 2*bw-player inner tournament (intra + cross pairs), later rounds only the bw cross rounds.
+// Tall inputs are first reduced by QR (SVD of the triangular factor), wide inputs are handled as the transpose.
+#include "xb_internal.cuh"
+
+namespace xb {
+
+constexpr double DBL_EPS = 2.220446049250313e-16;
+
+__global__ void svd_init_kernel(double* __restrict__ GT, const int ldg, const int npad, const int mdot, const int nw,
+                                const double* __restrict__ src, const long long rs, const long long cs) {
+	const size_t total = (size_t)npad * ldg;
+	for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+		const int j = int(e / ldg), i = int(e % ldg);
+		double v = 0.0;
+		if (j < nw) {
+			if (i < mdot) v = src[(long long)i * rs + (long long)j * cs];
+			else if (i - mdot == j) v = 1.0;
+		}
+		GT[e] = v;
+	}
+}
+
+// blockIdx.x = pair index inside outer round `round`; nblk even.  mode_full: all pairs among the 2*bw columns,
+// otherwise only the bw*bw cross pairs.  With loop != 0 (single block pair) the kernel sweeps until no rotation
+// happened in a sweep, and reports the number of sweeps in info[1].
+__global__ void jacobi_block_kernel(double* __restrict__ GT, const int ldg, const int mt, const int mdot, const int bw,
+                                    const int nblk, const int round, const int mode_full, const double tol,
+                                    unsigned int* __restrict__ info, const int loop, const int max_sweeps) {
+	extern __shared__ double S[];
+	__shared__ unsigned int s_rot;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	int pb, qb;
+	{
+		const int pi = blockIdx.x, N1 = nblk - 1;
+		if (nblk == 2) { pb = 0; qb = 1; }
+		else if (pi == 0) { pb = N1; qb = round % N1; }
+		else { pb = (round + pi) % N1; qb = (round - pi + N1) % N1; }
+	}
+	// load the two column blocks (rows of GT)
+	for (int r = warp; r < 2 * bw; r += nwarps) {
+		const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
+		const double* src = GT + (size_t)grow * ldg;
+		double* dst = S + (size_t)r * mt;
+		for (int i = lane; i < mt; i += 32) dst[i] = src[i];
+	}
+	if (threadIdx.x == 0) s_rot = 0;
+	__syncthreads();
+
+	const int N = 2 * bw;
+	const int inner_rounds = mode_full ? (N - 1) : bw;
+	unsigned int total_rot = 0;
+	int sweeps = 0;
+	for (;;) {
+		for (int rr = 0; rr < inner_rounds; ++rr) {
+			for (int pi = warp; pi < bw; pi += nwarps) {
+				int a, b;
+				if (mode_full) {
+					if (pi == 0) { a = N - 1; b = rr; }
+					else { a = (rr + pi) % (N - 1); b = (rr - pi + N - 1) % (N - 1); }
+				} else {
+					a = pi; b = bw + (pi + rr) % bw;
+				}
+				double* x = S + (size_t)a * mt;
+				double* y = S + (size_t)b * mt;
+				double aa = 0.0, bb = 0.0, ab = 0.0;
+				for (int i = lane; i < mdot; i += 32) {
+					const double xi = x[i], yi = y[i];
+					aa += xi * xi; bb += yi * yi; ab += xi * yi;
+				}
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) {
+					aa += __shfl_xor_sync(0xffffffffu, aa, o);
+					bb += __shfl_xor_sync(0xffffffffu, bb, o);
+					ab += __shfl_xor_sync(0xffffffffu, ab, o);
+				}
+				if (fabs(ab) > tol * sqrt(aa) * sqrt(bb)) {
+					const double zeta = (bb - aa) / (2.0 * ab);
+					const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+					const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+					for (int i = lane; i < mt; i += 32) {
+						const double xi = x[i], yi = y[i];
+						x[i] = c * xi - s * yi;
+						y[i] = s * xi + c * yi;
+					}
+					if (lane == 0) atomicAdd(&s_rot, 1u);
+				}
+			}
+			__syncthreads();
+		}
+		++sweeps;
+		const unsigned int rot = s_rot;
+		__syncthreads();
+		if (threadIdx.x == 0) s_rot = 0;
+		total_rot += rot;
+		if (!loop || rot == 0 || sweeps >= max_sweeps) {
+			if (threadIdx.x == 0 && loop) { info[1] = (unsigned)sweeps; info[2] = rot; }
+			break;
+		}
+		__syncthreads();
+	}
+	if (threadIdx.x == 0 && total_rot) atomicAdd(&info[0], total_rot);
+	// write back
+	for (int r = warp; r < 2 * bw; r += nwarps) {
+		const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
+		double* dst = GT + (size_t)grow * ldg;
+		const double* src = S + (size_t)r * mt;
+		for (int i = lane; i < mt; i += 32) dst[i] = src[i];
+	}
+}
+
+// singular values = column norms; rank them (descending, ties by index) -> Ssorted, perm.   single CTA
+__global__ void svd_sort_kernel(const double* __restrict__ GT, const int ldg, const int mdot, const int nw,
+                                double* __restrict__ Ssorted, int* __restrict__ perm) {
+	extern __shared__ double nrm[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	for (int j = warp; j < nw; j += nwarps) {
+		const double* x = GT + (size_t)j * ldg;
+		double s = 0.0;
+		for (int i = lane; i < mdot; i += 32) s += x[i] * x[i];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+		if (lane == 0) nrm[j] = sqrt(s);
+	}
+	__syncthreads();
+	for (int j = threadIdx.x; j < nw; j += blockDim.x) {
+		const double v = nrm[j];
+		int rank = 0;
+		for (int i = 0; i < nw; ++i) { const double u = nrm[i]; rank += (u > v || (u == v && i < j)) ? 1 : 0; }
+		Ssorted[rank] = v;
+		perm[rank] = j;
+	}
+}
+
+// blockIdx.x = output index r (< k).  X part -> outX[i*sxi + r*sxr] (i < mdot), V part -> outV[c*svc + r*svr] (c < nw).
+// The X part is normalised by sigma_r unless scale_x (then it keeps Sigma); the V part is multiplied by sigma_r if scale_v.
+__global__ void svd_extract_kernel(const double* __restrict__ GT, const int ldg, const int mdot, const int nw,
+                                   const double* __restrict__ Ssorted, const int* __restrict__ perm,
+                                   double* __restrict__ outX, const long long sxi, const long long sxr, const int scale_x,
+                                   double* __restrict__ outV, const long long svc, const long long svr, const int scale_v,
+                                   double* __restrict__ dS, const double soft) {
+	const int r = blockIdx.x;
+	const double sigma = Ssorted[r];
+	const double sigma_eff = fmax(0.0, sigma - soft);        // soft thresholding (tensorNetwork.cpp:766)
+	const double* g = GT + (size_t)perm[r] * ldg;
+	const double inv = sigma > 0.0 ? 1.0 / sigma : 0.0;
+	const double fx = scale_x ? (soft == 0.0 ? 1.0 : sigma_eff * inv) : inv;
+	const double fv = scale_v ? sigma_eff : 1.0;
+	for (int i = threadIdx.x; i < mdot; i += blockDim.x) outX[(long long)i * sxi + (long long)r * sxr] = g[i] * fx;
+	for (int c = threadIdx.x; c < nw; c += blockDim.x) outV[(long long)c * svc + (long long)r * svr] = g[mdot + c] * fv;
+	if (dS && threadIdx.x == 0) dS[r] = sigma_eff;
+}
+
+static int choose_bw(size_t mt, size_t nw, size_t smem_cap) {
+	int bw = 32;
+	while (bw > 1 && (size_t(2 * bw) * mt * sizeof(double) > smem_cap || size_t(bw) >= nw)) bw >>= 1;
+	return bw;
+}
+
+void Svd::factor(const double* A, size_t m_, size_t n_) {
+	XB_REQUIRE(m_ > 0 && n_ > 0, "SVD of an empty matrix");
+	ProfScope prof_total("svd");
+	m = m_; n = n_;
+	swapped = m < n;
+	mw = std::max(m, n); nw = std::min(m, n);
+	kmax = nw;
+	reduced = (mw > nw) && (mw > 32);
+	Context& c = ctx();
+	const size_t smem_cap = std::min<size_t>(c.max_smem_optin, 227 * 1024) - 1024;
+
+	const double* src; long long rs, cs; size_t mdot;
+	DBuf At, Rr;
+	if (reduced) {
+		Qred.resize(mw * nw); Rr.resize(nw * nw);
+		if (swapped) { At.resize(m * n); transpose(At, A, m, n); qr(Qred, Rr, At, mw, nw); }
+		else qr(Qred, Rr, A, mw, nw);
+		src = Rr; rs = (long long)nw; cs = 1; mdot = nw;
+	} else {
+		src = A; mdot = mw;
+		if (swapped) { rs = 1; cs = (long long)n; } else { rs = (long long)n; cs = 1; }
+	}
+	mt = mdot + nw;
+	XB_REQUIRE(2 * mt * sizeof(double) <= smem_cap, "SVD: matrix too large for the shared-memory Jacobi kernel (min(m,n) <= ~7000)");
+	const int bw = choose_bw(mt, nw, smem_cap);
+	size_t nblk = (nw + bw - 1) / bw;
+	if (nblk < 2) nblk = 2;
+	if (nblk & 1) ++nblk;
+	npad = nblk * bw;
+	GT.resize(npad * mt);
+	{
+		const size_t total = npad * mt;
+		const unsigned blocks = unsigned(std::min<size_t>((total + 255) / 256, size_t(c.num_sms) * 8));
+		svd_init_kernel<<<blocks, 256, 0, c.stream>>>(GT, int(mt), int(npad), int(mdot), int(nw), src, rs, cs);
+		XB_LAUNCH_CHECK();
+	}
+	const double tol = std::sqrt(double(mdot)) * DBL_EPS;
+	const size_t smem = size_t(2 * bw) * mt * sizeof(double);
+	static bool attr_set = false;
+	if (!attr_set) {
+		XB_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+		attr_set = true;
+	}
+	const int threads = std::max(64, std::min(1024, 32 * bw));
+	unsigned int* d_info = static_cast<unsigned int*>(dalloc_bytes(4 * sizeof(unsigned int)));
+	unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch);
+	sweeps = 0;
+	bool converged = false;
+	ProfScope* prof_jacobi = new ProfScope("svd_jacobi");
+	if (nblk == 2) {
+		XB_CUDA(cudaMemsetAsync(d_info, 0, 4 * sizeof(unsigned int), c.stream));
+		jacobi_block_kernel<<<1, threads, smem, c.stream>>>(GT, int(mt), int(mt), int(mdot), bw, 2, 0, 1, tol, d_info, 1, c.svd_max_sweeps);
+		XB_LAUNCH_CHECK();
+		XB_CUDA(cudaMemcpyAsync(h_info, d_info, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+		XB_CUDA(cudaStreamSynchronize(c.stream));
+		sweeps = int(h_info[1]);
+		converged = (h_info[2] == 0);
+	} else {
+		for (int sw = 0; sw < c.svd_max_sweeps && !converged; ++sw) {
+			XB_CUDA(cudaMemsetAsync(d_info, 0, 4 * sizeof(unsigned int), c.stream));
+			for (size_t round = 0; round + 1 < nblk; ++round) {
+				jacobi_block_kernel<<<unsigned(nblk / 2), threads, smem, c.stream>>>(GT, int(mt), int(mt), int(mdot), bw, int(nblk),
+				                                                                     int(round), round == 0 ? 1 : 0, tol, d_info, 0, 1);
+				XB_LAUNCH_CHECK();
+			}
+			XB_CUDA(cudaMemcpyAsync(h_info, d_info, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+			XB_CUDA(cudaStreamSynchronize(c.stream));
+			++sweeps;
+			converged = (h_info[0] == 0);
+		}
+	}
+	delete prof_jacobi;
+	dfree(d_info);
+	if (!converged) throw Error(XB_ERR_NUMERIC, "Jacobi SVD did not converge within svd_max_sweeps sweeps");
+
+	Ssorted.resize(nw);
+	perm.resize((nw + 1) / 2 + 1);   // nw ints
+	{
+		const size_t sm = nw * sizeof(double);
+		XB_REQUIRE(sm <= 48 * 1024, "SVD: too many columns for the sort kernel");
+		svd_sort_kernel<<<1, 1024, sm, c.stream>>>(GT, int(mt), int(mdot), int(nw), Ssorted, reinterpret_cast<int*>(perm.p));
+		XB_LAUNCH_CHECK();
+	}
+	S.resize(nw);
+	if (nw <= c.h_scratch_len) {
+		XB_CUDA(cudaMemcpyAsync(c.h_scratch, Ssorted.p, nw * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+		XB_CUDA(cudaStreamSynchronize(c.stream));
+		std::copy(c.h_scratch, c.h_scratch + nw, S.begin());
+	} else {
+		XB_CUDA(cudaMemcpyAsync(S.data(), Ssorted.p, nw * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+		XB_CUDA(cudaStreamSynchronize(c.stream));
+	}
+}
+
+void Svd::extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, double* dS) {
+	XB_REQUIRE(k >= 1 && k <= kmax, "SVD extract: rank out of range");
+	Context& c = ctx();
+	const size_t mdot = mt - nw;
+	const int* p = reinterpret_cast<const int*>(perm.p);
+	// The X part holds the left vectors of the working matrix G, the V part its right vectors;
+	// G = A (not swapped) or A^T (swapped); if reduced, G = Qred * (working matrix).
+	double* outX; long long sxi, sxr; int scale_x;
+	double* outV; long long svc, svr; int scale_v;
+	DBuf Xk;
+	if (reduced) { Xk.resize(nw * k); outX = Xk; sxi = (long long)k; sxr = 1; }
+	if (!swapped) {
+		if (!reduced) { outX = U; sxi = (long long)k; sxr = 1; }
+		scale_x = scale_u;
+		outV = Vt; svc = 1; svr = (long long)n; scale_v = scale_vt;
+	} else {
+		if (!reduced) { outX = Vt; sxi = 1; sxr = (long long)n; }
+		scale_x = scale_vt;
+		outV = U; svc = (long long)k; svr = 1; scale_v = scale_u;
+	}
+	svd_extract_kernel<<<unsigned(k), 256, 0, c.stream>>>(GT, int(mt), int(mdot), int(nw), Ssorted, p, outX, sxi, sxr, scale_x,
+	                                                       outV, svc, svr, scale_v, dS, soft_threshold);
+	XB_LAUNCH_CHECK();
+	if (reduced) {
+		if (!swapped) gemm(U, k, m, k, 1.0, Qred, nw, false, nw, Xk, k, false, 0.0);          // U = Qred * Xk
+		else gemm(Vt, n, k, n, 1.0, Xk, k, true, nw, Qred, nw, true, 0.0);                    // Vt = Xk^T * Qred^T
+	}
+}
+
+} // namespace xb

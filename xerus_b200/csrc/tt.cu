@@ -1,0 +1,463 @@
+// Device-resident tensor trains: the sweep layer of the C ABI.
+//
+// A xb_tt owns its cores in HBM for its whole life (row-major (r_left, n, r_right) resp. (r_left, m, n, r_right),
+// reference layout: src/xerus/ttNetwork.cpp:96-98, ttNetwork.h:146-149); left/right matricisations are
+// reinterpretations of the same buffer (reference: calculate_factorization_sizes, src/xerus/tensor.cpp:1361-1369).
+// move_core / round follow TTNetwork::move_core / round (src/xerus/ttNetwork.cpp:582-684) edge by edge through
+// transfer_core / round_edge (src/xerus/tensorNetwork.cpp:678-909); nothing leaves the device during a sweep except
+// the per-edge rank decision (singular values / one min-max pair), which the host needs to size the next launches.
+#include "xb_internal.cuh"
+
+using namespace xb;
+
+struct xb_tt {
+	size_t d = 0;
+	bool is_operator = false;
+	std::vector<size_t> dim_m, dim_n;   // external dims per site (dim_n unused for tensors)
+	std::vector<size_t> rank;           // d + 1 entries, rank[0] = rank[d] = 1
+	std::vector<DBuf> core;
+	bool canonicalized = false;
+	size_t core_position = 0;
+
+	size_t ext(size_t i) const { return is_operator ? dim_m[i] * dim_n[i] : dim_m[i]; }
+	size_t core_size(size_t i) const { return rank[i] * ext(i) * rank[i + 1]; }
+};
+
+namespace xb {
+
+static void check_idx(const xb_tt* t, size_t idx) { XB_REQUIRE(t && idx < t->d, "Illegal component index"); }
+
+// TensorNetwork::transfer_core for a TT chain (tensorNetwork.cpp:821-909).
+static void transfer_core(xb_tt* t, size_t from, size_t to, bool allow_rank_reduction) {
+	if (to == from + 1) {
+		const size_t rows = t->rank[from] * t->ext(from), cols = t->rank[from + 1];
+		const size_t kmax = std::min(rows, cols);
+		DBuf Q(rows * kmax), R(kmax * cols);
+		size_t k = kmax;
+		if (allow_rank_reduction) k = qc(Q, R, t->core[from], rows, cols);      // :843
+		else qr(Q, R, t->core[from], rows, cols);                              // :845
+		Q.n = rows * k;
+		const size_t ncols = t->ext(to) * t->rank[to + 1];
+		DBuf nt(k * ncols);
+		gemm(nt, ncols, k, ncols, 1.0, R, cols, false, cols, t->core[to], ncols, false, 0.0);   // to = R * to  (:877)
+		t->core[from] = std::move(Q);
+		t->core[to] = std::move(nt);
+		t->rank[from + 1] = k;
+	} else if (from == to + 1) {
+		const size_t rows = t->rank[from], cols = t->ext(from) * t->rank[from + 1];
+		const size_t kmax = std::min(rows, cols);
+		DBuf L(rows * kmax), Q(kmax * cols);
+		size_t k = kmax;
+		if (allow_rank_reduction) k = cq(L, Q, t->core[from], rows, cols);      // :835
+		else lq(L, Q, t->core[from], rows, cols);                              // :837 (any orthonormal-row factor serves)
+		Q.n = k * cols;
+		const size_t nrows = t->rank[to] * t->ext(to);
+		DBuf nt(nrows * k);
+		gemm(nt, k, nrows, k, 1.0, t->core[to], rows, false, rows, L, k, false, 0.0);           // to = to * L  (:880)
+		t->core[from] = std::move(Q);
+		t->core[to] = std::move(nt);
+		t->rank[from] = k;
+	} else {
+		throw Error(XB_ERR_INVALID, "transfer_core: nodes are not neighbours");
+	}
+}
+
+static bool exceeds_maximal_ranks(const xb_tt* t) {   // ttNetwork.cpp:349-359
+	for (size_t i = 0; i < t->d; ++i) {
+		const size_t e = t->ext(i);
+		if (t->rank[i] > e * t->rank[i + 1] || t->rank[i + 1] > e * t->rank[i]) return true;
+	}
+	return false;
+}
+
+static void move_core(xb_tt* t, size_t position, bool keep_rank) {   // ttNetwork.cpp:582-628
+	XB_REQUIRE(position < t->d, "Illegal core-position chosen for TTNetwork");
+	const bool arr = !keep_rank;
+	const size_t d = t->d;
+	if (t->canonicalized) {
+		for (size_t n = t->core_position; n < position; ++n) transfer_core(t, n, n + 1, arr);
+		for (size_t n = t->core_position; n > position; --n) transfer_core(t, n, n - 1, arr);
+	} else {
+		for (size_t n = 0; n < position; ++n) transfer_core(t, n, n + 1, arr);
+		for (size_t n = d - 1; n > position; --n) transfer_core(t, n, n - 1, arr);
+	}
+	while (exceeds_maximal_ranks(t)) {                                   // :609-624
+		for (size_t n = position; n > 0; --n) transfer_core(t, n, n - 1, arr);
+		for (size_t n = 0; n + 1 < d; ++n) transfer_core(t, n, n + 1, arr);
+		for (size_t n = d - 1; n > position; --n) transfer_core(t, n, n - 1, arr);
+	}
+	t->canonicalized = true;
+	t->core_position = position;
+}
+
+// TensorNetwork::round_edge as TTNetwork::round uses it (tensorNetwork.cpp:678-818): `from` is the right core,
+// `to` = from - 1 the left one; Sigma goes to the left core.  When the left core is known to be left-orthonormal
+// (always the case inside round(), which canonicalises to the right end first) its QC (:755) is an identity up to
+// signs and is skipped: the SVD of the right core's matricisation alone gives the same truncated pair.  The
+// wide-matrix reduction (the reference's CQ of `from`, :749) happens inside Svd::factor as the QR of the transpose.
+static void round_edge(xb_tt* t, size_t from, size_t max_rank, double eps, double soft_threshold, bool to_orthonormal,
+                       std::vector<double>* svals_out) {
+	const size_t to = from - 1;
+	const size_t r = t->rank[from];
+	const size_t fcols = t->ext(from) * t->rank[from + 1];
+	const size_t trows = t->rank[to] * t->ext(to);
+	Svd svd;
+	svd.soft_threshold = soft_threshold;
+	if (to_orthonormal) {
+		svd.factor(t->core[from], r, fcols);
+		const size_t k = truncation_rank(svd.S, max_rank, eps);               // tensor.cpp:1464-1474
+		DBuf US(r * k), nf(k * fcols), nt(trows * k);
+		svd.extract(US, nf, k, true, false, nullptr);                         // from = Vt_k ; U_k S_k
+		gemm(nt, k, trows, k, 1.0, t->core[to], r, false, r, US, k, false, 0.0);   // to = to * U_k S_k   (:779)
+		t->core[from] = std::move(nf);
+		t->core[to] = std::move(nt);
+		t->rank[from] = k;
+		if (svals_out) svals_out->assign(svd.S.begin(), svd.S.begin() + k);
+	} else {
+		// general case: to = Tq * B, M = B * from, M = U S Vt  ->  to = Tq * U_k S_k, from = Vt_k
+		const size_t kb = std::min(trows, r);
+		DBuf Tq(trows * kb), B(kb * r), M(kb * fcols);
+		qr(Tq, B, t->core[to], trows, r);
+		gemm(M, fcols, kb, fcols, 1.0, B, r, false, r, t->core[from], fcols, false, 0.0);
+		svd.factor(M, kb, fcols);
+		const size_t k = truncation_rank(svd.S, max_rank, eps);
+		DBuf US(kb * k), nf(k * fcols), nt(trows * k);
+		svd.extract(US, nf, k, true, false, nullptr);
+		gemm(nt, k, trows, k, 1.0, Tq, kb, false, kb, US, k, false, 0.0);
+		t->core[from] = std::move(nf);
+		t->core[to] = std::move(nt);
+		t->rank[from] = k;
+		if (svals_out) svals_out->assign(svd.S.begin(), svd.S.begin() + k);
+	}
+}
+
+static void round_tt(xb_tt* t, const size_t* max_ranks, double eps, double* svals, size_t stride) {   // ttNetwork.cpp:644-665
+	XB_REQUIRE(eps >= 0.0 && eps < 1.0, "_eps must be smaller than one.");
+	const size_t d = t->d;
+	const bool initial_canon = t->canonicalized;
+	const size_t initial_core = t->core_position;
+	move_core(t, d - 1, false);                                          // canonicalize_right (:654)
+	std::vector<double> sv;
+	for (size_t i = 0; i + 1 < d; ++i) {                                 // :656-658
+		const size_t from = d - 1 - i, edge = from - 1;
+		round_edge(t, from, max_ranks[edge], eps, 0.0, true, svals ? &sv : nullptr);
+		if (svals) {
+			XB_REQUIRE(sv.size() <= stride, "svals stride too small");
+			std::copy(sv.begin(), sv.end(), svals + edge * stride);
+			std::fill(svals + edge * stride + sv.size(), svals + (edge + 1) * stride, 0.0);
+		}
+	}
+	t->canonicalized = true;                                             // assume_core_position(0) (:660)
+	t->core_position = 0;
+	if (initial_canon) move_core(t, initial_core, false);                // :662-664
+}
+
+static double tt_inner(const xb_tt* a, const xb_tt* b) {
+	XB_REQUIRE(a->d == b->d && a->is_operator == b->is_operator, "TT inner product: formats differ");
+	for (size_t i = 0; i < a->d; ++i) XB_REQUIRE(a->ext(i) == b->ext(i), "TT inner product: dimensions differ");
+	DBuf E(1);
+	fill(E, 1.0, 1);
+	for (size_t i = 0; i < a->d; ++i) {
+		const size_t ra = a->rank[i], rb = b->rank[i], ra2 = a->rank[i + 1], rb2 = b->rank[i + 1], e = a->ext(i);
+		DBuf tmp(rb * e * ra2), E2(ra2 * rb2);
+		// tmp (rb x e*ra2) = E^T (rb x ra) * A_i (ra x e*ra2)
+		gemm(tmp, e * ra2, rb, e * ra2, 1.0, E, rb, true, ra, a->core[i], e * ra2, false, 0.0);
+		// E2 (ra2 x rb2) = tmp^T ((rb*e) x ra2)^T * B_i ((rb*e) x rb2)
+		gemm(E2, rb2, ra2, rb2, 1.0, tmp, ra2, true, rb * e, b->core[i], rb2, false, 0.0);
+		E = std::move(E2);
+	}
+	return read_scalar(E);
+}
+
+static double tt_frob_norm(const xb_tt* t) {   // ttNetwork.cpp:782-789
+	if (t->canonicalized) return two_norm(t->core[t->core_position], t->core_size(t->core_position));
+	return std::sqrt(std::max(0.0, tt_inner(t, t)));
+}
+
+static xb_tt* tt_clone(const xb_tt* t) {
+	xb_tt* c = new xb_tt();
+	c->d = t->d; c->is_operator = t->is_operator; c->dim_m = t->dim_m; c->dim_n = t->dim_n; c->rank = t->rank;
+	c->canonicalized = t->canonicalized; c->core_position = t->core_position;
+	c->core.resize(t->d);
+	for (size_t i = 0; i < t->d; ++i) { c->core[i].resize(t->core_size(i)); copy(c->core[i], t->core[i], t->core_size(i)); }
+	return c;
+}
+
+// TTNetwork::operator+= (ttNetwork.cpp:797-847): block stacking, then back to the caller's core position
+static xb_tt* tt_add(const xb_tt* a, const xb_tt* b, double beta_scale, bool recanonicalize) {
+	XB_REQUIRE(a->d == b->d && a->is_operator == b->is_operator, "The dimensions in TT sum must coincide");
+	for (size_t i = 0; i < a->d; ++i) XB_REQUIRE(a->ext(i) == b->ext(i), "The dimensions in TT sum must coincide");
+	const size_t d = a->d;
+	xb_tt* c = new xb_tt();
+	c->d = d; c->is_operator = a->is_operator; c->dim_m = a->dim_m; c->dim_n = a->dim_n;
+	c->rank.assign(d + 1, 1);
+	for (size_t i = 1; i < d; ++i) c->rank[i] = a->rank[i] + b->rank[i];
+	c->core.resize(d);
+	for (size_t i = 0; i < d; ++i) {
+		const size_t e = a->ext(i), la = a->rank[i], ra = a->rank[i + 1], lb = b->rank[i], rb = b->rank[i + 1];
+		const size_t rr = c->rank[i + 1];
+		c->core[i].resize(c->core_size(i));
+		if (d == 1) {
+			copy(c->core[i], a->core[i], e);
+			axpy(c->core[i], beta_scale, b->core[i], e);
+			continue;
+		}
+		fill(c->core[i], 0.0, c->core_size(i));
+		const size_t row_off = (i == 0) ? 0 : la * e, col_off = (i == d - 1) ? 0 : ra;
+		copy2d(c->core[i], rr, a->core[i], ra, la * e, ra);
+		copy2d(c->core[i].p + row_off * rr + col_off, rr, b->core[i], rb, lb * e, rb);
+	}
+	if (beta_scale != 1.0 && d > 1) {
+		// scale b's contribution once: its block of the first core
+		const size_t e = a->ext(0), ra = a->rank[1], rb = b->rank[1], rr = c->rank[1];
+		DBuf s(rr);
+		fill(s, 1.0, ra);
+		fill(s.p + ra, beta_scale, rb);
+		scale_cols(c->core[0], s, e, rr, rr);
+	}
+	c->canonicalized = false;
+	if (recanonicalize && a->canonicalized) move_core(c, a->core_position, false);
+	return c;
+}
+
+// y(i&0) = A(i/2, j/2) * x(j&0): per site ((a r), m, (b s)) = sum_n A(a, m, n, b) x(r, n, s)   (ttStack.cpp:197-300)
+static xb_tt* tt_apply(const xb_tt* A, const xb_tt* x) {
+	XB_REQUIRE(A->is_operator && !x->is_operator && A->d == x->d, "TT apply needs a TTOperator and a TTTensor of the same order");
+	const size_t d = A->d;
+	xb_tt* y = new xb_tt();
+	y->d = d; y->is_operator = false; y->dim_m.resize(d); y->dim_n.assign(d, 1);
+	y->rank.assign(d + 1, 1);
+	y->core.resize(d);
+	for (size_t i = 0; i < d; ++i) {
+		XB_REQUIRE(A->dim_n[i] == x->dim_m[i], "TT apply: dimensions do not coincide");
+		const size_t a = A->rank[i], b = A->rank[i + 1], m = A->dim_m[i], n = A->dim_n[i], r = x->rank[i], s = x->rank[i + 1];
+		y->dim_m[i] = m;
+		y->rank[i + 1] = (i + 1 == d) ? 1 : b * s;
+		// A (a,m,n,b) -> (a,m,b,n) ; x (r,n,s) -> (n,r,s) ; P ((a m b) x (r s)) ; (a,m,b,r,s) -> (a,r,m,b,s)
+		DBuf Ap(a * m * n * b), xp(n * r * s), P(a * m * b * r * s);
+		{ const size_t dims[4] = {a, m, n, b}, sh[4] = {0, 1, 3, 2}; permute(Ap, A->core[i], dims, sh, 4); }
+		{ const size_t dims[3] = {r, n, s}, sh[3] = {1, 0, 2}; permute(xp, x->core[i], dims, sh, 3); }
+		gemm(P, r * s, a * m * b, r * s, 1.0, Ap, n, false, n, xp, r * s, false, 0.0);
+		y->core[i].resize(a * r * m * b * s);
+		{ const size_t dims[5] = {a, m, b, r, s}, sh[5] = {0, 2, 3, 1, 4}; permute(y->core[i], P, dims, sh, 5); }
+	}
+	y->canonicalized = false;
+	return y;
+}
+
+static void tt_to_dense(const xb_tt* t, DBuf& out) {   // tensorNetwork.cpp:287-306
+	const size_t d = t->d;
+	DBuf cur(t->core_size(0));
+	copy(cur, t->core[0], t->core_size(0));
+	size_t rows = t->ext(0);
+	for (size_t i = 1; i < d; ++i) {
+		const size_t r = t->rank[i], cols = t->ext(i) * t->rank[i + 1];
+		DBuf nxt(rows * cols);
+		gemm(nxt, cols, rows, cols, 1.0, cur, r, false, r, t->core[i], cols, false, 0.0);
+		cur = std::move(nxt);
+		rows *= t->ext(i);
+	}
+	if (t->is_operator && d > 1) {
+		// (m1,n1,m2,n2,...) -> (m1..md, n1..nd)
+		std::vector<size_t> dims(2 * d), sh(2 * d);
+		for (size_t i = 0; i < d; ++i) { dims[2 * i] = t->dim_m[i]; dims[2 * i + 1] = t->dim_n[i]; sh[2 * i] = i; sh[2 * i + 1] = d + i; }
+		XB_REQUIRE(2 * d <= 16, "operator too long to densify (at most 8 sites)");
+		DBuf p(rows);
+		permute(p, cur, dims.data(), sh.data(), 2 * d);
+		cur = std::move(p);
+	}
+	out = std::move(cur);
+}
+
+} // namespace xb
+
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+xb_status xb_tt_create(xb_tt** out, size_t d, const size_t* dims, const size_t* ranks, int is_operator) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(out && dims && d > 0, "xb_tt_create: bad arguments");
+		XB_REQUIRE(d == 1 || ranks, "xb_tt_create: ranks missing");
+		xb_tt* t = new xb_tt();
+		t->d = d; t->is_operator = is_operator != 0;
+		t->dim_m.assign(dims, dims + d);
+		if (is_operator) t->dim_n.assign(dims + d, dims + 2 * d); else t->dim_n.assign(d, 1);
+		t->rank.assign(d + 1, 1);
+		for (size_t i = 0; i + 1 < d; ++i) { XB_REQUIRE(ranks[i] > 0, "rank 0 is illegal"); t->rank[i + 1] = ranks[i]; }
+		for (size_t i = 0; i < d; ++i) XB_REQUIRE(t->dim_m[i] > 0 && t->dim_n[i] > 0, "dimension 0 is not possible");
+		t->core.resize(d);
+		for (size_t i = 0; i < d; ++i) { t->core[i].resize(t->core_size(i)); fill(t->core[i], 0.0, t->core_size(i)); }
+		*out = t;
+	});
+}
+
+xb_status xb_tt_destroy(xb_tt* tt) { return guard([&] { if (tt) { ensure_init(); delete tt; } }); }
+
+xb_status xb_tt_clone(xb_tt** out, const xb_tt* tt) {
+	return guard([&] { ensure_init(); XB_REQUIRE(out && tt, "null"); *out = tt_clone(tt); });
+}
+
+xb_status xb_tt_degree(const xb_tt* tt, size_t* d, int* is_operator) {
+	return guard([&] { XB_REQUIRE(tt, "null"); if (d) *d = tt->d; if (is_operator) *is_operator = tt->is_operator; });
+}
+xb_status xb_tt_ranks(const xb_tt* tt, size_t* ranks) {
+	return guard([&] { XB_REQUIRE(tt && (ranks || tt->d == 1), "null"); for (size_t i = 0; i + 1 < tt->d; ++i) ranks[i] = tt->rank[i + 1]; });
+}
+xb_status xb_tt_dims(const xb_tt* tt, size_t* dims) {
+	return guard([&] {
+		XB_REQUIRE(tt && dims, "null");
+		for (size_t i = 0; i < tt->d; ++i) { dims[i] = tt->dim_m[i]; if (tt->is_operator) dims[tt->d + i] = tt->dim_n[i]; }
+	});
+}
+xb_status xb_tt_core_position(const xb_tt* tt, int* canonicalized, size_t* position) {
+	return guard([&] { XB_REQUIRE(tt, "null"); if (canonicalized) *canonicalized = tt->canonicalized; if (position) *position = tt->core_position; });
+}
+xb_status xb_tt_assume_core_position(xb_tt* tt, size_t position) {
+	return guard([&] { XB_REQUIRE(tt && position < tt->d, "Illegal core position"); tt->canonicalized = true; tt->core_position = position; });
+}
+
+xb_status xb_tt_set_component(xb_tt* tt, size_t idx, const double* host_core, size_t rl, size_t rr) {
+	return guard([&] {
+		ensure_init();
+		check_idx(tt, idx);
+		XB_REQUIRE(host_core && rl > 0 && rr > 0, "set_component: bad arguments");
+		XB_REQUIRE(idx > 0 || rl == 1, "first component must have left rank 1");
+		XB_REQUIRE(idx + 1 < tt->d || rr == 1, "last component must have right rank 1");
+		tt->rank[idx] = rl; tt->rank[idx + 1] = rr;      // link dimensions follow the written component (ttNetwork.cpp:480-488)
+		tt->core[idx].resize(tt->core_size(idx));
+		XB_CUDA(cudaMemcpyAsync(tt->core[idx].p, host_core, tt->core_size(idx) * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+		XB_CUDA(cudaStreamSynchronize(ctx().stream));
+		tt->canonicalized = tt->canonicalized && (tt->core_position == idx);   // ttNetwork.cpp:491
+	});
+}
+
+xb_status xb_tt_get_component(const xb_tt* tt, size_t idx, double* host_core) {
+	return guard([&] {
+		ensure_init();
+		check_idx(tt, idx);
+		XB_REQUIRE(host_core, "null");
+		XB_REQUIRE(tt->core[idx].n == tt->core_size(idx), "component dimensions are inconsistent with the bond ranks (set all components first)");
+		XB_CUDA(cudaMemcpyAsync(host_core, tt->core[idx].p, tt->core_size(idx) * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+		XB_CUDA(cudaStreamSynchronize(ctx().stream));
+	});
+}
+
+xb_status xb_tt_component_size(const xb_tt* tt, size_t idx, size_t* rl, size_t* ext, size_t* rr) {
+	return guard([&] { check_idx(tt, idx); if (rl) *rl = tt->rank[idx]; if (ext) *ext = tt->ext(idx); if (rr) *rr = tt->rank[idx + 1]; });
+}
+
+static void require_correct_format(const xb_tt* tt) {   // ttNetwork.cpp:290-341 (the structural part that can fail here)
+	XB_REQUIRE(tt, "null TT");
+	for (size_t i = 0; i < tt->d; ++i) XB_REQUIRE(tt->core[i].n == tt->core_size(i), "TT is not in correct format: component size does not match its bond ranks");
+}
+
+xb_status xb_tt_move_core(xb_tt* tt, size_t position, int keep_rank) {
+	return guard([&] { ensure_init(); require_correct_format(tt); move_core(tt, position, keep_rank != 0); });
+}
+
+xb_status xb_tt_round_svals(xb_tt* tt, const size_t* max_ranks, double eps, double* svals, size_t stride) {
+	return guard([&] {
+		ensure_init();
+		require_correct_format(tt);
+		XB_REQUIRE(max_ranks || tt->d == 1, "There must be exactly degree-1 maxRanks");
+		round_tt(tt, max_ranks, eps, svals, stride);
+	});
+}
+xb_status xb_tt_round(xb_tt* tt, const size_t* max_ranks, double eps) { return xb_tt_round_svals(tt, max_ranks, eps, nullptr, 0); }
+
+xb_status xb_tt_round_batched(xb_tt** tts, size_t batch, size_t max_rank, double eps) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(tts || batch == 0, "null");
+		for (size_t b = 0; b < batch; ++b) {
+			require_correct_format(tts[b]);
+			std::vector<size_t> mr(tts[b]->d > 1 ? tts[b]->d - 1 : 1, max_rank);
+			round_tt(tts[b], mr.data(), eps, nullptr, 0);
+		}
+	});
+}
+
+xb_status xb_tt_frob_norm(const xb_tt* tt, double* result) {
+	return guard([&] { ensure_init(); require_correct_format(tt); XB_REQUIRE(result, "null"); *result = tt_frob_norm(tt); });
+}
+xb_status xb_tt_inner(const xb_tt* a, const xb_tt* b, double* result) {
+	return guard([&] { ensure_init(); require_correct_format(a); require_correct_format(b); XB_REQUIRE(result, "null"); *result = tt_inner(a, b); });
+}
+xb_status xb_tt_distance(const xb_tt* a, const xb_tt* b, double* result) {
+	return guard([&] {
+		ensure_init(); require_correct_format(a); require_correct_format(b); XB_REQUIRE(result, "null");
+		xb_tt* diff = tt_add(a, b, -1.0, false);
+		try {
+			if (diff->d > 1) move_core(diff, diff->d - 1, true);     // QR sweep: ||a-b|| = ||last core||, no cancellation
+			*result = two_norm(diff->core[diff->d - 1], diff->core_size(diff->d - 1));
+		} catch (...) { delete diff; throw; }
+		delete diff;
+	});
+}
+xb_status xb_tt_scale(xb_tt* tt, double factor) {   // ttNetwork.cpp:860-868: scales the core (or component 0)
+	return guard([&] {
+		ensure_init(); require_correct_format(tt);
+		const size_t i = tt->canonicalized ? tt->core_position : 0;
+		scale(tt->core[i], factor, tt->core_size(i));
+	});
+}
+xb_status xb_tt_add(xb_tt** out, const xb_tt* a, const xb_tt* b) {
+	return guard([&] { ensure_init(); require_correct_format(a); require_correct_format(b); XB_REQUIRE(out, "null"); *out = tt_add(a, b, 1.0, true); });
+}
+xb_status xb_tt_apply(xb_tt** out, const xb_tt* A, const xb_tt* x) {
+	return guard([&] { ensure_init(); require_correct_format(A); require_correct_format(x); XB_REQUIRE(out, "null"); *out = tt_apply(A, x); });
+}
+
+xb_status xb_tt_to_dense(const xb_tt* tt, double* host) {
+	return guard([&] {
+		ensure_init(); require_correct_format(tt); XB_REQUIRE(host, "null");
+		DBuf dense;
+		tt_to_dense(tt, dense);
+		size_t n = 1;
+		for (size_t i = 0; i < tt->d; ++i) n *= tt->ext(i);
+		XB_CUDA(cudaMemcpyAsync(host, dense.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+		XB_CUDA(cudaStreamSynchronize(ctx().stream));
+	});
+}
+
+// TT-SVD constructor TTTensor(Tensor, eps, maxRank) (ttNetwork.cpp:112-160): successive SVDs from the right, Sigma
+// pushed into the left remainder (:151-155).  Result is canonicalised with the core at position 0.
+xb_status xb_tt_from_dense(xb_tt** out, const double* host, size_t d, const size_t* dims, double eps, size_t max_rank) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(out && host && dims && d > 0, "xb_tt_from_dense: bad arguments");
+		XB_REQUIRE(eps >= 0.0 && eps < 1.0, "eps must be in [0,1)");
+		size_t total = 1;
+		for (size_t i = 0; i < d; ++i) { XB_REQUIRE(dims[i] > 0, "dimension 0"); total *= dims[i]; }
+		xb_tt* t = new xb_tt();
+		try {
+			t->d = d; t->is_operator = false; t->dim_m.assign(dims, dims + d); t->dim_n.assign(d, 1);
+			t->rank.assign(d + 1, 1);
+			t->core.resize(d);
+			DBuf remains(total);
+			XB_CUDA(cudaMemcpyAsync(remains.p, host, total * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+			std::vector<size_t> prefix(d + 1, 1);
+			for (size_t i = 0; i < d; ++i) prefix[i + 1] = prefix[i] * dims[i];
+			size_t r = 1;                                     // remains is (n_0...n_pos-1) x (n_pos * r)
+			for (size_t pos = d - 1; pos > 0; --pos) {
+				const size_t lrows = prefix[pos], cols = dims[pos] * r;
+				Svd svd;
+				svd.factor(remains, lrows, cols);
+				const size_t k = truncation_rank(svd.S, max_rank, eps);
+				DBuf US(lrows * k), Vt(k * cols);
+				svd.extract(US, Vt, k, true, false, nullptr);
+				t->core[pos] = std::move(Vt);
+				t->rank[pos] = k;
+				remains = std::move(US);
+				r = k;
+			}
+			t->core[0] = std::move(remains);
+			t->canonicalized = true; t->core_position = 0;
+			for (size_t i = 0; i < d; ++i) XB_REQUIRE(t->core[i].n == t->core_size(i), "internal: TT-SVD core size");
+		} catch (...) { delete t; throw; }
+		*out = t;
+	});
+}
+
+} // extern "C"

@@ -1,0 +1,149 @@
+// Internal declarations shared by the xb200 translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/xb200.h"
+
+namespace xb {
+
+struct Error : std::runtime_error {
+	xb_status code;
+	Error(xb_status c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define XB_STR2(x) #x
+#define XB_STR(x) XB_STR2(x)
+#define XB_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+	throw ::xb::Error(XB_ERR_CUDA, std::string(#call " failed at " __FILE__ ":" XB_STR(__LINE__) ": ") + cudaGetErrorString(e__)); } while (0)
+#define XB_REQUIRE(cond, msg) do { if (!(cond)) \
+	throw ::xb::Error(XB_ERR_INVALID, std::string("REQUIRE(" #cond ") failed: ") + (msg)); } while (0)
+#define XB_LAUNCH_CHECK() do { ::xb::ctx().launches++; XB_CUDA(cudaGetLastError()); } while (0)
+
+void set_last_error(const std::string& msg);
+
+struct Context {
+	bool initialised = false;
+	int device = -1;
+	cudaStream_t stream = nullptr;
+	cudaMemPool_t pool = nullptr;
+	uint64_t launches = 0;
+	int num_sms = 148;
+	size_t max_smem_optin = 0;
+	// pinned scratch for small read-backs (ranks, convergence counters, singular values)
+	double* h_scratch = nullptr;   // 4096 doubles
+	size_t h_scratch_len = 4096;
+	// options
+	int svd_max_sweeps = 40;
+	int qr_panel = 32;
+	int gemm_force_small = 0;
+	bool profile = false;
+};
+Context& ctx();
+void ensure_init();
+
+// Optional CUDA-event timing of a kernel class (bench/roofline only; no-op unless xb_profile_enable(1)).
+struct ProfScope {
+	int slot = -1;
+	explicit ProfScope(const char* kernel_class);
+	~ProfScope();
+};
+
+// stream-ordered device allocations from the library pool
+double* dalloc(size_t n_doubles);
+void* dalloc_bytes(size_t bytes);
+void dfree(void* p);
+struct DBuf {   // RAII device buffer
+	double* p = nullptr; size_t n = 0;
+	DBuf() {}
+	explicit DBuf(size_t n_) : p(n_ ? dalloc(n_) : nullptr), n(n_) {}
+	DBuf(const DBuf&) = delete; DBuf& operator=(const DBuf&) = delete;
+	DBuf(DBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+	DBuf& operator=(DBuf&& o) noexcept { if (this != &o) { reset(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+	~DBuf() { reset(); }
+	void reset() { if (p) dfree(p); p = nullptr; n = 0; }
+	void resize(size_t n_) { reset(); if (n_) { p = dalloc(n_); n = n_; } }
+	operator double*() const { return p; }
+};
+
+template <class F> xb_status guard(F&& f) {
+	try { f(); return XB_OK; }
+	catch (const Error& e) { set_last_error(e.what()); return e.code; }
+	catch (const std::exception& e) { set_last_error(e.what()); return XB_ERR_INVALID; }
+}
+
+// ---- device primitives (all asynchronous on ctx().stream, device pointers) ---------------------------------------
+// C (m x n, ldc) = alpha * op(A) * op(B) + beta * C ; batched variant walks `batch` problems with element strides.
+void gemm(double* C, size_t ldc, size_t m, size_t n, double alpha, const double* A, size_t lda, bool transA, size_t k,
+          const double* B, size_t ldb, bool transB, double beta);
+void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, double alpha, const double* A, size_t lda,
+                  size_t strideA, bool transA, size_t k, const double* B, size_t ldb, size_t strideB, bool transB,
+                  double beta, size_t batch);
+
+// elementwise / movement
+void copy(double* dst, const double* src, size_t n);
+void copy2d(double* dst, size_t ldd, const double* src, size_t lds, size_t rows, size_t cols);
+void fill(double* dst, double value, size_t n);
+void set_identity(double* dst, size_t rows, size_t cols, size_t ld);      // ones on the main diagonal, zero elsewhere
+void scale(double* x, double alpha, size_t n);
+void axpy(double* y, double alpha, const double* x, size_t n);           // y += alpha x
+void transpose(double* out, const double* in, size_t rows, size_t cols); // out (cols x rows) = in^T, both packed
+void transpose_reverse(double* out, const double* in, size_t rows, size_t cols); // out(j,i) = in(rows-1-i, cols-1-j)
+void permute(double* out, const double* in, const size_t* dims, const size_t* shuffle, size_t degree);
+void scale_rows(double* A, const double* s, size_t rows, size_t cols, size_t ld);   // A[i,:] *= s[i]
+void scale_cols(double* A, const double* s, size_t rows, size_t cols, size_t ld);   // A[:,j] *= s[j]
+// reductions: result written to a device double
+void dot_dev(double* d_result, const double* x, const double* y, size_t n);
+void asum_dev(double* d_result, const double* x, size_t n);
+double read_scalar(const double* d_value);                                // D2H + sync
+double two_norm(const double* x, size_t n);
+double dot(const double* x, const double* y, size_t n);
+
+// factorizations
+// A (m x n packed, destroyed? no: const) -> Q (m x k packed), R (k x n packed), k = min(m,n)
+void qr(double* Q, double* R, const double* A, size_t m, size_t n);
+// A = L * Q : L m x k packed (lower trapezoidal), Q k x n packed, orthonormal rows
+void lq(double* L, double* Q, const double* A, size_t m, size_t n);
+// true RQ with LAPACK's convention (R upper-trapezoidal, bottom-right aligned)
+void rq(double* R, double* Q, const double* A, size_t m, size_t n);
+
+struct SvdWork;   // opaque between svd_factor and svd_extract
+// Jacobi SVD of A (m x n packed).  Returns singular values (descending) on the host, keeps vectors on device.
+// Then extract() writes the first k triplets: U (m x k), Vt (k x n); Sigma optionally folded into U or Vt.
+struct Svd {
+	size_t m = 0, n = 0, kmax = 0;
+	std::vector<double> S;     // host copy, descending
+	int sweeps = 0;
+	double soft_threshold = 0.0;   // applied to Sigma wherever extract() folds it in
+	// internals
+	bool swapped = false, reduced = false;
+	size_t mw = 0, nw = 0, npad = 0, mt = 0;
+	DBuf GT, Qred, Ssorted, perm;
+	void factor(const double* A, size_t m, size_t n);
+	void extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, double* dS /* optional device S (k) */);
+};
+
+// rank-revealing QC / CQ on device; returns the rank; Q, C are max-size device buffers that come back packed
+size_t qc(double* Q, double* C, const double* A, size_t m, size_t n);
+size_t cq(double* C, double* Q, const double* A, size_t m, size_t n);
+
+// dense solves on device (A n x n packed, destroyed; B n x nrhs packed, overwritten with X). Return false if not SPD.
+bool cholesky_solve(double* A, double* B, size_t n, size_t nrhs);
+void lu_solve(double* A, double* B, size_t n, size_t nrhs);
+void probe_symmetry(const double* A, size_t n, bool& symmetric, bool& definite_diag);
+
+// truncation rule of calculate_svd (reference: src/xerus/tensor.cpp:1464-1474)
+inline size_t truncation_rank(const std::vector<double>& S, size_t max_rank, double eps) {
+	size_t rank = S.size();
+	if (max_rank != 0) rank = std::min(rank, max_rank);
+	for (size_t j = 1; j < rank; ++j) if (S[j] <= eps * S[0]) { rank = j; break; }
+	return rank;
+}
+
+} // namespace xb
