@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — TT rounding (BASELINE config 3: degree 32, n=2, rank 256 -> 128, FP64) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl xb200|reference] [--workload c3|c1]
+
+One step = one TTTensor::round(128) of a device-resident TT with the ranks of TTTensor::random({2}x32, 256)
+(ranks 2,4,..,128,256 x17,128,..,2; 18.2 MB of cores).  Prints ONE JSON line (contract in the task statement):
+`value` = ms per round with the TT already resident in HBM (CUDA events on the library stream, max over ranks),
+`e2e` = the same through the host-pointer API (pinned host cores -> set_component H2D -> round -> get_component D2H),
+`roofline` for the dominant kernel class, `cpu_baseline` = the unmodified reference (oracle/_ref/ref_bench) timed on
+this box's host cores.  `--impl reference` times the reference's own CPU path for the same workload.
+Multi-GPU: a single TT rounding is a sequential chain (replicas only), so each rank rounds its own TT
+(weak scaling, no data-path collective); NCCL is used for the barrier and the max over ranks only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c3": dict(d=32, n=2, r=256, target=128, name="TT rounding degree 32, n=2, rank 256 -> 128 (BASELINE configs[2])"),
+    "c1": dict(d=8, n=4, r=32, target=16, name="TT rounding degree 8, n=4, rank 32 -> 16 (BASELINE configs[0])"),
+}
+REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+
+
+def algorithmic_counts(dims, ranks_in, ranks_out):
+    """Algorithmic flops / minimum HBM bytes of one round() with the reference operation sequence and LAWN-41 counts
+    (SURVEY.md §8d).  Returns (total_flops, svd_flops, qr_flops, gemm_flops, min_bytes)."""
+    d = len(dims)
+    rin = [1] + list(ranks_in) + [1]
+    rout = [1] + list(ranks_out) + [1]
+    qr = lambda m, n: 2 * max(m, n) * min(m, n) ** 2 - (2.0 / 3) * min(m, n) ** 3
+    qf = lambda m, n: 2 * m * min(m, n) ** 2 - (2.0 / 3) * min(m, n) ** 3
+    f_qr = f_svd = f_gemm = 0.0
+    for i in range(d - 1):                      # orthogonalisation sweep (transfer_core left -> right)
+        m, r = rin[i] * dims[i], rin[i + 1]
+        f_qr += qr(m, r) + qf(m, r)
+        f_gemm += 2 * min(m, r) * r * dims[i + 1] * rin[i + 2]
+    for e in range(d - 2, -1, -1):              # truncation sweep (round_edge right -> left)
+        a, r, c2 = rin[e], rin[e + 1], rout[e + 2]
+        k = rout[e + 1]
+        mr, ml = dims[e + 1] * c2, a * dims[e]
+        ra, rb = min(r, mr), min(r, ml)
+        f_qr += qr(mr, r) + qf(mr, r) + qr(ml, r) + qf(ml, r)
+        f_gemm += 2 * ra * r * rb
+        f_svd += 22 * min(ra, rb) ** 3
+        f_gemm += 2 * k * ra * mr + 2 * ml * rb * k
+    nbytes = 4 * 8 * sum(rin[i] * dims[i] * rin[i + 1] for i in range(d))
+    return f_qr + f_svd + f_gemm, f_svd, f_qr, f_gemm, nbytes
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_ref_bench(w, reps, threads=None, dump=None):
+    env = dict(os.environ)
+    if threads:
+        env["OPENBLAS_NUM_THREADS"] = str(threads)
+    cmd = [REF_BENCH, "round", str(w["d"]), str(w["n"]), str(w["r"]), str(w["target"]), str(reps)]
+    if dump:
+        cmd.append(dump)
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def oracle_port_ms(w, reps):
+    """Fallback CPU baseline: the numpy restatement (only when the compiled reference is not in the snapshot)."""
+    import numpy as np
+    from oracle import tt_oracle as O
+    rng = np.random.default_rng(0)
+    t = O.tt_random([w["n"]] * w["d"], w["r"], rng)
+    times = []
+    for _ in range(reps):
+        c = t.copy()
+        t0 = time.perf_counter()
+        c.round(w["target"])
+        times.append((time.perf_counter() - t0) * 1e3)
+    return times
+
+
+def reference_arm(args, w, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    if os.path.exists(REF_BENCH):
+        r = run_ref_bench(w, args.steps + args.warmup)
+        times = r["times_ms"][args.warmup:]
+        kind = "reference"
+    else:
+        times = oracle_port_ms(w, args.steps + args.warmup)[args.warmup:]
+        kind = "port"
+    ms = sum(times) / len(times)
+    line = {
+        "impl": "reference", "metric": "TT-round ms (FP64)", "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (TTTensor::random, seed 0xBAADF00D)",
+        "config": {"workload": w["name"], "d": w["d"], "n": w["n"], "rank_in": w["r"], "rank_out": w["target"]},
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": kind,
+                         "sample": "%d x TTTensor::round(%d), unmodified xerus + OpenBLAS, all host threads" % (len(times), w["target"])},
+        "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="xb200", choices=["xb200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "xb200" else args.warmup
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, w, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import xerus_b200 as xb
+
+    torch.cuda.set_device(local_rank)
+    xb.init(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.ExternalStream(xb.stream_handle(), device=local_rank)
+
+    # ---- input: ranks of TTTensor::random({n}^d, r); i.i.d. N(0,1) cores, canonicalised on the device (move_core(0))
+    rng = np.random.default_rng(0xBAADF00D + rank)
+    dims = [w["n"]] * w["d"]
+    base = xb.TTTensor.random(dims, w["r"], rng)
+    ranks_in = base.ranks()
+    host_cores = [torch.from_numpy(c).pin_memory() for c in base.cores()]     # pinned host copy for the e2e leg
+    h2d_bytes = sum(c.numel() * 8 for c in host_cores)
+
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        xb.synchronize()
+
+    def one_round(t):
+        with torch.cuda.stream(stream):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            t.round(w["target"])
+            e1.record(stream)
+        return e0, e1
+
+    # ---- device-resident timing -----------------------------------------------------------------------------------
+    clones = [base.copy() for _ in range(args.warmup + args.steps)]
+    for i in range(args.warmup):
+        one_round(clones[i])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = xb.kernel_launch_count()
+    t_wall0 = time.perf_counter()
+    events = []
+    for i in range(args.steps):
+        flush.zero_()                                  # L2 flush between timed iterations (outside the timed events)
+        torch.cuda.synchronize()
+        events.append(one_round(clones[args.warmup + i]))
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    launches = xb.kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in events]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / args.steps
+    out_t = clones[-1]
+    ranks_out = out_t.ranks()
+
+    # ---- end to end through the host-pointer API --------------------------------------------------------------------
+    def e2e_step():
+        t = xb.TTTensor.from_cores([c.numpy() for c in host_cores], core_position=0)   # H2D of every core (pinned)
+        t.round(w["target"])
+        res = t.cores()                                                                   # D2H of the rounded TT
+        return sum(c.size * 8 for c in res)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    d2h_bytes = 0
+    for _ in range(args.steps):
+        d2h_bytes = e2e_step()
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+
+    # ---- roofline of the dominant kernel class (extra profiled pass, CUDA events inside the library) ----------------
+    total_f, svd_f, qr_f, gemm_f, min_bytes = algorithmic_counts(dims, ranks_in, ranks_out)
+    prof = {}
+    if rank == 0:
+        xb.profile_enable(True)
+        p = base.copy()
+        p.round(w["target"])
+        xb.synchronize()
+        for k in ["svd_jacobi", "svd", "qr", "gemm"]:
+            prof[k] = xb.profile_get(k)
+        xb.profile_enable(False)
+        # FP64 yardstick: cuBLAS DGEMM 8192^3 through torch (MEASURED_PEAKS.json carries no FP64 entry)
+        a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+        b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+        torch.matmul(a, b)
+        best = 1e9
+        for _ in range(3):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(); torch.matmul(a, b); s1.record(); torch.cuda.synchronize()
+            best = min(best, s0.elapsed_time(s1))
+        fp64_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a, b
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    jac_scopes, jac_launches, jac_ms = prof["svd_jacobi"]
+    svd_tf = svd_f / (jac_ms * 1e-3) / 1e12 if jac_ms > 0 else 0.0
+    roofline = {
+        "kernel": "jacobi_block_kernel (one-sided block Jacobi SVD)", "bound": "tensor", "unit": "TFLOP/s",
+        "achieved": svd_tf, "peak": fp64_peak, "frac": svd_tf / fp64_peak if fp64_peak else None, "traffic": None,
+        "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (no FP64 entry in MEASURED_PEAKS.json; nominal ~40)",
+        "algorithmic_flops_per_round": svd_f, "accounting": "22*min(m,n)^3 per SVD (SURVEY §8d)",
+        "launches_per_round": jac_launches, "kernel_ms_per_round": jac_ms,
+        "share_of_step": jac_ms / ms_per_step if ms_per_step else None,
+        "classes_ms_per_round": {k: v[2] for k, v in prof.items()},
+        "whole_round": {"flops": total_f, "TFLOP/s": total_f / (ms_per_step * 1e-3) / 1e12, "min_hbm_bytes": min_bytes},
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            if os.path.exists(REF_BENCH):
+                reps = 12 if args.workload == "c3" else 200
+                r1 = run_ref_bench(w, reps, threads=1)
+                rN = run_ref_bench(w, reps)
+                best = min((r1["median_ms"], 1), (rN["median_ms"], os.cpu_count()))
+                cpu = {"value": best[0], "unit": "ms", "cores": best[1], "kind": "reference",
+                       "sample": "%d x TTTensor::round(%d) on the same shape, unmodified xerus v3.0.1 + OpenBLAS; median; "
+                                 "1 thread %.1f ms, %d threads %.1f ms" % (reps, w["target"], r1["median_ms"], os.cpu_count(), rN["median_ms"])}
+            else:
+                times = oracle_port_ms(w, 5)
+                cpu = {"value": statistics.median(times), "unit": "ms", "cores": os.cpu_count(), "kind": "port",
+                       "sample": "5 x numpy restatement (oracle/tt_oracle.py) of round(%d)" % w["target"]}
+        except Exception as ex:   # the baseline is a reported number, never a reason to lose the bench line
+            cpu = {"value": None, "unit": "ms", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (ex,)}
+
+    line = {
+        "metric": "TT-round ms (FP64)", "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic (i.i.d. N(0,1) cores, ranks of TTTensor::random)",
+        "config": {"workload": w["name"], "d": w["d"], "n": w["n"], "rank_in": w["r"], "rank_out": w["target"],
+                   "ranks_out": ranks_out, "l2": "flushed between timed iterations (512 MB write)",
+                   "parallelism": "replicas x%d (no data-path collective)" % world},
+        "e2e": {"value": float(e2e_ms.item()), "unit": "ms", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+        "gpu_launches": launches, "wall_ms_timed_region": wall_ms, "step_ms": step_ms,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

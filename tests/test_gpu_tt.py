@@ -208,7 +208,11 @@ def test_tt_svd_golden(golden):
 def test_sum_and_distance(golden):
     x = from_golden(golden, "sum.x")
     y = x + x
-    assert y.ranks() == [int(v) for v in golden["sum.y.ranks"]]
+    # operator+= re-canonicalises with the rank-revealing move_core (ttNetwork.cpp:842-844).  The reference keeps
+    # [3,10,12,3] here only because its rank test is sign dependent (blasLapackWrapper.cpp:269); this library's
+    # |.|-rule reveals the true ranks of x + x, which are those of x.
+    assert y.ranks() == x.ranks() == [3, 5, 6, 3]
+    assert all(a <= b for a, b in zip(y.ranks(), [int(v) for v in golden["sum.y.ranks"]]))
     assert rel(y.to_dense(), golden["sum.y.dense"]) < 1e-13
     assert abs(y.distance(x) - x.frob_norm()) < 1e-11 * x.frob_norm()
     assert x.distance(x) < 1e-13 * x.frob_norm()
