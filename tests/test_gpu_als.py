@@ -1,0 +1,170 @@
+"""Parity of the device-resident ALS / DMRG sweeps against golden vectors of the unmodified reference and against the
+CPU oracle.  The local problems are solved matrix-free by CG instead of the reference's dense direct solve, so the
+comparison is on what both define identically: the energy the reference returns (als.cpp:548), the residual, and
+the iterate once it is well conditioned (see tests/test_oracle_golden.py::test_als_spd on why a single half-sweep from
+a random start is an ill-conditioned map)."""
+import numpy as np
+import pytest
+
+import xerus_b200 as xb
+from conftest import golden_tt
+from oracle import tt_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def from_golden(g, name):
+    cores, core = golden_tt(g, name)
+    cls = xb.TTOperator if cores[0].ndim == 4 else xb.TTTensor
+    return cls.from_cores(cores, core_position=core)
+
+
+def to_oracle(t):
+    return O.TT(t.cores(), core_position=t.corePosition if t.canonicalized else None)
+
+
+@pytest.mark.parametrize("tag", ["als_small", "als_mid"])
+@pytest.mark.parametrize("hs", [1, 2, 4])
+def test_als_spd_golden(golden, tag, hs):
+    A, b, x = from_golden(golden, tag + ".A"), from_golden(golden, tag + ".b"), from_golden(golden, tag + ".x0")
+    energy = xb.ALS_SPD(A, x, b, hs)
+    e_ref = float(golden["%s.spd_hs%d.energy" % (tag, hs)])
+    assert abs(energy - e_ref) < 1e-9 * abs(e_ref)
+    ref = O.TT(golden_tt(golden, "%s.spd_hs%d.x" % (tag, hs))[0])
+    assert x.ranks() == ref.ranks() and x.corePosition == 0 and x.canonicalized
+    assert O.tt_distance_rel(to_oracle(x), ref) < (1e-5 if hs == 1 else 1e-9)     # local problems <= 1536: dense direct solve
+    r_ref = float(golden["%s.spd_hs%d.residual" % (tag, hs)])
+    res = O.residual(O.TT(golden_tt(golden, tag + ".A")[0]), to_oracle(x), O.TT(golden_tt(golden, tag + ".b")[0]))
+    assert abs(res - r_ref) < max(0.02 * r_ref, 1e-10)
+
+
+@pytest.mark.parametrize("tag", ["als_small", "als_mid"])
+def test_als_general_golden(golden, tag):
+    A, b, x = from_golden(golden, tag + ".A"), from_golden(golden, tag + ".b"), from_golden(golden, tag + ".x0")
+    res = xb.ALS(A, x, b, 2)
+    assert abs(res - float(golden[tag + ".gen_hs2.energy"])) < 1e-6
+    assert O.tt_distance_rel(to_oracle(x), O.TT(golden_tt(golden, tag + ".gen_hs2.x")[0])) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["als_small", "als_mid"])
+def test_dmrg_half_sweep_golden(golden, tag):
+    """The reference's two-site driver only survives one increasing half-sweep."""
+    A, b, x = from_golden(golden, tag + ".A"), from_golden(golden, tag + ".b"), from_golden(golden, tag + ".x0")
+    energy = xb.DMRG_SPD(A, x, b, 1)
+    e_ref = float(golden[tag + ".dmrg_hs1.energy"])
+    assert abs(energy - e_ref) < 1e-9 * abs(e_ref)
+    assert x.ranks() == [int(v) for v in golden[tag + ".dmrg_hs1.ranks"]]
+    assert O.tt_distance_rel(to_oracle(x), O.TT(golden_tt(golden, tag + ".dmrg_hs1.x")[0])) < 1e-5
+
+
+def test_dmrg_full_sweeps_converged(golden):
+    """Past the sweep turn the reference throws (als.cpp:371,:376); the fixed driver is checked at convergence against
+    the oracle with the same fix.  Intermediate half-sweeps are not comparable: the solution for b = ones is rank
+    deficient, so the rank-6 split re-admits noise directions (sigma ~ eps) that differ between any two implementations."""
+    A, b = from_golden(golden, "als_mid.A"), from_golden(golden, "als_mid.b")
+    Ao, bo = O.TT(golden_tt(golden, "als_mid.A")[0]), O.TT(golden_tt(golden, "als_mid.b")[0])
+    x = from_golden(golden, "als_mid.x0")
+    e = xb.DMRG_SPD(A, x, b, 4)
+    xo = O.TT(golden_tt(golden, "als_mid.x0")[0], core_position=0)
+    eo = O.ALSVariant(2, True, fix_dmrg_turn=True)(Ao, xo, bo, 4)
+    assert abs(e - eo) < 1e-9 * abs(eo)
+    assert x.ranks() == xo.ranks()
+    assert O.residual(Ao, to_oracle(x), bo) < 1e-5
+    e1 = xb.DMRG_SPD(A, from_golden(golden, "als_mid.x0"), b, 1)
+    assert e >= e1 - 1e-9 * abs(e1)          # |0.5 xAx - bx| grows towards 0.5 b A^-1 b
+
+
+def test_als_projection_golden(golden):
+    B, X = from_golden(golden, "proj.b"), from_golden(golden, "proj.x0")
+    before = X.distance(B)
+    xb.ALS_SPD(X, B, 1e-4)
+    after = X.distance(B)
+    assert abs(before - float(golden["proj.roundNorm"])) < 1e-9 * before
+    assert abs(after - float(golden["proj.projNorm"])) < 1e-7 * after
+    assert after < before                                   # als.cxx:100
+    assert O.tt_distance_rel(to_oracle(X), O.TT(golden_tt(golden, "proj.x")[0])) < 1e-8
+
+
+@pytest.mark.parametrize("d,n,r", [(5, 3, 2), (7, 4, 5), (6, 6, 8)])
+def test_als_spd_vs_oracle_random(d, n, r):
+    rng = np.random.default_rng(d * 100 + n * 10 + r)
+    A = xb.TTOperator.laplace(d, n)
+    b = xb.TTTensor.ones([n] * d)
+    x = xb.TTTensor.random([n] * d, r, rng)
+    xo = to_oracle(x)
+    e = xb.ALS_SPD(A, x, b, 4)
+    eo = O.ALS_SPD(O.laplace_operator(d, n), xo, O.tt_ones([n] * d), 4)
+    assert abs(e - eo) < 1e-9 * abs(eo)
+    assert O.tt_distance_rel(to_oracle(x), xo) < 1e-7
+
+
+def test_als_identity_operator():
+    # reference: src/unitTests/als.cxx:28-66 ("identity"): A = I, so ALS must reproduce b
+    rng = np.random.default_rng(2)
+    n, d = 5, 4
+    I = xb.TTOperator.from_cores([np.eye(n).reshape(1, n, n, 1) for _ in range(d)])
+    b = xb.TTTensor.random([n] * d, 3, rng)
+    x = xb.TTTensor.random([n] * d, 3, rng)
+    xb.ALS_SPD(I, x, b, 1e-4)
+    assert x.distance(b) < 1e-9 * b.frob_norm()
+
+
+def test_als_argument_checks():
+    A = xb.TTOperator.laplace(4, 3)
+    with pytest.raises(xb.XerusError):
+        xb.ALS_SPD(A, xb.TTTensor.ones([3] * 4), xb.TTTensor.ones([3] * 5), 2)
+    with pytest.raises(xb.XerusError):
+        xb.ALSVariant(0, 0, True)
+
+
+@pytest.fixture
+def force_cg():
+    """Routes every local problem through the matrix-free CG solver (what the full-size configs use)."""
+    xb.set_option("als_direct_max", 0)
+    yield
+    xb.set_option("als_direct_max", 1536)
+
+
+@pytest.mark.parametrize("tag", ["als_small", "als_mid"])
+def test_als_spd_matrix_free_cg(golden, tag, force_cg):
+    A, b, x = from_golden(golden, tag + ".A"), from_golden(golden, tag + ".b"), from_golden(golden, tag + ".x0")
+    variant = xb.ALSVariant(1, 0, True)
+    energy = variant(A, x, b, 4)
+    assert variant.last_local_iterations > 0
+    e_ref = float(golden["%s.spd_hs4.energy" % tag])
+    assert abs(energy - e_ref) < 1e-9 * abs(e_ref)
+    # converged iterate: CG tolerance 1e-12 on the local residual
+    assert O.tt_distance_rel(to_oracle(x), O.TT(golden_tt(golden, "%s.spd_hs4.x" % tag)[0])) < 1e-8
+
+
+def test_als_general_and_dmrg_matrix_free_cg(golden, force_cg):
+    tag = "als_mid"
+    A, b, x = from_golden(golden, tag + ".A"), from_golden(golden, tag + ".b"), from_golden(golden, tag + ".x0")
+    res = xb.ALS(A, x, b, 2)
+    assert abs(res - float(golden[tag + ".gen_hs2.energy"])) < 1e-6
+    x = from_golden(golden, tag + ".x0")
+    energy = xb.DMRG_SPD(A, x, b, 1)
+    e_ref = float(golden[tag + ".dmrg_hs1.energy"])
+    assert abs(energy - e_ref) < 1e-9 * abs(e_ref)
+    # singular values below the CG tolerance are cut: never more than the entry ranks, never fewer than the reference's
+    # singular values below the CG tolerance are noise and are cut (the reference cuts at EPSILON): ranks can only be
+    # lower than the reference's, never above the entry ranks
+    ref_ranks = [int(v) for v in golden[tag + ".dmrg_hs1.ranks"]]
+    assert all(a <= b for a, b in zip(x.ranks(), ref_ranks)) and min(x.ranks()) >= 5
+
+
+def test_als_config2_reduced_rank20_cg_runs():
+    """BASELINE config 2 at reduced rank (d=16, n=10, r=20; n_loc = 4000): matrix-free path, one full sweep.
+    The reference needs 34 s per sweep for this; checked here by energy monotonicity and residual."""
+    rng = np.random.default_rng(16)
+    d, n, r = 16, 10, 20
+    A, b = xb.TTOperator.laplace(d, n), xb.TTTensor.ones([n] * d)
+    x0 = xb.TTTensor.random([n] * d, r, rng)
+    x = x0.copy()
+    variant = xb.ALSVariant(1, 0, True)
+    e1 = variant(A, x, b, 1)
+    x = x0.copy()
+    e2 = variant(A, x, b, 2)
+    assert e2 >= e1 - 1e-9 * abs(e1)
+    Ax = A.apply(x)
+    assert Ax.distance(b) / b.frob_norm() < 1e-5     # iterative local solves: see test_als_spd_golden on conditioning

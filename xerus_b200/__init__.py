@@ -15,6 +15,12 @@ def init(device=0):
     call("xb_init", int(device))
 
 
+def set_option(key, value):
+    """Tuning / diagnostic knobs of the library: svd_max_sweeps, svd_persistent, als_direct_max, ..."""
+    from ._lib import call
+    call("xb_set_option", key.encode(), float(value))
+
+
 def synchronize():
     from ._lib import call
     call("xb_synchronize")

@@ -11,20 +11,22 @@
 // 2*bw-player inner tournament (intra + cross pairs), later rounds only the bw cross rounds.
 // Tall inputs are first reduced by QR (SVD of the triangular factor), wide inputs are handled as the transpose.
 #include "xb_internal.cuh"
+#include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace xb {
 
 constexpr double DBL_EPS = 2.220446049250313e-16;
 
-__global__ void svd_init_kernel(double* __restrict__ GT, const int ldg, const int npad, const int mdot, const int nw,
+__global__ void svd_init_kernel(double* __restrict__ GT, const int ld, const int npad, const int mdot, const int voff, const int nw,
                                 const double* __restrict__ src, const long long rs, const long long cs) {
-	const size_t total = (size_t)npad * ldg;
+	const size_t total = (size_t)npad * ld;
 	for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-		const int j = int(e / ldg), i = int(e % ldg);
+		const int j = int(e / ld), i = int(e % ld);
 		double v = 0.0;
 		if (j < nw) {
 			if (i < mdot) v = src[(long long)i * rs + (long long)j * cs];
-			else if (i - mdot == j) v = 1.0;
+			else if (i - voff == j) v = 1.0;
 		}
 		GT[e] = v;
 	}
@@ -118,6 +120,168 @@ __global__ void jacobi_block_kernel(double* __restrict__ GT, const int ldg, cons
 	}
 }
 
+// Persistent variant: ONE cooperative launch runs every round of every sweep (grid = nblk/2 CTAs, all co-resident),
+// separated by grid-wide barriers; convergence is decided on the device.
+//  * a warp owns one column pair per inner round and keeps both stacked columns in REGISTERS (EPL doubles per lane
+//    each): one batch of shared-memory loads, the cross product from the leading part, the rotation, one batch of
+//    stores — every element is read and written once per pair visit and all loads are in flight together;
+//  * only the cross product is reduced (warp shuffles): the squared column norms are cached in shared memory and
+//    updated with the rotation (alpha' = alpha - t*gamma, beta' = beta + t*gamma), refreshed whenever a block is loaded;
+//  * the rotation needs two rsqrt and one division: t = sign(d) 2g / (|d| + sqrt(d^2 + 4 g^2)), c = rsqrt(1 + t^2);
+//  * a sweep in which no pair had |cos| > 1e-9 is the last one (cyclic Jacobi converges quadratically), so no
+//    verification sweep is spent.
+// Rows of GT are [ x (mdot, zero padded to a multiple of 32) | v (nw, zero padded to a multiple of 32) ].
+template <int EH, int MAXT>   // EH >= max(voff, ld - voff) / 32 : register tile per column part
+__global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restrict__ GT, const int ld, const int epl_x, const int epl_v,
+                                                                const int bw, const int nblk, const double tol2,
+                                                                unsigned int* __restrict__ counters, unsigned int* __restrict__ info,
+                                                                const int max_sweeps) {
+	extern __shared__ double S[];
+	__shared__ unsigned int s_rot, s_big;
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	const int N = 2 * bw;
+	const int voff = 32 * epl_x;
+	double* nrm = S + (size_t)N * ld;           // [N] cached squared norms of the resident columns
+	// schedule of the full 2*bw-player tournament, precomputed once: keeps the integer modulo out of the per-round chain
+	unsigned short* sched = reinterpret_cast<unsigned short*>(nrm + N);      // [(N-1) * bw] : a | b << 8
+	for (int e = threadIdx.x; e < (N - 1) * bw; e += blockDim.x) {
+		const int rr = e / bw, pi = e % bw;
+		int a, b;
+		if (pi == 0) { a = N - 1; b = rr; }
+		else { a = (rr + pi) % (N - 1); b = (rr - pi + N - 1) % (N - 1); }
+		sched[e] = (unsigned short)(a | (b << 8));
+	}
+	const int nrounds = (nblk == 2) ? 1 : nblk - 1;
+	if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
+	__syncthreads();
+	int sweeps = 0;
+	unsigned int last_rot = 1, last_big = 1;
+	unsigned int my_rot = 0, my_big = 0;         // per-warp counters (lane 0), flushed once per visit
+	long long tk_load = 0, tk_inner = 0, tk_store = 0, tk_sync = 0, tk0 = 0;   // phase cycle counters (thread 0 of block 0)
+	const bool timing = (info[0] == 0xC10C) && blockIdx.x == 0 && threadIdx.x == 0;
+	for (; sweeps < max_sweeps; ) {
+		for (int round = 0; round < nrounds; ++round) {
+			int pb, qb;
+			{
+				const int pi = blockIdx.x, N1 = nblk - 1;
+				if (nblk == 2) { pb = 0; qb = 1; }
+				else if (pi == 0) { pb = N1; qb = round % N1; }
+				else { pb = (round + pi) % N1; qb = (round - pi + N1) % N1; }
+			}
+			if (timing) tk0 = clock64();
+			for (int r = warp; r < N; r += nwarps) {
+				const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
+				const double* src = GT + (size_t)grow * ld + lane;
+				double* dst = S + (size_t)r * ld + lane;
+				double v[EH], w[EH];
+#pragma unroll
+				for (int k = 0; k < EH; ++k) { v[k] = (k < epl_x) ? src[32 * k] : 0.0; w[k] = (k < epl_v) ? src[voff + 32 * k] : 0.0; }
+				double ss = 0.0;
+#pragma unroll
+				for (int k = 0; k < EH; ++k) {
+					if (k < epl_x) { dst[32 * k] = v[k]; ss += v[k] * v[k]; }
+					if (k < epl_v) dst[voff + 32 * k] = w[k];
+				}
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+				if (lane == 0) nrm[r] = ss;
+			}
+			__syncthreads();
+			if (timing) { const long long t1 = clock64(); tk_load += t1 - tk0; tk0 = t1; }
+			const bool full = (round == 0);
+			const int inner_rounds = full ? (N - 1) : bw;
+			for (int rr = 0; rr < inner_rounds; ++rr) {
+				for (int pi = warp; pi < bw; pi += nwarps) {
+					int a, b;
+					if (full) { const unsigned int ab_ = sched[rr * bw + pi]; a = ab_ & 255; b = ab_ >> 8; }
+					else { a = pi; b = bw + ((pi + rr) & (bw - 1)); }      // bw is a power of two
+					double* x = S + (size_t)a * ld + lane;
+					double* y = S + (size_t)b * ld + lane;
+					double xr[EH], yr[EH];
+#pragma unroll
+					for (int k = 0; k < EH; ++k) { xr[k] = (k < epl_x) ? x[32 * k] : 0.0; yr[k] = (k < epl_x) ? y[32 * k] : 0.0; }
+					double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+					for (int k = 0; k < EH; k += 2) {      // padding entries are zero: no predicate needed
+						g0 += xr[k] * yr[k];
+						if (k + 1 < EH) g1 += xr[k + 1] * yr[k + 1];
+					}
+					double g = g0 + g1;
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+					const double aa = nrm[a], bb = nrm[b];
+					const double gg = g * g, ab = aa * bb;
+					if (gg > tol2 * ab) {
+						// prefetch the accumulated-rotation part while the rotation parameters are computed
+						double xv[EH], yv[EH];
+#pragma unroll
+						for (int k = 0; k < EH; ++k) { xv[k] = (k < epl_v) ? x[voff + 32 * k] : 0.0; yv[k] = (k < epl_v) ? y[voff + 32 * k] : 0.0; }
+						// c^2 = (1 + |d|/h)/2, s = sign(d) 2g / (2 h c), t = s/c  with h = sqrt(d^2 + 4 g^2): two rsqrt, no division
+						const double d = bb - aa;
+						const double rh = rsqrt(d * d + 4.0 * gg);
+						const double c2 = 0.5 + 0.5 * fabs(d) * rh;
+						const double rc = rsqrt(c2);
+						const double c = c2 * rc;
+						const double s = (d >= 0.0 ? g : -g) * rh * rc;
+						const double t = s * rc;
+#pragma unroll
+						for (int k = 0; k < EH; ++k) if (k < epl_x) {
+							x[32 * k] = c * xr[k] - s * yr[k];
+							y[32 * k] = s * xr[k] + c * yr[k];
+						}
+#pragma unroll
+						for (int k = 0; k < EH; ++k) if (k < epl_v) {
+							x[voff + 32 * k] = c * xv[k] - s * yv[k];
+							y[voff + 32 * k] = s * xv[k] + c * yv[k];
+						}
+						if (lane == 0) {
+							nrm[a] = aa - t * g; nrm[b] = bb + t * g;
+							my_rot += 1;
+							if (gg > 1e-18 * ab) my_big += 1;
+						}
+					}
+				}
+				__syncthreads();
+			}
+			if (timing) { const long long t1 = clock64(); tk_inner += t1 - tk0; tk0 = t1; }
+			if (lane == 0 && my_rot) { atomicAdd(&s_rot, my_rot); atomicAdd(&s_big, my_big); my_rot = 0; my_big = 0; }
+			for (int r = warp; r < N; r += nwarps) {
+				const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
+				double* dst = GT + (size_t)grow * ld + lane;
+				const double* src = S + (size_t)r * ld + lane;
+				double v[EH], w[EH];
+#pragma unroll
+				for (int k = 0; k < EH; ++k) { v[k] = (k < epl_x) ? src[32 * k] : 0.0; w[k] = (k < epl_v) ? src[voff + 32 * k] : 0.0; }
+#pragma unroll
+				for (int k = 0; k < EH; ++k) { if (k < epl_x) dst[32 * k] = v[k]; if (k < epl_v) dst[voff + 32 * k] = w[k]; }
+			}
+			if (timing) { const long long t1 = clock64(); tk_store += t1 - tk0; tk0 = t1; }
+			if (nblk > 2) { __threadfence(); grid.sync(); }
+			else __syncthreads();
+			if (timing) { const long long t1 = clock64(); tk_sync += t1 - tk0; tk0 = t1; }
+		}
+		++sweeps;
+		unsigned int rot, big;
+		if (nblk > 2) {
+			if (threadIdx.x == 0) { atomicAdd(&counters[2 * (sweeps - 1)], s_rot); atomicAdd(&counters[2 * (sweeps - 1) + 1], s_big); s_rot = 0; s_big = 0; }
+			__threadfence();
+			grid.sync();
+			rot = *((volatile unsigned int*)&counters[2 * (sweeps - 1)]);
+			big = *((volatile unsigned int*)&counters[2 * (sweeps - 1) + 1]);
+		} else {
+			rot = s_rot; big = s_big;
+			__syncthreads();
+			if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
+			__syncthreads();
+		}
+		last_rot = rot; last_big = big;
+		if (big == 0) break;
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) { info[1] = (unsigned)sweeps; info[2] = last_big; info[3] = last_rot; }
+	if (timing) { info[4] = (unsigned)(tk_load >> 10); info[5] = (unsigned)(tk_inner >> 10); info[6] = (unsigned)(tk_store >> 10); info[7] = (unsigned)(tk_sync >> 10); }
+}
+
 // singular values = column norms; rank them (descending, ties by index) -> Ssorted, perm.   single CTA
 __global__ void svd_sort_kernel(const double* __restrict__ GT, const int ldg, const int mdot, const int nw,
                                 double* __restrict__ Ssorted, int* __restrict__ perm) {
@@ -143,7 +307,7 @@ __global__ void svd_sort_kernel(const double* __restrict__ GT, const int ldg, co
 
 // blockIdx.x = output index r (< k).  X part -> outX[i*sxi + r*sxr] (i < mdot), V part -> outV[c*svc + r*svr] (c < nw).
 // The X part is normalised by sigma_r unless scale_x (then it keeps Sigma); the V part is multiplied by sigma_r if scale_v.
-__global__ void svd_extract_kernel(const double* __restrict__ GT, const int ldg, const int mdot, const int nw,
+__global__ void svd_extract_kernel(const double* __restrict__ GT, const int ldg, const int mdot, const int voff, const int nw,
                                    const double* __restrict__ Ssorted, const int* __restrict__ perm,
                                    double* __restrict__ outX, const long long sxi, const long long sxr, const int scale_x,
                                    double* __restrict__ outV, const long long svc, const long long svr, const int scale_v,
@@ -156,14 +320,27 @@ __global__ void svd_extract_kernel(const double* __restrict__ GT, const int ldg,
 	const double fx = scale_x ? (soft == 0.0 ? 1.0 : sigma_eff * inv) : inv;
 	const double fv = scale_v ? sigma_eff : 1.0;
 	for (int i = threadIdx.x; i < mdot; i += blockDim.x) outX[(long long)i * sxi + (long long)r * sxr] = g[i] * fx;
-	for (int c = threadIdx.x; c < nw; c += blockDim.x) outV[(long long)c * svc + (long long)r * svr] = g[mdot + c] * fv;
+	for (int c = threadIdx.x; c < nw; c += blockDim.x) outV[(long long)c * svc + (long long)r * svr] = g[voff + c] * fv;
 	if (dS && threadIdx.x == 0) dS[r] = sigma_eff;
 }
 
-static int choose_bw(size_t mt, size_t nw, size_t smem_cap) {
-	int bw = 32;
-	while (bw > 1 && (size_t(2 * bw) * mt * sizeof(double) > smem_cap || size_t(bw) >= nw)) bw >>= 1;
+static int choose_bw(size_t ld, size_t nw, size_t smem_cap, int max_bw) {
+	int bw = max_bw;
+	while (bw > 1 && (size_t(2 * bw) * (ld + 1) * sizeof(double) + size_t(4 * bw) * bw + 16 > smem_cap || size_t(bw) >= nw)) bw >>= 1;
 	return bw;
+}
+
+template <int EPL, int MAXT>
+static void launch_persistent(double* gt, int ld, int epl, int epl_dot, int bw, int nblk, double tol2, unsigned int* d_cnt,
+                              unsigned int* d_info, int max_sweeps, int threads, size_t smem, size_t smem_cap) {
+	static bool attr = false;
+	if (!attr) {
+		XB_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<EPL, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+		attr = true;
+	}
+	void* args[] = {&gt, &ld, &epl, &epl_dot, &bw, &nblk, &tol2, &d_cnt, &d_info, &max_sweeps};
+	XB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<EPL, MAXT>, dim3(unsigned(nblk / 2)), dim3(threads), args, smem, ctx().stream));
+	ctx().launches++;
 }
 
 void Svd::factor(const double* A, size_t m_, size_t n_) {
@@ -177,7 +354,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	Context& c = ctx();
 	const size_t smem_cap = std::min<size_t>(c.max_smem_optin, 227 * 1024) - 1024;
 
-	const double* src; long long rs, cs; size_t mdot;
+	const double* src; long long rs, cs;
 	DBuf At, Rr;
 	if (reduced) {
 		Qred.resize(mw * nw); Rr.resize(nw * nw);
@@ -188,36 +365,65 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		src = A; mdot = mw;
 		if (swapped) { rs = 1; cs = (long long)n; } else { rs = (long long)n; cs = 1; }
 	}
-	mt = mdot + nw;
-	XB_REQUIRE(2 * mt * sizeof(double) <= smem_cap, "SVD: matrix too large for the shared-memory Jacobi kernel (min(m,n) <= ~7000)");
-	const int bw = choose_bw(mt, nw, smem_cap);
+	// row layout: [ x (mdot) padded to 32 | v (nw) padded to 32 ]
+	voff = (mdot + 31) / 32 * 32;
+	ld = voff + (nw + 31) / 32 * 32;
+	mt = ld;
+	XB_REQUIRE(2 * (ld + 1) * sizeof(double) <= smem_cap, "SVD: matrix too large for the shared-memory Jacobi kernel (min(m,n) <= ~7000)");
+	const int epl_x = int(voff / 32), epl_v = int((ld - voff) / 32), eh = std::max(epl_x, epl_v);
+	// register-tile variants of the persistent kernel: (EH, max threads) = (4, 1024), (8, 512), (16, 256)
+	// measured on B200 (scratch/svd_time.py): per inner round the dependent chain (reduce -> 2 rsqrt -> rotate -> barrier)
+	// costs ~1600 cycles regardless of the vector length, so more, smaller CTAs only pay off from 256 columns on
+	int max_bw = eh <= 8 ? (nw >= 256 ? 8 : 16) : (eh <= 16 ? 8 : 32);
+	if (c.svd_max_bw > 0) max_bw = std::min(max_bw, c.svd_max_bw);
+	const int bw = choose_bw(ld, nw, smem_cap, max_bw);
 	size_t nblk = (nw + bw - 1) / bw;
 	if (nblk < 2) nblk = 2;
 	if (nblk & 1) ++nblk;
 	npad = nblk * bw;
-	GT.resize(npad * mt);
+	GT.resize(npad * ld);
 	{
-		const size_t total = npad * mt;
+		const size_t total = npad * ld;
 		const unsigned blocks = unsigned(std::min<size_t>((total + 255) / 256, size_t(c.num_sms) * 8));
-		svd_init_kernel<<<blocks, 256, 0, c.stream>>>(GT, int(mt), int(npad), int(mdot), int(nw), src, rs, cs);
+		svd_init_kernel<<<blocks, 256, 0, c.stream>>>(GT, int(ld), int(npad), int(mdot), int(voff), int(nw), src, rs, cs);
 		XB_LAUNCH_CHECK();
 	}
 	const double tol = std::sqrt(double(mdot)) * DBL_EPS;
-	const size_t smem = size_t(2 * bw) * mt * sizeof(double);
+	const size_t smem = size_t(2 * bw) * ld * sizeof(double);
 	static bool attr_set = false;
 	if (!attr_set) {
 		XB_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
 		attr_set = true;
 	}
 	const int threads = std::max(64, std::min(1024, 32 * bw));
-	unsigned int* d_info = static_cast<unsigned int*>(dalloc_bytes(4 * sizeof(unsigned int)));
+	unsigned int* d_info = static_cast<unsigned int*>(dalloc_bytes(8 * sizeof(unsigned int)));
 	unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch);
 	sweeps = 0;
 	bool converged = false;
 	ProfScope* prof_jacobi = new ProfScope("svd_jacobi");
-	if (nblk == 2) {
+	const size_t smem_p = smem + size_t(2 * bw) * sizeof(double) + size_t(2 * bw) * bw * sizeof(unsigned short) + 16;
+	const bool persistent = c.svd_persistent && eh <= 16 && (nblk / 2) <= size_t(c.num_sms) && smem_p <= smem_cap;
+	if (persistent) {
+		// one cooperative launch for the whole SVD: rounds separated by grid barriers, convergence decided on device
+		const int max_sweeps = c.svd_max_sweeps;
+		unsigned int* d_cnt = static_cast<unsigned int*>(dalloc_bytes((2 * max_sweeps + 4) * sizeof(unsigned int)));
+		XB_CUDA(cudaMemsetAsync(d_cnt, 0, (2 * max_sweeps + 4) * sizeof(unsigned int), c.stream));
+		XB_CUDA(cudaMemsetAsync(d_info, 0, 8 * sizeof(unsigned int), c.stream));
+		if (getenv("XB_JACOBI_TIMING")) { const unsigned int flag = 0xC10C; XB_CUDA(cudaMemcpyAsync(d_info, &flag, 4, cudaMemcpyHostToDevice, c.stream)); }
+		const double tol2 = tol * tol;
+		if (eh <= 4) launch_persistent<4, 512>(GT.p, int(ld), epl_x, epl_v, bw, int(nblk), tol2, d_cnt, d_info, max_sweeps, threads, smem_p, smem_cap);
+		else if (eh <= 8) launch_persistent<8, 512>(GT.p, int(ld), epl_x, epl_v, bw, int(nblk), tol2, d_cnt, d_info, max_sweeps, threads, smem_p, smem_cap);
+		else launch_persistent<16, 256>(GT.p, int(ld), epl_x, epl_v, bw, int(nblk), tol2, d_cnt, d_info, max_sweeps, threads, smem_p, smem_cap);
+		XB_CUDA(cudaMemcpyAsync(h_info, d_info, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+		XB_CUDA(cudaStreamSynchronize(c.stream));
+		sweeps = int(h_info[1]);
+		converged = (h_info[2] == 0);
+		if (getenv("XB_JACOBI_TIMING")) fprintf(stderr, "[jacobi] %zux%zu bw=%d ctas=%zu sweeps=%d kcycles: load %u inner %u store %u sync %u\n",
+		                                       mdot, nw, bw, nblk / 2, sweeps, h_info[4], h_info[5], h_info[6], h_info[7]);
+		dfree(d_cnt);
+	} else if (nblk == 2) {
 		XB_CUDA(cudaMemsetAsync(d_info, 0, 4 * sizeof(unsigned int), c.stream));
-		jacobi_block_kernel<<<1, threads, smem, c.stream>>>(GT, int(mt), int(mt), int(mdot), bw, 2, 0, 1, tol, d_info, 1, c.svd_max_sweeps);
+		jacobi_block_kernel<<<1, threads, smem, c.stream>>>(GT, int(ld), int(ld), int(voff), bw, 2, 0, 1, tol, d_info, 1, c.svd_max_sweeps);
 		XB_LAUNCH_CHECK();
 		XB_CUDA(cudaMemcpyAsync(h_info, d_info, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
 		XB_CUDA(cudaStreamSynchronize(c.stream));
@@ -227,7 +433,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		for (int sw = 0; sw < c.svd_max_sweeps && !converged; ++sw) {
 			XB_CUDA(cudaMemsetAsync(d_info, 0, 4 * sizeof(unsigned int), c.stream));
 			for (size_t round = 0; round + 1 < nblk; ++round) {
-				jacobi_block_kernel<<<unsigned(nblk / 2), threads, smem, c.stream>>>(GT, int(mt), int(mt), int(mdot), bw, int(nblk),
+				jacobi_block_kernel<<<unsigned(nblk / 2), threads, smem, c.stream>>>(GT, int(ld), int(ld), int(voff), bw, int(nblk),
 				                                                                     int(round), round == 0 ? 1 : 0, tol, d_info, 0, 1);
 				XB_LAUNCH_CHECK();
 			}
@@ -246,7 +452,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	{
 		const size_t sm = nw * sizeof(double);
 		XB_REQUIRE(sm <= 48 * 1024, "SVD: too many columns for the sort kernel");
-		svd_sort_kernel<<<1, 1024, sm, c.stream>>>(GT, int(mt), int(mdot), int(nw), Ssorted, reinterpret_cast<int*>(perm.p));
+		svd_sort_kernel<<<1, 1024, sm, c.stream>>>(GT, int(ld), int(mdot), int(nw), Ssorted, reinterpret_cast<int*>(perm.p));
 		XB_LAUNCH_CHECK();
 	}
 	S.resize(nw);
@@ -263,7 +469,6 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 void Svd::extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, double* dS) {
 	XB_REQUIRE(k >= 1 && k <= kmax, "SVD extract: rank out of range");
 	Context& c = ctx();
-	const size_t mdot = mt - nw;
 	const int* p = reinterpret_cast<const int*>(perm.p);
 	// The X part holds the left vectors of the working matrix G, the V part its right vectors;
 	// G = A (not swapped) or A^T (swapped); if reduced, G = Qred * (working matrix).
@@ -280,7 +485,7 @@ void Svd::extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, 
 		scale_x = scale_vt;
 		outV = U; svc = (long long)k; svr = 1; scale_v = scale_u;
 	}
-	svd_extract_kernel<<<unsigned(k), 256, 0, c.stream>>>(GT, int(mt), int(mdot), int(nw), Ssorted, p, outX, sxi, sxr, scale_x,
+	svd_extract_kernel<<<unsigned(k), 256, 0, c.stream>>>(GT, int(ld), int(mdot), int(voff), int(nw), Ssorted, p, outX, sxi, sxr, scale_x,
 	                                                       outV, svc, svr, scale_v, dS, soft_threshold);
 	XB_LAUNCH_CHECK();
 	if (reduced) {

@@ -6,22 +6,9 @@
 // move_core / round follow TTNetwork::move_core / round (src/xerus/ttNetwork.cpp:582-684) edge by edge through
 // transfer_core / round_edge (src/xerus/tensorNetwork.cpp:678-909); nothing leaves the device during a sweep except
 // the per-edge rank decision (singular values / one min-max pair), which the host needs to size the next launches.
-#include "xb_internal.cuh"
+#include "tt_internal.cuh"
 
 using namespace xb;
-
-struct xb_tt {
-	size_t d = 0;
-	bool is_operator = false;
-	std::vector<size_t> dim_m, dim_n;   // external dims per site (dim_n unused for tensors)
-	std::vector<size_t> rank;           // d + 1 entries, rank[0] = rank[d] = 1
-	std::vector<DBuf> core;
-	bool canonicalized = false;
-	size_t core_position = 0;
-
-	size_t ext(size_t i) const { return is_operator ? dim_m[i] * dim_n[i] : dim_m[i]; }
-	size_t core_size(size_t i) const { return rank[i] * ext(i) * rank[i + 1]; }
-};
 
 namespace xb {
 
@@ -70,7 +57,7 @@ static bool exceeds_maximal_ranks(const xb_tt* t) {   // ttNetwork.cpp:349-359
 	return false;
 }
 
-static void move_core(xb_tt* t, size_t position, bool keep_rank) {   // ttNetwork.cpp:582-628
+void move_core(xb_tt* t, size_t position, bool keep_rank) {   // ttNetwork.cpp:582-628
 	XB_REQUIRE(position < t->d, "Illegal core-position chosen for TTNetwork");
 	const bool arr = !keep_rank;
 	const size_t d = t->d;
@@ -152,7 +139,7 @@ static void round_tt(xb_tt* t, const size_t* max_ranks, double eps, double* sval
 	if (initial_canon) move_core(t, initial_core, false);                // :662-664
 }
 
-static double tt_inner(const xb_tt* a, const xb_tt* b) {
+double tt_inner(const xb_tt* a, const xb_tt* b) {
 	XB_REQUIRE(a->d == b->d && a->is_operator == b->is_operator, "TT inner product: formats differ");
 	for (size_t i = 0; i < a->d; ++i) XB_REQUIRE(a->ext(i) == b->ext(i), "TT inner product: dimensions differ");
 	DBuf E(1);
@@ -169,12 +156,12 @@ static double tt_inner(const xb_tt* a, const xb_tt* b) {
 	return read_scalar(E);
 }
 
-static double tt_frob_norm(const xb_tt* t) {   // ttNetwork.cpp:782-789
+double tt_frob_norm(const xb_tt* t) {   // ttNetwork.cpp:782-789
 	if (t->canonicalized) return two_norm(t->core[t->core_position], t->core_size(t->core_position));
 	return std::sqrt(std::max(0.0, tt_inner(t, t)));
 }
 
-static xb_tt* tt_clone(const xb_tt* t) {
+xb_tt* tt_clone(const xb_tt* t) {
 	xb_tt* c = new xb_tt();
 	c->d = t->d; c->is_operator = t->is_operator; c->dim_m = t->dim_m; c->dim_n = t->dim_n; c->rank = t->rank;
 	c->canonicalized = t->canonicalized; c->core_position = t->core_position;
@@ -347,7 +334,7 @@ xb_status xb_tt_component_size(const xb_tt* tt, size_t idx, size_t* rl, size_t* 
 	return guard([&] { check_idx(tt, idx); if (rl) *rl = tt->rank[idx]; if (ext) *ext = tt->ext(idx); if (rr) *rr = tt->rank[idx + 1]; });
 }
 
-static void require_correct_format(const xb_tt* tt) {   // ttNetwork.cpp:290-341 (the structural part that can fail here)
+void require_correct_format(const xb_tt* tt) {   // ttNetwork.cpp:290-341 (the structural part that can fail here)
 	XB_REQUIRE(tt, "null TT");
 	for (size_t i = 0; i < tt->d; ++i) XB_REQUIRE(tt->core[i].n == tt->core_size(i), "TT is not in correct format: component size does not match its bond ranks");
 }

@@ -44,6 +44,9 @@ struct Context {
 	int qr_panel = 32;
 	int gemm_force_small = 0;
 	bool profile = false;
+	int svd_persistent = 1;
+	int svd_max_bw = 0;            // 0 = automatic block width of the Jacobi kernel
+	int als_direct_max = 1536;     // local problems up to this size are solved densely (reference semantics), larger ones by CG
 };
 Context& ctx();
 void ensure_init();
@@ -123,7 +126,7 @@ struct Svd {
 	double soft_threshold = 0.0;   // applied to Sigma wherever extract() folds it in
 	// internals
 	bool swapped = false, reduced = false;
-	size_t mw = 0, nw = 0, npad = 0, mt = 0;
+	size_t mw = 0, nw = 0, npad = 0, mt = 0, mdot = 0, voff = 0, ld = 0;
 	DBuf GT, Qred, Ssorted, perm;
 	void factor(const double* A, size_t m, size_t n);
 	void extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, double* dS /* optional device S (k) */);

@@ -99,7 +99,9 @@ class TTNetwork:
             cores = [np.ones((1, dimensions[i], dimensions[d + i], 1)) for i in range(d)]
         else:
             cores = [np.ones((1, n, 1)) for n in dimensions]
-        return cls.from_cores(cores, core_position=0)
+        t = cls.from_cores(cores)
+        t.canonicalize_left()                      # ttNetwork.cpp:189
+        return t
 
     def __del__(self):
         h = getattr(self, "_h", None)
