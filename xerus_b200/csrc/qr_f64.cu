@@ -45,19 +45,20 @@ __global__ void __launch_bounds__(QR_PANEL_WARPS * 32) qr_panel_kernel(double* _
 
 	const int kmax = min(nbe, mp);
 	for (int j = 0; j < kmax; ++j) {
-		// pass 1: g_c = sum_{i >= j} P[i][j] * P[i][c]
+		// pass 1: g_c = sum_{i >= j} P[i][j] * P[i][c] for c > j; lane j accumulates the TAIL sum_{i > j} P[i][j]^2 only, so
+		// that ||x||^2 - alpha^2 is never formed by subtraction (a nearly triangular input would lose its sub-diagonal mass)
 		double g = 0.0;
 		if (active && lane >= j) {
-			for (int i = j + warp; i < mp; i += NW) g += pe(i, j) * pe(i, lane);
+			for (int i = j + warp; i < mp; i += NW) { if (lane != j || i != j) g += pe(i, j) * pe(i, lane); }
 		}
 		red[warp * 33 + lane] = g;
 		__syncthreads();
 		if (warp == 0) {
 			double G = 0.0;
 			for (int w = 0; w < NW; ++w) G += red[w * 33 + lane];
-			const double sigma = __shfl_sync(0xffffffffu, G, j);
+			const double tail = __shfl_sync(0xffffffffu, G, j);
 			const double alpha = pe(j, j);
-			const double tail = sigma - alpha * alpha;
+			const double sigma = tail + alpha * alpha;
 			double beta = alpha, tau = 0.0, scl = 0.0;
 			if (tail > 0.0 && j + 1 < mp) {
 				beta = -copysign(sqrt(sigma), alpha);

@@ -324,6 +324,10 @@ __global__ void svd_extract_kernel(const double* __restrict__ GT, const int ldg,
 	if (dS && threadIdx.x == 0) dS[r] = sigma_eff;
 }
 
+__global__ void add_diag_kernel(double* __restrict__ M, const size_t n, const double v) {
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) M[i * n + i] += v;
+}
+
 static int choose_bw(size_t ld, size_t nw, size_t smem_cap, int max_bw) {
 	int bw = max_bw;
 	while (bw > 1 && (size_t(2 * bw) * (ld + 1) * sizeof(double) + size_t(4 * bw) * bw + 16 > smem_cap || size_t(bw) >= nw)) bw >>= 1;
@@ -403,9 +407,8 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	ProfScope* prof_jacobi = new ProfScope("svd_jacobi");
 	const size_t smem_p = smem + size_t(2 * bw) * sizeof(double) + size_t(2 * bw) * bw * sizeof(unsigned short) + 16;
 	const bool persistent = c.svd_persistent && eh <= 16 && (nblk / 2) <= size_t(c.num_sms) && smem_p <= smem_cap;
-	if (persistent) {
-		// one cooperative launch for the whole SVD: rounds separated by grid barriers, convergence decided on device
-		const int max_sweeps = c.svd_max_sweeps;
+	// one cooperative launch runs all sweeps: rounds separated by grid barriers, convergence decided on device
+	auto run_persistent = [&](int max_sweeps, int& sweeps_out) -> bool {
 		unsigned int* d_cnt = static_cast<unsigned int*>(dalloc_bytes((2 * max_sweeps + 4) * sizeof(unsigned int)));
 		XB_CUDA(cudaMemsetAsync(d_cnt, 0, (2 * max_sweeps + 4) * sizeof(unsigned int), c.stream));
 		XB_CUDA(cudaMemsetAsync(d_info, 0, 8 * sizeof(unsigned int), c.stream));
@@ -416,11 +419,14 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		else launch_persistent<16, 256>(GT.p, int(ld), epl_x, epl_v, bw, int(nblk), tol2, d_cnt, d_info, max_sweeps, threads, smem_p, smem_cap);
 		XB_CUDA(cudaMemcpyAsync(h_info, d_info, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
 		XB_CUDA(cudaStreamSynchronize(c.stream));
-		sweeps = int(h_info[1]);
-		converged = (h_info[2] == 0);
+		sweeps_out = int(h_info[1]);
 		if (getenv("XB_JACOBI_TIMING")) fprintf(stderr, "[jacobi] %zux%zu bw=%d ctas=%zu sweeps=%d kcycles: load %u inner %u store %u sync %u\n",
-		                                       mdot, nw, bw, nblk / 2, sweeps, h_info[4], h_info[5], h_info[6], h_info[7]);
+		                                       mdot, nw, bw, nblk / 2, sweeps_out, h_info[4], h_info[5], h_info[6], h_info[7]);
 		dfree(d_cnt);
+		return h_info[2] == 0;
+	};
+	if (persistent) {
+		converged = run_persistent(c.svd_max_sweeps, sweeps);
 	} else if (nblk == 2) {
 		XB_CUDA(cudaMemsetAsync(d_info, 0, 4 * sizeof(unsigned int), c.stream));
 		jacobi_block_kernel<<<1, threads, smem, c.stream>>>(GT, int(ld), int(ld), int(voff), bw, 2, 0, 1, tol, d_info, 1, c.svd_max_sweeps);
@@ -443,9 +449,29 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 			converged = (h_info[0] == 0);
 		}
 	}
+	if (!converged) { delete prof_jacobi; dfree(d_info); throw Error(XB_ERR_NUMERIC, "Jacobi SVD did not converge within svd_max_sweeps sweeps"); }
+
+	if (c.svd_polish) {
+		// Polish: thousands of plane rotations leave V orthogonal only to ~eps*sqrt(#rotations) and X = G V with the same
+		// drift.  One Newton-Schulz step re-orthogonalises V (V <- V (3I - V^T V)/2, quadratic), then the left part is
+		// recomputed from the untouched input, X = G0 V — backward error back at the eps*sqrt(n) level of LAPACK.
+		// In the transposed storage: VT <- (1.5 I - 0.5 VT VT^T) VT ; XT = VT G0^T.
+		double* VT = GT.p + voff;
+		DBuf M(nw * nw), T2(nw * nw);
+		gemm(M, nw, nw, nw, -0.5, VT, ld, false, nw, VT, ld, true, 0.0);
+		add_diag_kernel<<<unsigned((nw + 255) / 256), 256, 0, c.stream>>>(M, nw, 1.5);
+		XB_LAUNCH_CHECK();
+		gemm(T2, nw, nw, nw, 1.0, M, nw, false, nw, VT, ld, false, 0.0);
+		copy2d(VT, ld, T2, nw, nw, nw);
+		if (reduced) gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, Rr, nw, true, 0.0);
+		else if (!swapped) gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, A, n, true, 0.0);
+		else gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, A, n, false, 0.0);
+		// the recomputed columns are orthogonal only up to the angle errors of V (~1e-14): one clean-up sweep of tiny
+		// rotations restores |cos| <= tol between the left vectors without disturbing V's orthogonality
+		if (persistent && nw > 1) { int extra = 0; run_persistent(2, extra); sweeps += extra; }
+	}
 	delete prof_jacobi;
 	dfree(d_info);
-	if (!converged) throw Error(XB_ERR_NUMERIC, "Jacobi SVD did not converge within svd_max_sweeps sweeps");
 
 	Ssorted.resize(nw);
 	perm.resize((nw + 1) / 2 + 1);   // nw ints
