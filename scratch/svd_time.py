@@ -2,15 +2,18 @@ import sys, time; sys.path.insert(0,'.')
 import numpy as np, xerus_b200 as xb
 xb.init(0)
 rng=np.random.default_rng(0)
-for (m,n) in [(256,256),(512,512),(128,128),(64,64)]:
+for (m,n) in [(256,256),(512,512),(128,128),(64,64),(32,32)]:
     A=rng.standard_normal((m,n))
-    for bw in [0,16,8,4]:
-        xb.set_option("svd_max_bw",bw)
-        xb.blasWrapper.svd(A)
-        xb.profile_enable(True)
-        for _ in range(3): U,S,Vt=xb.blasWrapper.svd(A)
-        sc,l,ms=xb.profile_get("svd_jacobi")
-        xb.profile_enable(False)
-        err=np.abs((U*S)@Vt-A).max()
-        print(m,n,'bw',bw,'jacobi ms/svd %.3f'%(ms/sc),'err %.1e'%err)
-xb.set_option("svd_max_bw",0)
+    for (bw,wpp) in [(0,0),(8,1),(8,2),(8,4),(16,1),(16,2),(4,4)]:
+        xb.set_option("svd_max_bw",bw); xb.set_option("svd_wpp",wpp)
+        try:
+            xb.blasWrapper.svd(A)
+            xb.profile_enable(True)
+            for _ in range(3): U,S,Vt=xb.blasWrapper.svd(A)
+            sc,l,ms=xb.profile_get("svd_jacobi"); sc2,l2,ms2=xb.profile_get("svd")
+            xb.profile_enable(False)
+            err=np.linalg.norm((U*S)@Vt-A)/np.linalg.norm(A)
+            print(m,n,'bw',bw,'wpp',wpp,'jacobi ms/svd %.3f  svd total %.3f'%(ms/sc,ms2/sc2),'err %.1e'%err, flush=True)
+        except Exception as e:
+            print(m,n,bw,wpp,'ERR',e)
+xb.set_option("svd_max_bw",0); xb.set_option("svd_wpp",0)

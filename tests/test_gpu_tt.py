@@ -242,3 +242,22 @@ def test_round_batched():
     for t, o in zip(tts, refs):
         o.round(4)
         assert t.ranks() == o.ranks() and O.tt_distance_rel(to_oracle(t), o) < 1e-9
+
+
+def test_batch_sharding_single_rank():
+    """BASELINE config 5 (reduced): y_b = A x_b ; y_b.round(r) per item through the sharding helpers, device path."""
+    from xerus_b200 import parallel
+    d, n, r, items = 6, 4, 6, 5
+    A = xb.TTOperator.laplace(d, n)
+    Ao = O.laplace_operator(d, n)
+    make = lambda b: xb.TTTensor.random([n] * d, r, parallel.item_rng(99, b))
+    res = parallel.gather_by_item(parallel.matvec_round_batch(A, make, items, r), items)
+    for b, (ranks, nrm) in enumerate(res):
+        xo = to_oracle(make(b))
+        yo = O.tt_apply(Ao, xo); yo.round(r)
+        assert list(ranks) == yo.ranks() and abs(nrm - yo.frob_norm()) < 1e-10 * yo.frob_norm()
+    # two "ranks" processed one after the other cover every item exactly once and give the same answers
+    parts = {}
+    for rank in range(2):
+        parts.update(parallel.matvec_round_batch(A, make, items, r, rank, 2))
+    assert [parts[b] for b in range(items)] == res

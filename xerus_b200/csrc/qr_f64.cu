@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(QR_PANEL_WARPS * 32) qr_panel_kernel(double* _
 	double* Ps = s_misc + 4;                  // [mp][32] when SMEM
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int NW = blockDim.x >> 5;
+	constexpr int NW = QR_PANEL_WARPS;      // the launch always uses QR_PANEL_WARPS warps
 	const bool active = lane < nbe;
 	auto pe = [&](int i, int c) -> double& { return SMEM ? Ps[i * QR_NB + c] : W[(long long)i * ldw + c]; };
 
@@ -54,16 +54,22 @@ __global__ void __launch_bounds__(QR_PANEL_WARPS * 32) qr_panel_kernel(double* _
 		red[warp * 33 + lane] = g;
 		__syncthreads();
 		if (warp == 0) {
-			double G = 0.0;
-			for (int w = 0; w < NW; ++w) G += red[w * 33 + lane];
+			double G0 = 0.0, G1 = 0.0, G2 = 0.0, G3 = 0.0;
+#pragma unroll
+			for (int w = 0; w < NW; w += 4) {
+				G0 += red[w * 33 + lane]; G1 += red[(w + 1) * 33 + lane]; G2 += red[(w + 2) * 33 + lane]; G3 += red[(w + 3) * 33 + lane];
+			}
+			const double G = (G0 + G1) + (G2 + G3);
 			const double tail = __shfl_sync(0xffffffffu, G, j);
 			const double alpha = pe(j, j);
 			const double sigma = tail + alpha * alpha;
 			double beta = alpha, tau = 0.0, scl = 0.0;
 			if (tail > 0.0 && j + 1 < mp) {
-				beta = -copysign(sqrt(sigma), alpha);
-				tau = (beta - alpha) / beta;
-				scl = 1.0 / (alpha - beta);
+				// beta = -sign(alpha) ||x||, tau = (beta - alpha)/beta = 1 + |alpha|/||x||, 1/(alpha - beta) = sign(alpha)/(|alpha| + ||x||)
+				const double rs = rsqrt(sigma), nrmx = sigma * rs;
+				beta = -copysign(nrmx, alpha);
+				tau = 1.0 + fabs(alpha) * rs;
+				scl = copysign(1.0, alpha) / (fabs(alpha) + nrmx);
 			}
 			double wv = 0.0;
 			if (active && lane > j && tau != 0.0) wv = tau * (G - beta * pe(j, lane)) * scl;
@@ -92,18 +98,27 @@ __global__ void __launch_bounds__(QR_PANEL_WARPS * 32) qr_panel_kernel(double* _
 	for (int i = warp; i < mp; i += NW) Vbuf[(long long)i * QR_NB + lane] = vval(i, lane);
 	// GV = V^T V : warp w owns row w
 	if (warp < kmax) {
-		double acc = 0.0;
-		for (int i = warp; i < mp; ++i) acc += vval(i, warp) * vval(i, lane);
-		GV[warp * 33 + lane] = acc;
+		// rows below the top 32 x 32 block hold plain V entries (no unit-diagonal / zero masking needed)
+		double acc0 = 0.0, acc1 = 0.0;
+		const int top = min(mp, 32);
+		for (int i = warp; i < top; ++i) acc0 += vval(i, warp) * vval(i, lane);
+		if (lane < kmax) {
+			int i = 32;
+			for (; i + 1 < mp; i += 2) { acc0 += pe(i, warp) * pe(i, lane); acc1 += pe(i + 1, warp) * pe(i + 1, lane); }
+			if (i < mp) acc0 += pe(i, warp) * pe(i, lane);
+		}
+		GV[warp * 33 + lane] = acc0 + acc1;
 	}
 	__syncthreads();
 	// T(0:j, j) = -tau_j * T(0:j, 0:j) * GV(0:j, j) ; T(j, j) = tau_j
 	if (warp == 0) {
 		for (int j = 0; j < kmax; ++j) {
-			double t = 0.0;
-			if (lane < j) for (int c = lane; c < j; ++c) t += Ts[lane * 33 + c] * GV[c * 33 + j];
+			// T[lane][c] is zero for c < lane and for c >= j (not written yet): the full-length sum needs no per-lane bounds
+			double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+			for (int c = 0; c < 32; c += 2) { t0 += Ts[lane * 33 + c] * GV[c * 33 + j]; t1 += Ts[lane * 33 + c + 1] * GV[(c + 1) * 33 + j]; }
 			__syncwarp();
-			if (lane < j) Ts[lane * 33 + j] = -s_tau[j] * t;
+			if (lane < j) Ts[lane * 33 + j] = -s_tau[j] * (t0 + t1);
 			else if (lane == j) Ts[j * 33 + j] = s_tau[j];
 			__syncwarp();
 		}

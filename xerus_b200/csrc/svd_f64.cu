@@ -131,20 +131,27 @@ __global__ void jacobi_block_kernel(double* __restrict__ GT, const int ldg, cons
 //  * a sweep in which no pair had |cos| > 1e-9 is the last one (cyclic Jacobi converges quadratically), so no
 //    verification sweep is spent.
 // Rows of GT are [ x (mdot, zero padded to a multiple of 32) | v (nw, zero padded to a multiple of 32) ].
-template <int EH, int MAXT>   // EH >= max(voff, ld - voff) / 32 : register tile per column part
+// EH >= max(voff, ld - voff) / 32 : elements per lane of one column part; WPP warps share one column pair (each owns
+// EH / WPP of the k-slices), which shortens the per-round dependent chain — the kernel is latency/issue bound, not
+// bandwidth bound (ncu: 24 % issue utilisation, 8 cycles per issued instruction, profiles/r1_jacobi_persistent.txt).
+template <int EH, int WPP, int MAXT>
 __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restrict__ GT, const int ld, const int epl_x, const int epl_v,
                                                                 const int bw, const int nblk, const double tol2,
                                                                 unsigned int* __restrict__ counters, unsigned int* __restrict__ info,
                                                                 const int max_sweeps) {
+	constexpr int EHW = EH / WPP;
 	extern __shared__ double S[];
 	__shared__ unsigned int s_rot, s_big;
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 	const int N = 2 * bw;
 	const int voff = 32 * epl_x;
+	const int sub = warp % WPP;                  // which k-slices of the pair this warp owns
+	const int kbase = sub * EHW;
 	double* nrm = S + (size_t)N * ld;           // [N] cached squared norms of the resident columns
+	double* gpart = nrm + N;                    // [bw][WPP] partial cross products
 	// schedule of the full 2*bw-player tournament, precomputed once: keeps the integer modulo out of the per-round chain
-	unsigned short* sched = reinterpret_cast<unsigned short*>(nrm + N);      // [(N-1) * bw] : a | b << 8
+	unsigned short* sched = reinterpret_cast<unsigned short*>(gpart + bw * WPP);      // [(N-1) * bw] : a | b << 8
 	for (int e = threadIdx.x; e < (N - 1) * bw; e += blockDim.x) {
 		const int rr = e / bw, pi = e % bw;
 		int a, b;
@@ -157,8 +164,9 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restr
 	__syncthreads();
 	int sweeps = 0;
 	unsigned int last_rot = 1, last_big = 1;
-	unsigned int my_rot = 0, my_big = 0;         // per-warp counters (lane 0), flushed once per visit
+	unsigned int my_rot = 0, my_big = 0;         // per-pair counters (lane 0 of sub-warp 0), flushed once per visit
 	long long tk_load = 0, tk_inner = 0, tk_store = 0, tk_sync = 0, tk0 = 0;   // phase cycle counters (thread 0 of block 0)
+	long long tp_a = 0, tp_b = 0, tp_c = 0, tp_d = 0, tp0 = 0; unsigned int tp_n = 0;
 	const bool timing = (info[0] == 0xC10C) && blockIdx.x == 0 && threadIdx.x == 0;
 	for (; sweeps < max_sweeps; ) {
 		for (int round = 0; round < nrounds; ++round) {
@@ -174,14 +182,17 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restr
 				const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
 				const double* src = GT + (size_t)grow * ld + lane;
 				double* dst = S + (size_t)r * ld + lane;
-				double v[EH], w[EH];
-#pragma unroll
-				for (int k = 0; k < EH; ++k) { v[k] = (k < epl_x) ? src[32 * k] : 0.0; w[k] = (k < epl_v) ? src[voff + 32 * k] : 0.0; }
 				double ss = 0.0;
 #pragma unroll
-				for (int k = 0; k < EH; ++k) {
-					if (k < epl_x) { dst[32 * k] = v[k]; ss += v[k] * v[k]; }
-					if (k < epl_v) dst[voff + 32 * k] = w[k];
+				for (int k0 = 0; k0 < EH; k0 += 4) {
+					double v[4], w[4];
+#pragma unroll
+					for (int k = 0; k < 4; ++k) { v[k] = (k0 + k < epl_x) ? src[32 * (k0 + k)] : 0.0; w[k] = (k0 + k < epl_v) ? src[voff + 32 * (k0 + k)] : 0.0; }
+#pragma unroll
+					for (int k = 0; k < 4; ++k) {
+						if (k0 + k < epl_x) { dst[32 * (k0 + k)] = v[k]; ss += v[k] * v[k]; }
+						if (k0 + k < epl_v) dst[voff + 32 * (k0 + k)] = w[k];
+					}
 				}
 #pragma unroll
 				for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -192,31 +203,37 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restr
 			const bool full = (round == 0);
 			const int inner_rounds = full ? (N - 1) : bw;
 			for (int rr = 0; rr < inner_rounds; ++rr) {
-				for (int pi = warp; pi < bw; pi += nwarps) {
+				for (int pi = warp / WPP; pi < bw; pi += nwarps / WPP) {
 					int a, b;
 					if (full) { const unsigned int ab_ = sched[rr * bw + pi]; a = ab_ & 255; b = ab_ >> 8; }
 					else { a = pi; b = bw + ((pi + rr) & (bw - 1)); }      // bw is a power of two
-					double* x = S + (size_t)a * ld + lane;
-					double* y = S + (size_t)b * ld + lane;
-					double xr[EH], yr[EH];
+					if (timing) tp0 = clock64();
+					double* x = S + (size_t)a * ld + lane + 32 * kbase;
+					double* y = S + (size_t)b * ld + lane + 32 * kbase;
+					double xr[EHW], yr[EHW];
 #pragma unroll
-					for (int k = 0; k < EH; ++k) { xr[k] = (k < epl_x) ? x[32 * k] : 0.0; yr[k] = (k < epl_x) ? y[32 * k] : 0.0; }
-					double g0 = 0.0, g1 = 0.0;
+					for (int k = 0; k < EHW; ++k) { xr[k] = (kbase + k < epl_x) ? x[32 * k] : 0.0; yr[k] = (kbase + k < epl_x) ? y[32 * k] : 0.0; }
+					double gacc[4] = {0.0, 0.0, 0.0, 0.0};              // independent chains: DFMA latency is ~20 cycles here
 #pragma unroll
-					for (int k = 0; k < EH; k += 2) {      // padding entries are zero: no predicate needed
-						g0 += xr[k] * yr[k];
-						if (k + 1 < EH) g1 += xr[k + 1] * yr[k + 1];
-					}
-					double g = g0 + g1;
+					for (int k = 0; k < EHW; ++k) gacc[k & 3] += xr[k] * yr[k];      // padding entries are zero
+					double g = (gacc[0] + gacc[1]) + (gacc[2] + gacc[3]);
+					const double aa = nrm[a], bb = nrm[b];                 // read before the barrier below: updated after it
 #pragma unroll
 					for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-					const double aa = nrm[a], bb = nrm[b];
-					const double gg = g * g, ab = aa * bb;
-					if (gg > tol2 * ab) {
-						// prefetch the accumulated-rotation part while the rotation parameters are computed
-						double xv[EH], yv[EH];
+					if (WPP > 1) {
+						if (lane == 0) gpart[pi * WPP + sub] = g;
+						__syncthreads();                               // every warp passes here the same number of times
+						g = 0.0;
 #pragma unroll
-						for (int k = 0; k < EH; ++k) { xv[k] = (k < epl_v) ? x[voff + 32 * k] : 0.0; yv[k] = (k < epl_v) ? y[voff + 32 * k] : 0.0; }
+						for (int q = 0; q < WPP; ++q) g += gpart[pi * WPP + q];
+					}
+					const double gg = g * g, ab = aa * bb;
+					if (timing) { const long long t1 = clock64(); tp_a += t1 - tp0; tp0 = t1; tp_n++; }
+					if (gg > tol2 * ab) {
+						// the accumulated-rotation part is only touched by pairs that rotate: fetch it while the parameters are computed
+						double xv[EHW], yv[EHW];
+#pragma unroll
+						for (int k = 0; k < EHW; ++k) { xv[k] = (kbase + k < epl_v) ? x[voff + 32 * k] : 0.0; yv[k] = (kbase + k < epl_v) ? y[voff + 32 * k] : 0.0; }
 						// c^2 = (1 + |d|/h)/2, s = sign(d) 2g / (2 h c), t = s/c  with h = sqrt(d^2 + 4 g^2): two rsqrt, no division
 						const double d = bb - aa;
 						const double rh = rsqrt(d * d + 4.0 * gg);
@@ -224,25 +241,23 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restr
 						const double rc = rsqrt(c2);
 						const double c = c2 * rc;
 						const double s = (d >= 0.0 ? g : -g) * rh * rc;
-						const double t = s * rc;
+						if (timing) { const long long t1 = clock64(); tp_b += (t1 - tp0) + (long long)(c * 0.0); tp0 = t1; }
 #pragma unroll
-						for (int k = 0; k < EH; ++k) if (k < epl_x) {
-							x[32 * k] = c * xr[k] - s * yr[k];
-							y[32 * k] = s * xr[k] + c * yr[k];
+						for (int k = 0; k < EHW; ++k) {
+							if (kbase + k < epl_x) { x[32 * k] = c * xr[k] - s * yr[k]; y[32 * k] = s * xr[k] + c * yr[k]; }
+							if (kbase + k < epl_v) { x[voff + 32 * k] = c * xv[k] - s * yv[k]; y[voff + 32 * k] = s * xv[k] + c * yv[k]; }
 						}
-#pragma unroll
-						for (int k = 0; k < EH; ++k) if (k < epl_v) {
-							x[voff + 32 * k] = c * xv[k] - s * yv[k];
-							y[voff + 32 * k] = s * xv[k] + c * yv[k];
-						}
-						if (lane == 0) {
+						if (lane == 0 && sub == 0) {
+							const double t = s * rc;
 							nrm[a] = aa - t * g; nrm[b] = bb + t * g;
 							my_rot += 1;
 							if (gg > 1e-18 * ab) my_big += 1;
 						}
 					}
+					if (timing) { const long long t1 = clock64(); tp_c += t1 - tp0; tp0 = t1; }
 				}
 				__syncthreads();
+				if (timing) { const long long t1 = clock64(); tp_d += t1 - tp0; }
 			}
 			if (timing) { const long long t1 = clock64(); tk_inner += t1 - tk0; tk0 = t1; }
 			if (lane == 0 && my_rot) { atomicAdd(&s_rot, my_rot); atomicAdd(&s_big, my_big); my_rot = 0; my_big = 0; }
@@ -250,11 +265,14 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restr
 				const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
 				double* dst = GT + (size_t)grow * ld + lane;
 				const double* src = S + (size_t)r * ld + lane;
-				double v[EH], w[EH];
 #pragma unroll
-				for (int k = 0; k < EH; ++k) { v[k] = (k < epl_x) ? src[32 * k] : 0.0; w[k] = (k < epl_v) ? src[voff + 32 * k] : 0.0; }
+				for (int k0 = 0; k0 < EH; k0 += 4) {
+					double v[4], w[4];
 #pragma unroll
-				for (int k = 0; k < EH; ++k) { if (k < epl_x) dst[32 * k] = v[k]; if (k < epl_v) dst[voff + 32 * k] = w[k]; }
+					for (int k = 0; k < 4; ++k) { v[k] = (k0 + k < epl_x) ? src[32 * (k0 + k)] : 0.0; w[k] = (k0 + k < epl_v) ? src[voff + 32 * (k0 + k)] : 0.0; }
+#pragma unroll
+					for (int k = 0; k < 4; ++k) { if (k0 + k < epl_x) dst[32 * (k0 + k)] = v[k]; if (k0 + k < epl_v) dst[voff + 32 * (k0 + k)] = w[k]; }
+				}
 			}
 			if (timing) { const long long t1 = clock64(); tk_store += t1 - tk0; tk0 = t1; }
 			if (nblk > 2) { __threadfence(); grid.sync(); }
@@ -279,6 +297,7 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restr
 		if (big == 0) break;
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) { info[1] = (unsigned)sweeps; info[2] = last_big; info[3] = last_rot; }
+	if (timing) { counters[2 * max_sweeps] = (unsigned)(tp_a / (tp_n + 1)); counters[2 * max_sweeps + 1] = (unsigned)(tp_b / (tp_n + 1)); counters[2 * max_sweeps + 2] = (unsigned)(tp_c / (tp_n + 1)); counters[2 * max_sweeps + 3] = (unsigned)(tp_d / (tp_n + 1)); }
 	if (timing) { info[4] = (unsigned)(tk_load >> 10); info[5] = (unsigned)(tk_inner >> 10); info[6] = (unsigned)(tk_store >> 10); info[7] = (unsigned)(tk_sync >> 10); }
 }
 
@@ -330,20 +349,21 @@ __global__ void add_diag_kernel(double* __restrict__ M, const size_t n, const do
 
 static int choose_bw(size_t ld, size_t nw, size_t smem_cap, int max_bw) {
 	int bw = max_bw;
-	while (bw > 1 && (size_t(2 * bw) * (ld + 1) * sizeof(double) + size_t(4 * bw) * bw + 16 > smem_cap || size_t(bw) >= nw)) bw >>= 1;
+	while (bw > 1 && (size_t(2 * bw) * (ld + 3) * sizeof(double) + size_t(4 * bw) * bw + 16 > smem_cap || size_t(bw) >= nw)) bw >>= 1;
 	return bw;
 }
 
-template <int EPL, int MAXT>
-static void launch_persistent(double* gt, int ld, int epl, int epl_dot, int bw, int nblk, double tol2, unsigned int* d_cnt,
+template <int EH, int WPP, int MAXT>
+static void launch_persistent(double* gt, int ld, int epl_x, int epl_v, int bw, int nblk, double tol2, unsigned int* d_cnt,
                               unsigned int* d_info, int max_sweeps, int threads, size_t smem, size_t smem_cap) {
 	static bool attr = false;
 	if (!attr) {
-		XB_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<EPL, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+		XB_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<EH, WPP, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
 		attr = true;
 	}
-	void* args[] = {&gt, &ld, &epl, &epl_dot, &bw, &nblk, &tol2, &d_cnt, &d_info, &max_sweeps};
-	XB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<EPL, MAXT>, dim3(unsigned(nblk / 2)), dim3(threads), args, smem, ctx().stream));
+	XB_REQUIRE(threads <= MAXT, "internal: Jacobi launch exceeds its launch bound");
+	void* args[] = {&gt, &ld, &epl_x, &epl_v, &bw, &nblk, &tol2, &d_cnt, &d_info, &max_sweeps};
+	XB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<EH, WPP, MAXT>, dim3(unsigned(nblk / 2)), dim3(threads), args, smem, ctx().stream));
 	ctx().launches++;
 }
 
@@ -376,9 +396,10 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	XB_REQUIRE(2 * (ld + 1) * sizeof(double) <= smem_cap, "SVD: matrix too large for the shared-memory Jacobi kernel (min(m,n) <= ~7000)");
 	const int epl_x = int(voff / 32), epl_v = int((ld - voff) / 32), eh = std::max(epl_x, epl_v);
 	// register-tile variants of the persistent kernel: (EH, max threads) = (4, 1024), (8, 512), (16, 256)
-	// measured on B200 (scratch/svd_time.py): per inner round the dependent chain (reduce -> 2 rsqrt -> rotate -> barrier)
-	// costs ~1600 cycles regardless of the vector length, so more, smaller CTAs only pay off from 256 columns on
-	int max_bw = eh <= 8 ? (nw >= 256 ? 8 : 16) : (eh <= 16 ? 8 : 32);
+	// The kernel is latency/issue bound: an inner round costs a dependent chain whose length does not depend on the number
+	// of resident pairs, so (a) several warps share a pair (WPP) and (b) more, smaller CTAs only pay off from 256 columns on.
+	const int EH = eh <= 4 ? 4 : (eh <= 8 ? 8 : 16);
+	int max_bw = EH == 16 ? 4 : (nw >= 256 ? 8 : 16);
 	if (c.svd_max_bw > 0) max_bw = std::min(max_bw, c.svd_max_bw);
 	const int bw = choose_bw(ld, nw, smem_cap, max_bw);
 	size_t nblk = (nw + bw - 1) / bw;
@@ -399,13 +420,18 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		XB_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
 		attr_set = true;
 	}
-	const int threads = std::max(64, std::min(1024, 32 * bw));
+	// launch bound of the (EH, WPP) variant: the register tile is 4 * EH / WPP doubles
+	auto maxt = [&](int w) { const int ehw = EH / w; return ehw >= 8 ? (EH == 8 ? 512 : 256) : (ehw == 4 ? 512 : 1024); };
+	int wpp = (c.svd_wpp > 0) ? c.svd_wpp : 1;   // measured: the extra block barrier of WPP > 1 costs more than the shorter chain saves
+	while (wpp > 1 && (EH / wpp < 1 || 32 * bw * wpp > maxt(wpp))) wpp >>= 1;
+	const int threads = std::max(64, std::min(1024, 32 * bw * wpp));
+	if (threads != 32 * bw * wpp) wpp = 1;
 	unsigned int* d_info = static_cast<unsigned int*>(dalloc_bytes(8 * sizeof(unsigned int)));
 	unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch);
 	sweeps = 0;
 	bool converged = false;
 	ProfScope* prof_jacobi = new ProfScope("svd_jacobi");
-	const size_t smem_p = smem + size_t(2 * bw) * sizeof(double) + size_t(2 * bw) * bw * sizeof(unsigned short) + 16;
+	const size_t smem_p = smem + size_t(2 * bw + 4 * bw) * sizeof(double) + size_t(2 * bw) * bw * sizeof(unsigned short) + 16;
 	const bool persistent = c.svd_persistent && eh <= 16 && (nblk / 2) <= size_t(c.num_sms) && smem_p <= smem_cap;
 	// one cooperative launch runs all sweeps: rounds separated by grid barriers, convergence decided on device
 	auto run_persistent = [&](int max_sweeps, int& sweeps_out) -> bool {
@@ -414,14 +440,20 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		XB_CUDA(cudaMemsetAsync(d_info, 0, 8 * sizeof(unsigned int), c.stream));
 		if (getenv("XB_JACOBI_TIMING")) { const unsigned int flag = 0xC10C; XB_CUDA(cudaMemcpyAsync(d_info, &flag, 4, cudaMemcpyHostToDevice, c.stream)); }
 		const double tol2 = tol * tol;
-		if (eh <= 4) launch_persistent<4, 512>(GT.p, int(ld), epl_x, epl_v, bw, int(nblk), tol2, d_cnt, d_info, max_sweeps, threads, smem_p, smem_cap);
-		else if (eh <= 8) launch_persistent<8, 512>(GT.p, int(ld), epl_x, epl_v, bw, int(nblk), tol2, d_cnt, d_info, max_sweeps, threads, smem_p, smem_cap);
-		else launch_persistent<16, 256>(GT.p, int(ld), epl_x, epl_v, bw, int(nblk), tol2, d_cnt, d_info, max_sweeps, threads, smem_p, smem_cap);
+#define XB_JAC(E, W, T) launch_persistent<E, W, T>(GT.p, int(ld), epl_x, epl_v, bw, int(nblk), tol2, d_cnt, d_info, max_sweeps, threads, smem_p, smem_cap)
+		if (EH == 4) { if (wpp == 4) XB_JAC(4, 4, 1024); else if (wpp == 2) XB_JAC(4, 2, 1024); else XB_JAC(4, 1, 512); }
+		else if (EH == 8) { if (wpp == 4) XB_JAC(8, 4, 1024); else if (wpp == 2) XB_JAC(8, 2, 512); else XB_JAC(8, 1, 512); }
+		else { if (wpp == 4) XB_JAC(16, 4, 512); else if (wpp == 2) XB_JAC(16, 2, 256); else XB_JAC(16, 1, 256); }
+#undef XB_JAC
 		XB_CUDA(cudaMemcpyAsync(h_info, d_info, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
 		XB_CUDA(cudaStreamSynchronize(c.stream));
 		sweeps_out = int(h_info[1]);
-		if (getenv("XB_JACOBI_TIMING")) fprintf(stderr, "[jacobi] %zux%zu bw=%d ctas=%zu sweeps=%d kcycles: load %u inner %u store %u sync %u\n",
-		                                       mdot, nw, bw, nblk / 2, sweeps_out, h_info[4], h_info[5], h_info[6], h_info[7]);
+		if (getenv("XB_JACOBI_TIMING")) {
+			unsigned int hp[4];
+			XB_CUDA(cudaMemcpy(hp, d_cnt + 2 * max_sweeps, sizeof(hp), cudaMemcpyDeviceToHost));
+			fprintf(stderr, "[jacobi] %zux%zu bw=%d wpp=%d ctas=%zu sweeps=%d kcycles: load %u inner %u store %u sync %u | per pair-visit cycles: dot+reduce %u math %u rotate %u barrier %u\n",
+			        mdot, nw, bw, wpp, nblk / 2, sweeps_out, h_info[4], h_info[5], h_info[6], h_info[7], hp[0], hp[1], hp[2], hp[3]);
+		}
 		dfree(d_cnt);
 		return h_info[2] == 0;
 	};

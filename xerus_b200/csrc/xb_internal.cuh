@@ -46,6 +46,7 @@ struct Context {
 	bool profile = false;
 	int svd_persistent = 1;
 	int svd_polish = 1;            // Newton-Schulz re-orthogonalisation of V + recomputed left part after the Jacobi sweeps
+	int svd_wpp = 0;               // 0 = automatic number of warps sharing a column pair
 	int svd_max_bw = 0;            // 0 = automatic block width of the Jacobi kernel
 	int als_direct_max = 1536;     // local problems up to this size are solved densely (reference semantics), larger ones by CG
 };
