@@ -150,7 +150,8 @@ xb_status xb_set_option(const char* key, double value) {
 		else if (k == "gemm_force_small") ctx().gemm_force_small = int(value);
 		else if (k == "svd_persistent") ctx().svd_persistent = int(value);
 		else if (k == "svd_max_bw") ctx().svd_max_bw = int(value);
-		else if (k == "svd_wpp") ctx().svd_wpp = int(value);
+		else if (k == "svd_mixed") ctx().svd_mixed = int(value);
+		else if (k == "svd_mixed_min") ctx().svd_mixed_min = int(value);
 		else if (k == "svd_polish") ctx().svd_polish = int(value);
 		else if (k == "als_direct_max") ctx().als_direct_max = int(value);
 		else throw Error(XB_ERR_INVALID, "xb_set_option: unknown key " + k);

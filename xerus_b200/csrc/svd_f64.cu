@@ -131,27 +131,26 @@ __global__ void jacobi_block_kernel(double* __restrict__ GT, const int ldg, cons
 //  * a sweep in which no pair had |cos| > 1e-9 is the last one (cyclic Jacobi converges quadratically), so no
 //    verification sweep is spent.
 // Rows of GT are [ x (mdot, zero padded to a multiple of 32) | v (nw, zero padded to a multiple of 32) ].
-// EH >= max(voff, ld - voff) / 32 : elements per lane of one column part; WPP warps share one column pair (each owns
-// EH / WPP of the k-slices), which shortens the per-round dependent chain — the kernel is latency/issue bound, not
-// bandwidth bound (ncu: 24 % issue utilisation, 8 cycles per issued instruction, profiles/r1_jacobi_persistent.txt).
-template <int EH, int WPP, int MAXT>
-__global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restrict__ GT, const int ld, const int epl_x, const int epl_v,
-                                                                const int bw, const int nblk, const double tol2,
+__device__ __forceinline__ float xb_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double xb_rsqrt(double x) { return rsqrt(x); }
+
+// T = double, or float for the pre-conditioning sweeps of the mixed-precision path (see Svd::factor).
+// EH >= max(voff, ld - voff) / 32 : elements per lane of one column part (register tile of a warp = one column pair).
+template <typename T, int EH, int MAXT>
+__global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(T* __restrict__ GT, const int ld, const int epl_x, const int epl_v,
+                                                                const int bw, const int nblk, const T tol2, const T big2,
                                                                 unsigned int* __restrict__ counters, unsigned int* __restrict__ info,
                                                                 const int max_sweeps) {
-	constexpr int EHW = EH / WPP;
-	extern __shared__ double S[];
+	extern __shared__ double S_raw[];
+	T* S = reinterpret_cast<T*>(S_raw);
 	__shared__ unsigned int s_rot, s_big;
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 	const int N = 2 * bw;
 	const int voff = 32 * epl_x;
-	const int sub = warp % WPP;                  // which k-slices of the pair this warp owns
-	const int kbase = sub * EHW;
-	double* nrm = S + (size_t)N * ld;           // [N] cached squared norms of the resident columns
-	double* gpart = nrm + N;                    // [bw][WPP] partial cross products
+	T* nrm = S + (size_t)N * ld;                // [N] cached squared norms of the resident columns
 	// schedule of the full 2*bw-player tournament, precomputed once: keeps the integer modulo out of the per-round chain
-	unsigned short* sched = reinterpret_cast<unsigned short*>(gpart + bw * WPP);      // [(N-1) * bw] : a | b << 8
+	unsigned short* sched = reinterpret_cast<unsigned short*>(nrm + N + (N & 1));      // [(N-1) * bw] : a | b << 8
 	for (int e = threadIdx.x; e < (N - 1) * bw; e += blockDim.x) {
 		const int rr = e / bw, pi = e % bw;
 		int a, b;
@@ -164,9 +163,8 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restr
 	__syncthreads();
 	int sweeps = 0;
 	unsigned int last_rot = 1, last_big = 1;
-	unsigned int my_rot = 0, my_big = 0;         // per-pair counters (lane 0 of sub-warp 0), flushed once per visit
+	unsigned int my_rot = 0, my_big = 0;         // per-warp counters (lane 0), flushed once per visit
 	long long tk_load = 0, tk_inner = 0, tk_store = 0, tk_sync = 0, tk0 = 0;   // phase cycle counters (thread 0 of block 0)
-	long long tp_a = 0, tp_b = 0, tp_c = 0, tp_d = 0, tp0 = 0; unsigned int tp_n = 0;
 	const bool timing = (info[0] == 0xC10C) && blockIdx.x == 0 && threadIdx.x == 0;
 	for (; sweeps < max_sweeps; ) {
 		for (int round = 0; round < nrounds; ++round) {
@@ -180,14 +178,14 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restr
 			if (timing) tk0 = clock64();
 			for (int r = warp; r < N; r += nwarps) {
 				const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
-				const double* src = GT + (size_t)grow * ld + lane;
-				double* dst = S + (size_t)r * ld + lane;
-				double ss = 0.0;
+				const T* src = GT + (size_t)grow * ld + lane;
+				T* dst = S + (size_t)r * ld + lane;
+				T ss = T(0);
 #pragma unroll
 				for (int k0 = 0; k0 < EH; k0 += 4) {
-					double v[4], w[4];
+					T v[4], w[4];
 #pragma unroll
-					for (int k = 0; k < 4; ++k) { v[k] = (k0 + k < epl_x) ? src[32 * (k0 + k)] : 0.0; w[k] = (k0 + k < epl_v) ? src[voff + 32 * (k0 + k)] : 0.0; }
+					for (int k = 0; k < 4; ++k) { v[k] = (k0 + k < epl_x) ? src[32 * (k0 + k)] : T(0); w[k] = (k0 + k < epl_v) ? src[voff + 32 * (k0 + k)] : T(0); }
 #pragma unroll
 					for (int k = 0; k < 4; ++k) {
 						if (k0 + k < epl_x) { dst[32 * (k0 + k)] = v[k]; ss += v[k] * v[k]; }
@@ -203,73 +201,75 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restr
 			const bool full = (round == 0);
 			const int inner_rounds = full ? (N - 1) : bw;
 			for (int rr = 0; rr < inner_rounds; ++rr) {
-				for (int pi = warp / WPP; pi < bw; pi += nwarps / WPP) {
+				for (int pi = warp; pi < bw; pi += nwarps) {
 					int a, b;
 					if (full) { const unsigned int ab_ = sched[rr * bw + pi]; a = ab_ & 255; b = ab_ >> 8; }
 					else { a = pi; b = bw + ((pi + rr) & (bw - 1)); }      // bw is a power of two
-					if (timing) tp0 = clock64();
-					double* x = S + (size_t)a * ld + lane + 32 * kbase;
-					double* y = S + (size_t)b * ld + lane + 32 * kbase;
-					double xr[EHW], yr[EHW];
+					T* x = S + (size_t)a * ld + lane;
+					T* y = S + (size_t)b * ld + lane;
+					T xr[EH], yr[EH];
 #pragma unroll
-					for (int k = 0; k < EHW; ++k) { xr[k] = (kbase + k < epl_x) ? x[32 * k] : 0.0; yr[k] = (kbase + k < epl_x) ? y[32 * k] : 0.0; }
-					double gacc[4] = {0.0, 0.0, 0.0, 0.0};              // independent chains: DFMA latency is ~20 cycles here
+					for (int k = 0; k < EH; ++k) { xr[k] = (k < epl_x) ? x[32 * k] : T(0); yr[k] = (k < epl_x) ? y[32 * k] : T(0); }
+					T gacc[4] = {T(0), T(0), T(0), T(0)};                  // independent chains: DFMA latency is ~20 cycles here
 #pragma unroll
-					for (int k = 0; k < EHW; ++k) gacc[k & 3] += xr[k] * yr[k];      // padding entries are zero
-					double g = (gacc[0] + gacc[1]) + (gacc[2] + gacc[3]);
-					const double aa = nrm[a], bb = nrm[b];                 // read before the barrier below: updated after it
+					for (int k = 0; k < EH; ++k) gacc[k & 3] += xr[k] * yr[k];      // padding entries are zero
+					T g = (gacc[0] + gacc[1]) + (gacc[2] + gacc[3]);
+					const T aa = nrm[a], bb = nrm[b];
 #pragma unroll
 					for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-					if (WPP > 1) {
-						if (lane == 0) gpart[pi * WPP + sub] = g;
-						__syncthreads();                               // every warp passes here the same number of times
-						g = 0.0;
-#pragma unroll
-						for (int q = 0; q < WPP; ++q) g += gpart[pi * WPP + q];
-					}
-					const double gg = g * g, ab = aa * bb;
-					if (timing) { const long long t1 = clock64(); tp_a += t1 - tp0; tp0 = t1; tp_n++; }
+					const T gg = g * g, ab = aa * bb;
 					if (gg > tol2 * ab) {
 						// the accumulated-rotation part is only touched by pairs that rotate: fetch it while the parameters are computed
-						double xv[EHW], yv[EHW];
+						T xv[EH], yv[EH];
 #pragma unroll
-						for (int k = 0; k < EHW; ++k) { xv[k] = (kbase + k < epl_v) ? x[voff + 32 * k] : 0.0; yv[k] = (kbase + k < epl_v) ? y[voff + 32 * k] : 0.0; }
+						for (int k = 0; k < EH; ++k) { xv[k] = (k < epl_v) ? x[voff + 32 * k] : T(0); yv[k] = (k < epl_v) ? y[voff + 32 * k] : T(0); }
 						// c^2 = (1 + |d|/h)/2, s = sign(d) 2g / (2 h c), t = s/c  with h = sqrt(d^2 + 4 g^2): two rsqrt, no division
-						const double d = bb - aa;
-						const double rh = rsqrt(d * d + 4.0 * gg);
-						const double c2 = 0.5 + 0.5 * fabs(d) * rh;
-						const double rc = rsqrt(c2);
-						const double c = c2 * rc;
-						const double s = (d >= 0.0 ? g : -g) * rh * rc;
-						if (timing) { const long long t1 = clock64(); tp_b += (t1 - tp0) + (long long)(c * 0.0); tp0 = t1; }
+						const T d = bb - aa;
+						const T rh = xb_rsqrt(d * d + T(4) * gg);
+						const T c2 = T(0.5) + T(0.5) * fabs(d) * rh;
+						const T rc = xb_rsqrt(c2);
+						const T c = c2 * rc;
+						const T s = (d >= T(0) ? g : -g) * rh * rc;
 #pragma unroll
-						for (int k = 0; k < EHW; ++k) {
-							if (kbase + k < epl_x) { x[32 * k] = c * xr[k] - s * yr[k]; y[32 * k] = s * xr[k] + c * yr[k]; }
-							if (kbase + k < epl_v) { x[voff + 32 * k] = c * xv[k] - s * yv[k]; y[voff + 32 * k] = s * xv[k] + c * yv[k]; }
+						for (int k = 0; k < EH; ++k) {
+							if (k < epl_x) { x[32 * k] = c * xr[k] - s * yr[k]; y[32 * k] = s * xr[k] + c * yr[k]; }
+							if (k < epl_v) { x[voff + 32 * k] = c * xv[k] - s * yv[k]; y[voff + 32 * k] = s * xv[k] + c * yv[k]; }
 						}
-						if (lane == 0 && sub == 0) {
-							const double t = s * rc;
-							nrm[a] = aa - t * g; nrm[b] = bb + t * g;
+						// cached norms: alpha' = alpha - t*gamma, beta' = beta + t*gamma.  When a rotation moves most of a
+						// column's mass the update cancels; then both norms are recomputed from the rotated registers.
+						const T t = s * rc;
+						T na = aa - t * g, nb = bb + t * g;
+						if (na < T(0.25) * aa || nb < T(0.25) * bb) {
+							T sa = T(0), sb = T(0);
+#pragma unroll
+							for (int k = 0; k < EH; ++k) {
+								const T xn = c * xr[k] - s * yr[k], yn = s * xr[k] + c * yr[k];
+								sa += xn * xn; sb += yn * yn;
+							}
+#pragma unroll
+							for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+							na = sa; nb = sb;
+						}
+						if (lane == 0) {
+							nrm[a] = na; nrm[b] = nb;
 							my_rot += 1;
-							if (gg > 1e-18 * ab) my_big += 1;
+							if (gg > big2 * ab) my_big += 1;
 						}
 					}
-					if (timing) { const long long t1 = clock64(); tp_c += t1 - tp0; tp0 = t1; }
 				}
 				__syncthreads();
-				if (timing) { const long long t1 = clock64(); tp_d += t1 - tp0; }
 			}
 			if (timing) { const long long t1 = clock64(); tk_inner += t1 - tk0; tk0 = t1; }
 			if (lane == 0 && my_rot) { atomicAdd(&s_rot, my_rot); atomicAdd(&s_big, my_big); my_rot = 0; my_big = 0; }
 			for (int r = warp; r < N; r += nwarps) {
 				const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
-				double* dst = GT + (size_t)grow * ld + lane;
-				const double* src = S + (size_t)r * ld + lane;
+				T* dst = GT + (size_t)grow * ld + lane;
+				const T* src = S + (size_t)r * ld + lane;
 #pragma unroll
 				for (int k0 = 0; k0 < EH; k0 += 4) {
-					double v[4], w[4];
+					T v[4], w[4];
 #pragma unroll
-					for (int k = 0; k < 4; ++k) { v[k] = (k0 + k < epl_x) ? src[32 * (k0 + k)] : 0.0; w[k] = (k0 + k < epl_v) ? src[voff + 32 * (k0 + k)] : 0.0; }
+					for (int k = 0; k < 4; ++k) { v[k] = (k0 + k < epl_x) ? src[32 * (k0 + k)] : T(0); w[k] = (k0 + k < epl_v) ? src[voff + 32 * (k0 + k)] : T(0); }
 #pragma unroll
 					for (int k = 0; k < 4; ++k) { if (k0 + k < epl_x) dst[32 * (k0 + k)] = v[k]; if (k0 + k < epl_v) dst[voff + 32 * (k0 + k)] = w[k]; }
 				}
@@ -297,8 +297,39 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(double* __restr
 		if (big == 0) break;
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) { info[1] = (unsigned)sweeps; info[2] = last_big; info[3] = last_rot; }
-	if (timing) { counters[2 * max_sweeps] = (unsigned)(tp_a / (tp_n + 1)); counters[2 * max_sweeps + 1] = (unsigned)(tp_b / (tp_n + 1)); counters[2 * max_sweeps + 2] = (unsigned)(tp_c / (tp_n + 1)); counters[2 * max_sweeps + 3] = (unsigned)(tp_d / (tp_n + 1)); }
 	if (timing) { info[4] = (unsigned)(tk_load >> 10); info[5] = (unsigned)(tk_inner >> 10); info[6] = (unsigned)(tk_store >> 10); info[7] = (unsigned)(tk_sync >> 10); }
+}
+
+// mixed-precision helpers: scaled double -> float working copy, float V -> double V
+__global__ void svd_init_f32_kernel(float* __restrict__ GT, const int ld, const int npad, const int mdot, const int voff, const int nw,
+                                    const double* __restrict__ src, const long long rs, const long long cs, const double* __restrict__ amax) {
+	const double scale = (*amax > 0.0) ? 1.0 / *amax : 1.0;
+	const size_t total = (size_t)npad * ld;
+	for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+		const int j = int(e / ld), i = int(e % ld);
+		float v = 0.f;
+		if (j < nw) {
+			if (i < mdot) v = float(src[(long long)i * rs + (long long)j * cs] * scale);
+			else if (i - voff == j) v = 1.f;
+		}
+		GT[e] = v;
+	}
+}
+__global__ void svd_v32_to_f64_kernel(double* __restrict__ GT, const float* __restrict__ GT32, const int ld, const int voff, const int nw) {
+	const size_t total = (size_t)nw * nw;
+	for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+		const size_t j = e / nw, cidx = e % nw;
+		GT[j * ld + voff + cidx] = double(GT32[j * ld + voff + cidx]);
+	}
+}
+__global__ void amax_kernel(const double* __restrict__ x, const size_t n, double* __restrict__ out) {   // single CTA
+	__shared__ double sh[32];
+	double m = 0.0;
+	for (size_t i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(x[i]));
+	for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+	__syncthreads();
+	if (threadIdx.x == 0) { for (int w = 1; w < int(blockDim.x >> 5); ++w) m = fmax(m, sh[w]); *out = m; }
 }
 
 // singular values = column norms; rank them (descending, ties by index) -> Ssorted, perm.   single CTA
@@ -347,24 +378,78 @@ __global__ void add_diag_kernel(double* __restrict__ M, const size_t n, const do
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) M[i * n + i] += v;
 }
 
-static int choose_bw(size_t ld, size_t nw, size_t smem_cap, int max_bw) {
+// ---- launch plan of the persistent Jacobi kernel --------------------------------------------------------------------
+struct JacobiPlan {
+	int EH = 4, bw = 1, threads = 64;
+	size_t nblk = 2, npad = 2, smem = 0;
+	bool persistent = false;
+};
+
+static JacobiPlan plan_jacobi(size_t ld, size_t nw, size_t voff, size_t elem, size_t smem_cap) {
+	Context& c = ctx();
+	JacobiPlan p;
+	const int eh = int(std::max(voff, ld - voff) / 32);
+	p.EH = eh <= 4 ? 4 : (eh <= 8 ? 8 : 16);
+	// The kernel is latency / FP64-issue bound: an inner round costs a dependent chain (reduce -> 2 rsqrt -> rotate ->
+	// barrier) whose length barely depends on the vector length, and the FP64 pipe is shared by the warps of an SM.
+	// More, smaller CTAs only pay off from 256 columns on (measured: scratch/svd_time.py).
+	int max_bw = p.EH == 16 ? 8 : (nw >= 256 ? 8 : 16);
+	if (c.svd_max_bw > 0) max_bw = std::min(max_bw, c.svd_max_bw);
+	const int maxt = p.EH == 16 ? 256 : 512;
+	max_bw = std::min(max_bw, maxt / 32);
 	int bw = max_bw;
-	while (bw > 1 && (size_t(2 * bw) * (ld + 3) * sizeof(double) + size_t(4 * bw) * bw + 16 > smem_cap || size_t(bw) >= nw)) bw >>= 1;
-	return bw;
+	auto need = [&](int b) { return size_t(2 * b) * (ld + 2) * elem + size_t(4 * b) * b + 64; };
+	while (bw > 1 && (need(bw) > smem_cap || size_t(bw) >= nw)) bw >>= 1;
+	p.bw = bw;
+	p.nblk = (nw + bw - 1) / bw;
+	if (p.nblk < 2) p.nblk = 2;
+	if (p.nblk & 1) ++p.nblk;
+	p.npad = p.nblk * bw;
+	p.threads = std::max(64, 32 * bw);
+	p.smem = need(bw);
+	p.persistent = c.svd_persistent && eh <= 16 && (p.nblk / 2) <= size_t(c.num_sms) && p.smem <= smem_cap;
+	return p;
 }
 
-template <int EH, int WPP, int MAXT>
-static void launch_persistent(double* gt, int ld, int epl_x, int epl_v, int bw, int nblk, double tol2, unsigned int* d_cnt,
-                              unsigned int* d_info, int max_sweeps, int threads, size_t smem, size_t smem_cap) {
+template <typename T, int EH, int MAXT>
+static void launch_persistent(T* gt, int ld, int epl_x, int epl_v, const JacobiPlan& p, T tol2, T big2, unsigned int* d_cnt,
+                              unsigned int* d_info, int max_sweeps, size_t smem_cap) {
 	static bool attr = false;
 	if (!attr) {
-		XB_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<EH, WPP, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+		XB_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<T, EH, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
 		attr = true;
 	}
-	XB_REQUIRE(threads <= MAXT, "internal: Jacobi launch exceeds its launch bound");
-	void* args[] = {&gt, &ld, &epl_x, &epl_v, &bw, &nblk, &tol2, &d_cnt, &d_info, &max_sweeps};
-	XB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<EH, WPP, MAXT>, dim3(unsigned(nblk / 2)), dim3(threads), args, smem, ctx().stream));
+	XB_REQUIRE(p.threads <= MAXT, "internal: Jacobi launch exceeds its launch bound");
+	int bw = p.bw, nblk = int(p.nblk);
+	void* args[] = {&gt, &ld, &epl_x, &epl_v, &bw, &nblk, &tol2, &big2, &d_cnt, &d_info, &max_sweeps};
+	XB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<T, EH, MAXT>, dim3(unsigned(p.nblk / 2)), dim3(p.threads), args, p.smem, ctx().stream));
 	ctx().launches++;
+}
+
+// Runs sweeps until convergence (or max_sweeps) in one cooperative launch; returns {converged, sweeps}.
+template <typename T>
+static bool run_persistent(T* gt, size_t ld, size_t voff, const JacobiPlan& p, double tol, double big, int max_sweeps, int& sweeps_out,
+                           size_t smem_cap, const char* tag) {
+	Context& c = ctx();
+	unsigned int* d_cnt = static_cast<unsigned int*>(dalloc_bytes((2 * max_sweeps + 12) * sizeof(unsigned int)));
+	unsigned int* d_info = d_cnt + 2 * max_sweeps + 4;
+	XB_CUDA(cudaMemsetAsync(d_cnt, 0, (2 * max_sweeps + 12) * sizeof(unsigned int), c.stream));
+	const bool timing = getenv("XB_JACOBI_TIMING") != nullptr;
+	if (timing) { const unsigned int flag = 0xC10C; XB_CUDA(cudaMemcpyAsync(d_info, &flag, 4, cudaMemcpyHostToDevice, c.stream)); }
+	const int epl_x = int(voff / 32), epl_v = int((ld - voff) / 32);
+	const T tol2 = T(tol * tol), big2 = T(big * big);
+	if (p.EH == 4) launch_persistent<T, 4, 512>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
+	else if (p.EH == 8) launch_persistent<T, 8, 512>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
+	else launch_persistent<T, 16, 256>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
+	unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch);
+	XB_CUDA(cudaMemcpyAsync(h_info, d_info, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaStreamSynchronize(c.stream));
+	sweeps_out = int(h_info[1]);
+	const bool converged = h_info[2] == 0;
+	if (timing) fprintf(stderr, "[jacobi %s] ld=%zu bw=%d ctas=%zu sweeps=%d kcycles: load %u inner %u store %u sync %u\n", tag, ld, p.bw,
+	                    p.nblk / 2, sweeps_out, h_info[4], h_info[5], h_info[6], h_info[7]);
+	dfree(d_cnt);
+	return converged;
 }
 
 void Svd::factor(const double* A, size_t m_, size_t n_) {
@@ -393,101 +478,21 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	voff = (mdot + 31) / 32 * 32;
 	ld = voff + (nw + 31) / 32 * 32;
 	mt = ld;
-	XB_REQUIRE(2 * (ld + 1) * sizeof(double) <= smem_cap, "SVD: matrix too large for the shared-memory Jacobi kernel (min(m,n) <= ~7000)");
-	const int epl_x = int(voff / 32), epl_v = int((ld - voff) / 32), eh = std::max(epl_x, epl_v);
-	// register-tile variants of the persistent kernel: (EH, max threads) = (4, 1024), (8, 512), (16, 256)
-	// The kernel is latency/issue bound: an inner round costs a dependent chain whose length does not depend on the number
-	// of resident pairs, so (a) several warps share a pair (WPP) and (b) more, smaller CTAs only pay off from 256 columns on.
-	const int EH = eh <= 4 ? 4 : (eh <= 8 ? 8 : 16);
-	int max_bw = EH == 16 ? 4 : (nw >= 256 ? 8 : 16);
-	if (c.svd_max_bw > 0) max_bw = std::min(max_bw, c.svd_max_bw);
-	const int bw = choose_bw(ld, nw, smem_cap, max_bw);
-	size_t nblk = (nw + bw - 1) / bw;
-	if (nblk < 2) nblk = 2;
-	if (nblk & 1) ++nblk;
-	npad = nblk * bw;
+	XB_REQUIRE(2 * (ld + 2) * sizeof(double) + 128 <= smem_cap, "SVD: matrix too large for the shared-memory Jacobi kernel (min(m,n) <= ~7000)");
+	const JacobiPlan plan = plan_jacobi(ld, nw, voff, sizeof(double), smem_cap);
+	npad = plan.npad;
 	GT.resize(npad * ld);
-	{
-		const size_t total = npad * ld;
-		const unsigned blocks = unsigned(std::min<size_t>((total + 255) / 256, size_t(c.num_sms) * 8));
-		svd_init_kernel<<<blocks, 256, 0, c.stream>>>(GT, int(ld), int(npad), int(mdot), int(voff), int(nw), src, rs, cs);
-		XB_LAUNCH_CHECK();
-	}
 	const double tol = std::sqrt(double(mdot)) * DBL_EPS;
-	const size_t smem = size_t(2 * bw) * ld * sizeof(double);
-	static bool attr_set = false;
-	if (!attr_set) {
-		XB_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
-		attr_set = true;
-	}
-	// launch bound of the (EH, WPP) variant: the register tile is 4 * EH / WPP doubles
-	auto maxt = [&](int w) { const int ehw = EH / w; return ehw >= 8 ? (EH == 8 ? 512 : 256) : (ehw == 4 ? 512 : 1024); };
-	int wpp = (c.svd_wpp > 0) ? c.svd_wpp : 1;   // measured: the extra block barrier of WPP > 1 costs more than the shorter chain saves
-	while (wpp > 1 && (EH / wpp < 1 || 32 * bw * wpp > maxt(wpp))) wpp >>= 1;
-	const int threads = std::max(64, std::min(1024, 32 * bw * wpp));
-	if (threads != 32 * bw * wpp) wpp = 1;
-	unsigned int* d_info = static_cast<unsigned int*>(dalloc_bytes(8 * sizeof(unsigned int)));
-	unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch);
-	sweeps = 0;
-	bool converged = false;
-	ProfScope* prof_jacobi = new ProfScope("svd_jacobi");
-	const size_t smem_p = smem + size_t(2 * bw + 4 * bw) * sizeof(double) + size_t(2 * bw) * bw * sizeof(unsigned short) + 16;
-	const bool persistent = c.svd_persistent && eh <= 16 && (nblk / 2) <= size_t(c.num_sms) && smem_p <= smem_cap;
-	// one cooperative launch runs all sweeps: rounds separated by grid barriers, convergence decided on device
-	auto run_persistent = [&](int max_sweeps, int& sweeps_out) -> bool {
-		unsigned int* d_cnt = static_cast<unsigned int*>(dalloc_bytes((2 * max_sweeps + 4) * sizeof(unsigned int)));
-		XB_CUDA(cudaMemsetAsync(d_cnt, 0, (2 * max_sweeps + 4) * sizeof(unsigned int), c.stream));
-		XB_CUDA(cudaMemsetAsync(d_info, 0, 8 * sizeof(unsigned int), c.stream));
-		if (getenv("XB_JACOBI_TIMING")) { const unsigned int flag = 0xC10C; XB_CUDA(cudaMemcpyAsync(d_info, &flag, 4, cudaMemcpyHostToDevice, c.stream)); }
-		const double tol2 = tol * tol;
-#define XB_JAC(E, W, T) launch_persistent<E, W, T>(GT.p, int(ld), epl_x, epl_v, bw, int(nblk), tol2, d_cnt, d_info, max_sweeps, threads, smem_p, smem_cap)
-		if (EH == 4) { if (wpp == 4) XB_JAC(4, 4, 1024); else if (wpp == 2) XB_JAC(4, 2, 1024); else XB_JAC(4, 1, 512); }
-		else if (EH == 8) { if (wpp == 4) XB_JAC(8, 4, 1024); else if (wpp == 2) XB_JAC(8, 2, 512); else XB_JAC(8, 1, 512); }
-		else { if (wpp == 4) XB_JAC(16, 4, 512); else if (wpp == 2) XB_JAC(16, 2, 256); else XB_JAC(16, 1, 256); }
-#undef XB_JAC
-		XB_CUDA(cudaMemcpyAsync(h_info, d_info, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
-		XB_CUDA(cudaStreamSynchronize(c.stream));
-		sweeps_out = int(h_info[1]);
-		if (getenv("XB_JACOBI_TIMING")) {
-			unsigned int hp[4];
-			XB_CUDA(cudaMemcpy(hp, d_cnt + 2 * max_sweeps, sizeof(hp), cudaMemcpyDeviceToHost));
-			fprintf(stderr, "[jacobi] %zux%zu bw=%d wpp=%d ctas=%zu sweeps=%d kcycles: load %u inner %u store %u sync %u | per pair-visit cycles: dot+reduce %u math %u rotate %u barrier %u\n",
-			        mdot, nw, bw, wpp, nblk / 2, sweeps_out, h_info[4], h_info[5], h_info[6], h_info[7], hp[0], hp[1], hp[2], hp[3]);
-		}
-		dfree(d_cnt);
-		return h_info[2] == 0;
+	const unsigned init_blocks = unsigned(std::min<size_t>((npad * ld + 255) / 256, size_t(c.num_sms) * 8));
+	// G0 V = X recomputed from the untouched input (transposed storage: XT = VT G0^T)
+	auto recompute_left = [&]() {
+		double* VT = GT.p + voff;
+		if (reduced) gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, Rr, nw, true, 0.0);
+		else if (!swapped) gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, A, n, true, 0.0);
+		else gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, A, n, false, 0.0);
 	};
-	if (persistent) {
-		converged = run_persistent(c.svd_max_sweeps, sweeps);
-	} else if (nblk == 2) {
-		XB_CUDA(cudaMemsetAsync(d_info, 0, 4 * sizeof(unsigned int), c.stream));
-		jacobi_block_kernel<<<1, threads, smem, c.stream>>>(GT, int(ld), int(ld), int(voff), bw, 2, 0, 1, tol, d_info, 1, c.svd_max_sweeps);
-		XB_LAUNCH_CHECK();
-		XB_CUDA(cudaMemcpyAsync(h_info, d_info, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
-		XB_CUDA(cudaStreamSynchronize(c.stream));
-		sweeps = int(h_info[1]);
-		converged = (h_info[2] == 0);
-	} else {
-		for (int sw = 0; sw < c.svd_max_sweeps && !converged; ++sw) {
-			XB_CUDA(cudaMemsetAsync(d_info, 0, 4 * sizeof(unsigned int), c.stream));
-			for (size_t round = 0; round + 1 < nblk; ++round) {
-				jacobi_block_kernel<<<unsigned(nblk / 2), threads, smem, c.stream>>>(GT, int(ld), int(ld), int(voff), bw, int(nblk),
-				                                                                     int(round), round == 0 ? 1 : 0, tol, d_info, 0, 1);
-				XB_LAUNCH_CHECK();
-			}
-			XB_CUDA(cudaMemcpyAsync(h_info, d_info, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
-			XB_CUDA(cudaStreamSynchronize(c.stream));
-			++sweeps;
-			converged = (h_info[0] == 0);
-		}
-	}
-	if (!converged) { delete prof_jacobi; dfree(d_info); throw Error(XB_ERR_NUMERIC, "Jacobi SVD did not converge within svd_max_sweeps sweeps"); }
-
-	if (c.svd_polish) {
-		// Polish: thousands of plane rotations leave V orthogonal only to ~eps*sqrt(#rotations) and X = G V with the same
-		// drift.  One Newton-Schulz step re-orthogonalises V (V <- V (3I - V^T V)/2, quadratic), then the left part is
-		// recomputed from the untouched input, X = G0 V — backward error back at the eps*sqrt(n) level of LAPACK.
-		// In the transposed storage: VT <- (1.5 I - 0.5 VT VT^T) VT ; XT = VT G0^T.
+	// one Newton-Schulz step on V (quadratic): VT <- (1.5 I - 0.5 VT VT^T) VT
+	auto newton_schulz = [&]() {
 		double* VT = GT.p + voff;
 		DBuf M(nw * nw), T2(nw * nw);
 		gemm(M, nw, nw, nw, -0.5, VT, ld, false, nw, VT, ld, true, 0.0);
@@ -495,15 +500,93 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		XB_LAUNCH_CHECK();
 		gemm(T2, nw, nw, nw, 1.0, M, nw, false, nw, VT, ld, false, 0.0);
 		copy2d(VT, ld, T2, nw, nw, nw);
-		if (reduced) gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, Rr, nw, true, 0.0);
-		else if (!swapped) gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, A, n, true, 0.0);
-		else gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, A, n, false, 0.0);
-		// the recomputed columns are orthogonal only up to the angle errors of V (~1e-14): one clean-up sweep of tiny
-		// rotations restores |cos| <= tol between the left vectors without disturbing V's orthogonality
-		if (persistent && nw > 1) { int extra = 0; run_persistent(2, extra); sweeps += extra; }
+	};
+
+	sweeps = 0;
+	bool converged = false;
+	ProfScope* prof_jacobi = new ProfScope("svd_jacobi");
+	const bool mixed = plan.persistent && c.svd_mixed && nw >= size_t(c.svd_mixed_min);
+	if (mixed) {
+		// Mixed precision: the bulk of the sweeps run in FP32 on a scaled copy (FP32 issues 4x faster than FP64 here and
+		// halves the shared-memory traffic); its V (orthogonal to ~1e-6) is re-orthogonalised in FP64 by two Newton-Schulz
+		// steps, X = G0 V is formed in FP64, and FP64 sweeps finish the job from |cos| ~ 1e-6 (quadratic: 2-3 sweeps).
+		const JacobiPlan plan32 = plan_jacobi(ld, nw, voff, sizeof(float), smem_cap);
+		const size_t npad32 = plan32.npad;
+		float* GT32 = static_cast<float*>(dalloc_bytes(npad32 * ld * sizeof(float)));
+		DBuf amax(1);
+		{
+			// max |entry| of the Jacobi input (source matrix is contiguous in all three cases)
+			const size_t count = reduced ? nw * nw : m * n;
+			amax_kernel<<<1, 1024, 0, c.stream>>>(src, count, amax);
+			XB_LAUNCH_CHECK();
+			const unsigned blocks32 = unsigned(std::min<size_t>((npad32 * ld + 255) / 256, size_t(c.num_sms) * 8));
+			svd_init_f32_kernel<<<blocks32, 256, 0, c.stream>>>(GT32, int(ld), int(npad32), int(mdot), int(voff), int(nw), src, rs, cs, amax);
+			XB_LAUNCH_CHECK();
+		}
+		int sw32 = 0;
+		const double tol32 = std::sqrt(double(mdot)) * 6e-8;
+		run_persistent<float>(GT32, ld, voff, plan32, tol32, std::max(1e-3, 4 * tol32), c.svd_max_sweeps, sw32, smem_cap, "f32");
+		// FP64 working matrix: V from the FP32 run, X recomputed
+		XB_CUDA(cudaMemsetAsync(GT.p, 0, npad * ld * sizeof(double), c.stream));
+		svd_v32_to_f64_kernel<<<unsigned(std::min<size_t>((nw * nw + 255) / 256, size_t(c.num_sms) * 8)), 256, 0, c.stream>>>(GT, GT32, int(ld), int(voff), int(nw));
+		XB_LAUNCH_CHECK();
+		dfree(GT32);
+		newton_schulz();
+		newton_schulz();
+		recompute_left();
+		int sw64 = 0;
+		converged = run_persistent<double>(GT.p, ld, voff, plan, tol, 1e-7, c.svd_max_sweeps, sw64, smem_cap, "f64");
+		sweeps = sw32 + sw64;
+	} else {
+		svd_init_kernel<<<init_blocks, 256, 0, c.stream>>>(GT, int(ld), int(npad), int(mdot), int(voff), int(nw), src, rs, cs);
+		XB_LAUNCH_CHECK();
+		if (plan.persistent) {
+			converged = run_persistent<double>(GT.p, ld, voff, plan, tol, 1e-7, c.svd_max_sweeps, sweeps, smem_cap, "f64");
+		} else {
+			// fallback for shapes the cooperative kernel cannot hold: one launch per tournament round
+			const int bw = plan.bw;
+			const size_t nblk = plan.nblk;
+			const size_t smem = size_t(2 * bw) * ld * sizeof(double);
+			static bool attr_set = false;
+			if (!attr_set) {
+				XB_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+				attr_set = true;
+			}
+			unsigned int* d_info = static_cast<unsigned int*>(dalloc_bytes(8 * sizeof(unsigned int)));
+			unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch);
+			const int threads = std::max(64, std::min(1024, 32 * bw));
+			for (int sw = 0; sw < c.svd_max_sweeps && !converged; ++sw) {
+				XB_CUDA(cudaMemsetAsync(d_info, 0, 8 * sizeof(unsigned int), c.stream));
+				if (nblk == 2) {
+					jacobi_block_kernel<<<1, threads, smem, c.stream>>>(GT, int(ld), int(ld), int(voff), bw, 2, 0, 1, tol, d_info, 0, 1);
+					XB_LAUNCH_CHECK();
+				} else {
+					for (size_t round = 0; round + 1 < nblk; ++round) {
+						jacobi_block_kernel<<<unsigned(nblk / 2), threads, smem, c.stream>>>(GT, int(ld), int(ld), int(voff), bw, int(nblk),
+						                                                                     int(round), round == 0 ? 1 : 0, tol, d_info, 0, 1);
+						XB_LAUNCH_CHECK();
+					}
+				}
+				XB_CUDA(cudaMemcpyAsync(h_info, d_info, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+				XB_CUDA(cudaStreamSynchronize(c.stream));
+				++sweeps;
+				converged = (h_info[0] == 0);
+			}
+			dfree(d_info);
+		}
+	}
+	if (!converged) { delete prof_jacobi; throw Error(XB_ERR_NUMERIC, "Jacobi SVD did not converge within svd_max_sweeps sweeps"); }
+
+	if (c.svd_polish && !mixed) {
+		// Polish: thousands of plane rotations leave V orthogonal only to ~eps*sqrt(#rotations) and X = G V with the same
+		// drift.  One Newton-Schulz step re-orthogonalises V, the left part is recomputed from the untouched input, and one
+		// clean-up sweep of tiny rotations restores |cos| <= tol between the left vectors: backward error back at the
+		// eps*sqrt(n) level of LAPACK.  (The mixed path ends with 2-3 FP64 sweeps from a re-orthogonalised V: not needed.)
+		newton_schulz();
+		recompute_left();
+		if (plan.persistent && nw > 1) { int extra = 0; run_persistent<double>(GT.p, ld, voff, plan, tol, 1e-7, 2, extra, smem_cap, "clean"); sweeps += extra; }
 	}
 	delete prof_jacobi;
-	dfree(d_info);
 
 	Ssorted.resize(nw);
 	perm.resize((nw + 1) / 2 + 1);   // nw ints

@@ -40,13 +40,14 @@ struct Context {
 	double* h_scratch = nullptr;   // 4096 doubles
 	size_t h_scratch_len = 4096;
 	// options
-	int svd_max_sweeps = 40;
+	int svd_max_sweeps = 100;      // graded spectra (kappa ~ 1e14) need ~45 sweeps of the un-preconditioned Jacobi
 	int qr_panel = 32;
 	int gemm_force_small = 0;
 	bool profile = false;
 	int svd_persistent = 1;
 	int svd_polish = 1;            // Newton-Schulz re-orthogonalisation of V + recomputed left part after the Jacobi sweeps
-	int svd_wpp = 0;               // 0 = automatic number of warps sharing a column pair
+	int svd_mixed = 0;             // FP32 pre-conditioning sweeps + FP64 finishing sweeps (measured: no gain, kept as an experiment)
+	int svd_mixed_min = 64;        // smallest column count for the mixed path
 	int svd_max_bw = 0;            // 0 = automatic block width of the Jacobi kernel
 	int als_direct_max = 1536;     // local problems up to this size are solved densely (reference semantics), larger ones by CG
 };
