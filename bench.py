@@ -116,6 +116,109 @@ def oracle_port_ms(w, reps):
     return times
 
 
+def als_sweep_numbers(xb, np, torch, stream, args):
+    """ALS_SPD(A, x, b, 2) = one full sweep, device resident, matrix-free CG local solves."""
+    d, n, r = 16, 10, 50
+    rng = np.random.default_rng(16)
+    A, b = xb.TTOperator.laplace(d, n), xb.TTTensor.ones([n] * d)
+    x0 = xb.TTTensor.random([n] * d, r, rng)
+    variant = xb.ALSVariant(1, 0, True)
+    times, energy, x = [], None, None
+    for rep in range(4):
+        x = x0.copy()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        xb.synchronize()
+        e0.record(stream)
+        energy = variant(A, x, b, 2)
+        e1.record(stream)
+        xb.synchronize()
+        if rep > 0:
+            times.append(e0.elapsed_time(e1))
+    residual = A.apply(x).distance(b) / b.frob_norm()
+    apply_flops = 2 * 2 * (2 * n * r ** 3) + 2 * 2 * 2 * n * n * r * r          # SURVEY 8d: 5 + 2 + 5 MFLOP at C2
+    out = {"workload": "ALS_SPD, Laplace-like TTOperator d=16 n=10 (TT-rank 2), b = ones, solution rank 50, one full sweep",
+           "ms_per_sweep": sum(times) / len(times), "energy": energy, "residual": residual,
+           "local_solver": "matrix-free CG, %d operator applications per sweep" % variant.last_local_iterations,
+           "algorithmic_flops_per_sweep": variant.last_local_iterations * apply_flops,
+           "reference_cpu": "not runnable inside a bench run at r=50: ~1 h per sweep extrapolated (BASELINE.md section 2)"}
+    if os.path.exists(REF_BENCH) and not args.no_cpu_baseline:
+        try:
+            res = subprocess.run([REF_BENCH, "als", "16", "10", "8", "2", "2"], capture_output=True, text=True, check=True).stdout
+            ref = json.loads(res.strip().splitlines()[-1])
+            xr = xb.TTTensor.random([n] * d, 8, np.random.default_rng(16))
+            t0 = time.perf_counter()
+            variant(A, xr, b, 2)
+            xb.synchronize()
+            out["reduced_rank8"] = {"reference_cpu_ms": ref["best_ms"], "xb200_ms": (time.perf_counter() - t0) * 1e3,
+                                    "note": "n_loc = 640 <= als_direct_max: dense reference-semantics path on the GPU"}
+        except Exception as ex:
+            out["reduced_rank8"] = {"error": repr(ex)}
+    return out
+
+
+def batch_workload(args, rank, local_rank, world):
+    """--workload c5: BASELINE configs[4], reduced per step: every rank processes `items` independent items
+    (y_b = A x_b with x_b = random({4}x12, 64), then y_b.round(64)); items shard by index, no data-path collective."""
+    import numpy as np
+    import torch
+    import xerus_b200 as xb
+    from xerus_b200 import parallel
+    torch.cuda.set_device(local_rank)
+    xb.init(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.ExternalStream(xb.stream_handle(), device=local_rank)
+    d, n, r, per_rank = 12, 4, 64, args.items
+    n_items = per_rank * world
+    A = xb.TTOperator.laplace(d, n)
+    mine = parallel.shard_items(n_items, rank, world)
+    xs = {b: xb.TTTensor.random([n] * d, r, parallel.item_rng(5, b)) for b in mine}       # inputs resident in HBM
+
+    def one(b):
+        y = A.apply(xs[b])
+        y.round(r)
+        return b, y
+
+    def step():
+        if args.workers > 1:
+            return dict(parallel.run_on_workers(one, mine, args.workers))
+        return dict(one(b) for b in mine)
+
+    for _ in range(args.warmup):
+        step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(); xb.synchronize()
+    launches0 = xb.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        res = step()
+    xb.synchronize_all()
+    e1.record(stream)
+    xb.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    summaries = parallel.gather_by_item({b: (tuple(y.ranks()), float(y.frob_norm())) for b, y in res.items()}, n_items)
+    if rank == 0:
+        total_s = float(ms.item()) * 1e-3
+        line = {"metric": "TT mat-vec + rounding items/s (FP64)", "value": n_items * args.steps / total_s, "unit": "items/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(ms.item()) / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "batch of independent degree-12 rank-64 TT contractions + roundings (BASELINE configs[4]), %d items per GPU per step" % per_rank,
+                           "parallelism": "items sharded b mod %d, no data-path collective; %d workers (streams) per GPU" % (world, args.workers)},
+                "gpu_launches": xb.kernel_launch_count() - launches0,
+                "check": {"ranks_item0": list(summaries[0][0]), "algorithmic_flops_per_item": 1.0e9}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def reference_arm(args, w, rank, world):
     if rank != 0:
         return
@@ -146,12 +249,18 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="xb200", choices=["xb200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--items", type=int, default=8, help="items per GPU per step for --workload c5")
+    ap.add_argument("--workers", type=int, default=8, help="host threads / library workers (CUDA streams) per GPU for --workload c5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-als", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "xb200" else args.warmup
-    w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
+    if args.workload == "c5":
+        batch_workload(args, rank, int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
+        return
+    w = WORKLOADS[args.workload]
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -262,6 +371,14 @@ def main():
         fp64_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
         del a, b
 
+    # ---- second half of BASELINE's metric: one ALS_SPD sweep (configs[1]: Laplace-like A, d=16, n=10, r=50) ----------
+    als = None
+    if rank == 0 and not args.no_als:
+        try:
+            als = als_sweep_numbers(xb, np, torch, stream, args)
+        except Exception as ex:       # reported, never fatal for the bench line
+            als = {"error": repr(ex)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -307,7 +424,7 @@ def main():
                    "parallelism": "replicas x%d (no data-path collective)" % world},
         "e2e": {"value": float(e2e_ms.item()), "unit": "ms", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": launches, "wall_ms_timed_region": wall_ms, "step_ms": step_ms,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "als": als,
     }
     print(json.dumps(line))
     if dist is not None:

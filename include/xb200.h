@@ -42,6 +42,12 @@ xb_status   xb_shutdown(void);
 const char* xb_last_error(void);                 /* thread-local message of the last failing call */
 int         xb_version(void);
 xb_status   xb_synchronize(void);                /* waits for the library stream */
+/* Workers: a worker is a private {CUDA stream, pinned scratch} bound to the calling host thread (thread-local selection,
+ * created on demand, worker 0 by default).  Independent TT operations issued from different host threads on different
+ * workers overlap on the GPU (BASELINE config 5).  A device object must be used by one worker at a time; hand it over
+ * after xb_synchronize() on the producing worker. */
+xb_status   xb_worker_select(int worker);
+xb_status   xb_synchronize_all(void);            /* waits for the streams of all workers */
 xb_status   xb_get_stream(void** cuda_stream);   /* the cudaStream_t all work is enqueued on (for CUDA-event timing) */
 xb_status   xb_kernel_launch_count(uint64_t* n); /* number of xb200 kernels launched so far (bench: gpu_launches) */
 xb_status   xb_set_option(const char* key, double value); /* tuning/diagnostic knobs, see DESIGN.md */

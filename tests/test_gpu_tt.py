@@ -261,3 +261,14 @@ def test_batch_sharding_single_rank():
     for rank in range(2):
         parts.update(parallel.matvec_round_batch(A, make, items, r, rank, 2))
     assert [parts[b] for b in range(items)] == res
+
+
+def test_batch_on_multiple_workers_matches_sequential():
+    """Several host threads, each on its own library worker (CUDA stream), give bit-identical per-item results."""
+    from xerus_b200 import parallel
+    d, n, r, items = 6, 4, 6, 12
+    A = xb.TTOperator.laplace(d, n)
+    make = lambda b: xb.TTTensor.random([n] * d, r, parallel.item_rng(7, b))
+    seq = parallel.matvec_round_batch(A, make, items, r)
+    par = parallel.matvec_round_batch(A, make, items, r, workers=4)
+    assert seq == par

@@ -56,3 +56,14 @@ def profile_get(kernel_class):
     s, l, ms = C.c_uint64(), C.c_uint64(), C.c_double()
     call("xb_profile_get", kernel_class.encode(), C.byref(s), C.byref(l), C.byref(ms))
     return s.value, l.value, ms.value
+
+
+def worker_select(worker):
+    """Binds the calling host thread to a private worker (stream + scratch); see include/xb200.h."""
+    from ._lib import call
+    call("xb_worker_select", int(worker))
+
+
+def synchronize_all():
+    from ._lib import call
+    call("xb_synchronize_all")

@@ -39,7 +39,7 @@ P = C.POINTER
 dp, sz, szp, vp = P(C.c_double), C.c_size_t, P(C.c_size_t), C.c_void_p
 
 _SIGS = {
-    "xb_init": [C.c_int], "xb_shutdown": [], "xb_synchronize": [], "xb_get_stream": [P(vp)],
+    "xb_init": [C.c_int], "xb_shutdown": [], "xb_synchronize": [], "xb_get_stream": [P(vp)], "xb_worker_select": [C.c_int], "xb_synchronize_all": [],
     "xb_kernel_launch_count": [P(C.c_uint64)], "xb_set_option": [C.c_char_p, C.c_double],
     "xb_profile_enable": [C.c_int], "xb_profile_get": [C.c_char_p, P(C.c_uint64), P(C.c_uint64), dp],
     "xb_alloc": [P(vp), sz], "xb_free": [vp], "xb_alloc_host": [P(vp), sz], "xb_free_host": [vp],

@@ -325,44 +325,58 @@ struct Als {
 		return sol;
 	}
 
-	// conjugate gradients on the matrix-free local operator, warm start v0
+	// conjugate gradients on the matrix-free local operator, warm start v0.  The recurrence residual drifts from the true
+	// one by ~eps * ||r_0|| (a random start has ||r_0|| ~ 1e11 ||b||), so after the loop the true residual is recomputed and
+	// CG is restarted from the current iterate until it meets the tolerance (residual replacement).
 	DT local_solve_cg(const DT& rhs, const DT& v0) {
 		const size_t n = rhs.size();
 		const double tol = opt.local_tolerance > 0 ? opt.local_tolerance : 1e-12;
 		const size_t max_it = opt.local_max_iterations ? opt.local_max_iterations : std::min<size_t>(std::max<size_t>(4 * n, 64), 4000);
 		DT xv = dt_copy(v0);
 		xv.dims = rhs.dims;
-		DT r = dt_copy(rhs);
-		{ DT Ax = local_apply(xv); axpy(r.data(), -1.0, Ax.p, n); }
-		DT p = dt_copy(r);
 		DBuf sc(4);
 		Context& c = ctx();
 		const double bnorm2 = dt_dot(rhs, rhs);
-		dot_dev(sc.p + 0, r.p, r.p, n);
-		double rr = read_scalar(sc.p + 0);
-		const double rr0 = rr;
 		if (bnorm2 == 0.0) { fill(xv.data(), 0.0, n); return xv; }
 		const double target = tol * tol * bnorm2;
-		double best = rr; size_t since_best = 0;
-		size_t it = 0;
 		const unsigned grid = vec_grid(n);
-		while (rr > target && it < max_it) {
-			const size_t chunk = std::min<size_t>(8, max_it - it);
-			for (size_t j = 0; j < chunk; ++j) {
-				DT q = local_apply(p);
-				dot_dev(sc.p + 1, p.p, q.p, n);
-				cg_step1_kernel<<<grid, 256, 0, c.stream>>>(xv.data(), r.data(), p.p, q.p, sc.p, n);
-				XB_LAUNCH_CHECK();
-				dot_dev(sc.p + 2, r.p, r.p, n);
-				cg_step2_kernel<<<grid, 256, 0, c.stream>>>(p.data(), r.p, sc.p, n);
-				XB_LAUNCH_CHECK();
-				cg_shift_kernel<<<1, 32, 0, c.stream>>>(sc.p);
-				XB_LAUNCH_CHECK();
-			}
-			it += chunk;
+		size_t it = 0;
+		double rr = 0.0, rr0 = -1.0;
+		for (int restart = 0; restart < 6 && it < max_it; ++restart) {
+			DT r = dt_copy(rhs);
+			{ DT Ax = local_apply(xv); axpy(r.data(), -1.0, Ax.p, n); }      // true residual
+			dot_dev(sc.p + 0, r.p, r.p, n);
 			rr = read_scalar(sc.p + 0);
-			if (!(rr == rr)) throw Error(XB_ERR_NUMERIC, "local CG produced NaN (operator not positive definite?)");
-			if (rr < 0.5 * best) { best = rr; since_best = 0; } else { since_best += chunk; if (since_best >= 48) break; }   // stagnation at the rounding floor
+			if (rr0 < 0.0) rr0 = rr;
+			if (rr <= target) break;
+			if (restart == 0 && rr > 1e4 * bnorm2) {                         // useless warm start: begin from zero instead
+				fill(xv.data(), 0.0, n);
+				copy(r.data(), rhs.p, n);
+				dot_dev(sc.p + 0, r.p, r.p, n);
+				rr = bnorm2;
+			}
+			DT p = dt_copy(r);
+			double best = rr; size_t since_best = 0;
+			const double rr_start = rr;
+			while (rr > target && it < max_it) {
+				const size_t chunk = std::min<size_t>(8, max_it - it);
+				for (size_t j = 0; j < chunk; ++j) {
+					DT q = local_apply(p);
+					dot_dev(sc.p + 1, p.p, q.p, n);
+					cg_step1_kernel<<<grid, 256, 0, c.stream>>>(xv.data(), r.data(), p.p, q.p, sc.p, n);
+					XB_LAUNCH_CHECK();
+					dot_dev(sc.p + 2, r.p, r.p, n);
+					cg_step2_kernel<<<grid, 256, 0, c.stream>>>(p.data(), r.p, sc.p, n);
+					XB_LAUNCH_CHECK();
+					cg_shift_kernel<<<1, 32, 0, c.stream>>>(sc.p);
+					XB_LAUNCH_CHECK();
+				}
+				it += chunk;
+				rr = read_scalar(sc.p + 0);
+				if (!(rr == rr)) throw Error(XB_ERR_NUMERIC, "local CG produced NaN (operator not positive definite?)");
+				if (rr < 0.5 * best) { best = rr; since_best = 0; } else { since_best += chunk; if (since_best >= 48) break; }   // stagnation at the rounding floor
+				if (rr < 1e-20 * rr_start) break;                            // beyond what the recurrence can resolve: re-anchor
+			}
 		}
 		cg_iterations += it;
 		if (getenv("XB_DEBUG_ALS")) fprintf(stderr, "[als] site %zu n=%zu cg its=%zu rel res=%.3e (start %.3e)\n", cur, n, it, std::sqrt(rr / bnorm2), std::sqrt(rr0 / bnorm2));

@@ -125,7 +125,7 @@ __global__ void reduce_stage2(double* __restrict__ result, const double* __restr
 }
 
 static void reduce(double* d_result, const double* x, const double* y, size_t n, int mode) {
-	static double* partial = nullptr;
+	double*& partial = ctx().red_partial;
 	if (!partial) partial = dalloc(RED_MAX_BLOCKS);
 	unsigned blocks = unsigned(std::min<size_t>(RED_MAX_BLOCKS, std::max<size_t>(1, (n + RED_THREADS * 4 - 1) / (RED_THREADS * 4))));
 	if (mode == 0) reduce_stage1<0><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);

@@ -7,9 +7,13 @@ namespace xb {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
-static Context g_ctx;
+constexpr int XB_MAX_WORKERS = 64;
+static Context g_ctx;                              // worker 0
+static Context* g_workers[XB_MAX_WORKERS] = {&g_ctx};
+static int g_num_workers = 1;
+static thread_local int tl_worker = 0;
 static std::mutex g_ctx_mutex;
-Context& ctx() { return g_ctx; }
+Context& ctx() { return *g_workers[tl_worker]; }
 
 static void init_locked(int device) {
 	if (g_ctx.initialised) return;
@@ -47,6 +51,25 @@ void ensure_init() {
 	init_locked(0);
 }
 
+static void select_worker(int w) {
+	XB_REQUIRE(w >= 0 && w < XB_MAX_WORKERS, "worker index out of range");
+	ensure_init();
+	std::lock_guard<std::mutex> lock(g_ctx_mutex);
+	for (int i = g_num_workers; i <= w; ++i) {
+		Context* c = new Context();
+		c->initialised = true; c->worker = i; c->device = g_ctx.device; c->pool = g_ctx.pool;
+		c->num_sms = g_ctx.num_sms; c->max_smem_optin = g_ctx.max_smem_optin;
+		c->svd_max_sweeps = g_ctx.svd_max_sweeps; c->gemm_force_small = g_ctx.gemm_force_small;
+		c->svd_persistent = g_ctx.svd_persistent; c->svd_polish = g_ctx.svd_polish; c->svd_mixed = g_ctx.svd_mixed;
+		c->svd_mixed_min = g_ctx.svd_mixed_min; c->svd_max_bw = g_ctx.svd_max_bw; c->als_direct_max = g_ctx.als_direct_max;
+		XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+		XB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scratch), c->h_scratch_len * sizeof(double)));
+		g_workers[i] = c;
+		g_num_workers = i + 1;
+	}
+	tl_worker = w;
+}
+
 void* dalloc_bytes(size_t bytes) {
 	void* p = nullptr;
 	if (bytes == 0) bytes = 8;
@@ -64,10 +87,8 @@ double read_scalar(const double* d_value) {
 }
 
 // ---- profiling ----------------------------------------------------------------------------------------------------
-struct ProfRecord { std::string name; cudaEvent_t e0, e1; uint64_t launches0, launches1; };
-static std::vector<ProfRecord> g_prof_pending;
-struct ProfTotal { uint64_t scopes = 0, launches = 0; double ms = 0.0; };
-static std::vector<std::pair<std::string, ProfTotal>> g_prof_totals;
+#define g_prof_pending (ctx().prof_pending)
+#define g_prof_totals (ctx().prof_totals)
 
 ProfScope::ProfScope(const char* kernel_class) {
 	Context& c = ctx();
@@ -140,21 +161,38 @@ xb_status xb_synchronize(void) { return guard([&] { ensure_init(); XB_CUDA(cudaS
 
 xb_status xb_get_stream(void** s) { return guard([&] { ensure_init(); XB_REQUIRE(s, "null"); *s = ctx().stream; }); }
 
-xb_status xb_kernel_launch_count(uint64_t* n) { return guard([&] { XB_REQUIRE(n, "null"); *n = ctx().launches; }); }
+xb_status xb_kernel_launch_count(uint64_t* n) {
+	return guard([&] {
+		XB_REQUIRE(n, "null");
+		uint64_t total = 0;
+		for (int w = 0; w < g_num_workers; ++w) total += g_workers[w]->launches;
+		*n = total;
+	});
+}
+
+xb_status xb_worker_select(int worker) { return guard([&] { select_worker(worker); }); }
+
+xb_status xb_synchronize_all(void) {
+	return guard([&] { ensure_init(); for (int w = 0; w < g_num_workers; ++w) XB_CUDA(cudaStreamSynchronize(g_workers[w]->stream)); });
+}
 
 xb_status xb_set_option(const char* key, double value) {
 	return guard([&] {
 		XB_REQUIRE(key, "null key");
 		const std::string k(key);
-		if (k == "svd_max_sweeps") ctx().svd_max_sweeps = int(value);
-		else if (k == "gemm_force_small") ctx().gemm_force_small = int(value);
-		else if (k == "svd_persistent") ctx().svd_persistent = int(value);
-		else if (k == "svd_max_bw") ctx().svd_max_bw = int(value);
-		else if (k == "svd_mixed") ctx().svd_mixed = int(value);
-		else if (k == "svd_mixed_min") ctx().svd_mixed_min = int(value);
-		else if (k == "svd_polish") ctx().svd_polish = int(value);
-		else if (k == "als_direct_max") ctx().als_direct_max = int(value);
-		else throw Error(XB_ERR_INVALID, "xb_set_option: unknown key " + k);
+		std::lock_guard<std::mutex> lock(g_ctx_mutex);
+		for (int w = 0; w < g_num_workers; ++w) {
+			Context& c = *g_workers[w];
+			if (k == "svd_max_sweeps") c.svd_max_sweeps = int(value);
+			else if (k == "gemm_force_small") c.gemm_force_small = int(value);
+			else if (k == "svd_persistent") c.svd_persistent = int(value);
+			else if (k == "svd_max_bw") c.svd_max_bw = int(value);
+			else if (k == "svd_mixed") c.svd_mixed = int(value);
+			else if (k == "svd_mixed_min") c.svd_mixed_min = int(value);
+			else if (k == "svd_polish") c.svd_polish = int(value);
+			else if (k == "als_direct_max") c.als_direct_max = int(value);
+			else throw Error(XB_ERR_INVALID, "xb_set_option: unknown key " + k);
+		}
 	});
 }
 

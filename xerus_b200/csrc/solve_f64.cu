@@ -56,10 +56,12 @@ __global__ void __launch_bounds__(1024) cholesky_solve_kernel(double* __restrict
 		for (int c = j + threadIdx.x; c < n; c += blockDim.x) A[(size_t)j * n + c] = (c == j) ? d : sign * A[(size_t)j * n + c] / d;
 		__syncthreads();
 		// trailing update of the upper triangle: A[i][c] -= sign * U[j][i] * U[j][c]  (i > j, c >= i), in the signed matrix
-		const int rem = n - j - 1;
-		for (size_t e = threadIdx.x; e < (size_t)rem * rem; e += blockDim.x) {
-			const int i = j + 1 + int(e / rem), c = j + 1 + int(e % rem);
-			if (c >= i) A[(size_t)i * n + c] -= sign * A[(size_t)j * n + i] * A[(size_t)j * n + c];
+		{
+			const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nty = blockDim.x >> 5;
+			for (int i = j + 1 + ty; i < n; i += nty) {
+				const double uji = sign * A[(size_t)j * n + i];
+				for (int c = i + tx; c < n; c += 32) A[(size_t)i * n + c] -= uji * A[(size_t)j * n + c];
+			}
 		}
 		__syncthreads();
 	}
@@ -121,9 +123,12 @@ __global__ void __launch_bounds__(1024) lu_solve_kernel(double* __restrict__ A, 
 		for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) A[(size_t)i * n + j] /= piv;
 		__syncthreads();
 		const int rem = n - j - 1;
-		for (size_t e = threadIdx.x; e < (size_t)rem * rem; e += blockDim.x) {
-			const int i = j + 1 + int(e / rem), c = j + 1 + int(e % rem);
-			A[(size_t)i * n + c] -= A[(size_t)i * n + j] * A[(size_t)j * n + c];
+		{
+			const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nty = blockDim.x >> 5;
+			for (int i = j + 1 + ty; i < n; i += nty) {
+				const double lij = A[(size_t)i * n + j];
+				for (int c = j + 1 + tx; c < n; c += 32) A[(size_t)i * n + c] -= lij * A[(size_t)j * n + c];
+			}
 		}
 		for (size_t e = threadIdx.x; e < (size_t)rem * nrhs; e += blockDim.x) {
 			const int i = j + 1 + int(e / nrhs), r = int(e % nrhs);

@@ -28,8 +28,18 @@ struct Error : std::runtime_error {
 
 void set_last_error(const std::string& msg);
 
+struct ProfRecord { std::string name; cudaEvent_t e0, e1; uint64_t launches0, launches1; };
+struct ProfTotal { uint64_t scopes = 0, launches = 0; double ms = 0.0; };
+
+// One Context per worker: a worker is a host thread's private {stream, pinned scratch, counters}.  Worker 0 is created
+// by xb_init; more are created on demand by xb_worker_select (batches of independent TTs drive one worker per host
+// thread so that several sweeps are in flight on the GPU at once).  Device-wide facts and options are copied.
 struct Context {
 	bool initialised = false;
+	int worker = 0;
+	double* red_partial = nullptr;   // scratch of the two-stage reductions
+	std::vector<ProfRecord> prof_pending;
+	std::vector<std::pair<std::string, ProfTotal>> prof_totals;
 	int device = -1;
 	cudaStream_t stream = nullptr;
 	cudaMemPool_t pool = nullptr;
@@ -51,7 +61,7 @@ struct Context {
 	int svd_max_bw = 0;            // 0 = automatic block width of the Jacobi kernel
 	int als_direct_max = 1536;     // local problems up to this size are solved densely (reference semantics), larger ones by CG
 };
-Context& ctx();
+Context& ctx();               // the calling thread's current worker
 void ensure_init();
 
 // Optional CUDA-event timing of a kernel class (bench/roofline only; no-op unless xb_profile_enable(1)).

@@ -36,20 +36,44 @@ def gather_by_item(local, n_items, group=None):
     return [merged[b] for b in range(n_items)]
 
 
-def matvec_round_batch(A, make_x, n_items, max_rank, rank=0, world=1, process=None):
+def matvec_round_batch(A, make_x, n_items, max_rank, rank=0, world=1, process=None, workers=1):
     """BASELINE config 5 on this rank's shard: for every owned item b, y_b = A x_b (operator application) followed by
     y_b.round(max_rank).  `make_x(b)` returns the item's TTTensor (so inputs are a pure function of the item index and
     do not depend on the partitioning); `process` may replace the default apply+round (used by the CPU tests).
-    Returns {b: (ranks, frob_norm)} for the owned items."""
-    out = {}
-    for b in shard_items(n_items, rank, world):
+    With workers > 1 the items are driven by that many host threads, each bound to its own library worker (CUDA stream),
+    so several sweeps are in flight on the GPU at once.  Returns {b: (ranks, frob_norm)} for the owned items."""
+    mine = shard_items(n_items, rank, world)
+
+    def one(b):
         x = make_x(b)
         if process is not None:
-            out[b] = process(A, x, max_rank)
-            continue
+            return b, process(A, x, max_rank)
         y = A.apply(x)
         y.round(int(max_rank))
-        out[b] = (tuple(y.ranks()), float(y.frob_norm()))
+        return b, (tuple(y.ranks()), float(y.frob_norm()))
+
+    if workers <= 1 or process is not None:
+        return dict(one(b) for b in mine)
+    return dict(run_on_workers(one, mine, workers))
+
+
+def run_on_workers(fn, items, workers):
+    """Maps fn over items with `workers` host threads, thread i bound to library worker i+1 (worker 0 stays with the caller)."""
+    import concurrent.futures
+    import itertools
+    import threading
+    import xerus_b200 as xb
+    xb.synchronize()                       # inputs produced on the caller's worker are complete before hand-over
+    ids, lock = itertools.count(1), threading.Lock()
+
+    def bind():
+        with lock:
+            w = next(ids)
+        xb.worker_select(w)
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=workers, initializer=bind) as ex:
+        out = list(ex.map(fn, items))
+    xb.synchronize_all()
     return out
 
 
