@@ -158,6 +158,14 @@ xb_status xb_als_default_options(xb_als_options* opt, uint32_t sites, int assume
 xb_status xb_als_solve(const xb_tt* A, xb_tt* x, const xb_tt* b, const xb_als_options* opt, double* energy,
                        size_t* local_iterations /* optional: total CG iterations */);
 
+/* Matrix-free local-operator application y = {L, A_1..A_s, R} v of ALS/DMRG (the un-contracted network that
+ * construct_local_operator returns, als.cpp:383-401), SPD environments, on device pointers:
+ * L (l, a_left, l), A_p (A_dims[4p..4p+3] = r_l, m, n, r_r), R (r, a_right, r), v (l, n_1..n_s, r), y (l, m_1..m_s, r).
+ * [slab_begin, slab_end) restricts the contraction over the right bond r' to a slab: the partial results of disjoint
+ * slabs sum to the full application (BASELINE config 4: bond index split across GPUs + one NCCL all-reduce). */
+xb_status xb_env_apply(double* y, const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims,
+                       size_t sites, const double* R, size_t r, size_t a_right, const double* v, size_t slab_begin, size_t slab_end);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,3 +168,34 @@ def test_als_config2_reduced_rank20_cg_runs():
     assert e2 >= e1 - 1e-9 * abs(e1)
     Ax = A.apply(x)
     assert Ax.distance(b) / b.frob_norm() < 1e-5     # iterative local solves: see test_als_spd_golden on conditioning
+
+
+@pytest.mark.parametrize("sites", [1, 2])
+def test_env_apply_and_bond_split(sites):
+    """Matrix-free local operator (als.cpp:383-401) against einsum, and the bond split: partial applications over
+    disjoint slabs of the right bond sum to the full one (what the NCCL all-reduce assembles across GPUs)."""
+    import torch
+    from xerus_b200 import parallel
+    rng = np.random.default_rng(31 + sites)
+    l, r, a, n = 12, 10, 2, 3
+    L, R = rng.standard_normal((l, a, l)), rng.standard_normal((r, a, r))
+    As = [rng.standard_normal((a, n, n, a)) for _ in range(sites)]
+    v = rng.standard_normal((l,) + (n,) * sites + (r,))
+    if sites == 1:
+        ref = np.einsum("xay,ainb,zbw,ynw->xiz", L, As[0], R, v)
+    else:
+        ref = np.einsum("xay,ainb,bjmc,zcw,ynmw->xijz", L, As[0], As[1], R, v)
+    dev = lambda t: torch.from_numpy(np.ascontiguousarray(t)).cuda()
+    Ld, Rd, vd, Ad = dev(L), dev(R), dev(v), [dev(t) for t in As]
+    torch.cuda.synchronize()
+    y = parallel.env_apply(Ld, Ad, Rd, vd)
+    xb.synchronize()
+    assert np.linalg.norm(y.cpu().numpy() - ref) < 1e-12 * np.linalg.norm(ref)
+    for world in [2, 3]:
+        acc = torch.zeros_like(y)
+        for rank in range(world):
+            part = parallel.env_apply(Ld, Ad, Rd, vd, slab=parallel.slab_range(r, rank, world))
+            xb.synchronize()
+            acc += part
+        torch.cuda.synchronize()
+        assert np.linalg.norm(acc.cpu().numpy() - ref) < 1e-12 * np.linalg.norm(ref)

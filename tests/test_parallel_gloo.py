@@ -80,3 +80,49 @@ def test_batch_world2_matches_single_process():
 def test_gather_detects_missing_and_duplicate_items():
     with pytest.raises(RuntimeError):
         parallel.gather_by_item({0: 1, 2: 3}, 3)
+
+
+def test_slab_range_partition():
+    for r in [1, 7, 512, 513]:
+        for world in [1, 2, 3, 8]:
+            slabs = [parallel.slab_range(r, k, world) for k in range(world)]
+            assert slabs[0][0] == 0 and slabs[-1][1] == r
+            assert all(a[1] == b[0] for a, b in zip(slabs, slabs[1:]))
+            sizes = [e - b for b, e in slabs]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _bond_worker(rank, world, port, q):
+    """Bond-split local apply with a numpy stand-in for the device kernel: the slabs' partial results all-reduce (gloo)
+    to the full application on every rank."""
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(3)
+        l, r, a, n = 5, 7, 2, 3
+        L, R = rng.standard_normal((l, a, l)), rng.standard_normal((r, a, r))
+        A1, v = rng.standard_normal((a, n, n, a)), rng.standard_normal((l, n, r))
+        b, e = parallel.slab_range(r, rank, world)
+        part = np.einsum("xay,ainb,zbw,ynw->xiz", L, A1, R[:, :, b:e], v[:, :, b:e])
+        y = torch.from_numpy(part.copy())
+        dist.all_reduce(y)
+        full = np.einsum("xay,ainb,zbw,ynw->xiz", L, A1, R, v)
+        q.put((rank, float(np.linalg.norm(y.numpy() - full) / np.linalg.norm(full))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bond_split_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bond_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0] < 1e-13 and results[1] < 1e-13

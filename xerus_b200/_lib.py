@@ -69,6 +69,7 @@ _SIGS = {
     "xb_tt_from_dense": [P(vp), dp, sz, szp, C.c_double, sz], "xb_tt_to_dense": [vp, dp],
     "xb_als_default_options": [P(ALSOptions), C.c_uint32, C.c_int],
     "xb_als_solve": [vp, vp, vp, P(ALSOptions), dp, szp],
+    "xb_env_apply": [vp, vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz],
 }
 
 

@@ -106,6 +106,30 @@ __global__ void cg_shift_kernel(double* __restrict__ sc) { if (threadIdx.x == 0 
 
 unsigned vec_grid(size_t n) { return unsigned(std::min<size_t>(std::max<size_t>(1, (n + 255) / 256), size_t(ctx().num_sms) * 4)); }
 
+// y = {L, A_1..A_s, R} applied to v, SPD environments: L(l, a, l'), A_p(a, m, n, b), R(r, b, r'), v(l', n_1..n_s, r' [, col])
+// -> y(l, m_1..m_s, r [, col]).  One GEMM per factor, one reshuffle per operator core (als.cpp:383-401 un-contracted).
+DT spd_env_apply(const DT& L, const std::vector<DT>& Acores, const DT& R, const DT& v) {
+	const int s = int(Acores.size());
+	const bool batched = int(v.dims.size()) == s + 3;            // trailing column mode: (l, n.., r, col)
+	DT t = dt_contract(L, {2}, v, {0});                           // (l, a, n_1..n_s, r'[, col])
+	for (int p = 0; p < s; ++p) {
+		// t modes: (l, m_1..m_p, a, n_{p+1}..n_s, r')  ->  contract (a, n_{p+1}) with A(a, m, n, b)
+		DT u = dt_contract(t, {1 + p, 2 + p}, Acores[p], {0, 2});   // (l, m_1..m_p, n_{p+2}..n_s, r', m_{p+1}, b)
+		const int nu = int(u.dims.size());
+		std::vector<int> o;                                       // -> (l, m_1..m_{p+1}, b, n_{p+2}..n_s, r')
+		for (int i = 0; i <= p; ++i) o.push_back(i);
+		o.push_back(nu - 2); o.push_back(nu - 1);
+		for (int i = p + 1; i < nu - 2; ++i) o.push_back(i);
+		t = dt_permute(u, o);
+	}
+	DT y = dt_contract(t, {1 + s, 2 + s}, R, {1, 2});             // (l, m_1..m_s, [col,] r)
+	if (!batched) return y;
+	std::vector<int> o;                                           // (l, m.., col, r) -> (l, m.., r, col)
+	for (int i = 0; i <= s; ++i) o.push_back(i);
+	o.push_back(s + 2); o.push_back(s + 1);
+	return dt_permute(y, o);
+}
+
 // ---- the algorithm ---------------------------------------------------------------------------------------------------
 struct Als {
 	const xb_tt* A; xb_tt* x; const xb_tt* b;
@@ -247,19 +271,9 @@ struct Als {
 			return dt_permute(y, o);
 		};
 		if (opt.assume_spd) {
-			DT t = dt_contract(L, {2}, v, {0});                           // (l, a, n_1..n_s, r')
-			for (int p = 0; p < s; ++p) {
-				// t modes: (l, m_1..m_p, a, n_{p+1}..n_s, r')  ->  contract (a, n_{p+1}) with A(a, m, n, b)
-				DT u = dt_contract(t, {1 + p, 2 + p}, acore(cur + p), {0, 2});   // (l, m_1..m_p, n_{p+2}..n_s, r', m_{p+1}, b)
-				const int nu = int(u.dims.size());
-				std::vector<int> o;                                   // -> (l, m_1..m_{p+1}, b, n_{p+2}..n_s, r')
-				for (int i = 0; i <= p; ++i) o.push_back(i);
-				o.push_back(nu - 2); o.push_back(nu - 1);
-				for (int i = p + 1; i < nu - 2; ++i) o.push_back(i);
-				t = dt_permute(u, o);
-			}
-			// t: (l, m_1..m_s, b, r') ; R(r, b, r')
-			return finish(dt_contract(t, {1 + s, 2 + s}, R, {1, 2}));    // (l, m_1..m_s, r)
+			std::vector<DT> ac;
+			for (int p = 0; p < s; ++p) ac.push_back(acore(cur + p));
+			return spd_env_apply(L, ac, R, v);
 		}
 		// general: L(l, a1, a2, l'), per site A(a2, k, n, b2) then A(a1, k, m, b1); R(r, b1, b2, r')
 		DT t = dt_contract(L, {3}, v, {0});                               // (l, a1, a2, n_1..n_s, r')
@@ -492,6 +506,46 @@ xb_status xb_als_default_options(xb_als_options* opt, uint32_t sites, int assume
 		opt->preserve_core_position = 1;                           // als.h:138
 		opt->local_tolerance = 0.0;
 		opt->local_max_iterations = 0;
+	});
+}
+
+// Bond-split environment application (BASELINE config 4): the contribution of the right-bond slab r' in [begin, end)
+// to y = {L, A_1..A_s, R} v.  The chain is linear in v, so slabs of r' give partial results of full size whose sum over
+// the slabs (one NCCL all-reduce across the GPUs that own them) is the full application.  Device pointers.
+xb_status xb_env_apply(double* y, const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims,
+                       size_t sites, const double* R, size_t r, size_t a_right, const double* v, size_t slab_begin, size_t slab_end) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(y && L && A_cores && A_dims && R && v, "null");
+		XB_REQUIRE(sites >= 1 && sites <= 4, "1 to 4 sites");
+		XB_REQUIRE(slab_begin < slab_end && slab_end <= r, "illegal bond slab");
+		std::vector<DT> ac;
+		std::vector<size_t> vd = {l};
+		for (size_t p = 0; p < sites; ++p) {
+			const size_t* d = A_dims + 4 * p;
+			XB_REQUIRE(d[0] == (p == 0 ? a_left : A_dims[4 * (p - 1) + 3]), "operator bond dimensions do not coincide");
+			ac.push_back(dt_view(A_cores[p], {d[0], d[1], d[2], d[3]}));
+			vd.push_back(d[2]);
+		}
+		XB_REQUIRE(A_dims[4 * (sites - 1) + 3] == a_right, "operator bond dimensions do not coincide");
+		const size_t slab = slab_end - slab_begin;
+		size_t rows_v = l;
+		for (size_t p = 0; p < sites; ++p) rows_v *= A_dims[4 * p + 2];
+		DT Lv = dt_view(L, {l, a_left, l});
+		DT res;
+		if (slab == r) {
+			vd.push_back(r);
+			res = spd_env_apply(Lv, ac, dt_view(R, {r, a_right, r}), dt_view(v, vd));
+		} else {
+			// pack the slab of the last mode of v and R (strided -> contiguous), then the same chain
+			vd.push_back(slab);
+			DT vs = dt_alloc(vd);
+			copy2d(vs.data(), slab, v + slab_begin, r, rows_v, slab);
+			DT Rs = dt_alloc({r, a_right, slab});
+			copy2d(Rs.data(), slab, R + slab_begin, r, r * a_right, slab);
+			res = spd_env_apply(Lv, ac, Rs, vs);
+		}
+		copy(y, res.p, res.size());
 	});
 }
 

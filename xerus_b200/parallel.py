@@ -80,3 +80,46 @@ def run_on_workers(fn, items, workers):
 def item_rng(seed, b):
     """Per-item random stream: independent of how items are distributed over ranks."""
     return np.random.default_rng([int(seed), int(b)])
+
+
+# ---- bond-split environment application (BASELINE config 4) --------------------------------------------------------------
+def slab_range(r, rank, world):
+    """Contiguous slab of the right bond index owned by `rank`: balanced to +-1, disjoint, covering [0, r)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    base, extra = divmod(r, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def env_apply(L, A_cores, R, v, slab=None, out=None):
+    """y = {L, A_1..A_s, R} v (matrix-free local operator of ALS/DMRG, SPD environments) on CUDA float64 torch tensors:
+    L (l, a, l), A_p (a, m, n, b), R (r, b, r), v (l, n_1..n_s, r) -> y (l, m_1..m_s, r).  `slab` = (begin, end) restricts the
+    contraction over the right bond to that slab (partial result of full size).  Enqueued on the library stream."""
+    import ctypes as C
+    import torch
+    from ._lib import call
+    for t in [L, R, v] + list(A_cores):
+        if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+            raise ValueError("env_apply needs contiguous CUDA float64 tensors")
+    s = len(A_cores)
+    l, r = L.shape[0], R.shape[0]
+    if out is None:
+        out = torch.empty((l,) + tuple(a.shape[1] for a in A_cores) + (r,), dtype=torch.float64, device=v.device)
+    begin, end = slab if slab is not None else (0, r)
+    ptrs = (C.c_void_p * s)(*[a.data_ptr() for a in A_cores])
+    dims = (C.c_size_t * (4 * s))(*[int(x) for a in A_cores for x in a.shape])
+    call("xb_env_apply", out.data_ptr(), L.data_ptr(), l, L.shape[1], ptrs, dims, s, R.data_ptr(), r, R.shape[1],
+         v.data_ptr(), begin, end)
+    return out
+
+
+def bond_split_apply(L, A_cores, R, v, rank, world, out=None, group=None):
+    """The application split along the right bond index over `world` GPUs: every rank contracts its slab, then ONE sum
+    all-reduce (NCCL over NVLink) assembles y on all ranks.  Must run with the library stream current
+    (torch.cuda.stream(ExternalStream(xb.stream_handle()))) so the collective is ordered after the kernels."""
+    import torch.distributed as dist
+    y = env_apply(L, A_cores, R, v, slab=slab_range(R.shape[0], rank, world), out=out)
+    if world > 1:
+        dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+    return y
