@@ -1,11 +1,11 @@
-import sys, time; sys.path.insert(0,'.')
+import sys, time; sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import numpy as np, xerus_b200 as xb
 xb.init(0)
 rng=np.random.default_rng(0)
 for (m,n) in [(256,256),(512,512),(128,128),(64,64),(32,32)]:
     A=rng.standard_normal((m,n))
-    for (bw,wpp) in [(0,0),(8,1),(8,2),(8,4),(16,1),(16,2),(4,4)]:
-        xb.set_option("svd_max_bw",bw); xb.set_option("svd_wpp",wpp)
+    for bw in [0,16,8,4]:
+        xb.set_option("svd_max_bw",bw); wpp=1
         try:
             xb.blasWrapper.svd(A)
             xb.profile_enable(True)
@@ -16,4 +16,4 @@ for (m,n) in [(256,256),(512,512),(128,128),(64,64),(32,32)]:
             print(m,n,'bw',bw,'wpp',wpp,'jacobi ms/svd %.3f  svd total %.3f'%(ms/sc,ms2/sc2),'err %.1e'%err, flush=True)
         except Exception as e:
             print(m,n,bw,wpp,'ERR',e)
-xb.set_option("svd_max_bw",0); xb.set_option("svd_wpp",0)
+xb.set_option("svd_max_bw",0)

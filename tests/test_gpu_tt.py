@@ -272,3 +272,39 @@ def test_batch_on_multiple_workers_matches_sequential():
     seq = parallel.matvec_round_batch(A, make, items, r)
     par = parallel.matvec_round_batch(A, make, items, r, workers=4)
     assert seq == par
+
+
+# ---- edge cases the reference tests exercise (ttRounding.cxx:27-102: orders 1 and 2, modes of size 1, ragged dims) -----------
+@pytest.mark.parametrize("dims", [(2,), (2, 2), (2, 7), (5, 6, 3, 1, 4, 2, 8, 1), (1, 1, 1), (3, 1, 1, 4)])
+def test_round_trip_small_and_degenerate(dims):
+    rng = np.random.default_rng(sum(dims))
+    A = rng.standard_normal(dims)
+    t = xb.TTTensor.from_dense(A, 1e-14)
+    assert rel(t.to_dense(), A) < 1e-14                      # ttRounding.cxx: approx_equal(B, A, 1e-14)
+    t.round(1e-14)
+    assert rel(t.to_dense(), A) < 1e-14
+    t.round(int(np.prod(dims)))
+    assert rel(t.to_dense(), A) < 1e-14
+    for pos in range(len(dims)):
+        t.move_core(pos)
+        assert t.corePosition == pos and rel(t.to_dense(), A) < 1e-13
+
+
+def test_rank_one_and_zero_tensors():
+    ones = xb.TTTensor.ones([3, 4, 5])
+    assert ones.ranks() == [1, 1] and abs(ones.frob_norm() - np.sqrt(60)) < 1e-13
+    ones.round(5)
+    assert ones.ranks() == [1, 1] and rel(ones.to_dense(), np.ones((3, 4, 5))) < 1e-14
+    z = xb.TTTensor.from_cores([np.zeros((1, 3, 2)), np.zeros((2, 3, 1))])
+    z.round(1)                                               # rank never drops to 0 (tensor.cpp:1464-1474)
+    assert z.ranks() == [1] and np.all(z.to_dense() == 0)
+
+
+def test_round_large_magnitudes():
+    """Random TTs are not normalised (norm ~1e33 at config 3): everything is relative."""
+    rng = np.random.default_rng(77)
+    t = xb.TTTensor.random([2] * 10, 16, rng)
+    t *= 1e120                       # (the numpy oracle forms squares of the norm: stay below 1e150)
+    o = to_oracle(t)
+    t.round(5); o.round(5)
+    assert t.ranks() == o.ranks() and O.tt_distance_rel(to_oracle(t), o) < 1e-9

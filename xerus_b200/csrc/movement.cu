@@ -99,29 +99,56 @@ __global__ void permute_kernel(double* __restrict__ out, const double* __restric
 constexpr int RED_THREADS = 256;
 constexpr int RED_MAX_BLOCKS = 296;
 
-template <int MODE>   // 0: sum x*y   1: sum |x|
+// MODE 0: sum x*y   1: sum |x|   2: max |x|   3: sum (x * *y)^2  (y points to a device scalar: overflow-safe 2-norm)
+template <int MODE>
 __global__ void reduce_stage1(double* __restrict__ partial, const double* __restrict__ x, const double* __restrict__ y, size_t n) {
 	__shared__ double sh[RED_THREADS / 32];
 	double acc = 0.0;
+	const double sc = (MODE == 3) ? y[0] : 1.0;
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-		acc += (MODE == 0) ? x[i] * y[i] : fabs(x[i]);
+		if (MODE == 0) acc += x[i] * y[i];
+		else if (MODE == 1) acc += fabs(x[i]);
+		else if (MODE == 2) acc = fmax(acc, fabs(x[i]));
+		else { const double v = x[i] * sc; acc += v * v; }
 	}
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+	for (int o = 16; o > 0; o >>= 1) {
+		const double other = __shfl_down_sync(0xffffffffu, acc, o);
+		acc = (MODE == 2) ? fmax(acc, other) : acc + other;
+	}
 	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		double s = 0.0;
-		for (int w = 0; w < RED_THREADS / 32; ++w) s += sh[w];
+		for (int w = 0; w < RED_THREADS / 32; ++w) s = (MODE == 2) ? fmax(s, sh[w]) : s + sh[w];
 		partial[blockIdx.x] = s;
 	}
 }
+// MODE as above; for MODE 2 the result is turned into an exact power-of-two scaling pair
+//   result[0] = s with amax * s in [0.5, 1)   result[1] = 1 / s          (s = 1 for an all-zero input)
+template <int MODE>
 __global__ void reduce_stage2(double* __restrict__ result, const double* __restrict__ partial, int nblocks) {
 	if (threadIdx.x == 0 && blockIdx.x == 0) {
 		double s = 0.0;
-		for (int i = 0; i < nblocks; ++i) s += partial[i];
-		*result = s;
+		for (int i = 0; i < nblocks; ++i) s = (MODE == 2) ? fmax(s, partial[i]) : s + partial[i];
+		if (MODE == 2) {
+			int e = 0;
+			double sc = 1.0, inv = 1.0;
+			if (s > 0.0 && s < HUGE_VAL) { frexp(s, &e); sc = ldexp(1.0, -e); inv = ldexp(1.0, e); }
+			result[0] = sc; result[1] = inv;
+		} else {
+			*result = s;
+		}
 	}
+}
+__global__ void scale_by_dev_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t n, const double* __restrict__ factor) {
+	const double f = *factor;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i] * f;
+}
+__global__ void scale_block_by_dev_kernel(double* __restrict__ A, size_t ld, size_t rows, size_t cols, const double* __restrict__ factor) {
+	const double f = *factor;
+	const size_t n = rows * cols;
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) A[(i / cols) * ld + (i % cols)] *= f;
 }
 
 static void reduce(double* d_result, const double* x, const double* y, size_t n, int mode) {
@@ -129,9 +156,12 @@ static void reduce(double* d_result, const double* x, const double* y, size_t n,
 	if (!partial) partial = dalloc(RED_MAX_BLOCKS);
 	unsigned blocks = unsigned(std::min<size_t>(RED_MAX_BLOCKS, std::max<size_t>(1, (n + RED_THREADS * 4 - 1) / (RED_THREADS * 4))));
 	if (mode == 0) reduce_stage1<0><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);
-	else reduce_stage1<1><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);
+	else if (mode == 1) reduce_stage1<1><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);
+	else if (mode == 2) reduce_stage1<2><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);
+	else reduce_stage1<3><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);
 	XB_LAUNCH_CHECK();
-	reduce_stage2<<<1, 32, 0, ctx().stream>>>(d_result, partial, int(blocks));
+	if (mode == 2) reduce_stage2<2><<<1, 32, 0, ctx().stream>>>(d_result, partial, int(blocks));
+	else reduce_stage2<0><<<1, 32, 0, ctx().stream>>>(d_result, partial, int(blocks));
 	XB_LAUNCH_CHECK();
 }
 
@@ -235,11 +265,34 @@ void permute(double* out, const double* in, const size_t* dims, const size_t* sh
 void dot_dev(double* d_result, const double* x, const double* y, size_t n) { reduce(d_result, x, y, n, 0); }
 void asum_dev(double* d_result, const double* x, size_t n) { reduce(d_result, x, x, n, 1); }
 
+void amax_scale_dev(double* d_scale2, const double* x, size_t n) { reduce(d_scale2, x, x, n, 2); }
+void scale_by_dev(double* dst, const double* src, size_t n, const double* d_factor) {
+	if (!n) return;
+	scale_by_dev_kernel<<<grid_for(n, 256), 256, 0, ctx().stream>>>(dst, src, n, d_factor);
+	XB_LAUNCH_CHECK();
+}
+void scale_block_by_dev(double* A, size_t ld, size_t rows, size_t cols, const double* d_factor) {
+	if (!rows || !cols) return;
+	scale_block_by_dev_kernel<<<grid_for(rows * cols, 256), 256, 0, ctx().stream>>>(A, ld, rows, cols, d_factor);
+	XB_LAUNCH_CHECK();
+}
+
 double dot(const double* x, const double* y, size_t n) {
 	DBuf r(1);
 	dot_dev(r, x, y, n);
 	return read_scalar(r);
 }
-double two_norm(const double* x, size_t n) { return std::sqrt(std::max(0.0, dot(x, x, n))); }
+double two_norm(const double* x, size_t n) {
+	// overflow/underflow safe (TT cores carry norms like 1e33 .. 1e150): scale by an exact power of two first
+	if (!n) return 0.0;
+	DBuf sc(2), r(1);
+	amax_scale_dev(sc, x, n);
+	reduce(r, x, sc.p, n, 3);
+	Context& c = ctx();
+	XB_CUDA(cudaMemcpyAsync(c.h_scratch, r.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaMemcpyAsync(c.h_scratch + 1, sc.p + 1, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaStreamSynchronize(c.stream));
+	return std::sqrt(std::max(0.0, c.h_scratch[0])) * c.h_scratch[1];
+}
 
 } // namespace xb

@@ -182,11 +182,12 @@ __global__ void __launch_bounds__(1024) qr_update_kernel(double* __restrict__ C,
 	}
 }
 
-__global__ void qr_extract_r_kernel(double* __restrict__ R, const double* __restrict__ W, const size_t k, const size_t n) {
+__global__ void qr_extract_r_kernel(double* __restrict__ R, const double* __restrict__ W, const size_t k, const size_t n, const double* __restrict__ unscale) {
 	const size_t total = k * n;
+	const double f = *unscale;
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
 		const size_t r = i / n, c = i % n;
-		R[i] = (c >= r) ? W[i] : 0.0;
+		R[i] = (c >= r) ? W[i] * f : 0.0;
 	}
 }
 
@@ -219,7 +220,10 @@ void qr(double* Q, double* R, const double* A, size_t m, size_t n) {
 	const size_t nch_max = (m + QR_CHUNK - 1) / QR_CHUNK;
 	const size_t ncpad_max = ((std::max(n, k) + 31) / 32) * 32;
 	DBuf Wp(nch_max * 32 * ncpad_max);
-	copy(W, A, m * n);
+	// work on A * 2^-e (exact): the reflector norms are sums of squares and TT cores carry norms like 1e33 .. 1e150
+	DBuf sc(2);
+	amax_scale_dev(sc, A, m * n);
+	scale_by_dev(W, A, m * n, sc);
 
 	static bool attr_set = false;
 	const size_t fixed_smem = (3 * 32 * 33 + 32 + 32 + 4) * sizeof(double);
@@ -247,7 +251,7 @@ void qr(double* Q, double* R, const double* A, size_t m, size_t n) {
 	{
 		const size_t total = k * n;
 		const unsigned blocks = unsigned(std::min<size_t>((total + 255) / 256, size_t(ctx().num_sms) * 8));
-		qr_extract_r_kernel<<<blocks, 256, 0, ctx().stream>>>(R, W, k, n);
+		qr_extract_r_kernel<<<blocks, 256, 0, ctx().stream>>>(R, W, k, n, sc.p + 1);
 		XB_LAUNCH_CHECK();
 	}
 	// Q = H_1 ... H_k [I; 0] : apply the block reflectors in reverse order to the identity

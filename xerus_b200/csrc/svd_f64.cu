@@ -19,13 +19,14 @@ namespace xb {
 constexpr double DBL_EPS = 2.220446049250313e-16;
 
 __global__ void svd_init_kernel(double* __restrict__ GT, const int ld, const int npad, const int mdot, const int voff, const int nw,
-                                const double* __restrict__ src, const long long rs, const long long cs) {
+                                const double* __restrict__ src, const long long rs, const long long cs, const double* __restrict__ scale) {
+	const double sc = *scale;
 	const size_t total = (size_t)npad * ld;
 	for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
 		const int j = int(e / ld), i = int(e % ld);
 		double v = 0.0;
 		if (j < nw) {
-			if (i < mdot) v = src[(long long)i * rs + (long long)j * cs];
+			if (i < mdot) v = src[(long long)i * rs + (long long)j * cs] * sc;
 			else if (i - voff == j) v = 1.0;
 		}
 		GT[e] = v;
@@ -334,7 +335,7 @@ __global__ void amax_kernel(const double* __restrict__ x, const size_t n, double
 
 // singular values = column norms; rank them (descending, ties by index) -> Ssorted, perm.   single CTA
 __global__ void svd_sort_kernel(const double* __restrict__ GT, const int ldg, const int mdot, const int nw,
-                                double* __restrict__ Ssorted, int* __restrict__ perm) {
+                                double* __restrict__ Ssorted, int* __restrict__ perm, const double* __restrict__ unscale) {
 	extern __shared__ double nrm[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 	for (int j = warp; j < nw; j += nwarps) {
@@ -350,7 +351,7 @@ __global__ void svd_sort_kernel(const double* __restrict__ GT, const int ldg, co
 		const double v = nrm[j];
 		int rank = 0;
 		for (int i = 0; i < nw; ++i) { const double u = nrm[i]; rank += (u > v || (u == v && i < j)) ? 1 : 0; }
-		Ssorted[rank] = v;
+		Ssorted[rank] = v * (*unscale);
 		perm[rank] = j;
 	}
 }
@@ -361,13 +362,13 @@ __global__ void svd_extract_kernel(const double* __restrict__ GT, const int ldg,
                                    const double* __restrict__ Ssorted, const int* __restrict__ perm,
                                    double* __restrict__ outX, const long long sxi, const long long sxr, const int scale_x,
                                    double* __restrict__ outV, const long long svc, const long long svr, const int scale_v,
-                                   double* __restrict__ dS, const double soft) {
+                                   double* __restrict__ dS, const double soft, const double* __restrict__ scale2) {
 	const int r = blockIdx.x;
-	const double sigma = Ssorted[r];
+	const double sigma = Ssorted[r];                          // unscaled singular value; the X part of GT holds x * scale2[0]
 	const double sigma_eff = fmax(0.0, sigma - soft);        // soft thresholding (tensorNetwork.cpp:766)
 	const double* g = GT + (size_t)perm[r] * ldg;
-	const double inv = sigma > 0.0 ? 1.0 / sigma : 0.0;
-	const double fx = scale_x ? (soft == 0.0 ? 1.0 : sigma_eff * inv) : inv;
+	const double inv = sigma > 0.0 ? 1.0 / (sigma * scale2[0]) : 0.0;        // 1 / (scaled sigma)
+	const double fx = scale_x ? (soft == 0.0 ? scale2[1] : sigma_eff * inv) : inv;
 	const double fv = scale_v ? sigma_eff : 1.0;
 	for (int i = threadIdx.x; i < mdot; i += blockDim.x) outX[(long long)i * sxi + (long long)r * sxr] = g[i] * fx;
 	for (int c = threadIdx.x; c < nw; c += blockDim.x) outV[(long long)c * svc + (long long)r * svr] = g[voff + c] * fv;
@@ -482,6 +483,9 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	const JacobiPlan plan = plan_jacobi(ld, nw, voff, sizeof(double), smem_cap);
 	npad = plan.npad;
 	GT.resize(npad * ld);
+	// exact power-of-two scaling of the Jacobi input: norms and cross products are sums of squares
+	scale.resize(2);
+	amax_scale_dev(scale, src, reduced ? nw * nw : m * n);
 	const double tol = std::sqrt(double(mdot)) * DBL_EPS;
 	const unsigned init_blocks = unsigned(std::min<size_t>((npad * ld + 255) / 256, size_t(c.num_sms) * 8));
 	// G0 V = X recomputed from the untouched input (transposed storage: XT = VT G0^T)
@@ -490,6 +494,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		if (reduced) gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, Rr, nw, true, 0.0);
 		else if (!swapped) gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, A, n, true, 0.0);
 		else gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, A, n, false, 0.0);
+		scale_block_by_dev(GT.p, ld, nw, mdot, scale.p);
 	};
 	// one Newton-Schulz step on V (quadratic): VT <- (1.5 I - 0.5 VT VT^T) VT
 	auto newton_schulz = [&]() {
@@ -538,7 +543,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		converged = run_persistent<double>(GT.p, ld, voff, plan, tol, 1e-7, c.svd_max_sweeps, sw64, smem_cap, "f64");
 		sweeps = sw32 + sw64;
 	} else {
-		svd_init_kernel<<<init_blocks, 256, 0, c.stream>>>(GT, int(ld), int(npad), int(mdot), int(voff), int(nw), src, rs, cs);
+		svd_init_kernel<<<init_blocks, 256, 0, c.stream>>>(GT, int(ld), int(npad), int(mdot), int(voff), int(nw), src, rs, cs, scale.p);
 		XB_LAUNCH_CHECK();
 		if (plan.persistent) {
 			converged = run_persistent<double>(GT.p, ld, voff, plan, tol, 1e-7, c.svd_max_sweeps, sweeps, smem_cap, "f64");
@@ -593,7 +598,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	{
 		const size_t sm = nw * sizeof(double);
 		XB_REQUIRE(sm <= 48 * 1024, "SVD: too many columns for the sort kernel");
-		svd_sort_kernel<<<1, 1024, sm, c.stream>>>(GT, int(ld), int(mdot), int(nw), Ssorted, reinterpret_cast<int*>(perm.p));
+		svd_sort_kernel<<<1, 1024, sm, c.stream>>>(GT, int(ld), int(mdot), int(nw), Ssorted, reinterpret_cast<int*>(perm.p), scale.p + 1);
 		XB_LAUNCH_CHECK();
 	}
 	S.resize(nw);
@@ -627,7 +632,7 @@ void Svd::extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, 
 		outV = U; svc = (long long)k; svr = 1; scale_v = scale_u;
 	}
 	svd_extract_kernel<<<unsigned(k), 256, 0, c.stream>>>(GT, int(ld), int(mdot), int(voff), int(nw), Ssorted, p, outX, sxi, sxr, scale_x,
-	                                                       outV, svc, svr, scale_v, dS, soft_threshold);
+	                                                       outV, svc, svr, scale_v, dS, soft_threshold, scale.p);
 	XB_LAUNCH_CHECK();
 	if (reduced) {
 		if (!swapped) gemm(U, k, m, k, 1.0, Qred, nw, false, nw, Xk, k, false, 0.0);          // U = Qred * Xk

@@ -117,6 +117,9 @@ void scale_cols(double* A, const double* s, size_t rows, size_t cols, size_t ld)
 // reductions: result written to a device double
 void dot_dev(double* d_result, const double* x, const double* y, size_t n);
 void asum_dev(double* d_result, const double* x, size_t n);
+void amax_scale_dev(double* d_scale2, const double* x, size_t n);          // d_scale2[0] = 2^-e with max|x| * 2^-e in [0.5,1), [1] = 2^e
+void scale_by_dev(double* dst, const double* src, size_t n, const double* d_factor);
+void scale_block_by_dev(double* A, size_t ld, size_t rows, size_t cols, const double* d_factor);
 double read_scalar(const double* d_value);                                // D2H + sync
 double two_norm(const double* x, size_t n);
 double dot(const double* x, const double* y, size_t n);
@@ -140,7 +143,7 @@ struct Svd {
 	// internals
 	bool swapped = false, reduced = false;
 	size_t mw = 0, nw = 0, npad = 0, mt = 0, mdot = 0, voff = 0, ld = 0;
-	DBuf GT, Qred, Ssorted, perm;
+	DBuf GT, Qred, Ssorted, perm, scale;   // scale: [2^-e, 2^e] of the Jacobi input (squares must not overflow)
 	void factor(const double* A, size_t m, size_t n);
 	void extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, double* dS /* optional device S (k) */);
 };
