@@ -422,6 +422,7 @@ struct Als {
 		// two sites: split by SVD with the ranks x had on entry (als.cpp:51-70), Sigma pushed in sweep direction
 		const size_t l = x->rank[cur], n1 = x->dim_m[cur], n2 = x->dim_m[cur + 1], r = x->rank[cur + 2];
 		Svd svd;
+		svd.polish = ctx().tt_svd_polish;
 		svd.factor(sol.p, l * n1, n2 * r);
 		// the reference truncates the split with eps = EPSILON (als.cpp:55,:65); below the accuracy of an iterative
 		// local solve singular values are noise, so the CG path cuts at its own tolerance instead

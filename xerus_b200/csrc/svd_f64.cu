@@ -582,14 +582,14 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	}
 	if (!converged) { delete prof_jacobi; throw Error(XB_ERR_NUMERIC, "Jacobi SVD did not converge within svd_max_sweeps sweeps"); }
 
-	if (c.svd_polish && !mixed) {
+	if (c.svd_polish && polish > 0 && !mixed) {
 		// Polish: thousands of plane rotations leave V orthogonal only to ~eps*sqrt(#rotations) and X = G V with the same
 		// drift.  One Newton-Schulz step re-orthogonalises V, the left part is recomputed from the untouched input, and one
 		// clean-up sweep of tiny rotations restores |cos| <= tol between the left vectors: backward error back at the
 		// eps*sqrt(n) level of LAPACK.  (The mixed path ends with 2-3 FP64 sweeps from a re-orthogonalised V: not needed.)
 		newton_schulz();
 		recompute_left();
-		if (plan.persistent && nw > 1) { int extra = 0; run_persistent<double>(GT.p, ld, voff, plan, tol, 1e-7, 2, extra, smem_cap, "clean"); sweeps += extra; }
+		if (polish > 1 && plan.persistent && nw > 1) { int extra = 0; run_persistent<double>(GT.p, ld, voff, plan, tol, 1e-7, 2, extra, smem_cap, "clean"); sweeps += extra; }
 	}
 	delete prof_jacobi;
 

@@ -90,6 +90,7 @@ static void round_edge(xb_tt* t, size_t from, size_t max_rank, double eps, doubl
 	const size_t trows = t->rank[to] * t->ext(to);
 	Svd svd;
 	svd.soft_threshold = soft_threshold;
+	svd.polish = ctx().tt_svd_polish;
 	if (to_orthonormal) {
 		svd.factor(t->core[from], r, fcols);
 		const size_t k = truncation_rank(svd.S, max_rank, eps);               // tensor.cpp:1464-1474
@@ -430,6 +431,7 @@ xb_status xb_tt_from_dense(xb_tt** out, const double* host, size_t d, const size
 			for (size_t pos = d - 1; pos > 0; --pos) {
 				const size_t lrows = prefix[pos], cols = dims[pos] * r;
 				Svd svd;
+				svd.polish = ctx().tt_svd_polish;
 				svd.factor(remains, lrows, cols);
 				const size_t k = truncation_rank(svd.S, max_rank, eps);
 				DBuf US(lrows * k), Vt(k * cols);

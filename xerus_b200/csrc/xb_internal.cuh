@@ -55,6 +55,7 @@ struct Context {
 	int gemm_force_small = 0;
 	bool profile = false;
 	int svd_persistent = 1;
+	int tt_svd_polish = 1;         // polish level of the SVDs inside round() / TT-SVD / DMRG splits (see Svd::polish)
 	int svd_polish = 1;            // Newton-Schulz re-orthogonalisation of V + recomputed left part after the Jacobi sweeps
 	int svd_mixed = 0;             // FP32 pre-conditioning sweeps + FP64 finishing sweeps (measured: no gain, kept as an experiment)
 	int svd_mixed_min = 64;        // smallest column count for the mixed path
@@ -140,6 +141,9 @@ struct Svd {
 	std::vector<double> S;     // host copy, descending
 	int sweeps = 0;
 	double soft_threshold = 0.0;   // applied to Sigma wherever extract() folds it in
+	int polish = 2;                // 2: Newton-Schulz on V + recomputed left part + clean-up sweep (LAPACK-grade orthogonality of both
+	                               // factors, per-call layer); 1: without the clean-up sweep (sweep layer: exact projection, left vectors
+	                               // orthogonal to ~1e-12); 0: none
 	// internals
 	bool swapped = false, reduced = false;
 	size_t mw = 0, nw = 0, npad = 0, mt = 0, mdot = 0, voff = 0, ld = 0;
