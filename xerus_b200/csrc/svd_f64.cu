@@ -141,7 +141,7 @@ template <typename T, int EH, int MAXT>
 __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(T* __restrict__ GT, const int ld, const int epl_x, const int epl_v,
                                                                 const int bw, const int nblk, const T tol2, const T big2,
                                                                 unsigned int* __restrict__ counters, unsigned int* __restrict__ info,
-                                                                const int max_sweeps) {
+                                                                const int max_sweeps, unsigned int* ready, const int recursive) {
 	extern __shared__ double S_raw[];
 	T* S = reinterpret_cast<T*>(S_raw);
 	__shared__ unsigned int s_rot, s_big;
@@ -162,22 +162,43 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(T* __restrict__
 	const int nrounds = (nblk == 2) ? 1 : nblk - 1;
 	if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
 	__syncthreads();
-	int sweeps = 0;
+	int sweeps = 0, ground = 0;                  // ground: global round counter (version of the block flags)
 	unsigned int last_rot = 1, last_big = 1;
 	unsigned int my_rot = 0, my_big = 0;         // per-warp counters (lane 0), flushed once per visit
 	long long tk_load = 0, tk_inner = 0, tk_store = 0, tk_sync = 0, tk0 = 0;   // phase cycle counters (thread 0 of block 0)
 	const bool timing = (info[0] == 0xC10C) && blockIdx.x == 0 && threadIdx.x == 0;
 	for (; sweeps < max_sweeps; ) {
-		for (int round = 0; round < nrounds; ++round) {
+		for (int round = 0; round < nrounds; ++round, ++ground) {
 			int pb, qb;
-			{
+			bool loadp = true, storep = true, full = (round == 0);
+			if (recursive) {
+				// Recursive bipartite tournament (nblk a power of two): phase with groups of g blocks pairs the lower half of a
+				// group (stationary in this CTA for the whole phase) with the upper half, which rotates through the group's
+				// CTAs; then both halves are split again.  nblk/2 + nblk/4 + ... + 1 = nblk - 1 rounds, every block pair met
+				// once; the last phase (g = 2) also runs the pairs inside the two blocks.  Per round only ONE block moves, and
+				// a CTA depends only on the neighbour that held that block: point-to-point flags instead of a grid barrier.
+				int g = nblk, t = round;
+				while (t >= (g >> 1)) { t -= (g >> 1); g >>= 1; }
+				const int h = g >> 1, G = blockIdx.x / h, j = blockIdx.x % h;
+				pb = G * g + j; qb = G * g + h + ((j + t) & (h - 1));
+				loadp = (t == 0); storep = (t == h - 1); full = (g == 2);
+				if (threadIdx.x == 0) {
+					// wait until the global copies reflect round ground - 1 (bounded spin: never hang the GPU)
+					unsigned int spins = 0;
+					volatile unsigned int* rd = ready;
+					while ((rd[qb] < (unsigned)ground || (loadp && rd[pb] < (unsigned)ground)) && spins < (1u << 27)) ++spins;
+					if (spins >= (1u << 27)) atomicOr(&counters[2 * max_sweeps], 0xDEADu);
+					__threadfence();
+				}
+				__syncthreads();
+			} else {
 				const int pi = blockIdx.x, N1 = nblk - 1;
 				if (nblk == 2) { pb = 0; qb = 1; }
 				else if (pi == 0) { pb = N1; qb = round % N1; }
 				else { pb = (round + pi) % N1; qb = (round - pi + N1) % N1; }
 			}
 			if (timing) tk0 = clock64();
-			for (int r = warp; r < N; r += nwarps) {
+			for (int r = (loadp ? 0 : bw) + warp; r < N; r += nwarps) {
 				const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
 				const T* src = GT + (size_t)grow * ld + lane;
 				T* dst = S + (size_t)r * ld + lane;
@@ -186,7 +207,7 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(T* __restrict__
 				for (int k0 = 0; k0 < EH; k0 += 4) {
 					T v[4], w[4];
 #pragma unroll
-					for (int k = 0; k < 4; ++k) { v[k] = (k0 + k < epl_x) ? src[32 * (k0 + k)] : T(0); w[k] = (k0 + k < epl_v) ? src[voff + 32 * (k0 + k)] : T(0); }
+					for (int k = 0; k < 4; ++k) { v[k] = (k0 + k < epl_x) ? __ldcg(src + 32 * (k0 + k)) : T(0); w[k] = (k0 + k < epl_v) ? __ldcg(src + voff + 32 * (k0 + k)) : T(0); }
 #pragma unroll
 					for (int k = 0; k < 4; ++k) {
 						if (k0 + k < epl_x) { dst[32 * (k0 + k)] = v[k]; ss += v[k] * v[k]; }
@@ -199,7 +220,6 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(T* __restrict__
 			}
 			__syncthreads();
 			if (timing) { const long long t1 = clock64(); tk_load += t1 - tk0; tk0 = t1; }
-			const bool full = (round == 0);
 			const int inner_rounds = full ? (N - 1) : bw;
 			for (int rr = 0; rr < inner_rounds; ++rr) {
 				for (int pi = warp; pi < bw; pi += nwarps) {
@@ -262,7 +282,7 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(T* __restrict__
 			}
 			if (timing) { const long long t1 = clock64(); tk_inner += t1 - tk0; tk0 = t1; }
 			if (lane == 0 && my_rot) { atomicAdd(&s_rot, my_rot); atomicAdd(&s_big, my_big); my_rot = 0; my_big = 0; }
-			for (int r = warp; r < N; r += nwarps) {
+			for (int r = (storep ? 0 : bw) + warp; r < N; r += nwarps) {
 				const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
 				T* dst = GT + (size_t)grow * ld + lane;
 				const T* src = S + (size_t)r * ld + lane;
@@ -276,7 +296,15 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(T* __restrict__
 				}
 			}
 			if (timing) { const long long t1 = clock64(); tk_store += t1 - tk0; tk0 = t1; }
-			if (nblk > 2) { __threadfence(); grid.sync(); }
+			if (recursive) {
+				__threadfence();
+				__syncthreads();
+				if (threadIdx.x == 0) {
+					volatile unsigned int* rd = ready;
+					if (storep) rd[pb] = (unsigned)ground + 1u;
+					rd[qb] = (unsigned)ground + 1u;
+				}
+			} else if (nblk > 2) { __threadfence(); grid.sync(); }
 			else __syncthreads();
 			if (timing) { const long long t1 = clock64(); tk_sync += t1 - tk0; tk0 = t1; }
 		}
@@ -422,7 +450,9 @@ static void launch_persistent(T* gt, int ld, int epl_x, int epl_v, const JacobiP
 	}
 	XB_REQUIRE(p.threads <= MAXT, "internal: Jacobi launch exceeds its launch bound");
 	int bw = p.bw, nblk = int(p.nblk);
-	void* args[] = {&gt, &ld, &epl_x, &epl_v, &bw, &nblk, &tol2, &big2, &d_cnt, &d_info, &max_sweeps};
+	unsigned int* ready = d_cnt + 2 * max_sweeps + 12;
+	int recursive = (ctx().svd_recursive && nblk > 2 && (nblk & (nblk - 1)) == 0) ? 1 : 0;
+	void* args[] = {&gt, &ld, &epl_x, &epl_v, &bw, &nblk, &tol2, &big2, &d_cnt, &d_info, &max_sweeps, &ready, &recursive};
 	XB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_persistent_kernel<T, EH, MAXT>, dim3(unsigned(p.nblk / 2)), dim3(p.threads), args, p.smem, ctx().stream));
 	ctx().launches++;
 }
@@ -432,9 +462,10 @@ template <typename T>
 static bool run_persistent(T* gt, size_t ld, size_t voff, const JacobiPlan& p, double tol, double big, int max_sweeps, int& sweeps_out,
                            size_t smem_cap, const char* tag) {
 	Context& c = ctx();
-	unsigned int* d_cnt = static_cast<unsigned int*>(dalloc_bytes((2 * max_sweeps + 12) * sizeof(unsigned int)));
+	const size_t n_u32 = 2 * max_sweeps + 12 + p.nblk;      // sweep counters | info | per-block ready flags
+	unsigned int* d_cnt = static_cast<unsigned int*>(dalloc_bytes(n_u32 * sizeof(unsigned int)));
 	unsigned int* d_info = d_cnt + 2 * max_sweeps + 4;
-	XB_CUDA(cudaMemsetAsync(d_cnt, 0, (2 * max_sweeps + 12) * sizeof(unsigned int), c.stream));
+	XB_CUDA(cudaMemsetAsync(d_cnt, 0, n_u32 * sizeof(unsigned int), c.stream));
 	const bool timing = getenv("XB_JACOBI_TIMING") != nullptr;
 	if (timing) { const unsigned int flag = 0xC10C; XB_CUDA(cudaMemcpyAsync(d_info, &flag, 4, cudaMemcpyHostToDevice, c.stream)); }
 	const int epl_x = int(voff / 32), epl_v = int((ld - voff) / 32);
@@ -443,10 +474,13 @@ static bool run_persistent(T* gt, size_t ld, size_t voff, const JacobiPlan& p, d
 	else if (p.EH == 8) launch_persistent<T, 8, 512>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
 	else launch_persistent<T, 16, 256>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
 	unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch);
-	XB_CUDA(cudaMemcpyAsync(h_info, d_info, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaMemcpyAsync(h_info, d_info - 4, 12 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
 	XB_CUDA(cudaStreamSynchronize(c.stream));
+	const bool dead = h_info[0] == 0xDEADu;
+	h_info += 4;
 	sweeps_out = int(h_info[1]);
 	const bool converged = h_info[2] == 0;
+	if (dead) { dfree(d_cnt); throw Error(XB_ERR_CUDA, "Jacobi SVD: a block hand-over flag was never raised (internal scheduling error)"); }
 	if (timing) fprintf(stderr, "[jacobi %s] ld=%zu bw=%d ctas=%zu sweeps=%d kcycles: load %u inner %u store %u sync %u\n", tag, ld, p.bw,
 	                    p.nblk / 2, sweeps_out, h_info[4], h_info[5], h_info[6], h_info[7]);
 	dfree(d_cnt);

@@ -57,6 +57,7 @@ struct Context {
 	int svd_persistent = 1;
 	int tt_svd_polish = 1;         // polish level of the SVDs inside round() / TT-SVD / DMRG splits (see Svd::polish)
 	int svd_polish = 1;            // Newton-Schulz re-orthogonalisation of V + recomputed left part after the Jacobi sweeps
+	int svd_recursive = 1;         // recursive bipartite tournament with point-to-point block flags (power-of-two block counts)
 	int svd_mixed = 0;             // FP32 pre-conditioning sweeps + FP64 finishing sweeps (measured: no gain, kept as an experiment)
 	int svd_mixed_min = 64;        // smallest column count for the mixed path
 	int svd_max_bw = 0;            // 0 = automatic block width of the Jacobi kernel
