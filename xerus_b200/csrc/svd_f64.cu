@@ -494,8 +494,9 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	swapped = m < n;
 	mw = std::max(m, n); nw = std::min(m, n);
 	kmax = nw;
-	reduced = (mw > nw) && (mw > 32);
 	Context& c = ctx();
+	// square inputs take the QR step too (from 64 columns on): it is what makes the flipped orientation below possible
+	reduced = (mw > 32) && (mw > nw || (c.svd_flip != 0 && c.svd_square_qr != 0 && nw >= 64));
 	const size_t smem_cap = std::min<size_t>(c.max_smem_optin, 227 * 1024) - 1024;
 
 	const double* src; long long rs, cs;
@@ -504,8 +505,14 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		Qred.resize(mw * nw); Rr.resize(nw * nw);
 		if (swapped) { At.resize(m * n); transpose(At, A, m, n); qr(Qred, Rr, At, mw, nw); }
 		else qr(Qred, Rr, A, mw, nw);
-		src = Rr; rs = (long long)nw; cs = 1; mdot = nw;
+		// Jacobi runs on the columns of R^T (the rows of R), not of R: after a QR step the rows of the triangular factor are
+		// far closer to the left singular directions than its columns are to the right ones (Drmac & Veselic's
+		// pre-conditioning), so graded inputs need half the sweeps.  The two vector parts swap roles in extract().
+		flipped = c.svd_flip != 0;
+		src = Rr; mdot = nw;
+		if (flipped) { rs = 1; cs = (long long)nw; } else { rs = (long long)nw; cs = 1; }
 	} else {
+		flipped = false;
 		src = A; mdot = mw;
 		if (swapped) { rs = 1; cs = (long long)n; } else { rs = (long long)n; cs = 1; }
 	}
@@ -525,7 +532,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	// G0 V = X recomputed from the untouched input (transposed storage: XT = VT G0^T)
 	auto recompute_left = [&]() {
 		double* VT = GT.p + voff;
-		if (reduced) gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, Rr, nw, true, 0.0);
+		if (reduced) gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, Rr, nw, !flipped, 0.0);
 		else if (!swapped) gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, A, n, true, 0.0);
 		else gemm(GT.p, ld, nw, mdot, 1.0, VT, ld, false, nw, A, n, false, 0.0);
 		scale_block_by_dev(GT.p, ld, nw, mdot, scale.p);
@@ -664,6 +671,10 @@ void Svd::extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, 
 		if (!reduced) { outX = Vt; sxi = 1; sxr = (long long)n; }
 		scale_x = scale_vt;
 		outV = U; svc = (long long)k; svr = 1; scale_v = scale_u;
+	}
+	if (flipped) {
+		// working matrix was R^T: its left vectors (X part) are the right vectors of R and vice versa
+		std::swap(outX, outV); std::swap(sxi, svc); std::swap(sxr, svr); std::swap(scale_x, scale_v);
 	}
 	svd_extract_kernel<<<unsigned(k), 256, 0, c.stream>>>(GT, int(ld), int(mdot), int(voff), int(nw), Ssorted, p, outX, sxi, sxr, scale_x,
 	                                                       outV, svc, svr, scale_v, dS, soft_threshold, scale.p);

@@ -57,6 +57,8 @@ struct Context {
 	int svd_persistent = 1;
 	int tt_svd_polish = 1;         // polish level of the SVDs inside round() / TT-SVD / DMRG splits (see Svd::polish)
 	int svd_polish = 1;            // Newton-Schulz re-orthogonalisation of V + recomputed left part after the Jacobi sweeps
+	int svd_flip = 1;              // Jacobi on the rows of the triangular factor after a QR reduction (pre-conditioning)
+	int svd_square_qr = 1;         // square inputs also go through the QR reduction (needed for svd_flip)
 	int svd_recursive = 1;         // recursive bipartite tournament with point-to-point block flags (power-of-two block counts)
 	int svd_mixed = 0;             // FP32 pre-conditioning sweeps + FP64 finishing sweeps (measured: no gain, kept as an experiment)
 	int svd_mixed_min = 64;        // smallest column count for the mixed path
@@ -146,7 +148,7 @@ struct Svd {
 	                               // factors, per-call layer); 1: without the clean-up sweep (sweep layer: exact projection, left vectors
 	                               // orthogonal to ~1e-12); 0: none
 	// internals
-	bool swapped = false, reduced = false;
+	bool swapped = false, reduced = false, flipped = false;
 	size_t mw = 0, nw = 0, npad = 0, mt = 0, mdot = 0, voff = 0, ld = 0;
 	DBuf GT, Qred, Ssorted, perm, scale;   // scale: [2^-e, 2^e] of the Jacobi input (squares must not overflow)
 	void factor(const double* A, size_t m, size_t n);
