@@ -12,6 +12,7 @@
 //   qr_update_kernel  sums the partials, W2 = op(T) W, C -= V W2
 // The trailing update and the formation of the explicit thin Q use the same two kernels (op(T) = T^T resp. T).
 #include "xb_internal.cuh"
+#include <cooperative_groups.h>
 
 namespace xb {
 
@@ -130,6 +131,144 @@ __global__ void __launch_bounds__(QR_PANEL_WARPS * 32) qr_panel_kernel(double* _
 	}
 }
 
+
+// ---- cluster panel kernel ---------------------------------------------------------------------------------------------
+// The one-CTA panel kernel above is bound by the FP64 issue rate of a single SM and by its shared-memory read-modify-write
+// chain.  This variant spreads the panel rows over a thread-block cluster of QRC_CS CTAs (one SM each) and keeps every
+// row strip in REGISTERS (lane = panel column, RPT rows per thread); a column entry of another lane comes from a shuffle.
+// Per column there is ONE fused pass — apply reflector j, accumulate g_c = x_{j+1}^T a_c for the next column on the fly —
+// and one cluster-wide reduction: CTA partials are written into every CTA's shared memory (DSMEM), one cluster barrier,
+// then every warp derives beta / tau / w redundantly.  Lanes c < j are idle in the Householder step, so they accumulate
+// v_c^T x_j in the same pass, which gives column j of V^T V (needed for the compact-WY T) without a pass over V.
+constexpr int QRC_CS = 8;        // CTAs per cluster (portable maximum)
+constexpr int QRC_WARPS = 8;     // warps per CTA
+
+template <int RPT>
+__global__ void __cluster_dims__(QRC_CS, 1, 1) __launch_bounds__(QRC_WARPS * 32)
+qr_panel_cluster_kernel(double* __restrict__ W, const long long ldw, const int mp, const int nbe, double* __restrict__ Vbuf,
+                        double* __restrict__ Tout) {
+	namespace cg = cooperative_groups;
+	cg::cluster_group cluster = cg::this_cluster();
+	__shared__ double red[QRC_WARPS][32];
+	__shared__ double slots[2][QRC_CS][32];     // [parity][source CTA][lane] partial sums of the current column step
+	__shared__ double rowbuf[2][32];            // [parity][lane] row j of the panel as it stands before step j
+	__shared__ double GVs[32][33], Ts[32][33];  // used by CTA 0 only
+	__shared__ double s_tau[32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int rank = int(cluster.block_rank());
+	const int row0 = (rank * QRC_WARPS + warp) * RPT;
+	const bool active = lane < nbe;
+	const int kmax = min(nbe, mp);
+
+	double P[RPT];
+#pragma unroll
+	for (int k = 0; k < RPT; ++k) { const int i = row0 + k; P[k] = (active && i < mp) ? W[(long long)i * ldw + lane] : 0.0; }
+	if (rank == 0) {
+		for (int e = threadIdx.x; e < 32 * 33; e += blockDim.x) { (&GVs[0][0])[e] = 0.0; (&Ts[0][0])[e] = 0.0; }
+		if (threadIdx.x < 32) s_tau[threadIdx.x] = 0.0;
+	}
+	// g for column 0 (lane 0 accumulates the tail below the diagonal only); the owner of row 0 publishes it
+	double g = 0.0;
+#pragma unroll
+	for (int k = 0; k < RPT; ++k) {
+		const int i = row0 + k;
+		const double pn = __shfl_sync(0xffffffffu, P[k], 0);
+		if (!(lane == 0 && i == 0)) g += pn * P[k];
+	}
+	cluster.sync();                              // every CTA of the cluster is resident before the first remote store
+	if (row0 == 0) {
+#pragma unroll
+		for (int c = 0; c < QRC_CS; ++c) *cluster.map_shared_rank(&rowbuf[0][lane], c) = P[0];
+	}
+
+	for (int j = 0; j < kmax; ++j) {
+		const int par = j & 1;
+		red[warp][lane] = g;
+		__syncthreads();
+		if (warp == 0) {
+			const double s = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) + ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
+#pragma unroll
+			for (int c = 0; c < QRC_CS; ++c) *cluster.map_shared_rank(&slots[par][rank][lane], c) = s;
+		}
+		cluster.sync();
+		const double G = ((slots[par][0][lane] + slots[par][1][lane]) + (slots[par][2][lane] + slots[par][3][lane])) +
+		                 ((slots[par][4][lane] + slots[par][5][lane]) + (slots[par][6][lane] + slots[par][7][lane]));
+		const double rowj = rowbuf[par][lane];
+		const double tail = __shfl_sync(0xffffffffu, G, j);
+		const double alpha = __shfl_sync(0xffffffffu, rowj, j);
+		const double sigma = tail + alpha * alpha;
+		double beta = alpha, tau = 0.0, scl = 0.0;
+		if (tail > 0.0 && j + 1 < mp) {
+			// beta = -sign(alpha) ||x||, tau = 1 + |alpha|/||x||, 1/(alpha - beta) = sign(alpha)/(|alpha| + ||x||)
+			const double rs = rsqrt(sigma), nrmx = sigma * rs;
+			beta = -copysign(nrmx, alpha);
+			tau = 1.0 + fabs(alpha) * rs;
+			scl = copysign(1.0, alpha) / (fabs(alpha) + nrmx);
+		}
+		const double wv = (lane > j && tau != 0.0) ? tau * (G - beta * rowj) * scl : 0.0;
+		if (rank == 0 && warp == 0) {
+			// v_c^T v_j = v_c[j] + scl * (v_c^T x - v_c[j] * alpha)   for c < j   (rowj holds v_c[j] in lane c)
+			if (lane < j) GVs[lane][j] = (tau != 0.0) ? rowj + scl * (G - rowj * alpha) : 0.0;
+			if (lane == 0) s_tau[j] = tau;
+		}
+		// apply H_j to the strip, store v_j / beta in column j, accumulate the sums of step j + 1
+		g = 0.0;
+		const int jn = j + 1;
+#pragma unroll
+		for (int k = 0; k < RPT; ++k) {
+			const int i = row0 + k;
+			const double pj = __shfl_sync(0xffffffffu, P[k], j);
+			if (i >= j) {
+				const double vi = (i == j) ? 1.0 : pj * scl;
+				if (lane > j) P[k] -= wv * vi;
+				else if (lane == j) P[k] = (i == j) ? beta : ((tau != 0.0) ? vi : 0.0);
+			}
+			const double pn = __shfl_sync(0xffffffffu, P[k], jn & 31);
+			if (i >= jn && !(lane == jn && i == jn)) g += pn * P[k];
+			if (i == jn && jn < kmax) {
+#pragma unroll
+				for (int c = 0; c < QRC_CS; ++c) *cluster.map_shared_rank(&rowbuf[par ^ 1][lane], c) = P[k];
+			}
+		}
+	}
+
+	// results: panel in place (R on and above the diagonal, reflectors below), explicit V, compact-WY T
+#pragma unroll
+	for (int k = 0; k < RPT; ++k) {
+		const int i = row0 + k;
+		if (i < mp) {
+			if (active) W[(long long)i * ldw + lane] = P[k];
+			Vbuf[(long long)i * QR_NB + lane] = (lane >= kmax || i < lane) ? 0.0 : ((i == lane) ? 1.0 : P[k]);
+		}
+	}
+	if (rank == 0 && warp == 0) {
+		__syncwarp();
+		// T(0:j, j) = -tau_j * T(0:j, 0:j) * GV(0:j, j) ; T(j, j) = tau_j      (GV strictly upper, zero elsewhere)
+		for (int j = 0; j < kmax; ++j) {
+			double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+			for (int c = 0; c < 32; c += 2) { t0 += Ts[lane][c] * GVs[c][j]; t1 += Ts[lane][c + 1] * GVs[c + 1][j]; }
+			__syncwarp();
+			if (lane < j) Ts[lane][j] = -s_tau[j] * (t0 + t1);
+			else if (lane == j) Ts[j][j] = s_tau[j];
+			__syncwarp();
+		}
+		for (int e = lane; e < 32 * 32; e += 32) Tout[e] = Ts[e >> 5][e & 31];
+	}
+}
+
+static bool launch_panel_cluster(double* Wpanel, long long ldw, size_t mp, size_t nbe, double* Vp, double* Tp) {
+	if (!ctx().qr_cluster || mp < 128 || mp > size_t(QRC_CS * QRC_WARPS * 32)) return false;
+	const size_t rpt = (mp + QRC_CS * QRC_WARPS - 1) / (QRC_CS * QRC_WARPS);
+	cudaStream_t st = ctx().stream;
+	if (rpt <= 2) qr_panel_cluster_kernel<2><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp);
+	else if (rpt <= 4) qr_panel_cluster_kernel<4><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp);
+	else if (rpt <= 8) qr_panel_cluster_kernel<8><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp);
+	else if (rpt <= 16) qr_panel_cluster_kernel<16><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp);
+	else qr_panel_cluster_kernel<32><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp);
+	return true;
+}
+
 // Wp[chunk][kk][c] = sum_{rows of chunk} V[row][kk] * C[row][c]     block: 32 x 32 threads (warp = kk, lane = c)
 __global__ void __launch_bounds__(1024) qr_vtc_kernel(const double* __restrict__ Vbuf, const double* __restrict__ C, const long long ldc,
                                                      const int mp, const int nc, double* __restrict__ Wp, const int ncpad) {
@@ -238,7 +377,8 @@ void qr(double* Q, double* R, const double* A, size_t m, size_t n) {
 		double* Vp = Vall.p + p * m * QR_NB;
 		double* Tp = Tall.p + p * QR_NB * QR_NB;
 		const size_t need = fixed_smem + mp * QR_NB * sizeof(double);
-		if (need <= smem_cap) {
+		if (launch_panel_cluster(Wpanel, (long long)n, mp, nbe, Vp, Tp)) {
+		} else if (need <= smem_cap) {
 			qr_panel_kernel<true><<<1, QR_PANEL_WARPS * 32, need, ctx().stream>>>(Wpanel, (long long)n, int(mp), int(nbe), Vp, Tp);
 		} else {
 			qr_panel_kernel<false><<<1, QR_PANEL_WARPS * 32, fixed_smem, ctx().stream>>>(Wpanel, (long long)n, int(mp), int(nbe), Vp, Tp);

@@ -59,6 +59,7 @@ struct Context {
 	int svd_polish = 1;            // Newton-Schulz re-orthogonalisation of V + recomputed left part after the Jacobi sweeps
 	int svd_flip = 1;              // Jacobi on the rows of the triangular factor after a QR reduction (pre-conditioning)
 	int svd_square_qr = 1;         // square inputs also go through the QR reduction (needed for svd_flip)
+	int qr_cluster = 1;            // QR panels of 128..2048 rows on a thread-block cluster (registers + DSMEM reduction)
 	int svd_recursive = 1;         // recursive bipartite tournament with point-to-point block flags (power-of-two block counts)
 	int svd_mixed = 0;             // FP32 pre-conditioning sweeps + FP64 finishing sweeps (measured: no gain, kept as an experiment)
 	int svd_mixed_min = 64;        // smallest column count for the mixed path
