@@ -3,9 +3,10 @@ import sys; sys.path.insert(0, __import__("os").path.dirname(__import__("os").pa
 import numpy as np, xerus_b200 as xb
 xb.init(0)
 rng=np.random.default_rng(0)
-for (m,n) in [(512,256),(512,32),(130,40),(256,256),(1000,100),(2048,64),(1500,33),(128,128),(3000,64)]:
+shapes = [tuple(map(int, a.split('x'))) for a in sys.argv[1:]] or [(512,256),(512,32),(130,40),(256,256),(1000,100),(2048,64),(1500,33),(128,128),(3000,64)]
+for (m,n) in shapes:
     A=rng.standard_normal((m,n))
-    for cl in [0,1]:
+    for cl in ([1] if len(sys.argv) > 1 else [0,1]):
         xb.set_option("qr_cluster",cl)
         xb.blasWrapper.qr(A)
         xb.profile_enable(True)

@@ -146,7 +146,7 @@ constexpr int QRC_WARPS = 8;     // warps per CTA
 template <int RPT>
 __global__ void __cluster_dims__(QRC_CS, 1, 1) __launch_bounds__(QRC_WARPS * 32)
 qr_panel_cluster_kernel(double* __restrict__ W, const long long ldw, const int mp, const int nbe, double* __restrict__ Vbuf,
-                        double* __restrict__ Tout) {
+                        double* __restrict__ Tout, long long* __restrict__ dbg) {
 	namespace cg = cooperative_groups;
 	cg::cluster_group cluster = cg::this_cluster();
 	__shared__ double red[QRC_WARPS][32];
@@ -156,13 +156,16 @@ qr_panel_cluster_kernel(double* __restrict__ W, const long long ldw, const int m
 	__shared__ double s_tau[32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int rank = int(cluster.block_rank());
-	const int row0 = (rank * QRC_WARPS + warp) * RPT;
+	// row of slot k of this warp: k * 64 + gw (cyclic over the 64 warps of the cluster).  Only slot 0 can hold one of the
+	// top 32 rows, so slots 1.. are always strictly below the current and the next column's diagonal: no masking there.
+	constexpr int NWC = QRC_CS * QRC_WARPS;
+	const int gw = rank * QRC_WARPS + warp;
 	const bool active = lane < nbe;
 	const int kmax = min(nbe, mp);
 
 	double P[RPT];
 #pragma unroll
-	for (int k = 0; k < RPT; ++k) { const int i = row0 + k; P[k] = (active && i < mp) ? W[(long long)i * ldw + lane] : 0.0; }
+	for (int k = 0; k < RPT; ++k) { const int i = k * NWC + gw; P[k] = (active && i < mp) ? W[(long long)i * ldw + lane] : 0.0; }
 	if (rank == 0) {
 		for (int e = threadIdx.x; e < 32 * 33; e += blockDim.x) { (&GVs[0][0])[e] = 0.0; (&Ts[0][0])[e] = 0.0; }
 		if (threadIdx.x < 32) s_tau[threadIdx.x] = 0.0;
@@ -171,18 +174,21 @@ qr_panel_cluster_kernel(double* __restrict__ W, const long long ldw, const int m
 	double g = 0.0;
 #pragma unroll
 	for (int k = 0; k < RPT; ++k) {
-		const int i = row0 + k;
 		const double pn = __shfl_sync(0xffffffffu, P[k], 0);
-		if (!(lane == 0 && i == 0)) g += pn * P[k];
+		if (!(lane == 0 && k == 0 && gw == 0)) g += pn * P[k];
 	}
 	cluster.sync();                              // every CTA of the cluster is resident before the first remote store
-	if (row0 == 0) {
+	if (gw == 0) {
 #pragma unroll
 		for (int c = 0; c < QRC_CS; ++c) *cluster.map_shared_rank(&rowbuf[0][lane], c) = P[0];
 	}
 
+	// optional phase timing (XB_QR_TIMING=1): cycles of [reduce + publish | cluster barrier | parameters | update]
+	const bool timing = dbg != nullptr && rank == 0 && threadIdx.x == 0;
+	long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0;
 	for (int j = 0; j < kmax; ++j) {
 		const int par = j & 1;
+		if (timing) t0 = clock64();
 		red[warp][lane] = g;
 		__syncthreads();
 		if (warp == 0) {
@@ -190,7 +196,9 @@ qr_panel_cluster_kernel(double* __restrict__ W, const long long ldw, const int m
 #pragma unroll
 			for (int c = 0; c < QRC_CS; ++c) *cluster.map_shared_rank(&slots[par][rank][lane], c) = s;
 		}
+		if (timing) { const long long t1 = clock64(); tk[0] += t1 - t0; t0 = t1; }
 		cluster.sync();
+		if (timing) { const long long t1 = clock64(); tk[1] += t1 - t0; t0 = t1; }
 		const double G = ((slots[par][0][lane] + slots[par][1][lane]) + (slots[par][2][lane] + slots[par][3][lane])) +
 		                 ((slots[par][4][lane] + slots[par][5][lane]) + (slots[par][6][lane] + slots[par][7][lane]));
 		const double rowj = rowbuf[par][lane];
@@ -203,39 +211,49 @@ qr_panel_cluster_kernel(double* __restrict__ W, const long long ldw, const int m
 			const double rs = rsqrt(sigma), nrmx = sigma * rs;
 			beta = -copysign(nrmx, alpha);
 			tau = 1.0 + fabs(alpha) * rs;
-			scl = copysign(1.0, alpha) / (fabs(alpha) + nrmx);
+			scl = copysign(__drcp_rn(fabs(alpha) + nrmx), alpha);
 		}
-		const double wv = (lane > j && tau != 0.0) ? tau * (G - beta * rowj) * scl : 0.0;
+		// w_c = tau * v^T a_c for the columns right of j; zero elsewhere, and zero altogether when tau == 0 (then scl == 0 too)
+		const double wv = (lane > j) ? (tau * scl) * (G - beta * rowj) : 0.0;
 		if (rank == 0 && warp == 0) {
 			// v_c^T v_j = v_c[j] + scl * (v_c^T x - v_c[j] * alpha)   for c < j   (rowj holds v_c[j] in lane c)
 			if (lane < j) GVs[lane][j] = (tau != 0.0) ? rowj + scl * (G - rowj * alpha) : 0.0;
 			if (lane == 0) s_tau[j] = tau;
 		}
-		// apply H_j to the strip, store v_j / beta in column j, accumulate the sums of step j + 1
-		g = 0.0;
+		if (timing) { const long long t1 = clock64(); tk[2] += t1 - t0 + (long long)(wv != wv); t0 = t1; }
+		// apply H_j to the strip, store v_j / beta in column j, accumulate the sums of step j + 1.  The shuffles of all rows
+		// are issued back to back (a shuffle inside the per-row dependency chain would serialise the rows).
 		const int jn = j + 1;
+		double pj[RPT];
 #pragma unroll
-		for (int k = 0; k < RPT; ++k) {
-			const int i = row0 + k;
-			const double pj = __shfl_sync(0xffffffffu, P[k], j);
-			if (i >= j) {
-				const double vi = (i == j) ? 1.0 : pj * scl;
-				if (lane > j) P[k] -= wv * vi;
-				else if (lane == j) P[k] = (i == j) ? beta : ((tau != 0.0) ? vi : 0.0);
-			}
-			const double pn = __shfl_sync(0xffffffffu, P[k], jn & 31);
-			if (i >= jn && !(lane == jn && i == jn)) g += pn * P[k];
-			if (i == jn && jn < kmax) {
+		for (int k = 0; k < RPT; ++k) pj[k] = __shfl_sync(0xffffffffu, P[k], j);
+		// slot 0: row gw may be above (done), on, or below the diagonal — warp-uniform branches
+		if (gw == j) P[0] = (lane > j) ? P[0] - wv : ((lane == j) ? beta : P[0]);
+		else if (gw > j) { const double vi = pj[0] * scl; P[0] = (lane == j) ? vi : P[0] - wv * vi; }
 #pragma unroll
-				for (int c = 0; c < QRC_CS; ++c) *cluster.map_shared_rank(&rowbuf[par ^ 1][lane], c) = P[k];
-			}
+		for (int k = 1; k < RPT; ++k) { const double vi = pj[k] * scl; P[k] = (lane == j) ? vi : P[k] - wv * vi; }
+		if (timing) { const long long t1 = clock64(); tk[4] += t1 - t0 + (long long)(P[0] != P[0]) + (long long)(P[RPT - 1] != P[RPT - 1]); t0 = t1; }
+		double pn[RPT];
+#pragma unroll
+		for (int k = 0; k < RPT; ++k) pn[k] = __shfl_sync(0xffffffffu, P[k], jn & 31);
+		double ga[4] = {0.0, 0.0, 0.0, 0.0};
+		if (gw > jn || (gw == jn && lane != jn)) ga[0] = pn[0] * P[0];      // row jn: lane jn keeps the tail below the diagonal only
+#pragma unroll
+		for (int k = 1; k < RPT; ++k) ga[k & 3] += pn[k] * P[k];
+		g = (ga[0] + ga[1]) + (ga[2] + ga[3]);
+		if (timing) { const long long t1 = clock64(); tk[5] += t1 - t0 + (long long)(g != g); t0 = t1; }
+		if (gw == jn && jn < kmax) {
+#pragma unroll
+			for (int c = 0; c < QRC_CS; ++c) *cluster.map_shared_rank(&rowbuf[par ^ 1][lane], c) = P[0];
 		}
+		if (timing) { const long long t1 = clock64(); tk[3] += t1 - t0; t0 = t1; }
 	}
+	if (timing) { for (int q = 0; q < 8; ++q) dbg[q] = tk[q]; }
 
 	// results: panel in place (R on and above the diagonal, reflectors below), explicit V, compact-WY T
 #pragma unroll
 	for (int k = 0; k < RPT; ++k) {
-		const int i = row0 + k;
+		const int i = k * NWC + gw;
 		if (i < mp) {
 			if (active) W[(long long)i * ldw + lane] = P[k];
 			Vbuf[(long long)i * QR_NB + lane] = (lane >= kmax || i < lane) ? 0.0 : ((i == lane) ? 1.0 : P[k]);
@@ -261,11 +279,16 @@ static bool launch_panel_cluster(double* Wpanel, long long ldw, size_t mp, size_
 	if (!ctx().qr_cluster || mp < 128 || mp > size_t(QRC_CS * QRC_WARPS * 32)) return false;
 	const size_t rpt = (mp + QRC_CS * QRC_WARPS - 1) / (QRC_CS * QRC_WARPS);
 	cudaStream_t st = ctx().stream;
-	if (rpt <= 2) qr_panel_cluster_kernel<2><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp);
-	else if (rpt <= 4) qr_panel_cluster_kernel<4><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp);
-	else if (rpt <= 8) qr_panel_cluster_kernel<8><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp);
-	else if (rpt <= 16) qr_panel_cluster_kernel<16><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp);
-	else qr_panel_cluster_kernel<32><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp);
+	static const bool timing = getenv("XB_QR_TIMING") != nullptr;
+	long long* dbg = nullptr;
+	if (timing) dbg = static_cast<long long*>(dalloc_bytes(8 * sizeof(long long)));
+	struct Report { long long* d; size_t mp; ~Report() { if (!d) return; long long h[8]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[qr panel] mp=%zu cycles: reduce+publish %lld barrier %lld params %lld apply %lld next-sums %lld row-publish %lld\n", mp, h[0], h[1], h[2], h[4], h[5], h[3]); dfree(d); } } report{dbg, mp};
+	if (rpt <= 2) qr_panel_cluster_kernel<2><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp, dbg);
+	else if (rpt <= 4) qr_panel_cluster_kernel<4><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp, dbg);
+	else if (rpt <= 8) qr_panel_cluster_kernel<8><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp, dbg);
+	else if (rpt <= 16) qr_panel_cluster_kernel<16><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp, dbg);
+	else qr_panel_cluster_kernel<32><<<QRC_CS, QRC_WARPS * 32, 0, st>>>(Wpanel, ldw, int(mp), int(nbe), Vp, Tp, dbg);
 	return true;
 }
 
@@ -338,8 +361,120 @@ __global__ void diag_minmax_kernel(const double* __restrict__ A, const size_t k,
 	if (threadIdx.x == 0) { out[0] = mn; out[1] = mx; }
 }
 
+
+// ---- cluster block-reflector kernel -----------------------------------------------------------------------------------
+// C -= V * (op(T) * (V^T C)) for one 32-column block of C per cluster: the QRC_CS CTAs of a cluster split the rows, each
+// forms its partial V^T C (32 x 32), the partials meet in an L2-resident scratch across ONE cluster barrier, every CTA
+// sums them in a fixed order (deterministic), applies op(T) and updates its rows — which are still in shared memory.
+// One launch instead of two, no second pass over C from global memory.
+constexpr int QRA_TILE = 64;
+constexpr int QRA_THREADS = 256;
+constexpr size_t QRA_SMEM = (size_t(QRA_TILE) * 32 + size_t(QRA_TILE) * 33 + 3 * 32 * 33) * sizeof(double);
+
+__global__ void __cluster_dims__(QRC_CS, 1, 1) __launch_bounds__(QRA_THREADS)
+qr_apply_cluster_kernel(double* __restrict__ C, const long long ldc, const int mp, const int nc, const double* __restrict__ Vbuf,
+                        const double* __restrict__ T, const int transT, double* Wp) {
+	namespace cg = cooperative_groups;
+	cg::cluster_group cluster = cg::this_cluster();
+	extern __shared__ __align__(16) double qra_sm[];
+	double (*Vs)[32] = reinterpret_cast<double (*)[32]>(qra_sm);
+	double (*Cs)[33] = reinterpret_cast<double (*)[33]>(qra_sm + QRA_TILE * 32);
+	double (*Ws)[33] = reinterpret_cast<double (*)[33]>(qra_sm + QRA_TILE * 32 + QRA_TILE * 33);
+	double (*W2s)[33] = Ws + 32;
+	double (*Tsm)[33] = Ws + 64;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int rank = int(cluster.block_rank()), cb = blockIdx.x / QRC_CS;
+	const int c = cb * 32 + lane;
+	const bool cok = c < nc;
+	const int rpc = (mp + QRC_CS - 1) / QRC_CS;
+	const int r_lo = min(mp, rank * rpc), r_hi = min(mp, r_lo + rpc);
+	const int ntiles = (r_hi - r_lo + QRA_TILE - 1) / QRA_TILE;
+	auto load_tile = [&](int t) {
+		for (int ii = warp; ii < QRA_TILE; ii += QRA_THREADS / 32) {
+			const int row = r_lo + t * QRA_TILE + ii;
+			const bool ok = row < r_hi;
+			Vs[ii][lane] = ok ? Vbuf[(long long)row * QR_NB + lane] : 0.0;
+			Cs[ii][lane] = (ok && cok) ? C[(long long)row * ldc + c] : 0.0;
+		}
+	};
+	for (int e = threadIdx.x; e < 32 * 32; e += QRA_THREADS) Tsm[e >> 5][e & 31] = T[e];
+	// phase 1: partial W = V^T C over this CTA's rows; thread (warp, lane) owns W[4 warp .. 4 warp + 3][lane]
+	double acc[4] = {0.0, 0.0, 0.0, 0.0};
+	for (int t = 0; t < ntiles; ++t) {
+		if (t > 0) __syncthreads();
+		load_tile(t);
+		__syncthreads();
+#pragma unroll 8
+		for (int ii = 0; ii < QRA_TILE; ++ii) {
+			const double cv = Cs[ii][lane];
+			const double2 va = *reinterpret_cast<const double2*>(&Vs[ii][4 * warp]);
+			const double2 vb = *reinterpret_cast<const double2*>(&Vs[ii][4 * warp + 2]);
+			acc[0] += va.x * cv; acc[1] += va.y * cv; acc[2] += vb.x * cv; acc[3] += vb.y * cv;
+		}
+	}
+	double* mine = Wp + ((size_t)blockIdx.x * 32 + 4 * warp) * 32 + lane;
+#pragma unroll
+	for (int q = 0; q < 4; ++q) mine[q * 32] = acc[q];
+	__threadfence();
+	cluster.sync();
+	// phase 2: W = sum of the partials (fixed order), W2 = op(T) W
+	{
+		const double* base = Wp + ((size_t)cb * QRC_CS * 32 + 4 * warp) * 32 + lane;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			double s = 0.0;
+#pragma unroll
+			for (int r = 0; r < QRC_CS; ++r) s += __ldcg(base + (size_t)r * 1024 + q * 32);
+			Ws[4 * warp + q][lane] = s;
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		const int kk = 4 * warp + q;
+		double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+		for (int l = 0; l < 32; l += 2) {
+			a0 += (transT ? Tsm[l][kk] : Tsm[kk][l]) * Ws[l][lane];
+			a1 += (transT ? Tsm[l + 1][kk] : Tsm[kk][l + 1]) * Ws[l + 1][lane];
+		}
+		W2s[kk][lane] = a0 + a1;
+	}
+	__syncthreads();
+	double w2[32];
+#pragma unroll
+	for (int kk = 0; kk < 32; ++kk) w2[kk] = W2s[kk][lane];
+	// phase 3: C -= V W2 on this CTA's rows
+	for (int t = 0; t < ntiles; ++t) {
+		if (ntiles > 1) { __syncthreads(); load_tile(t); __syncthreads(); }
+		for (int ii = warp; ii < QRA_TILE; ii += QRA_THREADS / 32) {
+			const int row = r_lo + t * QRA_TILE + ii;
+			if (row < r_hi && cok) {
+				double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+				for (int kk = 0; kk < 32; kk += 2) {
+					const double2 v = *reinterpret_cast<const double2*>(&Vs[ii][kk]);
+					d0 += v.x * w2[kk]; d1 += v.y * w2[kk + 1];
+				}
+				C[(long long)row * ldc + c] = Cs[ii][lane] - (d0 + d1);
+			}
+		}
+	}
+}
+
 static void apply_block_reflector(double* C, size_t ldc, size_t mp, size_t nc, const double* Vbuf, const double* T, bool transT, double* Wp) {
 	if (nc == 0 || mp == 0) return;
+	if (ctx().qr_cluster && mp >= 64) {
+		static bool attr_set = false;
+		if (!attr_set) {
+			XB_CUDA(cudaFuncSetAttribute(qr_apply_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(QRA_SMEM)));
+			attr_set = true;
+		}
+		const unsigned ncb = unsigned((nc + 31) / 32);
+		qr_apply_cluster_kernel<<<ncb * QRC_CS, QRA_THREADS, QRA_SMEM, ctx().stream>>>(C, (long long)ldc, int(mp), int(nc), Vbuf, T, transT ? 1 : 0, Wp);
+		XB_LAUNCH_CHECK();
+		return;
+	}
 	const unsigned ncb = unsigned((nc + 31) / 32), nch = unsigned((mp + QR_CHUNK - 1) / QR_CHUNK);
 	const int ncpad = int(ncb * 32);
 	dim3 grid(ncb, nch);
@@ -358,7 +493,7 @@ void qr(double* Q, double* R, const double* A, size_t m, size_t n) {
 	DBuf W(m * n), Vall(npanels * m * QR_NB), Tall(npanels * QR_NB * QR_NB);
 	const size_t nch_max = (m + QR_CHUNK - 1) / QR_CHUNK;
 	const size_t ncpad_max = ((std::max(n, k) + 31) / 32) * 32;
-	DBuf Wp(nch_max * 32 * ncpad_max);
+	DBuf Wp(std::max<size_t>(nch_max, QRC_CS) * 32 * ncpad_max);     // partial V^T C: [row chunk or cluster rank][32][columns]
 	// work on A * 2^-e (exact): the reflector norms are sums of squares and TT cores carry norms like 1e33 .. 1e150
 	DBuf sc(2);
 	amax_scale_dev(sc, A, m * n);
