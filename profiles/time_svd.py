@@ -4,7 +4,8 @@ import sys; sys.path.insert(0, __import__("os").path.dirname(__import__("os").pa
 import numpy as np, xerus_b200 as xb
 xb.init(0)
 rng=np.random.default_rng(0)
-for (m,n) in [(256,256),(512,512),(128,128),(64,64),(300,100)]:
+shapes = [tuple(map(int, a.split('x'))) for a in sys.argv[1:]] or [(256,256),(512,512),(128,128),(64,64),(300,100)]
+for (m,n) in shapes:
     A=rng.standard_normal((m,n))
     for rec in [0,1]:
         xb.set_option("svd_recursive",rec)

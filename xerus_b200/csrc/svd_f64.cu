@@ -329,6 +329,346 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(T* __restrict__
 	if (timing) { info[4] = (unsigned)(tk_load >> 10); info[5] = (unsigned)(tk_inner >> 10); info[6] = (unsigned)(tk_store >> 10); info[7] = (unsigned)(tk_sync >> 10); }
 }
 
+// D(8x8) += A(8x4) B(4x8) on the FP64 tensor pipe.  Lane (g = lane >> 2, t = lane & 3) holds A[g][t], B[t][g], D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, const double a, const double b) {
+	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// V_new(r, :) = sum_r' Js(r, r') V_old(r', :) for the N = 8 MT = 4 KT resident rows (accumulated-rotation part).  Every warp
+// owns 8-element tiles of the row length: it loads its tile of all N rows, multiplies on the tensor pipe, writes the tile back.
+template <int MT, int KT>
+__device__ __forceinline__ void apply_rotations_to_v(double* __restrict__ Sv, const int lds, const double* __restrict__ Js, const int ldj,
+                                                    const int ntiles, const int warp, const int nwarps, const int lane) {
+	const int g = lane >> 2, t = lane & 3;
+	double afr[MT][KT];
+#pragma unroll
+	for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+		for (int kt = 0; kt < KT; ++kt) afr[mt][kt] = Js[(8 * mt + g) * ldj + 4 * kt + t];
+	for (int tile = warp; tile < ntiles; tile += nwarps) {
+		double* base = Sv + 8 * tile;
+		double bfr[KT];
+#pragma unroll
+		for (int kt = 0; kt < KT; ++kt) bfr[kt] = base[(size_t)(4 * kt + t) * lds + g];
+		double acc[MT][2];
+#pragma unroll
+		for (int mt = 0; mt < MT; ++mt) { acc[mt][0] = 0.0; acc[mt][1] = 0.0; }
+#pragma unroll
+		for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+			for (int mt = 0; mt < MT; ++mt) dmma_884(acc[mt][0], acc[mt][1], afr[mt][kt], bfr[kt]);
+		__syncwarp();
+#pragma unroll
+		for (int mt = 0; mt < MT; ++mt) *reinterpret_cast<double2*>(base + (size_t)(8 * mt + g) * lds + 2 * t) = make_double2(acc[mt][0], acc[mt][1]);
+	}
+}
+
+// ---- specialised persistent kernel (FP64, both row parts 64 * EP2 doubles long) ------------------------------------------
+// Same algorithm and schedule as jacobi_persistent_kernel, rebuilt around what bounds an inner round on sm_100a (measured,
+// profiles/micro/fp64_micro.cu): the shared-memory pipe (128 B/clk: moving both 4 KB rows of 8 pairs in and out is 1024
+// cycles), instruction issue, and a ~650-cycle dependent chain (load, dot, 5-stage butterfly, two rsqrt, rotate, barrier).
+//  * row length is a template parameter, a lane owns PAIRS of consecutive elements: 128-bit accesses, no bounds predicates;
+//  * in a cross visit (block p against block q) warp w keeps column w of p in REGISTERS for all rounds; only the q column
+//    travels through shared memory;
+//  * JACC (8-column blocks): the accumulated-rotation part of the rows is not rotated pair by pair.  The rotations of a visit
+//    are multiplied up in a 16 x 16 matrix (rows of 16 entries) and applied once per visit as Js * V with DMMA: the same
+//    arithmetic, off the latency chain and off the shared-memory pipe.
+template <int EP2, int MAXT, bool JACC>
+__global__ void __launch_bounds__(MAXT) jacobi_fast_kernel(double* __restrict__ GT, const int bw, const int nblk, const double tol2, const double big2,
+                                                          unsigned int* __restrict__ counters, unsigned int* __restrict__ info,
+                                                          const int max_sweeps, unsigned int* ready, const int recursive) {
+	constexpr int LD = 128 * EP2;               // doubles per row in global memory: [x : 64 EP2 | v : 64 EP2]
+	constexpr int LDS = LD + 4;                 // shared-memory row stride: 4 rows x 8 elements of a DMMA operand on distinct banks
+	constexpr int V2 = 32 * EP2;                // offset of the v part in double2 units
+	extern __shared__ double S_fast[];
+	double* S = S_fast;
+	__shared__ unsigned int s_rot, s_big;
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	const int N = 2 * bw;
+	const int ldj = N + 4;
+	double* nrm = S + (size_t)N * LDS;
+	unsigned short* sched = reinterpret_cast<unsigned short*>(nrm + N + (N & 1));
+	double* Js = reinterpret_cast<double*>(reinterpret_cast<char*>(sched) + ((size_t(N - 1) * bw * sizeof(unsigned short) + 15) / 16) * 16);
+	for (int e = threadIdx.x; e < (N - 1) * bw; e += blockDim.x) {
+		const int rr = e / bw, pi = e % bw;
+		int a, b;
+		if (pi == 0) { a = N - 1; b = rr; }
+		else { a = (rr + pi) % (N - 1); b = (rr - pi + N - 1) % (N - 1); }
+		sched[e] = (unsigned short)(a | (b << 8));
+	}
+	const int nrounds = (nblk == 2) ? 1 : nblk - 1;
+	if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
+	__syncthreads();
+	int sweeps = 0, ground = 0;
+	unsigned int last_rot = 1, last_big = 1;
+	unsigned int my_rot = 0, my_big = 0;
+	long long tk_load = 0, tk_inner = 0, tk_store = 0, tk_sync = 0, tk0 = 0;
+	const bool timing = (info[0] == 0xC10C) && blockIdx.x == 0 && threadIdx.x == 0;
+
+	// rotation parameters of a pair with squared norms aa, bb and cross product g (gg = g^2):
+	//   c^2 = (1 + |d|/h)/2, s = sign(d) 2g / (2 h c) with d = bb - aa, h = sqrt(d^2 + 4 g^2): two rsqrt, no division
+	auto rotation = [](const double aa, const double bb, const double g, const double gg, double& c, double& s, double& t) {
+		const double d = bb - aa;
+		const double rh = rsqrt(d * d + 4.0 * gg);
+		const double c2 = 0.5 + 0.5 * fabs(d) * rh;
+		const double rc = rsqrt(c2);
+		c = c2 * rc;
+		s = (d >= 0.0 ? g : -g) * rh * rc;
+		t = s * rc;
+	};
+
+	for (; sweeps < max_sweeps; ) {
+		for (int round = 0; round < nrounds; ++round, ++ground) {
+			int pb, qb;
+			bool loadp = true, storep = true, full = (round == 0);
+			if (recursive) {
+				// recursive bipartite tournament with point-to-point block flags: see jacobi_persistent_kernel
+				int g = nblk, t = round;
+				while (t >= (g >> 1)) { t -= (g >> 1); g >>= 1; }
+				const int h = g >> 1, G = blockIdx.x / h, j = blockIdx.x % h;
+				pb = G * g + j; qb = G * g + h + ((j + t) & (h - 1));
+				loadp = (t == 0); storep = (t == h - 1); full = (g == 2);
+				if (threadIdx.x == 0) {
+					unsigned int spins = 0;
+					volatile unsigned int* rd = ready;
+					while ((rd[qb] < (unsigned)ground || (loadp && rd[pb] < (unsigned)ground)) && spins < (1u << 27)) ++spins;
+					if (spins >= (1u << 27)) atomicOr(&counters[2 * max_sweeps], 0xDEADu);
+					__threadfence();
+				}
+				__syncthreads();
+			} else {
+				const int pi = blockIdx.x, N1 = nblk - 1;
+				if (nblk == 2) { pb = 0; qb = 1; }
+				else if (pi == 0) { pb = N1; qb = round % N1; }
+				else { pb = (round + pi) % N1; qb = (round - pi + N1) % N1; }
+			}
+			if (timing) tk0 = clock64();
+			for (int r = (loadp ? 0 : bw) + warp; r < N; r += nwarps) {
+				const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
+				const double2* src = reinterpret_cast<const double2*>(GT + (size_t)grow * LD) + lane;
+				double2* dst = reinterpret_cast<double2*>(S + (size_t)r * LDS) + lane;
+				double2 v[EP2], w[EP2];
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) { v[k] = __ldcg(src + 32 * k); w[k] = __ldcg(src + V2 + 32 * k); }
+				double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) { dst[32 * k] = v[k]; dst[V2 + 32 * k] = w[k]; s0 += v[k].x * v[k].x; s1 += v[k].y * v[k].y; }
+				double ss = s0 + s1;
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+				if (lane == 0) nrm[r] = ss;
+			}
+			if (JACC) { for (int e = threadIdx.x; e < N * N; e += blockDim.x) Js[(e / N) * ldj + (e % N)] = (e / N == e % N) ? 1.0 : 0.0; }
+			unsigned int visit_rot = 0;
+			__syncthreads();
+			if (timing) { const long long t1 = clock64(); tk_load += t1 - tk0; tk0 = t1; }
+
+			if (full) {
+				// all pairs among the 2 bw resident columns: both columns of a pair change owner every round
+				for (int rr = 0; rr < N - 1; ++rr) {
+					if (warp < bw) {
+						const unsigned int ab_ = sched[rr * bw + warp];
+						const int a = ab_ & 255, b = ab_ >> 8;
+						double2* x = reinterpret_cast<double2*>(S + (size_t)a * LDS) + lane;
+						double2* y = reinterpret_cast<double2*>(S + (size_t)b * LDS) + lane;
+						double2 xr[EP2], yr[EP2];
+#pragma unroll
+						for (int k = 0; k < EP2; ++k) { xr[k] = x[32 * k]; yr[k] = y[32 * k]; }
+						double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+						for (int k = 0; k < EP2; ++k) {
+							if (k & 1) { g2 += xr[k].x * yr[k].x; g3 += xr[k].y * yr[k].y; }
+							else { g0 += xr[k].x * yr[k].x; g1 += xr[k].y * yr[k].y; }
+						}
+						double g = (g0 + g1) + (g2 + g3);
+						const double aa = nrm[a], bb = nrm[b];
+#pragma unroll
+						for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+						const double gg = g * g, ab = aa * bb;
+						if (gg > tol2 * ab) {
+							double2 xv[EP2], yv[EP2];
+							double ja = 0.0, jb = 0.0;
+							if (JACC) { if (lane < N) { ja = Js[a * ldj + lane]; jb = Js[b * ldj + lane]; } }
+							else {
+#pragma unroll
+								for (int k = 0; k < EP2; ++k) { xv[k] = x[V2 + 32 * k]; yv[k] = y[V2 + 32 * k]; }
+							}
+							double c, s, t;
+							rotation(aa, bb, g, gg, c, s, t);
+#pragma unroll
+							for (int k = 0; k < EP2; ++k) {
+								x[32 * k] = make_double2(c * xr[k].x - s * yr[k].x, c * xr[k].y - s * yr[k].y);
+								y[32 * k] = make_double2(s * xr[k].x + c * yr[k].x, s * xr[k].y + c * yr[k].y);
+								if (!JACC) {
+									x[V2 + 32 * k] = make_double2(c * xv[k].x - s * yv[k].x, c * xv[k].y - s * yv[k].y);
+									y[V2 + 32 * k] = make_double2(s * xv[k].x + c * yv[k].x, s * xv[k].y + c * yv[k].y);
+								}
+							}
+							if (JACC && lane < N) { Js[a * ldj + lane] = c * ja - s * jb; Js[b * ldj + lane] = s * ja + c * jb; }
+							// cached norms: alpha' = alpha - t*gamma, beta' = beta + t*gamma; recomputed when the update cancels
+							double na = aa - t * g, nb = bb + t * g;
+							if (na < 0.25 * aa || nb < 0.25 * bb) {
+								double sa = 0.0, sb = 0.0;
+#pragma unroll
+								for (int k = 0; k < EP2; ++k) {
+									const double xn0 = c * xr[k].x - s * yr[k].x, yn0 = s * xr[k].x + c * yr[k].x;
+									const double xn1 = c * xr[k].y - s * yr[k].y, yn1 = s * xr[k].y + c * yr[k].y;
+									sa += xn0 * xn0 + xn1 * xn1; sb += yn0 * yn0 + yn1 * yn1;
+								}
+#pragma unroll
+								for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+								na = sa; nb = sb;
+							}
+							visit_rot = 1;
+							if (lane == 0) {
+								nrm[a] = na; nrm[b] = nb;
+								my_rot += 1;
+								if (gg > big2 * ab) my_big += 1;
+							}
+						}
+					}
+					__syncthreads();
+				}
+			} else {
+				// block p against block q: warp w keeps column w of p (x part, its norm, its row of Js; the v part too without JACC)
+				// in registers for all bw rounds and meets column (w + rr) mod bw of q in round rr
+				const bool has = warp < bw;
+				const int a = warp;
+				double2* x = reinterpret_cast<double2*>(S + (size_t)a * LDS) + lane;
+				double2 xr[EP2], xv[EP2];
+				double aa = 0.0, ja = 0.0;
+				if (has) {
+#pragma unroll
+					for (int k = 0; k < EP2; ++k) { xr[k] = x[32 * k]; if (!JACC) xv[k] = x[V2 + 32 * k]; }
+					aa = nrm[a];
+					if (JACC && lane < N) ja = Js[a * ldj + lane];
+				}
+				for (int rr = 0; rr < bw; ++rr) {
+					if (has) {
+						const int b = bw + ((warp + rr) & (bw - 1));
+						double2* y = reinterpret_cast<double2*>(S + (size_t)b * LDS) + lane;
+						double2 yr[EP2];
+#pragma unroll
+						for (int k = 0; k < EP2; ++k) yr[k] = y[32 * k];
+						double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+						for (int k = 0; k < EP2; ++k) {
+							if (k & 1) { g2 += xr[k].x * yr[k].x; g3 += xr[k].y * yr[k].y; }
+							else { g0 += xr[k].x * yr[k].x; g1 += xr[k].y * yr[k].y; }
+						}
+						double g = (g0 + g1) + (g2 + g3);
+						const double bb = nrm[b];
+#pragma unroll
+						for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+						const double gg = g * g, ab = aa * bb;
+						if (gg > tol2 * ab) {
+							double2 yv[EP2];
+							double jb = 0.0;
+							if (JACC) { if (lane < N) jb = Js[b * ldj + lane]; }
+							else {
+#pragma unroll
+								for (int k = 0; k < EP2; ++k) yv[k] = y[V2 + 32 * k];
+							}
+							double c, s, t;
+							rotation(aa, bb, g, gg, c, s, t);
+							double sa = 0.0, sb = 0.0;
+#pragma unroll
+							for (int k = 0; k < EP2; ++k) {
+								const double2 xn = make_double2(c * xr[k].x - s * yr[k].x, c * xr[k].y - s * yr[k].y);
+								const double2 yn = make_double2(s * xr[k].x + c * yr[k].x, s * xr[k].y + c * yr[k].y);
+								xr[k] = xn; y[32 * k] = yn;
+								if (!JACC) {
+									const double2 vn = make_double2(c * xv[k].x - s * yv[k].x, c * xv[k].y - s * yv[k].y);
+									y[V2 + 32 * k] = make_double2(s * xv[k].x + c * yv[k].x, s * xv[k].y + c * yv[k].y);
+									xv[k] = vn;
+								}
+							}
+							if (JACC && lane < N) { Js[b * ldj + lane] = s * ja + c * jb; ja = c * ja - s * jb; }
+							double na = aa - t * g, nb = bb + t * g;
+							if (na < 0.25 * aa || nb < 0.25 * bb) {
+								// the cached-norm update cancelled: both norms from the rotated columns (y is re-read: this path is rare)
+#pragma unroll
+								for (int k = 0; k < EP2; ++k) {
+									const double2 yn = y[32 * k];
+									sa += xr[k].x * xr[k].x + xr[k].y * xr[k].y; sb += yn.x * yn.x + yn.y * yn.y;
+								}
+#pragma unroll
+								for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+								na = sa; nb = sb;
+							}
+							aa = na;
+							visit_rot = 1;
+							if (lane == 0) {
+								nrm[b] = nb;
+								my_rot += 1;
+								if (gg > big2 * ab) my_big += 1;
+							}
+						}
+					}
+					__syncthreads();
+				}
+				if (has) {
+#pragma unroll
+					for (int k = 0; k < EP2; ++k) { x[32 * k] = xr[k]; if (!JACC) x[V2 + 32 * k] = xv[k]; }
+					if (lane == 0) nrm[a] = aa;
+					if (JACC && lane < N) Js[a * ldj + lane] = ja;
+				}
+				__syncthreads();
+			}
+			if (JACC) {
+				if (__syncthreads_or(int(visit_rot))) {
+					if (N == 16) apply_rotations_to_v<2, 4>(S + 64 * EP2, LDS, Js, ldj, 8 * EP2, warp, nwarps, lane);
+					else apply_rotations_to_v<1, 2>(S + 64 * EP2, LDS, Js, ldj, 8 * EP2, warp, nwarps, lane);
+					__syncthreads();
+				}
+			}
+			if (timing) { const long long t1 = clock64(); tk_inner += t1 - tk0; tk0 = t1; }
+			if (lane == 0 && my_rot) { atomicAdd(&s_rot, my_rot); atomicAdd(&s_big, my_big); my_rot = 0; my_big = 0; }
+			for (int r = (storep ? 0 : bw) + warp; r < N; r += nwarps) {
+				const int grow = (r < bw ? pb * bw + r : qb * bw + (r - bw));
+				double2* dst = reinterpret_cast<double2*>(GT + (size_t)grow * LD) + lane;
+				const double2* src = reinterpret_cast<const double2*>(S + (size_t)r * LDS) + lane;
+				double2 v[EP2], w[EP2];
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) { v[k] = src[32 * k]; w[k] = src[V2 + 32 * k]; }
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) { dst[32 * k] = v[k]; dst[V2 + 32 * k] = w[k]; }
+			}
+			if (timing) { const long long t1 = clock64(); tk_store += t1 - tk0; tk0 = t1; }
+			if (recursive) {
+				__threadfence();
+				__syncthreads();
+				if (threadIdx.x == 0) {
+					volatile unsigned int* rd = ready;
+					if (storep) rd[pb] = (unsigned)ground + 1u;
+					rd[qb] = (unsigned)ground + 1u;
+				}
+			} else if (nblk > 2) { __threadfence(); grid.sync(); }
+			else __syncthreads();
+			if (timing) { const long long t1 = clock64(); tk_sync += t1 - tk0; tk0 = t1; }
+		}
+		++sweeps;
+		unsigned int rot, big;
+		if (nblk > 2) {
+			if (threadIdx.x == 0) { atomicAdd(&counters[2 * (sweeps - 1)], s_rot); atomicAdd(&counters[2 * (sweeps - 1) + 1], s_big); s_rot = 0; s_big = 0; }
+			__threadfence();
+			grid.sync();
+			rot = *((volatile unsigned int*)&counters[2 * (sweeps - 1)]);
+			big = *((volatile unsigned int*)&counters[2 * (sweeps - 1) + 1]);
+		} else {
+			rot = s_rot; big = s_big;
+			__syncthreads();
+			if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
+			__syncthreads();
+		}
+		last_rot = rot; last_big = big;
+		if (big == 0) break;
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) { info[1] = (unsigned)sweeps; info[2] = last_big; info[3] = last_rot; }
+	if (timing) { info[4] = (unsigned)(tk_load >> 10); info[5] = (unsigned)(tk_inner >> 10); info[6] = (unsigned)(tk_store >> 10); info[7] = (unsigned)(tk_sync >> 10); }
+}
+
 // mixed-precision helpers: scaled double -> float working copy, float V -> double V
 __global__ void svd_init_f32_kernel(float* __restrict__ GT, const int ld, const int npad, const int mdot, const int voff, const int nw,
                                     const double* __restrict__ src, const long long rs, const long long cs, const double* __restrict__ amax) {
@@ -412,6 +752,7 @@ struct JacobiPlan {
 	int EH = 4, bw = 1, threads = 64;
 	size_t nblk = 2, npad = 2, smem = 0;
 	bool persistent = false;
+	int ep2 = 0;             // > 0: jacobi_fast_kernel<ep2> applies (both row parts 64 * ep2 doubles)
 };
 
 static JacobiPlan plan_jacobi(size_t ld, size_t nw, size_t voff, size_t elem, size_t smem_cap) {
@@ -422,12 +763,13 @@ static JacobiPlan plan_jacobi(size_t ld, size_t nw, size_t voff, size_t elem, si
 	// The kernel is latency / FP64-issue bound: an inner round costs a dependent chain (reduce -> 2 rsqrt -> rotate ->
 	// barrier) whose length barely depends on the vector length, and the FP64 pipe is shared by the warps of an SM.
 	// More, smaller CTAs only pay off from 256 columns on (measured: scratch/svd_time.py).
-	int max_bw = p.EH == 16 ? 8 : (nw >= 256 ? 8 : 16);
+	int max_bw = 8;      // 16-column blocks (4 warps per scheduler) were slower at every size (profiles/bw_svd.py)
 	if (c.svd_max_bw > 0) max_bw = std::min(max_bw, c.svd_max_bw);
 	const int maxt = p.EH == 16 ? 256 : 512;
 	max_bw = std::min(max_bw, maxt / 32);
 	int bw = max_bw;
-	auto need = [&](int b) { return size_t(2 * b) * (ld + 2) * elem + size_t(4 * b) * b + 64; };
+	// rows [2b][ld + 4] | norms [2b] | schedule (2b - 1) b u16 | rotation product [2b][2b + 4]
+	auto need = [&](int b) { return size_t(2 * b) * (ld + 4 + 2) * elem + size_t(4 * b) * b + size_t(2 * b) * (2 * b + 4) * elem + 96; };
 	while (bw > 1 && (need(bw) > smem_cap || size_t(bw) >= nw)) bw >>= 1;
 	p.bw = bw;
 	p.nblk = (nw + bw - 1) / bw;
@@ -457,6 +799,40 @@ static void launch_persistent(T* gt, int ld, int epl_x, int epl_v, const JacobiP
 	ctx().launches++;
 }
 
+template <int EP2, int MAXT, bool JACC>
+static void launch_fast(double* gt, const JacobiPlan& p, double tol2, double big2, unsigned int* d_cnt, unsigned int* d_info, int max_sweeps,
+                        size_t smem_cap) {
+	static bool attr = false;
+	if (!attr) {
+		XB_CUDA(cudaFuncSetAttribute(jacobi_fast_kernel<EP2, MAXT, JACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+		attr = true;
+	}
+	XB_REQUIRE(p.threads <= MAXT, "internal: Jacobi launch exceeds its launch bound");
+	int bw = p.bw, nblk = int(p.nblk);
+	unsigned int* ready = d_cnt + 2 * max_sweeps + 12;
+	int recursive = (ctx().svd_recursive && nblk > 2 && (nblk & (nblk - 1)) == 0) ? 1 : 0;
+	void* args[] = {&gt, &bw, &nblk, &tol2, &big2, &d_cnt, &d_info, &max_sweeps, &ready, &recursive};
+	XB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_fast_kernel<EP2, MAXT, JACC>, dim3(unsigned(p.nblk / 2)), dim3(p.threads), args, p.smem, ctx().stream));
+	ctx().launches++;
+}
+
+static void launch_fast_any(double* gt, const JacobiPlan& p, double tol2, double big2, unsigned int* d_cnt, unsigned int* d_info, int max_sweeps,
+                            size_t smem_cap) {
+	const bool jacc = ctx().svd_jacc && (p.bw == 8 || p.bw == 4);
+	switch (p.ep2) {
+		case 1: if (jacc) launch_fast<1, 256, true>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); else launch_fast<1, 256, false>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); break;
+		case 2: if (jacc) launch_fast<2, 256, true>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); else launch_fast<2, 256, false>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); break;
+		case 3: if (jacc) launch_fast<3, 256, true>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); else launch_fast<3, 256, false>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); break;
+		case 4: if (jacc) launch_fast<4, 256, true>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); else launch_fast<4, 256, false>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); break;
+		case 6: if (jacc) launch_fast<6, 256, true>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); else launch_fast<6, 256, false>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); break;
+		case 8: if (jacc) launch_fast<8, 256, true>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); else launch_fast<8, 256, false>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); break;
+		default: throw Error(XB_ERR_UNSUPPORTED, "internal: no specialised Jacobi kernel for this row length");
+	}
+}
+static void launch_fast_any(float*, const JacobiPlan&, float, float, unsigned int*, unsigned int*, int, size_t) {
+	throw Error(XB_ERR_UNSUPPORTED, "internal: the specialised Jacobi kernel is FP64 only");
+}
+
 // Runs sweeps until convergence (or max_sweeps) in one cooperative launch; returns {converged, sweeps}.
 template <typename T>
 static bool run_persistent(T* gt, size_t ld, size_t voff, const JacobiPlan& p, double tol, double big, int max_sweeps, int& sweeps_out,
@@ -470,7 +846,8 @@ static bool run_persistent(T* gt, size_t ld, size_t voff, const JacobiPlan& p, d
 	if (timing) { const unsigned int flag = 0xC10C; XB_CUDA(cudaMemcpyAsync(d_info, &flag, 4, cudaMemcpyHostToDevice, c.stream)); }
 	const int epl_x = int(voff / 32), epl_v = int((ld - voff) / 32);
 	const T tol2 = T(tol * tol), big2 = T(big * big);
-	if (p.EH == 4) launch_persistent<T, 4, 512>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
+	if (p.ep2 > 0) launch_fast_any(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
+	else if (p.EH == 4) launch_persistent<T, 4, 512>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
 	else if (p.EH == 8) launch_persistent<T, 8, 512>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
 	else launch_persistent<T, 16, 256>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
 	unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch);
@@ -516,12 +893,21 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		src = A; mdot = mw;
 		if (swapped) { rs = 1; cs = (long long)n; } else { rs = (long long)n; cs = 1; }
 	}
-	// row layout: [ x (mdot) padded to 32 | v (nw) padded to 32 ]
+	// row layout: [ x (mdot) padded to 32 | v (nw) padded to 32 ]; up to 512 elements per part both parts are padded to
+	// the same multiple of 64 that the specialised kernel is instantiated for
 	voff = (mdot + 31) / 32 * 32;
 	ld = voff + (nw + 31) / 32 * 32;
+	int ep2 = 0;
+	if (c.svd_fast && std::max(mdot, nw) <= 512 && !(c.svd_mixed && nw >= size_t(c.svd_mixed_min))) {
+		ep2 = int((std::max(mdot, nw) + 63) / 64);
+		if (ep2 == 5) ep2 = 6;
+		if (ep2 == 7) ep2 = 8;
+		voff = size_t(64) * ep2; ld = 2 * voff;
+	}
 	mt = ld;
 	XB_REQUIRE(2 * (ld + 2) * sizeof(double) + 128 <= smem_cap, "SVD: matrix too large for the shared-memory Jacobi kernel (min(m,n) <= ~7000)");
-	const JacobiPlan plan = plan_jacobi(ld, nw, voff, sizeof(double), smem_cap);
+	JacobiPlan plan = plan_jacobi(ld, nw, voff, sizeof(double), smem_cap);
+	if (plan.persistent) plan.ep2 = ep2;
 	npad = plan.npad;
 	GT.resize(npad * ld);
 	// exact power-of-two scaling of the Jacobi input: norms and cross products are sums of squares

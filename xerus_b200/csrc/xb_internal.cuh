@@ -60,6 +60,8 @@ struct Context {
 	int svd_flip = 1;              // Jacobi on the rows of the triangular factor after a QR reduction (pre-conditioning)
 	int svd_square_qr = 1;         // square inputs also go through the QR reduction (needed for svd_flip)
 	int qr_cluster = 1;            // QR panels of 128..2048 rows on a thread-block cluster (registers + DSMEM reduction)
+	int svd_fast = 1;              // specialised Jacobi kernel (compile-time row length, 128-bit accesses) up to 512 columns
+	int svd_jacc = 1;              // specialised Jacobi kernel: rotations of a block visit accumulated, applied to V once (DMMA)
 	int svd_recursive = 1;         // recursive bipartite tournament with point-to-point block flags (power-of-two block counts)
 	int svd_mixed = 0;             // FP32 pre-conditioning sweeps + FP64 finishing sweeps (measured: no gain, kept as an experiment)
 	int svd_mixed_min = 64;        // smallest column count for the mixed path
