@@ -108,8 +108,11 @@ def test_index_notation_example(golden):
 
 
 # ---- factorizations --------------------------------------------------------------------------------------------
+# (127|128|129, ...) and (2048|2049, ...) straddle the row range of the cluster panel kernel, 1030 / 1500 / 2048 its larger
+# register tiles, (600, 33) a one-column last panel, (3000, 40) the one-CTA kernel working in global memory
 QR_SHAPES = [(1, 1), (5, 1), (1, 5), (8, 8), (40, 12), (12, 40), (33, 32), (64, 64), (100, 37), (37, 100), (512, 256),
-             (256, 256), (500, 50), (1000, 70), (130, 129)]
+             (256, 256), (500, 50), (1000, 70), (130, 129), (127, 20), (128, 64), (129, 129), (600, 33), (1030, 40),
+             (1500, 33), (2048, 48), (2049, 16), (3000, 40), (70, 300)]
 
 
 @pytest.mark.parametrize("m,n", QR_SHAPES)
@@ -169,8 +172,11 @@ def test_qc_cq_golden(golden, idx):
         assert np.linalg.norm(Qref - Q @ (Q.T @ Qref)) < 1e-10
 
 
+# min(m, n) = 7 .. 512 walks through every instantiation of the specialised Jacobi kernel (64, 128, 192, 256, 384, 512
+# elements per row part) and its block widths; (1100, 600) takes the generic kernel
 SVD_SHAPES = [(1, 1), (4, 4), (33, 21), (21, 33), (32, 32), (64, 64), (100, 30), (30, 100), (128, 128), (256, 256),
-              (512, 256), (256, 512), (300, 7), (7, 300), (257, 129)]
+              (512, 256), (256, 512), (300, 7), (7, 300), (257, 129), (190, 180), (400, 300), (330, 520), (512, 512),
+              (1100, 600)]
 
 
 @pytest.mark.parametrize("m,n", SVD_SHAPES)
@@ -185,6 +191,26 @@ def test_svd_vs_oracle(m, n):
     assert np.all(np.diff(S) <= 0)                                # descending
     assert rel((U * S) @ Vt, A) < 1e-12
     assert np.linalg.norm(U.T @ U - np.eye(k)) < 1e-11 and np.linalg.norm(Vt @ Vt.T - np.eye(k)) < 1e-11
+
+
+@pytest.mark.parametrize("option", ["svd_fast", "svd_jacc", "svd_recursive", "svd_flip", "qr_cluster"])
+def test_factorization_kernel_variants_agree(option):
+    """Every optimisation of the factorisation kernels can be switched off; both settings must give the same factors."""
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((200, 260)) @ np.diag(np.logspace(0, -6, 260)) @ rng.standard_normal((260, 150))
+    res = []
+    try:
+        for v in (0, 1):
+            xb.set_option(option, v)
+            U, S, Vt = BW.svd(A)
+            Q, R = BW.qr(A)
+            assert rel((U * S) @ Vt, A) < 1e-12 and rel(Q @ R, A) < 1e-13
+            assert np.linalg.norm(U.T @ U - np.eye(150)) < 1e-11 and np.linalg.norm(Q.T @ Q - np.eye(150)) < 1e-12
+            res.append((S, np.abs(R)))
+    finally:
+        xb.set_option(option, 1)
+    assert np.max(np.abs(res[0][0] - res[1][0])) < 1e-13 * res[0][0][0]
+    assert np.allclose(res[0][1], res[1][1], rtol=1e-9, atol=1e-12 * res[0][1].max())
 
 
 @pytest.mark.parametrize("tag", ["svd.tall", "svd.wide"])
