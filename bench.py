@@ -485,7 +485,7 @@ def main():
     jac_scopes, jac_launches, jac_ms = prof["svd_jacobi"]
     svd_tf = svd_f / (jac_ms * 1e-3) / 1e12 if jac_ms > 0 else 0.0
     roofline = {
-        "kernel": "jacobi_block_kernel (one-sided block Jacobi SVD)", "bound": "tensor", "unit": "TFLOP/s",
+        "kernel": "jacobi_fast_kernel / jacobi_persistent_kernel (one-sided block Jacobi SVD, one cooperative launch per SVD)", "bound": "tensor", "unit": "TFLOP/s",
         "achieved": svd_tf, "peak": fp64_peak, "frac": svd_tf / fp64_peak if fp64_peak else None, "traffic": None,
         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (no FP64 entry in MEASURED_PEAKS.json; nominal ~40)",
         "algorithmic_flops_per_round": svd_f, "accounting": "22*min(m,n)^3 per SVD (SURVEY §8d)",

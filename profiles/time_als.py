@@ -1,6 +1,8 @@
 import sys, time; sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import numpy as np, xerus_b200 as xb
 xb.init(0)
+import os
+if os.environ.get('XB_GEMM_SMALL'): xb.set_option('gemm_force_small', 1)
 d,n=16,10
 for r in [8,20,50]:
     rng=np.random.default_rng(16)

@@ -14,6 +14,7 @@
 // The two-site driver applies the obvious fix for the reference's sweep-turn defect (als.cpp:371,:376 push the slice
 // of site currIndex where currIndex + sites - 1 is needed).
 #include "tt_internal.cuh"
+#include <cooperative_groups.h>
 #include <cstdlib>
 
 using namespace xb;
@@ -106,6 +107,79 @@ __global__ void cg_shift_kernel(double* __restrict__ sc) { if (threadIdx.x == 0 
 
 unsigned vec_grid(size_t n) { return unsigned(std::min<size_t>(std::max<size_t>(1, (n + 255) / 256), size_t(ctx().num_sms) * 4)); }
 
+// One CG iteration's vector work in a single CTA (local problems up to CG_FUSED_MAX unknowns: at BASELINE config 2 a vector
+// is 200 KB and the five separate launches cost more than the arithmetic): with q = A p,
+//   alpha = rr / p.q ; x += alpha p ; r -= alpha q ; rr' = r.r ; p = r + (rr'/rr) p ; sc[0] = rr', sc[1] = p.q
+// Reductions run in a fixed order (deterministic).
+constexpr size_t CG_FUSED_MAX = 262144;
+constexpr int CG_CS = 8;           // CTAs per cluster
+// sum over the whole cluster: warp shuffle, CTA partial to every CTA's slot (DSMEM), one cluster barrier, fixed-order sum
+__device__ __forceinline__ double cluster_sum(double v, double (*slots)[CG_CS], double* sh, const int phase,
+                                              cooperative_groups::cluster_group& cluster) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0) sh[phase * 32 + (threadIdx.x >> 5)] = v;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		double t = sh[phase * 32 + threadIdx.x];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+		if (threadIdx.x < CG_CS) *cluster.map_shared_rank(&slots[phase][cluster.block_rank()], threadIdx.x) = t;
+	}
+	cluster.sync();
+	double s = 0.0;
+#pragma unroll
+	for (int c = 0; c < CG_CS; ++c) s += slots[phase][c];
+	return s;
+}
+__global__ void __cluster_dims__(CG_CS, 1, 1) __launch_bounds__(1024) cg_fused_kernel(double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
+                                                                                     const double* __restrict__ q, double* __restrict__ sc, const int n) {
+	cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+	__shared__ double sh[64];
+	__shared__ double slots[2][CG_CS];
+	const double rr = sc[0];
+	const int stride = CG_CS * 1024, first = blockIdx.x * 1024 + threadIdx.x;
+	double acc = 0.0;
+	for (int i = first; i < n; i += stride) acc += p[i] * q[i];
+	const double pq = cluster_sum(acc, slots, sh, 0, cluster);
+	const double alpha = (pq != 0.0) ? rr / pq : 0.0;
+	acc = 0.0;
+	for (int i = first; i < n; i += stride) {
+		x[i] += alpha * p[i];
+		const double rn = r[i] - alpha * q[i];
+		r[i] = rn;
+		acc += rn * rn;
+	}
+	const double rrn = cluster_sum(acc, slots, sh, 1, cluster);
+	const double beta = (rr != 0.0) ? rrn / rr : 0.0;
+	for (int i = first; i < n; i += stride) p[i] = r[i] + beta * p[i];
+	// sc[0] is read by every CTA at entry: nobody may overwrite it before all have passed the second barrier (they have)
+	if (blockIdx.x == 0 && threadIdx.x == 0) { sc[0] = rrn; sc[1] = pq; sc[2] = rrn; }
+}
+
+// One-site SPD local operator prepared once per site: y(l,m,r) = sum L(l,a,l') A(a,m,n,b) R(r,b,r') v(l',n,r').
+// With the operator core pre-shuffled to (m,b | a,n) the application is three GEMMs into fixed workspaces and no
+// reshuffle:  t1(l,a | n,r') = L v ;  u(l | m,b | r') = A2 t1(l)  (batched over l) ;  y(l,m | r) = u R^T.
+struct SpdSiteApply {
+	size_t l = 0, a = 0, m = 0, n = 0, b = 0, r = 0;
+	const double* L = nullptr; const double* R = nullptr;
+	DBuf A2, t1, u;
+	void prepare(const DT& Lenv, const DT& Acore, const DT& Renv) {
+		l = Lenv.dims[0]; a = Lenv.dims[1]; r = Renv.dims[0]; b = Renv.dims[1];
+		m = Acore.dims[1]; n = Acore.dims[2];
+		XB_REQUIRE(Lenv.dims[2] == l && Renv.dims[2] == r && Acore.dims[0] == a && Acore.dims[3] == b, "internal: local operator shapes");
+		L = Lenv.p; R = Renv.p;
+		DT s = dt_permute(Acore, {1, 3, 0, 2});          // (m, b, a, n)
+		A2 = std::move(s.own);
+		t1.resize(l * a * n * r); u.resize(l * m * b * r);
+	}
+	void apply(const double* v, double* y) {
+		gemm(t1, n * r, l * a, n * r, 1.0, L, l, false, l, v, n * r, false, 0.0);
+		gemm_batched(u, r, m * b * r, m * b, r, 1.0, A2, a * n, 0, false, a * n, t1, r, a * n * r, false, 0.0, l);
+		gemm(y, r, l * m, r, 1.0, u, b * r, false, b * r, R, b * r, true, 0.0);
+	}
+};
+
 // y = {L, A_1..A_s, R} applied to v, SPD environments: L(l, a, l'), A_p(a, m, n, b), R(r, b, r'), v(l', n_1..n_s, r' [, col])
 // -> y(l, m_1..m_s, r [, col]).  One GEMM per factor, one reshuffle per operator core (als.cpp:383-401 un-contracted).
 DT spd_env_apply(const DT& L, const std::vector<DT>& Acores, const DT& R, const DT& v) {
@@ -143,6 +217,8 @@ struct Als {
 	double normB = 0.0;
 	size_t cg_iterations = 0, direct_solves = 0;
 	bool used_cg = false;
+	SpdSiteApply* site_apply = nullptr;     // set while a one-site SPD local problem is being solved by CG
+	unsigned long long graph_nodes = 0;     // kernels inside one captured chunk of CG iterations
 
 	DT xcore(size_t i) const { return dt_view(x->core[i], {x->rank[i], x->dim_m[i], x->rank[i + 1]}); }
 	DT bcore(size_t i) const { return dt_view(b->core[i], {b->rank[i], b->dim_m[i], b->rank[i + 1]}); }
@@ -350,6 +426,16 @@ struct Als {
 		xv.dims = rhs.dims;
 		DBuf sc(4);
 		Context& c = ctx();
+		SpdSiteApply fast_apply;
+		DT qbuf;
+		site_apply = nullptr;
+		if (sites == 1 && opt.assume_spd && A && v0.dims.size() == 3) {
+			fast_apply.prepare(opL.back(), acore(cur), opR.back());
+			site_apply = &fast_apply;
+			qbuf = dt_alloc(rhs.dims);
+		}
+		struct Reset { SpdSiteApply*& p; ~Reset() { p = nullptr; } } reset{site_apply};
+		const bool fused_update = n <= CG_FUSED_MAX;
 		const double bnorm2 = dt_dot(rhs, rhs);
 		if (bnorm2 == 0.0) { fill(xv.data(), 0.0, n); return xv; }
 		const double target = tol * tol * bnorm2;
@@ -358,7 +444,8 @@ struct Als {
 		double rr = 0.0, rr0 = -1.0;
 		for (int restart = 0; restart < 6 && it < max_it; ++restart) {
 			DT r = dt_copy(rhs);
-			{ DT Ax = local_apply(xv); axpy(r.data(), -1.0, Ax.p, n); }      // true residual
+			if (site_apply) { site_apply->apply(xv.p, qbuf.data()); axpy(r.data(), -1.0, qbuf.p, n); }
+			else { DT Ax = local_apply(xv); axpy(r.data(), -1.0, Ax.p, n); }      // true residual
 			dot_dev(sc.p + 0, r.p, r.p, n);
 			rr = read_scalar(sc.p + 0);
 			if (rr0 < 0.0) rr0 = rr;
@@ -372,12 +459,43 @@ struct Als {
 			DT p = dt_copy(r);
 			double best = rr; size_t since_best = 0;
 			const double rr_start = rr;
+			// The iteration is a fixed launch sequence on fixed buffers (scalars stay on the device): chunks of 8 iterations
+			// are captured once per (site, restart) into a CUDA graph and replayed — the host enqueue of 32 small kernels
+			// costs more than their execution.
+			struct GraphHolder { cudaGraph_t g = nullptr; cudaGraphExec_t e = nullptr;
+				~GraphHolder() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); } } graph;
+			const bool use_graph = site_apply && fused_update && c.als_graph && !c.profile;
 			while (rr > target && it < max_it) {
 				const size_t chunk = std::min<size_t>(8, max_it - it);
+				if (use_graph && chunk == 8) {
+					if (!graph.e) {
+						const unsigned long long l0 = c.launches;
+						XB_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+						for (size_t j = 0; j < chunk; ++j) {
+							site_apply->apply(p.p, qbuf.data());
+							cg_fused_kernel<<<CG_CS, 1024, 0, c.stream>>>(xv.data(), r.data(), p.data(), qbuf.p, sc.p, int(n));
+							c.launches++;
+						}
+						XB_CUDA(cudaStreamEndCapture(c.stream, &graph.g));
+						XB_CUDA(cudaGraphInstantiate(&graph.e, graph.g, 0));
+						graph_nodes = c.launches - l0;
+						c.launches = l0;
+					}
+					XB_CUDA(cudaGraphLaunch(graph.e, c.stream));
+					c.launches += graph_nodes;
+				} else
 				for (size_t j = 0; j < chunk; ++j) {
-					DT q = local_apply(p);
-					dot_dev(sc.p + 1, p.p, q.p, n);
-					cg_step1_kernel<<<grid, 256, 0, c.stream>>>(xv.data(), r.data(), p.p, q.p, sc.p, n);
+					DT q;
+					const double* qp;
+					if (site_apply) { site_apply->apply(p.p, qbuf.data()); qp = qbuf.p; }
+					else { q = local_apply(p); qp = q.p; }
+					if (fused_update) {
+						cg_fused_kernel<<<CG_CS, 1024, 0, c.stream>>>(xv.data(), r.data(), p.data(), qp, sc.p, int(n));
+						XB_LAUNCH_CHECK();
+						continue;
+					}
+					dot_dev(sc.p + 1, p.p, qp, n);
+					cg_step1_kernel<<<grid, 256, 0, c.stream>>>(xv.data(), r.data(), p.p, qp, sc.p, n);
 					XB_LAUNCH_CHECK();
 					dot_dev(sc.p + 2, r.p, r.p, n);
 					cg_step2_kernel<<<grid, 256, 0, c.stream>>>(p.data(), r.p, sc.p, n);
