@@ -9,19 +9,22 @@ namespace xb {
 
 // out[0] = max entry (signed, as the reference's is_symmetric :501-505), out[1] = max |A - A^T|,
 // out[2] = 1 if the diagonal is all > eps or all < -eps (pos_neg_definite_diagonal :519-537) else 0, out[3] = A[0][0]
-__global__ void sym_probe_kernel(const double* __restrict__ A, const int n, double* __restrict__ out) {
-	__shared__ double s_max[32], s_asym[32];
-	__shared__ int s_bad[32];
+__global__ void __launch_bounds__(256) sym_probe_kernel(const double* __restrict__ A, const int n, double* __restrict__ part) {
+	__shared__ double s_max[8], s_asym[8];
+	__shared__ int s_bad[8];
 	double mx = -HUGE_VAL, asym = 0.0;
 	int bad = 0;
 	const bool positive = A[0] > 0.0;
 	const double eps = 2.220446049250313e-16;
-	for (size_t e = threadIdx.x; e < (size_t)n * n; e += blockDim.x) {
-		const int i = int(e / n), j = int(e % n);
-		const double v = A[e];
-		mx = fmax(mx, v);
-		if (j > i) asym = fmax(asym, fabs(v - A[(size_t)j * n + i]));
-		if (i == j && i > 0) { if (positive ? (v < eps) : (v > -eps)) bad = 1; }
+	// CTA b owns rows b, b + gridDim.x, ...; a warp reads a row segment (coalesced) and the mirrored column segment
+	for (int i = blockIdx.x; i < n; i += gridDim.x) {
+		const double* row = A + (size_t)i * n;
+		for (int j = threadIdx.x; j < n; j += blockDim.x) {
+			const double v = row[j];
+			mx = fmax(mx, v);
+			if (j > i) asym = fmax(asym, fabs(v - A[(size_t)j * n + i]));
+			if (i == j && i > 0) { if (positive ? (v < eps) : (v > -eps)) bad = 1; }
+		}
 	}
 	for (int o = 16; o > 0; o >>= 1) {
 		mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -32,8 +35,18 @@ __global__ void sym_probe_kernel(const double* __restrict__ A, const int n, doub
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		for (int w = 1; w < int(blockDim.x >> 5); ++w) { mx = fmax(mx, s_max[w]); asym = fmax(asym, s_asym[w]); bad |= s_bad[w]; }
-		out[0] = mx; out[1] = asym; out[2] = bad ? 0.0 : 1.0; out[3] = A[0];
+		part[blockIdx.x * 4 + 0] = mx; part[blockIdx.x * 4 + 1] = asym; part[blockIdx.x * 4 + 2] = bad ? 0.0 : 1.0;
 	}
+}
+__global__ void sym_probe_final_kernel(const double* __restrict__ part, const int nparts, const double* __restrict__ A, double* __restrict__ out) {
+	double mx = -HUGE_VAL, asym = 0.0, ok = 1.0;
+	for (int p = threadIdx.x; p < nparts; p += 32) { mx = fmax(mx, part[p * 4]); asym = fmax(asym, part[p * 4 + 1]); ok = fmin(ok, part[p * 4 + 2]); }
+	for (int o = 16; o > 0; o >>= 1) {
+		mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+		asym = fmax(asym, __shfl_xor_sync(0xffffffffu, asym, o));
+		ok = fmin(ok, __shfl_xor_sync(0xffffffffu, ok, o));
+	}
+	if (threadIdx.x == 0) { out[0] = mx; out[1] = asym; out[2] = ok; out[3] = A[0]; }
 }
 
 // In-place upper Cholesky A = U^T U (row-major, upper triangle), then solves U^T U X = B in place.
@@ -148,6 +161,116 @@ __global__ void __launch_bounds__(1024) lu_solve_kernel(double* __restrict__ A, 
 	if (threadIdx.x == 0) status[0] = 0;
 }
 
+// ---- blocked Cholesky --------------------------------------------------------------------------------------------------
+constexpr int CH_NB = 64;
+
+// In-place upper Cholesky of the nb x nb diagonal block at A (row stride lda).  status[0] = k0 + j + 1 on a non-positive pivot.
+__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, const long long lda, const int nb, const int k0, int* __restrict__ status) {
+	__shared__ double U[CH_NB][CH_NB + 1];
+	__shared__ int s_fail;
+	for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) { const int i = e / nb, c = e % nb; U[i][c] = (c >= i) ? A[(long long)i * lda + c] : 0.0; }
+	if (threadIdx.x == 0) s_fail = 0;
+	__syncthreads();
+	for (int j = 0; j < nb; ++j) {
+		const double a = U[j][j];
+		if (!(a > 0.0)) { if (threadIdx.x == 0) s_fail = k0 + j + 1; }
+		__syncthreads();
+		if (s_fail) break;
+		const double inv = 1.0 / sqrt(a);
+		if (threadIdx.x >= j && threadIdx.x < nb) U[j][threadIdx.x] = (threadIdx.x == j) ? sqrt(a) : U[j][threadIdx.x] * inv;
+		__syncthreads();
+		// trailing update of the upper triangle: U[i][c] -= U[j][i] * U[j][c]   (i > j, c >= i)
+		const int rem = nb - j - 1;
+		for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
+			const int i = j + 1 + e / rem, c = j + 1 + e % rem;
+			if (c >= i) U[i][c] -= U[j][i] * U[j][c];
+		}
+		__syncthreads();
+	}
+	if (s_fail) { if (threadIdx.x == 0 && status[0] == 0) status[0] = s_fail; return; }
+	for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) { const int i = e / nb, c = e % nb; if (c >= i) A[(long long)i * lda + c] = U[i][c]; }
+}
+
+// X = U^-T X (LOWER = true: forward substitution with U^T) or X = U^-1 X (back substitution) for the nb x nb upper block U
+// and the nb x ncols matrix X (row stride ldx): one thread per column of X, U broadcast from shared memory.
+template <bool LOWER>
+__global__ void __launch_bounds__(128) chol_trsm_kernel(const double* __restrict__ Ublk, const long long ldu, double* __restrict__ X, const long long ldx,
+                                                       const int nb, const int ncols) {
+	__shared__ double U[CH_NB][CH_NB];
+	__shared__ double invd[CH_NB];
+	for (int e = threadIdx.x; e < CH_NB * CH_NB; e += blockDim.x) {
+		const int i = e / CH_NB, c = e % CH_NB;
+		U[i][c] = (i < nb && c < nb && c >= i) ? Ublk[(long long)i * ldu + c] : 0.0;
+	}
+	__syncthreads();
+	if (threadIdx.x < CH_NB) invd[threadIdx.x] = (threadIdx.x < nb) ? 1.0 / U[threadIdx.x][threadIdx.x] : 0.0;
+	__syncthreads();
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= ncols) return;
+	double a[CH_NB];
+#pragma unroll
+	for (int i = 0; i < CH_NB; ++i) a[i] = (i < nb) ? X[(long long)i * ldx + c] : 0.0;
+	if (LOWER) {
+#pragma unroll
+		for (int i = 0; i < CH_NB; ++i) {
+			const double xi = a[i] * invd[i];
+			a[i] = xi;
+#pragma unroll
+			for (int j = i + 1; j < CH_NB; ++j) a[j] -= U[i][j] * xi;
+		}
+	} else {
+#pragma unroll
+		for (int i = CH_NB - 1; i >= 0; --i) {
+			const double xi = a[i] * invd[i];
+			a[i] = xi;
+#pragma unroll
+			for (int j = 0; j < i; ++j) a[j] -= U[j][i] * xi;
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < CH_NB; ++i) if (i < nb) X[(long long)i * ldx + c] = a[i];
+}
+
+static bool cholesky_solve_blocked(double* A, double* B, size_t n, size_t nrhs) {
+	cudaStream_t st = ctx().stream;
+	int* d_status = static_cast<int*>(dalloc_bytes(sizeof(int)));
+	XB_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+	// factorisation A = U^T U, right looking
+	for (size_t k0 = 0; k0 < n; k0 += CH_NB) {
+		const size_t nb = std::min<size_t>(CH_NB, n - k0), n2 = n - k0 - nb;
+		double* Akk = A + k0 * n + k0;
+		chol_diag_kernel<<<1, 256, 0, st>>>(Akk, (long long)n, int(nb), int(k0), d_status);
+		XB_LAUNCH_CHECK();
+		if (n2 == 0) break;
+		double* A12 = Akk + nb;
+		chol_trsm_kernel<true><<<unsigned((n2 + 127) / 128), 128, 0, st>>>(Akk, (long long)n, A12, (long long)n, int(nb), int(n2));
+		XB_LAUNCH_CHECK();
+		gemm(Akk + nb * n + nb, n, n2, n2, -1.0, A12, n, true, nb, A12, n, false, 1.0);        // A22 -= U12^T U12
+	}
+	const int st_fact = [&] { int* h = reinterpret_cast<int*>(ctx().h_scratch);
+		XB_CUDA(cudaMemcpyAsync(h, d_status, sizeof(int), cudaMemcpyDeviceToHost, st)); XB_CUDA(cudaStreamSynchronize(st)); return h[0]; }();
+	dfree(d_status);
+	if (st_fact != 0) return false;
+	// U^T Y = B (forward), U X = Y (backward), block by block
+	for (size_t k0 = 0; k0 < n; k0 += CH_NB) {
+		const size_t nb = std::min<size_t>(CH_NB, n - k0), n2 = n - k0 - nb;
+		const double* Akk = A + k0 * n + k0;
+		double* B1 = B + k0 * nrhs;
+		chol_trsm_kernel<true><<<unsigned((nrhs + 127) / 128), 128, 0, st>>>(Akk, (long long)n, B1, (long long)nrhs, int(nb), int(nrhs));
+		XB_LAUNCH_CHECK();
+		if (n2) gemm(B1 + nb * nrhs, nrhs, n2, nrhs, -1.0, Akk + nb, n, true, nb, B1, nrhs, false, 1.0);     // B2 -= U12^T Y1
+	}
+	for (size_t kb = (n + CH_NB - 1) / CH_NB; kb-- > 0;) {
+		const size_t k0 = kb * CH_NB, nb = std::min<size_t>(CH_NB, n - k0), n2 = n - k0 - nb;
+		const double* Akk = A + k0 * n + k0;
+		double* B1 = B + k0 * nrhs;
+		if (n2) gemm(B1, nrhs, nb, nrhs, -1.0, Akk + nb, n, false, n2, B1 + nb * nrhs, nrhs, false, 1.0);    // B1 -= U12 X2
+		chol_trsm_kernel<false><<<unsigned((nrhs + 127) / 128), 128, 0, st>>>(Akk, (long long)n, B1, (long long)nrhs, int(nb), int(nrhs));
+		XB_LAUNCH_CHECK();
+	}
+	return true;
+}
+
 static int read_status(int* d_status) {
 	Context& c = ctx();
 	int* h = reinterpret_cast<int*>(c.h_scratch);
@@ -158,6 +281,7 @@ static int read_status(int* d_status) {
 
 // sign = +1 for a positive, -1 for a negative diagonal (the reference's dpotrf2 only succeeds for +1)
 bool cholesky_solve(double* A, double* B, size_t n, size_t nrhs) {
+	if (n > size_t(CH_NB)) return cholesky_solve_blocked(A, B, n, nrhs);
 	int* d_status = static_cast<int*>(dalloc_bytes(sizeof(int)));
 	cholesky_solve_kernel<<<1, 1024, 0, ctx().stream>>>(A, B, int(n), int(nrhs), 1.0, d_status);
 	XB_LAUNCH_CHECK();
@@ -178,7 +302,11 @@ void lu_solve(double* A, double* B, size_t n, size_t nrhs) {
 // returns {symmetric, definite diagonal}
 void probe_symmetry(const double* A, size_t n, bool& symmetric, bool& definite_diag) {
 	DBuf out(4);
-	sym_probe_kernel<<<1, 1024, 0, ctx().stream>>>(A, int(n), out);
+	const unsigned parts = unsigned(std::min<size_t>(n, size_t(ctx().num_sms) * 4));
+	DBuf part(size_t(parts) * 4);
+	sym_probe_kernel<<<parts, 256, 0, ctx().stream>>>(A, int(n), part);
+	XB_LAUNCH_CHECK();
+	sym_probe_final_kernel<<<1, 32, 0, ctx().stream>>>(part, int(parts), A, out);
 	XB_LAUNCH_CHECK();
 	Context& c = ctx();
 	XB_CUDA(cudaMemcpyAsync(c.h_scratch, out.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
