@@ -83,6 +83,23 @@ __global__ void smem_kernel(double* out, long long* cyc, int iters) {
 	if (threadIdx.x == 0) cyc[1] = t3 - t2;
 }
 
+template <int CHAINS>
+__global__ void dmma_kernel(double* out, long long* cyc, int iters, double a, double b) {
+	double d[CHAINS][2];
+	for (int c = 0; c < CHAINS; ++c) { d[c][0] = threadIdx.x * 1e-3 + c; d[c][1] = 1.0; }
+	__syncthreads();
+	const long long t0 = clock64();
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int c = 0; c < CHAINS; ++c)
+			asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d[c][0]), "+d"(d[c][1]) : "d"(a), "d"(b));
+	}
+	const long long t1 = clock64();
+	double s = 0; for (int c = 0; c < CHAINS; ++c) s += d[c][0] + d[c][1];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+	if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
 int main() {
 	double* out; long long* cyc;
 	cudaMalloc(&out, 1 << 20); cudaMallocManaged(&cyc, 64);
@@ -92,6 +109,10 @@ int main() {
 	printf("  chains %d warps/SM %2d (per SMSP %g): %.2f cycles/step  -> %.2f cycles per warp-instruction per SMSP\n", CH, THREADS / 32, THREADS / 128.0, double(*cyc) / iters, double(*cyc) / iters / (CH * (THREADS / 128.0 < 1 ? 1 : THREADS / 128.0))); }
 	RUN(1, 32) RUN(2, 32) RUN(4, 32) RUN(8, 32) RUN(16, 32)
 	RUN(8, 128) RUN(8, 256) RUN(8, 512) RUN(8, 1024) RUN(1, 256) RUN(1, 512) RUN(1, 1024) RUN(2, 256)
+	printf("DMMA m8n8k4: cycles per step of CHAINS independent mma (one SM)\n");
+#define RUNM(CH, THREADS) { dmma_kernel<CH><<<1, THREADS>>>(out, cyc, iters, 1e-3, 1e-3); cudaDeviceSynchronize(); \
+	printf("  chains %d warps/SM %2d: %.2f cycles/step -> %.2f cycles per DMMA per SM\n", CH, THREADS / 32, double(*cyc) / iters, double(*cyc) / iters / (CH * (THREADS / 32))); }
+	RUNM(1, 32) RUNM(2, 32) RUNM(4, 32) RUNM(8, 32) RUNM(1, 128) RUNM(4, 128) RUNM(1, 256) RUNM(2, 256) RUNM(4, 256) RUNM(8, 256)
 	rsqrt_kernel<<<1, 32>>>(out, cyc, iters, 1e-9); cudaDeviceSynchronize();
 	printf("dependent latency: rsqrt(double) %.1f  __drcp_rn %.1f  sqrt %.1f  div %.1f  rsqrtf %.1f cycles (incl. one DADD/FADD)\n", double(cyc[0]) / iters, double(cyc[1]) / iters, double(cyc[2]) / iters, double(cyc[3]) / iters, double(cyc[4]) / iters);
 	shfl_kernel<<<1, 32>>>(out, cyc, iters); cudaDeviceSynchronize();

@@ -193,7 +193,10 @@ def test_svd_vs_oracle(m, n):
     assert np.linalg.norm(U.T @ U - np.eye(k)) < 1e-11 and np.linalg.norm(Vt @ Vt.T - np.eye(k)) < 1e-11
 
 
-@pytest.mark.parametrize("option", ["svd_fast", "svd_jacc", "svd_recursive", "svd_flip", "qr_cluster"])
+VARIANT_DEFAULTS = {"svd_fast": 1, "svd_jacc": 1, "svd_recursive": 1, "svd_flip": 1, "qr_cluster": 1, "svd_gram": 0}
+
+
+@pytest.mark.parametrize("option", sorted(VARIANT_DEFAULTS))
 def test_factorization_kernel_variants_agree(option):
     """Every optimisation of the factorisation kernels can be switched off; both settings must give the same factors."""
     rng = np.random.default_rng(11)
@@ -208,7 +211,7 @@ def test_factorization_kernel_variants_agree(option):
             assert np.linalg.norm(U.T @ U - np.eye(150)) < 1e-11 and np.linalg.norm(Q.T @ Q - np.eye(150)) < 1e-12
             res.append((S, np.abs(R)))
     finally:
-        xb.set_option(option, 1)
+        xb.set_option(option, VARIANT_DEFAULTS[option])
     assert np.max(np.abs(res[0][0] - res[1][0])) < 1e-13 * res[0][0][0]
     assert np.allclose(res[0][1], res[1][1], rtol=1e-9, atol=1e-12 * res[0][1].max())
 
@@ -268,6 +271,28 @@ def test_solve_multi_rhs_and_least_squares():
     W = rng.standard_normal((20, 50))
     b2 = rng.standard_normal((20, 1))
     assert rel(BW.solve(W, b2), np.linalg.lstsq(W, b2, rcond=None)[0]) < 1e-10   # m != n -> least squares (:553-559)
+
+
+@pytest.mark.parametrize("n,nrhs", [(64, 1), (65, 2), (130, 1), (200, 5), (700, 1), (1000, 3)])
+def test_solve_blocked_factorizations(n, nrhs):
+    """Above 64 unknowns `solve` runs the blocked Cholesky (symmetric, definite diagonal: blasLapackWrapper.cpp:590-610) or
+    the blocked LU with partial pivoting (:570); the last block is ragged for every size here but 64."""
+    rng = np.random.default_rng(n + nrhs)
+    G = rng.standard_normal((n, n))
+    spd = G @ G.T + n * np.eye(n)
+    B = rng.standard_normal((n, nrhs))
+    X = BW.solve(spd, B)
+    assert rel(X, np.linalg.solve(spd, B)) < 1e-11 and rel(spd @ X, B) < 1e-12
+    X = BW.solve(G, B)
+    assert rel(G @ X, B) < 1e-9 and rel(X, np.linalg.solve(G, B)) < 1e-7           # cond(G) ~ n .. 1e4
+    P = np.eye(n)[rng.permutation(n)] * rng.choice([-1.0, 1.0], n)                   # pivoting is unavoidable here
+    X = BW.solve(P, B)
+    assert rel(X, P.T @ B) < 1e-14
+    sym_indef = G + G.T                                                              # symmetric, indefinite: Cholesky fails, LU takes over
+    X = BW.solve(sym_indef, B)
+    assert rel(sym_indef @ X, B) < 1e-8
+    with pytest.raises(xb.XerusError):
+        BW.solve(np.ones((n, n)), B)                                                 # singular
 
 
 def test_error_behaviour():

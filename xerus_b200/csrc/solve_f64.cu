@@ -279,6 +279,140 @@ static int read_status(int* d_status) {
 	return h[0];
 }
 
+// ---- blocked LU with partial pivoting ---------------------------------------------------------------------------------
+// Right-looking, 64-column panels: the panel is factored by one CTA working in L2-resident global memory (pivot search,
+// row swap inside the panel, scaling, rank-1 update), the row swaps are then applied to the rest of the matrix and to B,
+// U12 = L11^-1 A12 is one thread per column with L11 in shared memory, and the trailing update A22 -= L21 U12 is the DMMA
+// GEMM.  B rides along as extra columns, so only the back substitution is left after the loop.
+__global__ void __launch_bounds__(1024) lu_panel_kernel(double* __restrict__ A, const long long n, const int k0, const int nb, int* __restrict__ ipiv,
+                                                       int* __restrict__ status) {
+	__shared__ double s_val[32];
+	__shared__ int s_idx[32];
+	__shared__ double s_row[CH_NB];
+	__shared__ int s_piv, s_fail;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_fail = 0;
+	__syncthreads();
+	for (int j = 0; j < nb; ++j) {
+		const long long col = k0 + j;
+		double best = -1.0; int bi = int(col);
+		for (long long i = col + threadIdx.x; i < n; i += blockDim.x) { const double v = fabs(A[i * n + col]); if (v > best) { best = v; bi = int(i); } }
+		for (int o = 16; o > 0; o >>= 1) {
+			const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+			const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+			if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+		}
+		if (lane == 0) { s_val[warp] = best; s_idx[warp] = bi; }
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			for (int w = 1; w < 32; ++w) if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) { best = s_val[w]; bi = s_idx[w]; }
+			s_piv = bi;
+			ipiv[col] = bi;
+			if (!(best > 0.0)) s_fail = int(col) + 1;
+		}
+		__syncthreads();
+		if (s_fail) { if (threadIdx.x == 0 && status[0] == 0) status[0] = s_fail; return; }
+		const long long p = s_piv;
+		if (threadIdx.x < nb) {
+			const long long c = k0 + threadIdx.x;
+			const double top = A[col * n + c], bot = A[p * n + c];
+			if (p != col) { A[col * n + c] = bot; A[p * n + c] = top; }
+			s_row[threadIdx.x] = bot;                        // the pivot row inside the panel (after the swap)
+		}
+		__syncthreads();
+		const double inv = 1.0 / s_row[j];
+		// rows below the pivot: l = a / pivot, then a rank-1 update of the panel columns right of j
+		for (long long i = col + 1 + warp; i < n; i += 32) {
+			double* row = A + i * n + k0;
+			const double l = row[j] * inv;
+			__syncwarp();
+			if (lane == 0) row[j] = l;
+			for (int c = j + 1 + lane; c < nb; c += 32) row[c] -= l * s_row[c];
+		}
+		__syncthreads();
+	}
+}
+
+__global__ void lu_iota_kernel(int* __restrict__ ipiv, const int n) {
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) ipiv[i] = i;
+}
+
+// applies the nb row interchanges of a panel to `cols` columns starting at M (row stride ld): one thread per column
+__global__ void lu_swap_kernel(double* __restrict__ M, const long long ld, const int cols, const int* __restrict__ ipiv, const int k0, const int nb) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= cols) return;
+	for (int j = 0; j < nb; ++j) {
+		const long long r = k0 + j, p = ipiv[r];
+		if (p != r) { const double t = M[r * ld + c]; M[r * ld + c] = M[p * ld + c]; M[p * ld + c] = t; }
+	}
+}
+
+// X = L^-1 X for the unit lower nb x nb block L (row stride ldl) and the nb x ncols matrix X: one thread per column
+__global__ void __launch_bounds__(128) lu_trsm_kernel(const double* __restrict__ Lblk, const long long ldl, double* __restrict__ X, const long long ldx,
+                                                     const int nb, const int ncols) {
+	__shared__ double L[CH_NB][CH_NB + 1];
+	for (int e = threadIdx.x; e < CH_NB * CH_NB; e += blockDim.x) {
+		const int i = e / CH_NB, c = e % CH_NB;
+		L[i][c] = (i < nb && c < i) ? Lblk[(long long)i * ldl + c] : 0.0;
+	}
+	__syncthreads();
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= ncols) return;
+	double a[CH_NB];
+#pragma unroll
+	for (int i = 0; i < CH_NB; ++i) a[i] = (i < nb) ? X[(long long)i * ldx + c] : 0.0;
+#pragma unroll
+	for (int j = 0; j < CH_NB; ++j) {
+#pragma unroll
+		for (int i = j + 1; i < CH_NB; ++i) a[i] -= L[i][j] * a[j];
+	}
+#pragma unroll
+	for (int i = 0; i < CH_NB; ++i) if (i < nb) X[(long long)i * ldx + c] = a[i];
+}
+
+static void lu_solve_blocked(double* A, double* B, size_t n, size_t nrhs) {
+	cudaStream_t st = ctx().stream;
+	int* d_status = static_cast<int*>(dalloc_bytes(sizeof(int)));
+	int* ipiv = static_cast<int*>(dalloc_bytes(n * sizeof(int)));
+	XB_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+	// identity pivots: a panel that meets a zero pivot returns early, the kernels queued behind it must stay harmless
+	lu_iota_kernel<<<unsigned(std::min<size_t>((n + 255) / 256, 1024)), 256, 0, st>>>(ipiv, int(n));
+	XB_LAUNCH_CHECK();
+	for (size_t k0 = 0; k0 < n; k0 += CH_NB) {
+		const size_t nb = std::min<size_t>(CH_NB, n - k0), n2 = n - k0 - nb;
+		lu_panel_kernel<<<1, 1024, 0, st>>>(A, (long long)n, int(k0), int(nb), ipiv, d_status);
+		XB_LAUNCH_CHECK();
+		if (k0) { lu_swap_kernel<<<unsigned((k0 + 127) / 128), 128, 0, st>>>(A, (long long)n, int(k0), ipiv, int(k0), int(nb)); XB_LAUNCH_CHECK(); }
+		if (n2) { lu_swap_kernel<<<unsigned((n2 + 127) / 128), 128, 0, st>>>(A + k0 + nb, (long long)n, int(n2), ipiv, int(k0), int(nb)); XB_LAUNCH_CHECK(); }
+		lu_swap_kernel<<<unsigned((nrhs + 127) / 128), 128, 0, st>>>(B, (long long)nrhs, int(nrhs), ipiv, int(k0), int(nb));
+		XB_LAUNCH_CHECK();
+		const double* L11 = A + k0 * n + k0;
+		double* B1 = B + k0 * nrhs;
+		lu_trsm_kernel<<<unsigned((nrhs + 127) / 128), 128, 0, st>>>(L11, (long long)n, B1, (long long)nrhs, int(nb), int(nrhs));
+		XB_LAUNCH_CHECK();
+		if (n2 == 0) break;
+		double* A12 = A + k0 * n + k0 + nb;
+		const double* L21 = A + (k0 + nb) * n + k0;
+		lu_trsm_kernel<<<unsigned((n2 + 127) / 128), 128, 0, st>>>(L11, (long long)n, A12, (long long)n, int(nb), int(n2));
+		XB_LAUNCH_CHECK();
+		gemm(A + (k0 + nb) * n + k0 + nb, n, n2, n2, -1.0, L21, n, false, nb, A12, n, false, 1.0);       // A22 -= L21 U12
+		gemm(B1 + nb * nrhs, nrhs, n2, nrhs, -1.0, L21, n, false, nb, B1, nrhs, false, 1.0);             // B2  -= L21 Y1
+	}
+	const int stat = read_status(d_status);
+	dfree(d_status);
+	dfree(ipiv);
+	if (stat != 0) throw Error(XB_ERR_NUMERIC, "Unable to solve Ax = b (PLU solver): zero pivot in column " + std::to_string(stat - 1));
+	// U X = Y, block by block from the bottom
+	for (size_t kb = (n + CH_NB - 1) / CH_NB; kb-- > 0;) {
+		const size_t k0 = kb * CH_NB, nb = std::min<size_t>(CH_NB, n - k0), n2 = n - k0 - nb;
+		const double* Akk = A + k0 * n + k0;
+		double* B1 = B + k0 * nrhs;
+		if (n2) gemm(B1, nrhs, nb, nrhs, -1.0, Akk + nb, n, false, n2, B1 + nb * nrhs, nrhs, false, 1.0);    // B1 -= U12 X2
+		chol_trsm_kernel<false><<<unsigned((nrhs + 127) / 128), 128, 0, st>>>(Akk, (long long)n, B1, (long long)nrhs, int(nb), int(nrhs));
+		XB_LAUNCH_CHECK();
+	}
+}
+
 // sign = +1 for a positive, -1 for a negative diagonal (the reference's dpotrf2 only succeeds for +1)
 bool cholesky_solve(double* A, double* B, size_t n, size_t nrhs) {
 	if (n > size_t(CH_NB)) return cholesky_solve_blocked(A, B, n, nrhs);
@@ -291,6 +425,7 @@ bool cholesky_solve(double* A, double* B, size_t n, size_t nrhs) {
 }
 
 void lu_solve(double* A, double* B, size_t n, size_t nrhs) {
+	if (n > size_t(CH_NB)) { lu_solve_blocked(A, B, n, nrhs); return; }
 	int* d_status = static_cast<int*>(dalloc_bytes(sizeof(int)));
 	lu_solve_kernel<<<1, 1024, 0, ctx().stream>>>(A, B, int(n), int(nrhs), d_status);
 	XB_LAUNCH_CHECK();

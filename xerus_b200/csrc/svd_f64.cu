@@ -365,6 +365,43 @@ __device__ __forceinline__ void apply_rotations_to_v(double* __restrict__ Sv, co
 	}
 }
 
+// As apply_rotations_to_v, but TB tiles per step so that consecutive DMMAs are independent (a chain of dependent DMMAs
+// costs their full latency each): the warp's tile count must be a multiple of TB.
+template <int MT, int KT, int TB>
+__device__ __forceinline__ void apply_rotations_tiles(double* __restrict__ Sv, const int lds, const double* __restrict__ Js, const int ldj,
+                                                     const int ntiles, const int warp, const int nwarps, const int lane) {
+	const int g = lane >> 2, t = lane & 3;
+	double afr[MT][KT];
+#pragma unroll
+	for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+		for (int kt = 0; kt < KT; ++kt) afr[mt][kt] = Js[(8 * mt + g) * ldj + 4 * kt + t];
+	for (int tile0 = warp; tile0 < ntiles; tile0 += nwarps * TB) {
+		double bfr[TB][KT];
+#pragma unroll
+		for (int tb = 0; tb < TB; ++tb)
+#pragma unroll
+			for (int kt = 0; kt < KT; ++kt) bfr[tb][kt] = Sv[(size_t)(4 * kt + t) * lds + 8 * (tile0 + tb * nwarps) + g];
+		double acc[TB][MT][2];
+#pragma unroll
+		for (int tb = 0; tb < TB; ++tb)
+#pragma unroll
+			for (int mt = 0; mt < MT; ++mt) { acc[tb][mt][0] = 0.0; acc[tb][mt][1] = 0.0; }
+#pragma unroll
+		for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+			for (int tb = 0; tb < TB; ++tb)
+#pragma unroll
+				for (int mt = 0; mt < MT; ++mt) dmma_884(acc[tb][mt][0], acc[tb][mt][1], afr[mt][kt], bfr[tb][kt]);
+		__syncwarp();
+#pragma unroll
+		for (int tb = 0; tb < TB; ++tb)
+#pragma unroll
+			for (int mt = 0; mt < MT; ++mt)
+				*reinterpret_cast<double2*>(Sv + (size_t)(8 * mt + g) * lds + 8 * (tile0 + tb * nwarps) + 2 * t) = make_double2(acc[tb][mt][0], acc[tb][mt][1]);
+	}
+}
+
 // ---- specialised persistent kernel (FP64, both row parts 64 * EP2 doubles long) ------------------------------------------
 // Same algorithm and schedule as jacobi_persistent_kernel, rebuilt around what bounds an inner round on sm_100a (measured,
 // profiles/micro/fp64_micro.cu): the shared-memory pipe (128 B/clk: moving both 4 KB rows of 8 pairs in and out is 1024
@@ -673,6 +710,250 @@ __global__ void __launch_bounds__(MAXT) jacobi_fast_kernel(double* __restrict__ 
 	if (timing) { info[4] = (unsigned)(tk_load >> 10); info[5] = (unsigned)(tk_inner >> 10); info[6] = (unsigned)(tk_store >> 10); info[7] = (unsigned)(tk_sync >> 10); }
 }
 
+// ---- Gram-space block Jacobi kernel (FP64, 8-column blocks, both row parts 64 * EP2 doubles long) -------------------------
+// jacobi_fast_kernel pays a ~1 100-cycle dependent chain (load, dot, 5-stage butterfly, two rsqrt, rotate, barrier) for every
+// one of the 8 rounds of a block visit, on full-length vectors.  Here a visit (block p against block q, 16 columns) is
+//   1. G = X^T X of the 16 resident columns (x part), once, on the tensor pipe (partials per warp, fixed-order sum);
+//   2. the same 8 rounds of 8 disjoint rotations, but carried out on the 16 x 16 Gram matrix: the cross product and the
+//      norms of a pair are matrix entries (no dot, no butterfly), G <- R^T G R and Js <- R^T Js are one entry per thread;
+//   3. rows <- Js * rows for the x AND the accumulated-rotation part, once, with DMMA.
+// In exact arithmetic this is the same sequence of rotations as the column-space kernel.  In floating point the entries of
+// G used by the later rounds of a visit carry errors of eps * |G|_max instead of eps * |a||b|; every visit starts from a
+// fresh Gram matrix of the actual columns, so the convergence criterion is evaluated on true cosines for the pairs that
+// matter and errors never accumulate across visits.  Sweep counts and final accuracy are unchanged (numpy emulation of
+// both variants on Gaussian, graded 1e-8 / 1e-14 and rank-deficient inputs; GPU tests), absolute accuracy eps * sigma_max as
+// for LAPACK's dgesdd, which is the reference.
+template <int EP2>
+__global__ void __launch_bounds__(256) jacobi_gram_kernel(double* __restrict__ GT, const int nblk, const double tol2, const double big2,
+                                                         unsigned int* __restrict__ counters, unsigned int* __restrict__ info,
+                                                         const int max_sweeps, unsigned int* ready, const int recursive) {
+	constexpr int BW = 8, N = 16;
+	constexpr int LD = 128 * EP2;               // doubles per row in global memory: [x : 64 EP2 | v : 64 EP2]
+	constexpr int LDS = LD + 4;                 // shared-memory row stride (DMMA operand loads of 4 rows x 8 elements: distinct banks)
+	constexpr int V2 = 32 * EP2;                // offset of the v part in double2 units
+	constexpr int LG = 17;
+	extern __shared__ double S_gram[];
+	double* S = S_gram;                         // [N][LDS]
+	double* Gp = S + (size_t)N * LDS;           // [8][256] per-warp partial Gram matrices
+	double* Gm = Gp + 8 * 256;                  // [2][N][LG]  Gram matrix, double buffered
+	double* Jm = Gm + 2 * N * LG;               // [2][N][LG]  product of the rotations of the visit (row operations)
+	unsigned short* sched = reinterpret_cast<unsigned short*>(Jm + 2 * N * LG);   // [(N-1)][8] : a | b << 8   (all-pairs visits)
+	unsigned char* role = reinterpret_cast<unsigned char*>(sched + (N - 1) * BW + 8); // [(N-1)][16] : pair | is_b << 7
+	__shared__ double tabc[N], tabs[N];
+	__shared__ int tab_any_s;
+	int* tab_any = &tab_any_s;
+	__shared__ unsigned int s_rot, s_big;
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int e = threadIdx.x; e < (N - 1) * BW; e += blockDim.x) {
+		const int rr = e / BW, pi = e % BW;
+		int a, b;
+		if (pi == 0) { a = N - 1; b = rr; }
+		else { a = (rr + pi) % (N - 1); b = (rr - pi + N - 1) % (N - 1); }
+		sched[e] = (unsigned short)(a | (b << 8));
+		role[rr * N + a] = (unsigned char)pi;
+		role[rr * N + b] = (unsigned char)(pi | 128);
+	}
+	const int nrounds = (nblk == 2) ? 1 : nblk - 1;
+	if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
+	__syncthreads();
+	int sweeps = 0, ground = 0;
+	unsigned int last_rot = 1, last_big = 1;
+	unsigned int my_rot = 0, my_big = 0;
+	long long tk_load = 0, tk_inner = 0, tk_store = 0, tk_sync = 0, tk0 = 0, tk_gram = 0, tk_solve = 0, tk_apply = 0, tq = 0;
+	const bool timing = (info[0] == 0xC10C) && blockIdx.x == 0 && threadIdx.x == 0;
+	const int fg = lane >> 2, ft = lane & 3;    // DMMA fragment coordinates
+
+	for (; sweeps < max_sweeps; ) {
+		for (int round = 0; round < nrounds; ++round, ++ground) {
+			int pb, qb;
+			bool loadp = true, storep = true, full = (round == 0);
+			if (recursive) {
+				// recursive bipartite tournament with point-to-point block flags: see jacobi_persistent_kernel
+				int g = nblk, t = round;
+				while (t >= (g >> 1)) { t -= (g >> 1); g >>= 1; }
+				const int h = g >> 1, G = blockIdx.x / h, j = blockIdx.x % h;
+				pb = G * g + j; qb = G * g + h + ((j + t) & (h - 1));
+				loadp = (t == 0); storep = (t == h - 1); full = (g == 2);
+				if (threadIdx.x == 0) {
+					unsigned int spins = 0;
+					volatile unsigned int* rd = ready;
+					while ((rd[qb] < (unsigned)ground || (loadp && rd[pb] < (unsigned)ground)) && spins < (1u << 27)) ++spins;
+					if (spins >= (1u << 27)) atomicOr(&counters[2 * max_sweeps], 0xDEADu);
+					__threadfence();
+				}
+				__syncthreads();
+			} else {
+				const int pi = blockIdx.x, N1 = nblk - 1;
+				if (nblk == 2) { pb = 0; qb = 1; }
+				else if (pi == 0) { pb = N1; qb = round % N1; }
+				else { pb = (round + pi) % N1; qb = (round - pi + N1) % N1; }
+			}
+			if (timing) tk0 = clock64();
+			for (int r = (loadp ? 0 : BW) + warp; r < N; r += 8) {
+				const int grow = (r < BW ? pb * BW + r : qb * BW + (r - BW));
+				const double2* src = reinterpret_cast<const double2*>(GT + (size_t)grow * LD) + lane;
+				double2* dst = reinterpret_cast<double2*>(S + (size_t)r * LDS) + lane;
+				double2 v[EP2], w[EP2];
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) { v[k] = __ldcg(src + 32 * k); w[k] = __ldcg(src + V2 + 32 * k); }
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) { dst[32 * k] = v[k]; dst[V2 + 32 * k] = w[k]; }
+			}
+			__syncthreads();
+			if (timing) { const long long t1 = clock64(); tk_load += t1 - tk0; tk0 = t1; }
+
+			if (timing) tq = clock64();
+			// 1. Gram matrix of the x parts: warp w takes the k-steps w, w + 8, ... (two interleaved accumulator sets: a DMMA
+			//    depends on the previous one of its chain); tile (1,0) is the mirror of (0,1)
+			{
+				double a00[2] = {0.0, 0.0}, a01[2] = {0.0, 0.0}, a11[2] = {0.0, 0.0};
+				double b00[2] = {0.0, 0.0}, b01[2] = {0.0, 0.0}, b11[2] = {0.0, 0.0};
+				const double* s0 = S + (size_t)fg * LDS + ft;
+				const double* s1 = S + (size_t)(8 + fg) * LDS + ft;
+#pragma unroll
+				for (int i = 0; i < EP2; ++i) {
+					const int ks = warp + 16 * i;
+					const double f0 = s0[4 * ks], f1 = s1[4 * ks], h0 = s0[4 * (ks + 8)], h1 = s1[4 * (ks + 8)];
+					dmma_884(a00[0], a00[1], f0, f0);
+					dmma_884(b00[0], b00[1], h0, h0);
+					dmma_884(a01[0], a01[1], f0, f1);
+					dmma_884(b01[0], b01[1], h0, h1);
+					dmma_884(a11[0], a11[1], f1, f1);
+					dmma_884(b11[0], b11[1], h1, h1);
+				}
+				double* gp = Gp + warp * 256;
+				*reinterpret_cast<double2*>(gp + fg * 16 + 2 * ft) = make_double2(a00[0] + b00[0], a00[1] + b00[1]);
+				*reinterpret_cast<double2*>(gp + fg * 16 + 8 + 2 * ft) = make_double2(a01[0] + b01[0], a01[1] + b01[1]);
+				*reinterpret_cast<double2*>(gp + (8 + fg) * 16 + 8 + 2 * ft) = make_double2(a11[0] + b11[0], a11[1] + b11[1]);
+			}
+			__syncthreads();
+			{
+				const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
+				const int e = (r >= 8 && c < 8) ? c * 16 + r : r * 16 + c;
+				double sum = 0.0;
+#pragma unroll
+				for (int w = 0; w < 8; ++w) sum += Gp[w * 256 + e];
+				Gm[r * LG + c] = sum;
+				Jm[r * LG + c] = (r == c) ? 1.0 : 0.0;
+			}
+			__syncthreads();
+
+			if (timing) { const long long t1 = clock64(); tk_gram += t1 - tq; tq = t1; }
+			// 2. the rounds of the visit on G.  Lanes 0..7 of warp 0 derive the 8 rotations of a round and publish, per column
+			//    index r, the row operation  row_r' = tabc[r] row_r + tabs[r] row_partner(r)  (row_a' = c row_a - s row_b,
+			//    row_b' = s row_a + c row_b); every thread then updates one entry of G (R^T G R) and of Js (R^T Js).  The entries a
+			//    thread needs depend on the schedule only, so they are fetched while warp 0 works on the parameters.
+			int cur = 0;
+			bool any_rot = false;
+			const int nr = full ? (N - 1) : BW;
+			const int r0 = threadIdx.x >> 4, c0 = threadIdx.x & 15;
+			for (int rr = 0; rr < nr; ++rr) {
+				const double* Gc = Gm + cur * N * LG;
+				const double* Jc = Jm + cur * N * LG;
+				int rp, cp;                                  // partners of this thread's row and column index in this round
+				if (full) {
+					const unsigned int rl = role[rr * N + r0], cl = role[rr * N + c0];
+					const unsigned int pr_ = sched[rr * BW + (rl & 127)], pc_ = sched[rr * BW + (cl & 127)];
+					rp = (rl >> 7) ? (pr_ & 255) : (pr_ >> 8);
+					cp = (cl >> 7) ? (pc_ & 255) : (pc_ >> 8);
+				} else {
+					rp = (r0 < BW) ? BW + ((r0 + rr) & 7) : ((r0 - BW - rr) & 7);
+					cp = (c0 < BW) ? BW + ((c0 + rr) & 7) : ((c0 - BW - rr) & 7);
+				}
+				const double g00 = Gc[r0 * LG + c0], g01 = Gc[r0 * LG + cp], g10 = Gc[rp * LG + c0], g11 = Gc[rp * LG + cp];
+				const double j0 = Jc[r0 * LG + c0], j1 = Jc[rp * LG + c0];
+				if (warp == 0) {
+					int a, b;
+					if (full) { const unsigned int ab_ = sched[rr * BW + (lane & 7)]; a = ab_ & 255; b = ab_ >> 8; }
+					else { a = lane & 7; b = BW + (((lane & 7) + rr) & 7); }
+					const double aa = Gc[a * LG + a], bb = Gc[b * LG + b], g = Gc[a * LG + b];
+					const double gg = g * g, ab = aa * bb;
+					const bool rot = gg > tol2 * ab;
+					const bool any = __any_sync(0xffffffffu, rot);
+					if (any && lane < 8) {
+						double c = 1.0, s = 0.0;
+						if (rot) {
+							// c^2 = (1 + |d|/h)/2, s = sign(d) 2g / (2 h c) with d = bb - aa, h = sqrt(d^2 + 4 g^2): two rsqrt, no division
+							const double d = bb - aa;
+							const double rh = rsqrt(d * d + 4.0 * gg);
+							const double c2 = 0.5 + 0.5 * fabs(d) * rh;
+							const double rc = rsqrt(c2);
+							c = c2 * rc;
+							s = (d >= 0.0 ? g : -g) * rh * rc;
+							my_rot += 1;
+							if (gg > big2 * ab) my_big += 1;
+						}
+						tabc[a] = c; tabs[a] = -s; tabc[b] = c; tabs[b] = s;
+					}
+					if (lane == 0) *tab_any = any ? 1 : 0;
+				}
+				__syncthreads();
+				if (*tab_any == 0) { __syncthreads(); continue; }     // (second barrier: warp 0 may not overwrite the flag before all have read it)
+				any_rot = true;
+				const double rc_ = tabc[r0], rs_ = tabs[r0], tc = tabc[c0], ts = tabs[c0];
+				double* Gn = Gm + (cur ^ 1) * N * LG;
+				double* Jn = Jm + (cur ^ 1) * N * LG;
+				Gn[r0 * LG + c0] = rc_ * (tc * g00 + ts * g01) + rs_ * (tc * g10 + ts * g11);
+				Jn[r0 * LG + c0] = rc_ * j0 + rs_ * j1;
+				cur ^= 1;
+				__syncthreads();
+			}
+			if (timing) { const long long t1 = clock64(); tk_solve += t1 - tq; tq = t1; }
+			// 3. rows <- Js * rows (both parts)
+			if (any_rot) {
+				apply_rotations_tiles<2, 4, (EP2 % 2 == 0) ? 4 : 2>(S, LDS, Jm + cur * N * LG, LG, LD / 8, warp, 8, lane);
+				__syncthreads();
+			}
+			if (timing) { const long long t1 = clock64(); tk_apply += t1 - tq; tk_inner += t1 - tk0; tk0 = t1; }
+			if (warp == 0 && my_rot) { atomicAdd(&s_rot, my_rot); atomicAdd(&s_big, my_big); my_rot = 0; my_big = 0; }
+			for (int r = (storep ? 0 : BW) + warp; r < N; r += 8) {
+				const int grow = (r < BW ? pb * BW + r : qb * BW + (r - BW));
+				double2* dst = reinterpret_cast<double2*>(GT + (size_t)grow * LD) + lane;
+				const double2* src = reinterpret_cast<const double2*>(S + (size_t)r * LDS) + lane;
+				double2 v[EP2], w[EP2];
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) { v[k] = src[32 * k]; w[k] = src[V2 + 32 * k]; }
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) { dst[32 * k] = v[k]; dst[V2 + 32 * k] = w[k]; }
+			}
+			if (timing) { const long long t1 = clock64(); tk_store += t1 - tk0; tk0 = t1; }
+			if (recursive) {
+				__syncthreads();
+				if (threadIdx.x == 0) {
+					__threadfence();
+					volatile unsigned int* rd = ready;
+					if (storep) rd[pb] = (unsigned)ground + 1u;
+					rd[qb] = (unsigned)ground + 1u;
+				}
+			} else if (nblk > 2) { __threadfence(); grid.sync(); }
+			else __syncthreads();
+			if (timing) { const long long t1 = clock64(); tk_sync += t1 - tk0; tk0 = t1; }
+		}
+		++sweeps;
+		unsigned int rot, big;
+		if (nblk > 2) {
+			if (threadIdx.x == 0) { atomicAdd(&counters[2 * (sweeps - 1)], s_rot); atomicAdd(&counters[2 * (sweeps - 1) + 1], s_big); s_rot = 0; s_big = 0; }
+			__threadfence();
+			grid.sync();
+			rot = *((volatile unsigned int*)&counters[2 * (sweeps - 1)]);
+			big = *((volatile unsigned int*)&counters[2 * (sweeps - 1) + 1]);
+		} else {
+			rot = s_rot; big = s_big;
+			__syncthreads();
+			if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
+			__syncthreads();
+		}
+		last_rot = rot; last_big = big;
+		if (big == 0) break;
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) { info[1] = (unsigned)sweeps; info[2] = last_big; info[3] = last_rot; }
+	if (timing) {
+		info[4] = (unsigned)(tk_load >> 10); info[5] = (unsigned)(tk_inner >> 10); info[6] = (unsigned)(tk_store >> 10); info[7] = (unsigned)(tk_sync >> 10);
+		counters[2 * max_sweeps + 1] = (unsigned)(tk_gram >> 10); counters[2 * max_sweeps + 2] = (unsigned)(tk_solve >> 10); counters[2 * max_sweeps + 3] = (unsigned)(tk_apply >> 10);
+	}
+}
+
 // mixed-precision helpers: scaled double -> float working copy, float V -> double V
 __global__ void svd_init_f32_kernel(float* __restrict__ GT, const int ld, const int npad, const int mdot, const int voff, const int nw,
                                     const double* __restrict__ src, const long long rs, const long long cs, const double* __restrict__ amax) {
@@ -820,9 +1101,38 @@ static void launch_fast(double* gt, const JacobiPlan& p, double tol2, double big
 	ctx().launches++;
 }
 
+template <int EP2>
+static void launch_gram(double* gt, const JacobiPlan& p, double tol2, double big2, unsigned int* d_cnt, unsigned int* d_info, int max_sweeps,
+                        size_t smem_cap) {
+	static bool attr = false;
+	if (!attr) {
+		XB_CUDA(cudaFuncSetAttribute(jacobi_gram_kernel<EP2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+		attr = true;
+	}
+	int nblk = int(p.nblk);
+	unsigned int* ready = d_cnt + 2 * max_sweeps + 12;
+	int recursive = (ctx().svd_recursive && nblk > 2 && (nblk & (nblk - 1)) == 0) ? 1 : 0;
+	const size_t smem = (size_t(16) * (128 * EP2 + 4) + 8 * 256 + 4 * 16 * 17) * sizeof(double) + 15 * 8 * 2 + 16 + 15 * 16 + 64;
+	XB_REQUIRE(smem <= smem_cap, "internal: Gram Jacobi kernel exceeds shared memory");
+	void* args[] = {&gt, &nblk, &tol2, &big2, &d_cnt, &d_info, &max_sweeps, &ready, &recursive};
+	XB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_gram_kernel<EP2>, dim3(unsigned(p.nblk / 2)), dim3(256), args, smem, ctx().stream));
+	ctx().launches++;
+}
+
 static void launch_fast_any(double* gt, const JacobiPlan& p, double tol2, double big2, unsigned int* d_cnt, unsigned int* d_info, int max_sweeps,
                             size_t smem_cap) {
 	const bool jacc = ctx().svd_jacc && (p.bw == 8 || p.bw == 4);
+	if (ctx().svd_gram && p.bw == 8) {
+		switch (p.ep2) {
+			case 1: launch_gram<1>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			case 2: launch_gram<2>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			case 3: launch_gram<3>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			case 4: launch_gram<4>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			case 6: launch_gram<6>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			case 8: launch_gram<8>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			default: break;
+		}
+	}
 	switch (p.ep2) {
 		case 1: if (jacc) launch_fast<1, 256, true>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); else launch_fast<1, 256, false>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); break;
 		case 2: if (jacc) launch_fast<2, 256, true>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); else launch_fast<2, 256, false>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); break;
@@ -862,6 +1172,7 @@ static bool run_persistent(T* gt, size_t ld, size_t voff, const JacobiPlan& p, d
 	sweeps_out = int(h_info[1]);
 	const bool converged = h_info[2] == 0;
 	if (dead) { dfree(d_cnt); throw Error(XB_ERR_CUDA, "Jacobi SVD: a block hand-over flag was never raised (internal scheduling error)"); }
+	if (timing && h_info[-3]) fprintf(stderr, "[jacobi %s] inner = gram %u + rounds on G %u + apply %u kcycles\n", tag, h_info[-3], h_info[-2], h_info[-1]);
 	if (timing) fprintf(stderr, "[jacobi %s] ld=%zu bw=%d ctas=%zu sweeps=%d kcycles: load %u inner %u store %u sync %u\n", tag, ld, p.bw,
 	                    p.nblk / 2, sweeps_out, h_info[4], h_info[5], h_info[6], h_info[7]);
 	dfree(d_cnt);

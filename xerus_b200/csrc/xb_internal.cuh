@@ -63,6 +63,8 @@ struct Context {
 	int svd_fast = 1;              // specialised Jacobi kernel (compile-time row length, 128-bit accesses) up to 512 columns
 	int svd_jacc = 1;              // specialised Jacobi kernel: rotations of a block visit accumulated, applied to V once (DMMA)
 	int als_graph = 1;             // one-site SPD CG: chunks of 8 iterations replayed as a CUDA graph
+	int svd_gram = 0;              // experimental: Jacobi block visits in Gram space (one Gram matrix, 16 x 16 rounds, one DMMA apply
+	                               // per visit); correct, but not faster than the column-space kernel on one SM per block pair
 	int svd_recursive = 1;         // recursive bipartite tournament with point-to-point block flags (power-of-two block counts)
 	int svd_mixed = 0;             // FP32 pre-conditioning sweeps + FP64 finishing sweeps (measured: no gain, kept as an experiment)
 	int svd_mixed_min = 64;        // smallest column count for the mixed path
