@@ -193,7 +193,7 @@ def test_svd_vs_oracle(m, n):
     assert np.linalg.norm(U.T @ U - np.eye(k)) < 1e-11 and np.linalg.norm(Vt @ Vt.T - np.eye(k)) < 1e-11
 
 
-VARIANT_DEFAULTS = {"svd_fast": 1, "svd_jacc": 1, "svd_recursive": 1, "svd_flip": 1, "qr_cluster": 1, "svd_gram": 0}
+VARIANT_DEFAULTS = {"svd_fast": 1, "svd_jacc": 1, "svd_recursive": 1, "svd_flip": 1, "qr_cluster": 1, "svd_gram": 0, "svd_split": 1}
 
 
 @pytest.mark.parametrize("option", sorted(VARIANT_DEFAULTS))

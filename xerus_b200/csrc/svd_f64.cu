@@ -710,6 +710,285 @@ __global__ void __launch_bounds__(MAXT) jacobi_fast_kernel(double* __restrict__ 
 	if (timing) { info[4] = (unsigned)(tk_load >> 10); info[5] = (unsigned)(tk_inner >> 10); info[6] = (unsigned)(tk_store >> 10); info[7] = (unsigned)(tk_sync >> 10); }
 }
 
+// ---- split kernel: X workers and V workers -------------------------------------------------------------------------------
+// With the rotations of a visit accumulated in Js, the accumulated-rotation halves of the rows are pure bookkeeping: nothing
+// in the Jacobi iteration reads them.  Here they leave the critical path altogether.  The grid is doubled: CTA w < nblk/2 is
+// the X worker of jacobi_fast_kernel reduced to the x halves (load, rounds, store, hand-over); CTA nblk/2 + w is its V worker,
+// which follows the same tournament one step behind: it waits for the product Js_k its X worker logs after visit k (a ring of
+// JS_DEPTH slots in global memory, with back-pressure), applies it to the v halves with DMMA and hands the travelling block's
+// v half to the next V worker through its own ready flags.  Measured upper bound of the gain (V work deleted): -16 %.
+constexpr int JS_DEPTH = 4;
+template <int EP2>
+__global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ GT, const int nblk, const double tol2, const double big2,
+                                                          unsigned int* __restrict__ counters, unsigned int* __restrict__ info,
+                                                          const int max_sweeps, unsigned int* flags, double* jlog) {
+	constexpr int BW = 8, N = 16;
+	constexpr int LD = 128 * EP2;               // doubles per row in global memory: [x : 64 EP2 | v : 64 EP2]
+	constexpr int HL = 64 * EP2;                // one half
+	constexpr int HLS = HL + 4;                 // shared-memory row stride
+	constexpr int ldj = N + 4;
+	constexpr int SLOT = N * N + 8;
+	constexpr int TB = (EP2 % 4 == 0) ? 4 : ((EP2 % 2 == 0) ? 2 : 1);
+	extern __shared__ double S_split[];
+	double* S = S_split;                        // [N][HLS]
+	double* nrm = S + (size_t)N * HLS;          // [N]
+	unsigned short* sched = reinterpret_cast<unsigned short*>(nrm + N);              // [(N-1)][BW]
+	double* Js = reinterpret_cast<double*>(sched + ((N - 1) * BW + 8));              // [N][ldj]   ((N-1)*BW + 8 = 128 shorts)
+	__shared__ unsigned int s_rot, s_big;
+	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int nw = nblk >> 1;
+	const bool vrole = int(blockIdx.x) >= nw;
+	const int wid = vrole ? int(blockIdx.x) - nw : int(blockIdx.x);
+	unsigned int* xready = flags;
+	unsigned int* vready = flags + nblk;
+	unsigned int* jready = flags + 2 * nblk;
+	unsigned int* jdone = jready + nw;
+	unsigned int* rdy = vrole ? vready : xready;
+	const size_t hoff = vrole ? HL : 0;
+	for (int e = threadIdx.x; e < (N - 1) * BW; e += blockDim.x) {
+		const int rr = e / BW, pi = e % BW;
+		int a, b;
+		if (pi == 0) { a = N - 1; b = rr; }
+		else { a = (rr + pi) % (N - 1); b = (rr - pi + N - 1) % (N - 1); }
+		sched[e] = (unsigned short)(a | (b << 8));
+	}
+	const int nrounds = nblk - 1;
+	if (threadIdx.x == 0) { s_rot = 0; s_big = 0; }
+	__syncthreads();
+	int sweeps = 0, ground = 0;
+	unsigned int last_rot = 1, last_big = 1;
+	unsigned int my_rot = 0, my_big = 0;
+	long long tk_load = 0, tk_inner = 0, tk_store = 0, tk_sync = 0, tk0 = 0;
+	const bool timing = (info[0] == 0xC10C) && blockIdx.x == 0 && threadIdx.x == 0;
+
+	auto rotation = [](const double aa, const double bb, const double g, const double gg, double& c, double& s, double& t) {
+		const double d = bb - aa;
+		const double rh = rsqrt(d * d + 4.0 * gg);
+		const double c2 = 0.5 + 0.5 * fabs(d) * rh;
+		const double rc = rsqrt(c2);
+		c = c2 * rc;
+		s = (d >= 0.0 ? g : -g) * rh * rc;
+		t = s * rc;
+	};
+
+	for (; sweeps < max_sweeps; ) {
+		for (int round = 0; round < nrounds; ++round, ++ground) {
+			// recursive bipartite tournament with point-to-point block flags: see jacobi_persistent_kernel
+			int g = nblk, t = round;
+			while (t >= (g >> 1)) { t -= (g >> 1); g >>= 1; }
+			const int h = g >> 1, G = wid / h, j = wid % h;
+			const int pb = G * g + j, qb = G * g + h + ((j + t) & (h - 1));
+			const bool loadp = (t == 0), storep = (t == h - 1), full = (g == 2);
+			double* slot = jlog + ((size_t)wid * JS_DEPTH + (ground % JS_DEPTH)) * SLOT;
+			if (threadIdx.x == 0) {
+				unsigned int spins = 0;
+				volatile unsigned int* rd = rdy;
+				volatile unsigned int* jr = jready;
+				volatile unsigned int* jd = jdone;
+				for (;;) {
+					bool ok = rd[qb] >= (unsigned)ground && (!loadp || rd[pb] >= (unsigned)ground);
+					if (vrole) ok = ok && jr[wid] >= (unsigned)ground + 1u;                      // the product of this visit is logged
+					else ok = ok && jd[wid] + JS_DEPTH >= (unsigned)ground + 1u;                  // the ring slot is free again
+					if (ok || ++spins >= (1u << 27)) break;
+				}
+				if (spins >= (1u << 27)) atomicOr(&counters[2 * max_sweeps], 0xDEADu);
+				__threadfence();
+			}
+			__syncthreads();
+			if (timing) tk0 = clock64();
+			for (int r = (loadp ? 0 : BW) + warp; r < N; r += 8) {
+				const int grow = (r < BW ? pb * BW + r : qb * BW + (r - BW));
+				const double2* src = reinterpret_cast<const double2*>(GT + (size_t)grow * LD + hoff) + lane;
+				double2* dst = reinterpret_cast<double2*>(S + (size_t)r * HLS) + lane;
+				double2 v[EP2];
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) v[k] = __ldcg(src + 32 * k);
+				double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) { dst[32 * k] = v[k]; s0 += v[k].x * v[k].x; s1 += v[k].y * v[k].y; }
+				if (!vrole) {
+					double ss = s0 + s1;
+#pragma unroll
+					for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+					if (lane == 0) nrm[r] = ss;
+				}
+			}
+			if (vrole) {
+				// V worker: fetch the logged product, apply it to the v halves
+				Js[(threadIdx.x >> 4) * ldj + (threadIdx.x & 15)] = __ldcg(slot + threadIdx.x);
+				const bool rotated = __ldcg(slot + N * N) != 0.0;
+				__syncthreads();
+				if (timing) { const long long t1 = clock64(); tk_load += t1 - tk0; tk0 = t1; }
+				if (rotated) {
+					apply_rotations_tiles<2, 4, TB>(S, HLS, Js, ldj, HL / 8, warp, 8, lane);
+					__syncthreads();
+				}
+			} else {
+				Js[(threadIdx.x >> 4) * ldj + (threadIdx.x & 15)] = ((threadIdx.x >> 4) == (threadIdx.x & 15)) ? 1.0 : 0.0;
+				unsigned int visit_rot = 0;
+				__syncthreads();
+				if (timing) { const long long t1 = clock64(); tk_load += t1 - tk0; tk0 = t1; }
+				if (full) {
+					// all pairs among the 16 resident columns: both columns of a pair change owner every round
+					for (int rr = 0; rr < N - 1; ++rr) {
+						const unsigned int ab_ = sched[rr * BW + warp];
+						const int a = ab_ & 255, b = ab_ >> 8;
+						double2* x = reinterpret_cast<double2*>(S + (size_t)a * HLS) + lane;
+						double2* y = reinterpret_cast<double2*>(S + (size_t)b * HLS) + lane;
+						double2 xr[EP2], yr[EP2];
+#pragma unroll
+						for (int k = 0; k < EP2; ++k) { xr[k] = x[32 * k]; yr[k] = y[32 * k]; }
+						double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+						for (int k = 0; k < EP2; ++k) {
+							if (k & 1) { g2 += xr[k].x * yr[k].x; g3 += xr[k].y * yr[k].y; }
+							else { g0 += xr[k].x * yr[k].x; g1 += xr[k].y * yr[k].y; }
+						}
+						double gs = (g0 + g1) + (g2 + g3);
+						const double aa = nrm[a], bb = nrm[b];
+#pragma unroll
+						for (int o = 16; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+						const double gg = gs * gs, ab = aa * bb;
+						if (gg > tol2 * ab) {
+							double ja = 0.0, jb = 0.0;
+							if (lane < N) { ja = Js[a * ldj + lane]; jb = Js[b * ldj + lane]; }
+							double c, s, tt;
+							rotation(aa, bb, gs, gg, c, s, tt);
+#pragma unroll
+							for (int k = 0; k < EP2; ++k) {
+								x[32 * k] = make_double2(c * xr[k].x - s * yr[k].x, c * xr[k].y - s * yr[k].y);
+								y[32 * k] = make_double2(s * xr[k].x + c * yr[k].x, s * xr[k].y + c * yr[k].y);
+							}
+							if (lane < N) { Js[a * ldj + lane] = c * ja - s * jb; Js[b * ldj + lane] = s * ja + c * jb; }
+							double na = aa - tt * gs, nb = bb + tt * gs;
+							if (na < 0.25 * aa || nb < 0.25 * bb) {
+								double sa = 0.0, sb = 0.0;
+#pragma unroll
+								for (int k = 0; k < EP2; ++k) {
+									const double xn0 = c * xr[k].x - s * yr[k].x, yn0 = s * xr[k].x + c * yr[k].x;
+									const double xn1 = c * xr[k].y - s * yr[k].y, yn1 = s * xr[k].y + c * yr[k].y;
+									sa += xn0 * xn0 + xn1 * xn1; sb += yn0 * yn0 + yn1 * yn1;
+								}
+#pragma unroll
+								for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+								na = sa; nb = sb;
+							}
+							visit_rot = 1;
+							if (lane == 0) {
+								nrm[a] = na; nrm[b] = nb;
+								my_rot += 1;
+								if (gg > big2 * ab) my_big += 1;
+							}
+						}
+						__syncthreads();
+					}
+				} else {
+					// block p against block q: warp w keeps column w of p in registers and meets column (w + rr) mod 8 of q in round rr
+					const int a = warp;
+					double2* x = reinterpret_cast<double2*>(S + (size_t)a * HLS) + lane;
+					double2 xr[EP2];
+#pragma unroll
+					for (int k = 0; k < EP2; ++k) xr[k] = x[32 * k];
+					double aa = nrm[a], ja = (lane < N) ? Js[a * ldj + lane] : 0.0;
+					for (int rr = 0; rr < BW; ++rr) {
+						const int b = BW + ((warp + rr) & (BW - 1));
+						double2* y = reinterpret_cast<double2*>(S + (size_t)b * HLS) + lane;
+						double2 yr[EP2];
+#pragma unroll
+						for (int k = 0; k < EP2; ++k) yr[k] = y[32 * k];
+						double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+						for (int k = 0; k < EP2; ++k) {
+							if (k & 1) { g2 += xr[k].x * yr[k].x; g3 += xr[k].y * yr[k].y; }
+							else { g0 += xr[k].x * yr[k].x; g1 += xr[k].y * yr[k].y; }
+						}
+						double gs = (g0 + g1) + (g2 + g3);
+						const double bb = nrm[b];
+#pragma unroll
+						for (int o = 16; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+						const double gg = gs * gs, ab = aa * bb;
+						if (gg > tol2 * ab) {
+							const double jb = (lane < N) ? Js[b * ldj + lane] : 0.0;
+							double c, s, tt;
+							rotation(aa, bb, gs, gg, c, s, tt);
+#pragma unroll
+							for (int k = 0; k < EP2; ++k) {
+								const double2 xn = make_double2(c * xr[k].x - s * yr[k].x, c * xr[k].y - s * yr[k].y);
+								y[32 * k] = make_double2(s * xr[k].x + c * yr[k].x, s * xr[k].y + c * yr[k].y);
+								xr[k] = xn;
+							}
+							if (lane < N) { Js[b * ldj + lane] = s * ja + c * jb; ja = c * ja - s * jb; }
+							double na = aa - tt * gs, nb = bb + tt * gs;
+							if (na < 0.25 * aa || nb < 0.25 * bb) {
+								double sa = 0.0, sb = 0.0;
+#pragma unroll
+								for (int k = 0; k < EP2; ++k) {
+									const double2 yn = y[32 * k];
+									sa += xr[k].x * xr[k].x + xr[k].y * xr[k].y; sb += yn.x * yn.x + yn.y * yn.y;
+								}
+#pragma unroll
+								for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+								na = sa; nb = sb;
+							}
+							aa = na;
+							visit_rot = 1;
+							if (lane == 0) {
+								nrm[b] = nb;
+								my_rot += 1;
+								if (gg > big2 * ab) my_big += 1;
+							}
+						}
+						__syncthreads();
+					}
+#pragma unroll
+					for (int k = 0; k < EP2; ++k) x[32 * k] = xr[k];
+					if (lane == 0) nrm[a] = aa;
+					if (lane < N) Js[a * ldj + lane] = ja;
+				}
+				// log the product of this visit for the V worker
+				const int any = __syncthreads_or(int(visit_rot));
+				slot[threadIdx.x] = Js[(threadIdx.x >> 4) * ldj + (threadIdx.x & 15)];
+				if (threadIdx.x == 0) slot[N * N] = any ? 1.0 : 0.0;
+				__syncthreads();
+				if (threadIdx.x == 0) { __threadfence(); *((volatile unsigned int*)&jready[wid]) = (unsigned)ground + 1u; }
+			}
+			if (timing) { const long long t1 = clock64(); tk_inner += t1 - tk0; tk0 = t1; }
+			if (lane == 0 && my_rot) { atomicAdd(&s_rot, my_rot); atomicAdd(&s_big, my_big); my_rot = 0; my_big = 0; }
+			for (int r = (storep ? 0 : BW) + warp; r < N; r += 8) {
+				const int grow = (r < BW ? pb * BW + r : qb * BW + (r - BW));
+				double2* dst = reinterpret_cast<double2*>(GT + (size_t)grow * LD + hoff) + lane;
+				const double2* src = reinterpret_cast<const double2*>(S + (size_t)r * HLS) + lane;
+				double2 v[EP2];
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) v[k] = src[32 * k];
+#pragma unroll
+				for (int k = 0; k < EP2; ++k) dst[32 * k] = v[k];
+			}
+			if (timing) { const long long t1 = clock64(); tk_store += t1 - tk0; tk0 = t1; }
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				__threadfence();
+				volatile unsigned int* rd = rdy;
+				if (storep) rd[pb] = (unsigned)ground + 1u;
+				rd[qb] = (unsigned)ground + 1u;
+				if (vrole) *((volatile unsigned int*)&jdone[wid]) = (unsigned)ground + 1u;
+			}
+			if (timing) { const long long t1 = clock64(); tk_sync += t1 - tk0; tk0 = t1; }
+		}
+		++sweeps;
+		if (threadIdx.x == 0 && !vrole) { atomicAdd(&counters[2 * (sweeps - 1)], s_rot); atomicAdd(&counters[2 * (sweeps - 1) + 1], s_big); s_rot = 0; s_big = 0; }
+		__threadfence();
+		grid.sync();
+		const unsigned int rot = *((volatile unsigned int*)&counters[2 * (sweeps - 1)]);
+		const unsigned int big = *((volatile unsigned int*)&counters[2 * (sweeps - 1) + 1]);
+		last_rot = rot; last_big = big;
+		if (big == 0) break;
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) { info[1] = (unsigned)sweeps; info[2] = last_big; info[3] = last_rot; }
+	if (timing) { info[4] = (unsigned)(tk_load >> 10); info[5] = (unsigned)(tk_inner >> 10); info[6] = (unsigned)(tk_store >> 10); info[7] = (unsigned)(tk_sync >> 10); }
+}
+
 // ---- Gram-space block Jacobi kernel (FP64, 8-column blocks, both row parts 64 * EP2 doubles long) -------------------------
 // jacobi_fast_kernel pays a ~1 100-cycle dependent chain (load, dot, 5-stage butterfly, two rsqrt, rotate, barrier) for every
 // one of the 8 rounds of a block visit, on full-length vectors.  Here a visit (block p against block q, 16 columns) is
@@ -1119,9 +1398,40 @@ static void launch_gram(double* gt, const JacobiPlan& p, double tol2, double big
 	ctx().launches++;
 }
 
+template <int EP2>
+static void launch_split(double* gt, const JacobiPlan& p, double tol2, double big2, unsigned int* d_cnt, unsigned int* d_info, int max_sweeps,
+                         size_t smem_cap) {
+	static bool attr = false;
+	if (!attr) {
+		XB_CUDA(cudaFuncSetAttribute(jacobi_split_kernel<EP2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+		attr = true;
+	}
+	int nblk = int(p.nblk);
+	unsigned int* flags = d_cnt + 2 * max_sweeps + 12;
+	const size_t smem = (size_t(16) * (64 * EP2 + 4) + 16 + 16 * 20) * sizeof(double) + 256 + 64;
+	XB_REQUIRE(smem <= smem_cap, "internal: split Jacobi kernel exceeds shared memory");
+	DBuf jlog(size_t(nblk / 2) * JS_DEPTH * (16 * 16 + 8));
+	double* jl = jlog.p;
+	void* args[] = {&gt, &nblk, &tol2, &big2, &d_cnt, &d_info, &max_sweeps, &flags, &jl};
+	XB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_split_kernel<EP2>, dim3(unsigned(nblk)), dim3(256), args, smem, ctx().stream));
+	ctx().launches++;
+}
+
 static void launch_fast_any(double* gt, const JacobiPlan& p, double tol2, double big2, unsigned int* d_cnt, unsigned int* d_info, int max_sweeps,
                             size_t smem_cap) {
 	const bool jacc = ctx().svd_jacc && (p.bw == 8 || p.bw == 4);
+	const bool pow2 = p.nblk > 2 && (p.nblk & (p.nblk - 1)) == 0;
+	if (ctx().svd_split && jacc && p.bw == 8 && pow2 && ctx().svd_recursive && p.nblk <= size_t(ctx().num_sms)) {
+		switch (p.ep2) {
+			case 1: launch_split<1>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			case 2: launch_split<2>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			case 3: launch_split<3>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			case 4: launch_split<4>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			case 6: launch_split<6>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			case 8: launch_split<8>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
+			default: break;
+		}
+	}
 	if (ctx().svd_gram && p.bw == 8) {
 		switch (p.ep2) {
 			case 1: launch_gram<1>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap); return;
@@ -1152,7 +1462,7 @@ template <typename T>
 static bool run_persistent(T* gt, size_t ld, size_t voff, const JacobiPlan& p, double tol, double big, int max_sweeps, int& sweeps_out,
                            size_t smem_cap, const char* tag) {
 	Context& c = ctx();
-	const size_t n_u32 = 2 * max_sweeps + 12 + p.nblk;      // sweep counters | info | per-block ready flags
+	const size_t n_u32 = 2 * max_sweeps + 12 + 4 * p.nblk;  // sweep counters | info | ready flags (x blocks, v blocks, product log)
 	unsigned int* d_cnt = static_cast<unsigned int*>(dalloc_bytes(n_u32 * sizeof(unsigned int)));
 	unsigned int* d_info = d_cnt + 2 * max_sweeps + 4;
 	XB_CUDA(cudaMemsetAsync(d_cnt, 0, n_u32 * sizeof(unsigned int), c.stream));
