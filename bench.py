@@ -145,11 +145,17 @@ def als_sweep_numbers(xb, np, torch, stream, args):
         try:
             res = subprocess.run([REF_BENCH, "als", "16", "10", "8", "2", "2"], capture_output=True, text=True, check=True).stdout
             ref = json.loads(res.strip().splitlines()[-1])
-            xr = xb.TTTensor.random([n] * d, 8, np.random.default_rng(16))
-            t0 = time.perf_counter()
-            variant(A, xr, b, 2)
-            xb.synchronize()
-            out["reduced_rank8"] = {"reference_cpu_ms": ref["best_ms"], "xb200_ms": (time.perf_counter() - t0) * 1e3,
+            xr0 = xb.TTTensor.random([n] * d, 8, np.random.default_rng(16))
+            best = float("inf")
+            for rep in range(3):                                       # first repetition loads the solver kernels (lazy module loading)
+                xr = xr0.copy()
+                xb.synchronize()
+                t0 = time.perf_counter()
+                variant(A, xr, b, 2)
+                xb.synchronize()
+                if rep > 0:
+                    best = min(best, (time.perf_counter() - t0) * 1e3)
+            out["reduced_rank8"] = {"reference_cpu_ms": ref["best_ms"], "xb200_ms": best,
                                     "note": "n_loc = 640 <= als_direct_max: dense reference-semantics path on the GPU"}
         except Exception as ex:
             out["reduced_rank8"] = {"error": repr(ex)}
