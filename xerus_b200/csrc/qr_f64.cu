@@ -137,9 +137,35 @@ __global__ void __launch_bounds__(QR_PANEL_WARPS * 32) qr_panel_kernel(double* _
 // chain.  This variant spreads the panel rows over a thread-block cluster of QRC_CS CTAs (one SM each) and keeps every
 // row strip in REGISTERS (lane = panel column, RPT rows per thread); a column entry of another lane comes from a shuffle.
 // Per column there is ONE fused pass — apply reflector j, accumulate g_c = x_{j+1}^T a_c for the next column on the fly —
-// and one cluster-wide reduction: CTA partials are written into every CTA's shared memory (DSMEM), one cluster barrier,
-// then every warp derives beta / tau / w redundantly.  Lanes c < j are idle in the Householder step, so they accumulate
+// and one cluster-wide reduction: CTA partials are written into every CTA's shared memory with st.async (DSMEM stores that
+// complete a transaction count on the receiving CTA's mbarrier — no cluster barrier, no fence in the column loop), every
+// warp waits on its own CTA's mbarrier and derives beta / tau / w redundantly.  Lanes c < j are idle in the Householder step, so they accumulate
 // v_c^T x_j in the same pass, which gives column j of V^T V (needed for the compact-WY T) without a pass over V.
+// ---- DSMEM signalling: remote 8-byte stores that complete a transaction count on the remote CTA's mbarrier ---------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+	unsigned r;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+	return r;
+}
+__device__ __forceinline__ void st_async_f64(unsigned raddr, double v, unsigned rmbar) {
+	asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+	             :: "r"(raddr), "l"(__double_as_longlong(v)), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+	unsigned done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+	} while (!done);
+}
+
 constexpr int QRC_CS = 8;        // CTAs per cluster (portable maximum)
 constexpr int QRC_WARPS = 8;     // warps per CTA
 
@@ -154,6 +180,8 @@ qr_panel_cluster_kernel(double* __restrict__ W, const long long ldw, const int m
 	__shared__ double rowbuf[2][32];            // [parity][lane] row j of the panel as it stands before step j
 	__shared__ double GVs[32][33], Ts[32][33];  // used by CTA 0 only
 	__shared__ double s_tau[32];
+	__shared__ __align__(8) unsigned long long mbar[2];   // [parity] all partial sums + row j of a column step have arrived
+	constexpr unsigned TX_BYTES = (QRC_CS * 32 + 32) * sizeof(double);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int rank = int(cluster.block_rank());
 	// row of slot k of this warp: k * 64 + gw (cyclic over the 64 warps of the cluster).  Only slot 0 can hold one of the
@@ -177,10 +205,17 @@ qr_panel_cluster_kernel(double* __restrict__ W, const long long ldw, const int m
 		const double pn = __shfl_sync(0xffffffffu, P[k], 0);
 		if (!(lane == 0 && k == 0 && gw == 0)) g += pn * P[k];
 	}
-	cluster.sync();                              // every CTA of the cluster is resident before the first remote store
+	if (threadIdx.x == 0) {
+		mbar_init(smem_u32(&mbar[0]), 1); mbar_init(smem_u32(&mbar[1]), 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		mbar_arrive_expect_tx(smem_u32(&mbar[0]), TX_BYTES);         // column steps 0 and 1
+		mbar_arrive_expect_tx(smem_u32(&mbar[1]), TX_BYTES);
+	}
+	cluster.sync();                              // every CTA is resident and its barriers are initialised before the first remote store
 	if (gw == 0) {
+		const unsigned a = smem_u32(&rowbuf[0][lane]), mb = smem_u32(&mbar[0]);
 #pragma unroll
-		for (int c = 0; c < QRC_CS; ++c) *cluster.map_shared_rank(&rowbuf[0][lane], c) = P[0];
+		for (int c = 0; c < QRC_CS; ++c) st_async_f64(mapa_u32(a, c), P[0], mapa_u32(mb, c));
 	}
 
 	// optional phase timing (XB_QR_TIMING=1): cycles of [reduce + publish | cluster barrier | parameters | update]
@@ -193,11 +228,14 @@ qr_panel_cluster_kernel(double* __restrict__ W, const long long ldw, const int m
 		__syncthreads();
 		if (warp == 0) {
 			const double s = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) + ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
+			const unsigned a = smem_u32(&slots[par][rank][lane]), mb = smem_u32(&mbar[par]);
 #pragma unroll
-			for (int c = 0; c < QRC_CS; ++c) *cluster.map_shared_rank(&slots[par][rank][lane], c) = s;
+			for (int c = 0; c < QRC_CS; ++c) st_async_f64(mapa_u32(a, c), s, mapa_u32(mb, c));
 		}
 		if (timing) { const long long t1 = clock64(); tk[0] += t1 - t0; t0 = t1; }
-		cluster.sync();
+		mbar_wait(smem_u32(&mbar[par]), (j >> 1) & 1);
+		// re-arm this parity for column step j + 2 (its stores may already be under way: the transaction count may run negative)
+		if (threadIdx.x == 0 && j + 2 < kmax) mbar_arrive_expect_tx(smem_u32(&mbar[par]), TX_BYTES);
 		if (timing) { const long long t1 = clock64(); tk[1] += t1 - t0; t0 = t1; }
 		const double G = ((slots[par][0][lane] + slots[par][1][lane]) + (slots[par][2][lane] + slots[par][3][lane])) +
 		                 ((slots[par][4][lane] + slots[par][5][lane]) + (slots[par][6][lane] + slots[par][7][lane]));
@@ -243,12 +281,14 @@ qr_panel_cluster_kernel(double* __restrict__ W, const long long ldw, const int m
 		g = (ga[0] + ga[1]) + (ga[2] + ga[3]);
 		if (timing) { const long long t1 = clock64(); tk[5] += t1 - t0 + (long long)(g != g); t0 = t1; }
 		if (gw == jn && jn < kmax) {
+			const unsigned a = smem_u32(&rowbuf[par ^ 1][lane]), mb = smem_u32(&mbar[par ^ 1]);
 #pragma unroll
-			for (int c = 0; c < QRC_CS; ++c) *cluster.map_shared_rank(&rowbuf[par ^ 1][lane], c) = P[0];
+			for (int c = 0; c < QRC_CS; ++c) st_async_f64(mapa_u32(a, c), P[0], mapa_u32(mb, c));
 		}
 		if (timing) { const long long t1 = clock64(); tk[3] += t1 - t0; t0 = t1; }
 	}
 	if (timing) { for (int q = 0; q < 8; ++q) dbg[q] = tk[q]; }
+	cluster.sync();                              // no CTA leaves while stores to its shared memory could still be in flight
 
 	// results: panel in place (R on and above the diagonal, reflectors below), explicit V, compact-WY T
 #pragma unroll
