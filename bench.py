@@ -225,6 +225,15 @@ def batch_workload(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written, HBM copy GB/s and bf16 TF/s of this pool's B200s); {} if absent."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
 def bond_split_workload(args, rank, local_rank, world):
     """--workload c4: BASELINE configs[3], the two-site DMRG local-operator application at bond rank 512 (n = 4,
     operator rank 2), contraction split along the right bond index across the GPUs + one NCCL sum all-reduce.
@@ -284,7 +293,11 @@ def bond_split_workload(args, rank, local_rank, world):
     parallel.env_apply(L, [A1, A2], R, v, slab=parallel.slab_range(r, rank, world))
     xb.synchronize()
     gsc, glaunch, gms = xb.profile_get("gemm")
+    _, mlaunch, mms = xb.profile_get("mid_apply")
     xb.profile_enable(False)
+    # the GEMM class holds the two bond contractions (L.v and .R); the operator cores go through mid_apply_kernel (HBM bound)
+    gemm_flops = 2 * (r * a) * r * (n * n * r) + 2 * (r * n * n) * (a * r) * r
+    mid_bytes = 2 * 2 * 8 * (r * a * n * n * r)                           # per application: two passes, each reads and writes r*a*n*n*r doubles
     if rank == 0:
         aa = torch.randn(8192, 8192, dtype=torch.float64, device="cuda"); bb = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
         torch.matmul(aa, bb)
@@ -295,7 +308,8 @@ def bond_split_workload(args, rank, local_rank, world):
             best = min(best, s0.elapsed_time(s1))
         peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
         t = float(ms.item())
-        achieved = flops / world / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        achieved = gemm_flops / world / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        hbm_peak = measured_peaks().get("hbm_gbs") or 6540.2
         line = {"metric": "DMRG two-site local-operator application ms (FP64, bond %d)" % r, "value": t, "unit": "ms", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t, "higher_is_better": False, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic (i.i.d. N(0,1) environments, operator cores and vector)",
@@ -304,10 +318,15 @@ def bond_split_workload(args, rank, local_rank, world):
                            "l2": "flushed between timed iterations", "allreduce_bytes": int(y.numel() * 8) if world > 1 else 0},
                 "gpu_launches": launches, "check": {"rel_err_vs_unsplit": err},
                 "whole_job_tflops": flops / (t * 1e-3) / 1e12,
-                "roofline": {"kernel": "gemm_f64_kernel (DMMA m8n8k4)", "bound": "tensor", "unit": "TFLOP/s", "achieved": achieved,
-                             "peak": peak, "frac": achieved / peak, "traffic": None,
+                "whole_job_frac_of_peak": flops / (t * 1e-3) / 1e12 / peak,
+                "roofline": {"kernel": "gemm_f64_big_kernel (128x128 tiles, cp.async, DMMA m8n8k4)", "bound": "tensor", "unit": "TFLOP/s",
+                             "achieved": achieved, "peak": peak, "frac": achieved / peak, "traffic": None,
                              "peak_source": "cuBLAS DGEMM 8192^3 measured in this run",
-                             "algorithmic_flops_per_rank": flops / world, "gemm_ms_per_apply": gms, "gemm_launches": glaunch}}
+                             "algorithmic_flops_per_rank": gemm_flops / world, "gemm_ms_per_apply": gms, "gemm_launches": glaunch},
+                "roofline_mid_apply": {"kernel": "mid_apply_kernel (operator cores, r_A*n = 8)", "bound": "hbm", "unit": "GB/s",
+                                       "achieved": (mid_bytes / world / (mms * 1e-3) / 1e9) if mms > 0 else 0.0, "peak": hbm_peak,
+                                       "frac": (mid_bytes / world / (mms * 1e-3) / 1e9 / hbm_peak) if mms > 0 else 0.0,
+                                       "algorithmic_bytes_per_rank": mid_bytes / world, "ms_per_apply": mms, "launches": mlaunch}}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -63,6 +63,44 @@ def test_product_1000x1000_consistency():
     assert np.array_equal(C, BW.matrix_matrix_product(1.0, At, True, Bt, True))
 
 
+# ---- large-tile (128 x 128, cp.async) GEMM kernel: taken from about a wave of tiles on (csrc/gemm_f64.cu) -------------------
+@pytest.mark.parametrize("m,n,k", [(1536, 1536, 256), (1500, 1302, 130), (1024, 2048, 64), (2050, 1026, 272)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_large_tile_kernel(m, n, k, ta, tb):
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    A = rng.standard_normal((k, m) if ta else (m, k))
+    B = rng.standard_normal((n, k) if tb else (k, n))
+    try:
+        xb.set_option("gemm_big", 0)
+        C_small = BW.matrix_matrix_product(-0.75, A, ta, B, tb)
+    finally:
+        xb.set_option("gemm_big", 1)
+    C_big = BW.matrix_matrix_product(-0.75, A, ta, B, tb)
+    assert rel(C_big, O.matrix_matrix_product(-0.75, A, ta, B, tb)) < 1e-10
+    # same summation order in both kernels: the tile size never changes the bits
+    assert np.array_equal(C_big, C_small)
+
+
+def test_gemm_large_tile_beta_and_odd_shapes():
+    # device layer, beta != 0 (the trailing updates of the blocked factorizations), odd ldc (scalar epilogue), and an odd
+    # extent that must fall back to the 64 x 64 kernel
+    import torch
+    from xerus_b200._lib import call
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for (m, n, k, ldc) in [(1536, 1408, 192, 1408), (1536, 1407, 192, 1407), (1537, 1408, 190, 1410)]:
+        A = torch.randn(m, k, dtype=torch.float64, generator=g)
+        B = torch.randn(k, n, dtype=torch.float64, generator=g)
+        C0 = torch.randn(m, ldc, dtype=torch.float64, generator=g)
+        dA, dB, dC = A.to(dev), B.to(dev), C0.to(dev)
+        torch.cuda.synchronize()
+        call("xb_dev_gemm", dC.data_ptr(), ldc, m, n, 0.5, dA.data_ptr(), k, 0, k, dB.data_ptr(), n, 0, -2.0)
+        xb.synchronize()
+        want = C0.clone()
+        want[:, :n] = 0.5 * (A @ B) - 2.0 * C0[:, :n]
+        assert rel(dC.cpu().numpy(), want.numpy()) < 1e-13
+
+
 def test_gemv_ger_level1(golden):
     rng = np.random.default_rng(3)
     A, y = rng.standard_normal((37, 23)), rng.standard_normal(23)

@@ -188,6 +188,23 @@ DT spd_env_apply(const DT& L, const std::vector<DT>& Acores, const DT& R, const 
 	DT t = dt_contract(L, {2}, v, {0});                           // (l, a, n_1..n_s, r'[, col])
 	for (int p = 0; p < s; ++p) {
 		// t modes: (l, m_1..m_p, a, n_{p+1}..n_s, r')  ->  contract (a, n_{p+1}) with A(a, m, n, b)
+		{
+			// the operator core as a (m b) x (a n) matrix applied to the middle of t in one pass over HBM (no reshuffle of t)
+			const size_t P = t.dims[1 + p] * t.dims[2 + p], Q = Acores[p].dims[1] * Acores[p].dims[3];
+			if (P <= 64 && Q <= 32) {
+				XB_REQUIRE(Acores[p].dims[0] == t.dims[1 + p] && Acores[p].dims[2] == t.dims[2 + p], "Index dimensions do not coincide");
+				size_t outer = 1, inner = 1;
+				std::vector<size_t> nd;
+				for (int i = 0; i <= p; ++i) { outer *= t.dims[i]; nd.push_back(t.dims[i]); }
+				nd.push_back(Acores[p].dims[1]); nd.push_back(Acores[p].dims[3]);
+				for (size_t i = 3 + p; i < t.dims.size(); ++i) { inner *= t.dims[i]; nd.push_back(t.dims[i]); }
+				DT W = dt_permute(Acores[p], {1, 3, 0, 2});                   // (m, b | a, n)
+				DT u = dt_alloc(nd);
+				mid_apply(u.data(), t.p, W.p, outer, P, Q, inner);
+				t = std::move(u);
+				continue;
+			}
+		}
 		DT u = dt_contract(t, {1 + p, 2 + p}, Acores[p], {0, 2});   // (l, m_1..m_p, n_{p+2}..n_s, r', m_{p+1}, b)
 		const int nu = int(u.dims.size());
 		std::vector<int> o;                                       // -> (l, m_1..m_{p+1}, b, n_{p+2}..n_s, r')

@@ -135,6 +135,148 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g
 	}
 }
 
+
+// ---- large-tile kernel: 128 x 128 CTA tile, cp.async pipeline ---------------------------------------------------------------
+// The 64 x 64 kernel above moves 16 bytes from L2 per 8 x 8 x 4 DMMA-tile of work: with the whole GPU multiplying, that is
+// 4.6 TB/s of L2 -> SM traffic at the tensor pipe's peak, more than the L2 delivers, and it is why the bond-512 contractions of
+// the DMRG local apply ran at 46 % of the measured DGEMM peak.  Here a CTA of 8 warps (2 x 4, warp tile 64 x 32 = 8 x 4 DMMA
+// fragments, 128 accumulator registers per thread) owns a 128 x 128 tile: half the L2 traffic per flop, 16-byte cp.async.cg
+// copies straight into shared memory (no register staging), three stages of BK = 16.  An operand whose k index is
+// contiguous in global memory is stored [row][k] with a row stride of 20 doubles, one whose row/column index is contiguous
+// is stored [k][row] with a stride of 132: in both layouts the DMMA fragment loads (lane -> (row = lane / 4, k = lane % 4))
+// of a half-warp hit 16 distinct 8-byte banks.  The k loop adds the products in the same order as the kernel above (ascending
+// k, one accumulator per output element), so both kernels and all four transposition cases give bit-identical results.
+constexpr int BIG_BM = 128, BIG_BN = 128, BIG_BK = 16, BIG_STAGES = 3, BIG_THREADS = 256;
+constexpr int BIG_LDK = BIG_BK + 4;       // [row][k] layout
+constexpr int BIG_LDR = BIG_BM + 4;       // [k][row] layout
+constexpr int BIG_TILE = (BIG_BM * BIG_LDK > BIG_BK * BIG_LDR) ? BIG_BM * BIG_LDK : BIG_BK * BIG_LDR;   // doubles per operand and stage
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gmem_src, const bool valid) {
+	const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+	const int bytes = valid ? 16 : 0;      // src-size 0: the 16 destination bytes are zero-filled, nothing is read
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
+}
+
+// KMINOR: element (row r of the tile, k) sits at base[r * ld + k] in global memory (k contiguous) -> shared [row][k];
+// otherwise at base[k * ld + r] (r contiguous) -> shared [k][row].  rows = valid tile rows, kk = valid k entries (both even
+// or the chunk grid is aligned with them: the host checks that).
+template <bool KMINOR>
+__device__ __forceinline__ void big_load_tile(double* __restrict__ sm, const double* __restrict__ base, const long long ld,
+                                              const int rows, const int kk, const int tid) {
+#pragma unroll
+	for (int it = 0; it < BIG_BM * BIG_BK / 2 / BIG_THREADS; ++it) {
+		const int c = tid + it * BIG_THREADS;
+		if (KMINOR) {
+			const int r = c >> 3, k = (c & 7) * 2;
+			const bool ok = r < rows && k < kk;
+			cp_async16(sm + r * BIG_LDK + k, ok ? base + (long long)r * ld + k : base, ok);
+		} else {
+			const int k = c >> 6, r = (c & 63) * 2;
+			const bool ok = r < rows && k < kk;
+			cp_async16(sm + k * BIG_LDR + r, ok ? base + (long long)k * ld + r : base, ok);
+		}
+	}
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(BIG_THREADS, 1) gemm_f64_big_kernel(const GemmArgs g, const int vec_store) {
+	extern __shared__ __align__(16) double big_smem[];
+	double* As = big_smem;                               // [STAGES][BIG_TILE]
+	double* Bs = big_smem + BIG_STAGES * BIG_TILE;       // [STAGES][BIG_TILE]
+	constexpr bool A_KMINOR = !TA;                       // A stored m x k row-major: k contiguous
+	constexpr bool B_KMINOR = TB;                        // B stored n x k row-major when transposed
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int wm = warp >> 2, wn = warp & 3;             // 2 x 4 warps, warp tile 64 x 32
+	const int grp = lane >> 2, tig = lane & 3;
+	const int m0 = blockIdx.y * BIG_BM, n0 = blockIdx.x * BIG_BN;
+	const double* __restrict__ A = g.A + (long long)blockIdx.z * g.strideA;
+	const double* __restrict__ B = g.B + (long long)blockIdx.z * g.strideB;
+	double* __restrict__ C = g.C + (long long)blockIdx.z * g.strideC;
+	const int mrows = min(BIG_BM, g.m - m0), ncols = min(BIG_BN, g.n - n0);
+	const double* Abase = TA ? A + m0 : A + (long long)m0 * g.lda;
+	const double* Bbase = TB ? B + (long long)n0 * g.ldb : B + n0;
+
+	double acc[8][4][2];
+#pragma unroll
+	for (int i = 0; i < 8; ++i)
+#pragma unroll
+		for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+	const int nt = (g.k + BIG_BK - 1) / BIG_BK;
+	auto load_stage = [&](const int t) {
+		const int s = t % BIG_STAGES, k0 = t * BIG_BK, kk = min(BIG_BK, g.k - k0);
+		big_load_tile<A_KMINOR>(As + s * BIG_TILE, TA ? Abase + (long long)k0 * g.lda : Abase + k0, g.lda, mrows, kk, tid);
+		big_load_tile<B_KMINOR>(Bs + s * BIG_TILE, TB ? Bbase + k0 : Bbase + (long long)k0 * g.ldb, g.ldb, ncols, kk, tid);
+	};
+#pragma unroll
+	for (int s = 0; s < BIG_STAGES - 1; ++s) {
+		if (s < nt) load_stage(s);
+		asm volatile("cp.async.commit_group;\n" ::: "memory");
+	}
+	for (int t = 0; t < nt; ++t) {
+		asm volatile("cp.async.wait_group %0;\n" :: "n"(BIG_STAGES - 2) : "memory");
+		__syncthreads();                                 // tile t has landed for everybody; stage (t - 1) % STAGES is free again
+		if (t + BIG_STAGES - 1 < nt) load_stage(t + BIG_STAGES - 1);
+		asm volatile("cp.async.commit_group;\n" ::: "memory");
+		const double* as = As + (t % BIG_STAGES) * BIG_TILE;
+		const double* bs = Bs + (t % BIG_STAGES) * BIG_TILE;
+#pragma unroll
+		for (int k4 = 0; k4 < BIG_BK / 4; ++k4) {
+			double af[8], bf[4];
+#pragma unroll
+			for (int i = 0; i < 8; ++i)
+				af[i] = A_KMINOR ? as[(wm * 64 + i * 8 + grp) * BIG_LDK + k4 * 4 + tig] : as[(k4 * 4 + tig) * BIG_LDR + wm * 64 + i * 8 + grp];
+#pragma unroll
+			for (int j = 0; j < 4; ++j)
+				bf[j] = B_KMINOR ? bs[(wn * 32 + j * 8 + grp) * BIG_LDK + k4 * 4 + tig] : bs[(k4 * 4 + tig) * BIG_LDR + wn * 32 + j * 8 + grp];
+#pragma unroll
+			for (int i = 0; i < 8; ++i)
+#pragma unroll
+				for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+		}
+	}
+	asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+
+#pragma unroll
+	for (int i = 0; i < 8; ++i) {
+		const int row = m0 + wm * 64 + i * 8 + grp;
+		if (row >= g.m) continue;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int col = n0 + wn * 32 + j * 8 + tig * 2;
+			double* p = C + (long long)row * g.ldc + col;
+			if (vec_store && col + 1 < g.n) {
+				double2 v = make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
+				if (g.beta != 0.0) { const double2 o = *reinterpret_cast<const double2*>(p); v.x += g.beta * o.x; v.y += g.beta * o.y; }
+				*reinterpret_cast<double2*>(p) = v;
+			} else {
+#pragma unroll
+				for (int c = 0; c < 2; ++c) {
+					if (col + c < g.n) {
+						double v = g.alpha * acc[i][j][c];
+						if (g.beta != 0.0) v += g.beta * p[c];
+						p[c] = v;
+					}
+				}
+			}
+		}
+	}
+}
+
+template <bool TA, bool TB>
+static void launch_big(const GemmArgs& g, const dim3 grid, const int vec_store) {
+	constexpr size_t smem = size_t(2) * BIG_STAGES * BIG_TILE * sizeof(double);
+	static bool attr = false;
+	if (!attr) {
+		XB_CUDA(cudaFuncSetAttribute(gemm_f64_big_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		attr = true;
+	}
+	gemm_f64_big_kernel<TA, TB><<<grid, BIG_THREADS, smem, ctx().stream>>>(g, vec_store);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, double alpha, const double* A, size_t lda,
                   size_t strideA, bool transA, size_t k, const double* B, size_t ldb, size_t strideB, bool transB,
                   double beta, size_t batch) {
@@ -148,6 +290,20 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
 	g.strideC = (long long)strideC; g.strideA = (long long)strideA; g.strideB = (long long)strideB;
 	g.m = int(m); g.n = int(n); g.k = int(k);
 	g.transA = transA; g.transB = transB; g.alpha = alpha; g.beta = beta;
+	// large-tile path: at least ~0.8 waves of 128 x 128 tiles, and every 16-byte cp.async chunk aligned and either fully
+	// inside or fully outside its operand (the choice never changes the bits of the result, see gemm_f64_big_kernel)
+	const size_t tiles128 = ((m + 127) / 128) * ((n + 127) / 128) * batch;
+	if (ctx().gemm_big && !ctx().gemm_force_small && tiles128 * 5 >= size_t(ctx().num_sms) * 4 && k >= 64 && k % 2 == 0 &&
+	    lda % 2 == 0 && ldb % 2 == 0 && strideA % 2 == 0 && strideB % 2 == 0 && aligned16(A) && aligned16(B) &&
+	    (!transA || m % 2 == 0) && (transB || n % 2 == 0)) {
+		dim3 grid(unsigned((n + 127) / 128), unsigned((m + 127) / 128), unsigned(batch));
+		XB_REQUIRE(grid.y <= 65535, "m too large for the GEMM grid");
+		const int vec_store = (ldc % 2 == 0 && strideC % 2 == 0 && aligned16(C)) ? 1 : 0;
+		if (transA) { if (transB) launch_big<true, true>(g, grid, vec_store); else launch_big<true, false>(g, grid, vec_store); }
+		else { if (transB) launch_big<false, true>(g, grid, vec_store); else launch_big<false, false>(g, grid, vec_store); }
+		XB_LAUNCH_CHECK();
+		return;
+	}
 	const size_t tiles64 = ((m + 63) / 64) * ((n + 63) / 64) * batch;
 	const bool small = ctx().gemm_force_small || tiles64 < size_t(ctx().num_sms);
 	if (small) {

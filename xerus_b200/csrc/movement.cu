@@ -221,6 +221,73 @@ void transpose_reverse(double* out, const double* in, size_t rows, size_t cols) 
 	XB_LAUNCH_CHECK();
 }
 
+// out(o, q, j) = sum_p W(q, p) in(o, p, j): a small dense matrix applied to the middle mode of a three-mode view.  This is the
+// operator-core step of the matrix-free local apply (the un-contracted network of als.cpp:383-401): o = left bond and the sites
+// already applied, p = (a, n), q = (m, b), j = the remaining sites and the right bond.  P and Q are a handful (r_A * n), so the
+// step is pure HBM traffic: every input element is read once and every output element written once, with
+// 16-byte accesses along j; W sits in shared memory and is read as a broadcast.
+template <int QMAX, int VEC>
+__global__ void __launch_bounds__(256) mid_apply_kernel(double* __restrict__ out, const double* __restrict__ in, const double* __restrict__ W,
+                                                         const size_t outer, const int P, const int Q, const size_t inner) {
+	__shared__ double Ws[QMAX * 64];
+	for (int e = threadIdx.x; e < P * Q; e += blockDim.x) Ws[e] = W[e];
+	__syncthreads();
+	const size_t jv = inner / VEC, total = outer * jv;
+	for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+		const size_t o = e / jv, j = (e % jv) * VEC;
+		const double* src = in + o * P * inner + j;
+		double acc[QMAX][VEC];
+#pragma unroll
+		for (int q = 0; q < QMAX; ++q)
+#pragma unroll
+			for (int v = 0; v < VEC; ++v) acc[q][v] = 0.0;
+#pragma unroll 4
+		for (int p = 0; p < P; ++p) {
+			double x[VEC];
+			if (VEC == 2) { const double2 t = __ldcs(reinterpret_cast<const double2*>(src + (size_t)p * inner)); x[0] = t.x; x[VEC - 1] = t.y; }
+			else x[0] = __ldcs(src + (size_t)p * inner);
+#pragma unroll
+			for (int q = 0; q < QMAX; ++q) {
+				if (q < Q) {
+					const double w = Ws[q * P + p];
+#pragma unroll
+					for (int v = 0; v < VEC; ++v) acc[q][v] += w * x[v];
+				}
+			}
+		}
+		double* dst = out + o * Q * inner + j;
+#pragma unroll
+		for (int q = 0; q < QMAX; ++q) {
+			if (q < Q) {
+				if (VEC == 2) *reinterpret_cast<double2*>(dst + (size_t)q * inner) = make_double2(acc[q][0], acc[q][VEC - 1]);
+				else dst[(size_t)q * inner] = acc[q][0];
+			}
+		}
+	}
+}
+
+bool mid_apply(double* out, const double* in, const double* W, size_t outer, size_t P, size_t Q, size_t inner) {
+	if (P == 0 || Q == 0 || P > 64 || Q > 32) return false;
+	if (outer == 0 || inner == 0) return true;
+	ProfScope prof("mid_apply");
+	const bool vec = inner % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+	const size_t work = outer * (vec ? inner / 2 : inner);
+	const unsigned grid = unsigned(std::min<size_t>((work + 255) / 256, size_t(ctx().num_sms) * 16));
+	cudaStream_t st = ctx().stream;
+	const int p = int(P), q = int(Q);
+	if (vec) {
+		if (Q <= 8) mid_apply_kernel<8, 2><<<grid, 256, 0, st>>>(out, in, W, outer, p, q, inner);
+		else if (Q <= 16) mid_apply_kernel<16, 2><<<grid, 256, 0, st>>>(out, in, W, outer, p, q, inner);
+		else mid_apply_kernel<32, 2><<<grid, 256, 0, st>>>(out, in, W, outer, p, q, inner);
+	} else {
+		if (Q <= 8) mid_apply_kernel<8, 1><<<grid, 256, 0, st>>>(out, in, W, outer, p, q, inner);
+		else if (Q <= 16) mid_apply_kernel<16, 1><<<grid, 256, 0, st>>>(out, in, W, outer, p, q, inner);
+		else mid_apply_kernel<32, 1><<<grid, 256, 0, st>>>(out, in, W, outer, p, q, inner);
+	}
+	XB_LAUNCH_CHECK();
+	return true;
+}
+
 void permute(double* out, const double* in, const size_t* dims, const size_t* shuffle, size_t degree) {
 	XB_REQUIRE(out != in, "in-place reshuffle is not supported at this level");
 	// validate: shuffle must be a permutation (reference: indexedTensor_tensor_evaluate.cpp:57-71)

@@ -59,7 +59,7 @@ static void select_worker(int w) {
 		Context* c = new Context();
 		c->initialised = true; c->worker = i; c->device = g_ctx.device; c->pool = g_ctx.pool;
 		c->num_sms = g_ctx.num_sms; c->max_smem_optin = g_ctx.max_smem_optin;
-		c->svd_max_sweeps = g_ctx.svd_max_sweeps; c->gemm_force_small = g_ctx.gemm_force_small;
+		c->svd_max_sweeps = g_ctx.svd_max_sweeps; c->gemm_force_small = g_ctx.gemm_force_small; c->gemm_big = g_ctx.gemm_big;
 		c->svd_persistent = g_ctx.svd_persistent; c->svd_polish = g_ctx.svd_polish; c->tt_svd_polish = g_ctx.tt_svd_polish; c->svd_mixed = g_ctx.svd_mixed; c->svd_recursive = g_ctx.svd_recursive; c->svd_flip = g_ctx.svd_flip; c->svd_split = g_ctx.svd_split; c->svd_gram = g_ctx.svd_gram; c->als_graph = g_ctx.als_graph; c->svd_jacc = g_ctx.svd_jacc; c->svd_fast = g_ctx.svd_fast; c->qr_cluster = g_ctx.qr_cluster; c->svd_square_qr = g_ctx.svd_square_qr;
 		c->svd_mixed_min = g_ctx.svd_mixed_min; c->svd_max_bw = g_ctx.svd_max_bw; c->als_direct_max = g_ctx.als_direct_max;
 		XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -185,6 +185,7 @@ xb_status xb_set_option(const char* key, double value) {
 			Context& c = *g_workers[w];
 			if (k == "svd_max_sweeps") c.svd_max_sweeps = int(value);
 			else if (k == "gemm_force_small") c.gemm_force_small = int(value);
+			else if (k == "gemm_big") c.gemm_big = int(value);
 			else if (k == "svd_persistent") c.svd_persistent = int(value);
 			else if (k == "svd_max_bw") c.svd_max_bw = int(value);
 			else if (k == "svd_mixed") c.svd_mixed = int(value);

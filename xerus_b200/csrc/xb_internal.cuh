@@ -53,6 +53,7 @@ struct Context {
 	int svd_max_sweeps = 100;      // graded spectra (kappa ~ 1e14) need ~45 sweeps of the un-preconditioned Jacobi
 	int qr_panel = 32;
 	int gemm_force_small = 0;
+	int gemm_big = 1;              // 128 x 128 cp.async GEMM kernel for outputs of about a wave of such tiles or more
 	bool profile = false;
 	int svd_persistent = 1;
 	int tt_svd_polish = 1;         // polish level of the SVDs inside round() / TT-SVD / DMRG splits (see Svd::polish)
@@ -123,6 +124,8 @@ void axpy(double* y, double alpha, const double* x, size_t n);           // y +=
 void transpose(double* out, const double* in, size_t rows, size_t cols); // out (cols x rows) = in^T, both packed
 void transpose_reverse(double* out, const double* in, size_t rows, size_t cols); // out(j,i) = in(rows-1-i, cols-1-j)
 void permute(double* out, const double* in, const size_t* dims, const size_t* shuffle, size_t degree);
+// out(o,q,j) = sum_p W(q,p) in(o,p,j) for small P, Q (one pass over HBM); false if P > 64 or Q > 32 (caller takes the GEMM route)
+bool mid_apply(double* out, const double* in, const double* W, size_t outer, size_t P, size_t Q, size_t inner);
 void scale_rows(double* A, const double* s, size_t rows, size_t cols, size_t ld);   // A[i,:] *= s[i]
 void scale_cols(double* A, const double* s, size_t rows, size_t cols, size_t ld);   // A[:,j] *= s[j]
 // reductions: result written to a device double
