@@ -166,6 +166,26 @@ xb_status xb_als_solve(const xb_tt* A, xb_tt* x, const xb_tt* b, const xb_als_op
 xb_status xb_env_apply(double* y, const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims,
                        size_t sites, const double* R, size_t r, size_t a_right, const double* v, size_t slab_begin, size_t slab_end);
 
+/* ---- 4. data files: the reference's own save_to_file / load_from_file format, Binary and TSV ------------------------
+ * (misc::save_to_file / load_from_file, include/xerus/misc/fileIO.h:102-164; stream_writer / stream_reader of Tensor,
+ * src/xerus/tensor.cpp:1781-1845, of TensorNetwork, src/xerus/tensorNetwork.cpp:1429-1505, and of TTNetwork,
+ * src/xerus/ttNetwork.cpp:1455-1488).  Files written by xerus load here and files written here load in xerus.
+ * xb_file_* are host-side and need no device; xb_tt_load / xb_tt_save move the cores to / from a device-resident TT. */
+typedef struct xb_file xb_file;
+xb_status xb_file_open(xb_file** out, const char* filename);     /* parses the whole file; sparse tensors are densified */
+xb_status xb_file_close(xb_file* f);
+/* kind: 0 = Tensor, 1 = TTTensor, 2 = TTOperator; n_dims = entries of xb_file_dims (Tensor: degree; TT: d or 2d) */
+xb_status xb_file_info(const xb_file* f, int* kind, size_t* n_dims, int* canonicalized, size_t* core_position);
+xb_status xb_file_dims(const xb_file* f, size_t* dims);
+xb_status xb_file_ranks(const xb_file* f, size_t* ranks /* d-1, TT files only */);
+/* TT: row-major component idx, (rl, n, rr) / (rl, m, n, rr); Tensor: idx 0 = the dense row-major data */
+xb_status xb_file_read_component(const xb_file* f, size_t idx, double* host);
+xb_status xb_file_write_tensor(const char* filename, int tsv, const double* data, const size_t* dims, size_t degree);
+xb_status xb_file_write_tt(const char* filename, int tsv, size_t d, const size_t* dims /* d or 2d */, const size_t* ranks /* d-1 */,
+                           int is_operator, int canonicalized, size_t core_position, const double* const* cores);
+xb_status xb_tt_load(xb_tt** out, const char* filename);         /* misc::load_from_file<TTTensor / TTOperator> */
+xb_status xb_tt_save(const xb_tt* tt, const char* filename, int tsv); /* misc::save_to_file(tt, filename, format) */
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,12 @@ _SIGS = {
     "xb_als_default_options": [P(ALSOptions), C.c_uint32, C.c_int],
     "xb_als_solve": [vp, vp, vp, P(ALSOptions), dp, szp],
     "xb_env_apply": [vp, vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz],
+    "xb_file_open": [P(vp), C.c_char_p], "xb_file_close": [vp],
+    "xb_file_info": [vp, P(C.c_int), szp, P(C.c_int), szp], "xb_file_dims": [vp, szp], "xb_file_ranks": [vp, szp],
+    "xb_file_read_component": [vp, sz, dp],
+    "xb_file_write_tensor": [C.c_char_p, C.c_int, dp, szp, sz],
+    "xb_file_write_tt": [C.c_char_p, C.c_int, sz, szp, szp, C.c_int, C.c_int, sz, P(dp)],
+    "xb_tt_load": [P(vp), C.c_char_p], "xb_tt_save": [vp, C.c_char_p, C.c_int],
 }
 
 
