@@ -3,6 +3,7 @@ import numpy as np, xerus_b200 as xb
 xb.init(0)
 import os
 if os.environ.get('XB_GEMM_SMALL'): xb.set_option('gemm_force_small', 1)
+if os.environ.get('XB_ALS_PCG'): xb.set_option('als_persistent_cg', int(os.environ['XB_ALS_PCG']))
 d,n=16,10
 for r in [8,20,50]:
     rng=np.random.default_rng(16)

@@ -180,6 +180,307 @@ struct SpdSiteApply {
 	}
 };
 
+// ---- persistent CG for the one-site SPD local problem -----------------------------------------------------------------------
+// At BASELINE config 2 an operator application is 12 MFLOP: as three GEMM launches plus the fused vector kernel a CG iteration
+// costs ~35 us of launch and drain latency for ~1 us of arithmetic.  Here a whole CG run is ONE cooperative launch.  CTA g owns
+// the slices li = g, g + G, ... of the left bond: for a slice the three factors chain without leaving the SM,
+//   t1(a,n | r') = L(li, a, :) p          (reads all of p from L2 — the only all-to-all step of an iteration)
+//   u(m,b | r')  = A2 t1                  (shared memory)
+//   y(li, m, r)  = u(m | b,r') R(r | b,r')^T   (R stays transposed in shared memory for the whole run)
+// and the CTA also owns the matching segments of x, r, p.  Per iteration there are two reductions (p.q and r.r: per-CTA
+// partials in global memory, summed by every CTA in the same fixed order, so all CTAs take identical decisions) and three
+// grid barriers.  The stopping logic of the host loop (target, stagnation at the rounding floor, re-anchoring) runs on the
+// device; the host reads one status record per launch.
+struct SpdCgArgs {
+	const double* L; const double* A2; const double* R;
+	double* x; double* r; double* p; double* partial; double* sc; unsigned int* info; unsigned int* barrier;
+	int l, a, n, m, b, rr;           // L (l, a, l), A2 (m b | a n), R (rr, b, rr); vectors (l, n, rr) with m == n
+	int nsl;                         // slices per CTA (1 whenever l <= number of co-resident CTAs)
+	int max_it;
+	double target, rr_start;
+};
+constexpr int CGP_THREADS = 256;
+constexpr int CGP_AMAX = 4;          // operator bond dimension handled by the register accumulators of step 1
+constexpr int CGP_ROWS = 25;         // rows of p in flight per thread in step 1
+
+__device__ __forceinline__ double cgp_block_sum(double v, double* red) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	__syncthreads();
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	double t = 0.0;
+#pragma unroll
+	for (int w = 0; w < CGP_THREADS / 32; ++w) t += red[w];
+	return t;
+}
+// sum of the G per-CTA partials, same order in every CTA (bit-identical results everywhere)
+__device__ __forceinline__ double cgp_grid_sum(const double* partial, const int G, double* red) {
+	double t = 0.0;
+	if (threadIdx.x < 32) {
+		for (int i = threadIdx.x; i < G; i += 32) t += __ldcg(partial + i);
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+		if (threadIdx.x == 0) red[16] = t;
+	}
+	__syncthreads();
+	const double s = red[16];
+	__syncthreads();
+	return s;
+}
+// Grid barrier on a monotone counter (the launch is cooperative, so all CTAs are resident).  The CTA barrier orders every
+// thread's global stores before thread 0's fence, which is cumulative; readers use ld.global.cg afterwards.  Bounded spin.
+__device__ __forceinline__ void cgp_grid_barrier(unsigned int* counter, unsigned int& expected, const int G, unsigned int* info) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		expected += (unsigned)G;
+		__threadfence();
+		atomicAdd(counter, 1u);
+		unsigned int spins = 0;
+		while (*((volatile unsigned int*)counter) < expected && ++spins < (1u << 26)) {}
+		if (spins >= (1u << 26)) info[2] = 0xDEADu;
+		__threadfence();
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) {
+	extern __shared__ double cgp_smem[];
+	const int l = g.l, a = g.a, n = g.n, m = g.m, b = g.b, R = g.rr, nsl = g.nsl;
+	const int Cin = n * R, Cout = m * R, KA = a * n, QA = m * b, KR = b * R;
+	const int Rp = (R + 1) & ~1;                   // row strides padded to even: 16-byte shared-memory accesses
+	double* Rt = cgp_smem;                         // [KR][Rp]   Rt[(bb, r')][ro] = R[ro][bb][r']
+	double* A2s = Rt + (size_t)KR * Rp;            // [QA][KA]
+	double* Ls = A2s + ((QA * KA + 1) & ~1);       // [l][CGP_AMAX]  weights of the current slice, transposed, zero padded
+	double* t1s = Ls + CGP_AMAX * l;               // [KA][Rp]
+	double* us = t1s + KA * Rp;                    // [m][KR]  (KR even or odd: scalar reads of u)
+	double* xs = us + ((m * KR + 1) & ~1);         // [nsl][Cout] owned segments of x, r, p, q
+	double* rs = xs + (size_t)nsl * Cout;
+	double* ps = rs + (size_t)nsl * Cout;
+	double* qs = ps + (size_t)nsl * Cout;
+	double* red = qs + (size_t)nsl * Cout;         // [32]
+	const int tid = threadIdx.x, G = gridDim.x;
+	for (int e = tid; e < KR * R; e += CGP_THREADS) { const int ro = e / KR, k = e % KR; Rt[k * Rp + ro] = g.R[e]; }
+	if (Rp != R) for (int k = tid; k < KR; k += CGP_THREADS) Rt[k * Rp + R] = 0.0;
+	for (int e = tid; e < QA * KA; e += CGP_THREADS) A2s[e] = g.A2[e];
+	for (int s = 0; s < nsl; ++s) {
+		const int li = blockIdx.x + s * G;
+		if (li < l) for (int e = tid; e < Cout; e += CGP_THREADS) {
+			const size_t o = (size_t)li * Cout + e;
+			xs[s * Cout + e] = g.x[o]; rs[s * Cout + e] = g.r[o]; ps[s * Cout + e] = g.p[o];
+		}
+	}
+	__syncthreads();
+
+	double rr = g.sc[0];                           // r.r of the start residual (written by the host path before the launch)
+	double best = rr;
+	int since_best = 0, it = 0;
+	unsigned int reason = 0;                       // 1 target, 2 stagnation, 3 re-anchor, 4 NaN, 0 iteration budget
+	unsigned int bar_expected = 0;
+	const bool timing = g.info[3] == 0xC10C && blockIdx.x == 0 && tid == 0;
+	long long tk[6] = {0, 0, 0, 0, 0, 0}, t0 = 0;  // step 1 | steps 2-3 | barrier 1 | update | barrier 2 | barrier 3
+	const bool vec_ok = (Cin & 1) == 0;
+	for (; it < g.max_it; ++it) {
+		double* part = g.partial + (size_t)(it & 1) * 2 * G;
+		if (timing) t0 = clock64();
+		// ---- q = A p on the owned slices, and the partial of p.q
+		double pq_local = 0.0;
+		for (int s = 0; s < nsl; ++s) {
+			const int li = blockIdx.x + s * G;
+			if (li >= l) break;                      // uniform per CTA
+			// weights of the slice, transposed and zero padded to CGP_AMAX per row: Ls[lp][aa] = L(li, aa, lp)
+			for (int e = tid; e < CGP_AMAX * l; e += CGP_THREADS) { const int lp = e / CGP_AMAX, aa = e % CGP_AMAX; Ls[e] = (aa < a) ? g.L[((size_t)li * a + aa) * l + lp] : 0.0; }
+			__syncthreads();
+			// step 1: t1(aa, j) = sum_l' L(li, aa, l') p(l', j).  Every CTA needs all of p (ld.global.cg: other CTAs wrote it):
+			// CGP_ROWS 16-byte loads in flight per thread, the weights of a row come as one broadcast 16-byte shared-memory load.
+			if (vec_ok) {
+				for (int j2 = tid; j2 < (Cin >> 1); j2 += CGP_THREADS) {
+					double acc[CGP_AMAX][2];
+#pragma unroll
+					for (int aa = 0; aa < CGP_AMAX; ++aa) { acc[aa][0] = 0.0; acc[aa][1] = 0.0; }
+					const double2* pj = reinterpret_cast<const double2*>(g.p) + j2;
+					for (int base = 0; base < l; base += CGP_ROWS) {
+						double2 pv[CGP_ROWS];
+#pragma unroll
+						for (int i = 0; i < CGP_ROWS; ++i) pv[i] = (base + i < l) ? __ldcg(pj + (size_t)(base + i) * (Cin >> 1)) : make_double2(0.0, 0.0);
+#pragma unroll
+						for (int i = 0; i < CGP_ROWS; ++i) {
+							if (base + i < l) {
+								const double2 w01 = *reinterpret_cast<const double2*>(Ls + (base + i) * CGP_AMAX);
+								acc[0][0] += w01.x * pv[i].x; acc[0][1] += w01.x * pv[i].y;
+								acc[1][0] += w01.y * pv[i].x; acc[1][1] += w01.y * pv[i].y;
+								if (a > 2) {
+									const double2 w23 = *reinterpret_cast<const double2*>(Ls + (base + i) * CGP_AMAX + 2);
+									acc[2][0] += w23.x * pv[i].x; acc[2][1] += w23.x * pv[i].y;
+									acc[3][0] += w23.y * pv[i].x; acc[3][1] += w23.y * pv[i].y;
+								}
+							}
+						}
+					}
+					// t1s rows are indexed (aa, nidx) with row stride Rp: column j = nidx * R + r'
+					const int j = 2 * j2, n0 = j / R, r0 = j - n0 * R;
+					const int n1 = (r0 + 1 < R) ? n0 : n0 + 1, r1 = (r0 + 1 < R) ? r0 + 1 : 0;
+#pragma unroll
+					for (int aa = 0; aa < CGP_AMAX; ++aa) if (aa < a) { t1s[(aa * n + n0) * Rp + r0] = acc[aa][0]; t1s[(aa * n + n1) * Rp + r1] = acc[aa][1]; }
+				}
+			} else {
+				for (int j = tid; j < Cin; j += CGP_THREADS) {
+					double acc[CGP_AMAX] = {0.0, 0.0, 0.0, 0.0};
+					const double* pj = g.p + j;
+#pragma unroll 8
+					for (int lp = 0; lp < l; ++lp) {
+						const double pv = __ldcg(pj + (size_t)lp * Cin);
+#pragma unroll
+						for (int aa = 0; aa < CGP_AMAX; ++aa) acc[aa] += Ls[lp * CGP_AMAX + aa] * pv;
+					}
+#pragma unroll
+					for (int aa = 0; aa < CGP_AMAX; ++aa) if (aa < a) t1s[(aa * n + j / R) * Rp + j % R] = acc[aa];
+				}
+			}
+			__syncthreads();
+			if (timing) { const long long t1 = clock64(); tk[0] += t1 - t0; t0 = t1; }
+			// step 2: u(q, r') = sum_k A2(q, k) t1(k, r'): 2 x 2 outputs per thread
+			for (int e = tid; e < ((QA + 1) / 2) * (Rp / 2); e += CGP_THREADS) {
+				const int q0 = (e / (Rp / 2)) * 2, rp = (e % (Rp / 2)) * 2;
+				const int q1 = (q0 + 1 < QA) ? q0 + 1 : q0;
+				double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+#pragma unroll 4
+				for (int k = 0; k < KA; ++k) {
+					const double2 tv = *reinterpret_cast<const double2*>(t1s + k * Rp + rp);
+					const double w0 = A2s[q0 * KA + k], w1 = A2s[q1 * KA + k];
+					a00 += w0 * tv.x; a01 += w0 * tv.y; a10 += w1 * tv.x; a11 += w1 * tv.y;
+				}
+				// us is indexed [mm][(bb, r')] = flat q * R + r'
+				us[q0 * R + rp] = a00; if (rp + 1 < R) us[q0 * R + rp + 1] = a01;
+				if (q1 != q0) { us[q1 * R + rp] = a10; if (rp + 1 < R) us[q1 * R + rp + 1] = a11; }
+			}
+			__syncthreads();
+			// step 3: y(mm, ro) = sum_kk u(mm, kk) Rt(kk, ro): 2 x 2 outputs per thread; p.q on the fly
+			for (int e = tid; e < ((m + 1) / 2) * (Rp / 2); e += CGP_THREADS) {
+				const int m0 = (e / (Rp / 2)) * 2, ro = (e % (Rp / 2)) * 2;
+				const int m1 = (m0 + 1 < m) ? m0 + 1 : m0;
+				const double* u0 = us + (size_t)m0 * KR;
+				const double* u1 = us + (size_t)m1 * KR;
+				double y00 = 0.0, y01 = 0.0, y10 = 0.0, y11 = 0.0;
+#pragma unroll 4
+				for (int kk = 0; kk < KR; ++kk) {
+					const double2 rv = *reinterpret_cast<const double2*>(Rt + kk * Rp + ro);
+					const double ua = u0[kk], ub = u1[kk];
+					y00 += ua * rv.x; y01 += ua * rv.y; y10 += ub * rv.x; y11 += ub * rv.y;
+				}
+				const int o0 = s * Cout + m0 * R + ro;
+				qs[o0] = y00; pq_local += ps[o0] * y00;
+				if (ro + 1 < R) { qs[o0 + 1] = y01; pq_local += ps[o0 + 1] * y01; }
+				if (m1 != m0) {
+					qs[o0 + R] = y10; pq_local += ps[o0 + R] * y10;
+					if (ro + 1 < R) { qs[o0 + R + 1] = y11; pq_local += ps[o0 + R + 1] * y11; }
+				}
+			}
+			__syncthreads();
+		}
+		const double pq_cta = cgp_block_sum(pq_local, red);
+		if (tid == 0) __stcg(part + blockIdx.x, pq_cta);
+		if (timing) { const long long t1 = clock64(); tk[1] += t1 - t0; t0 = t1; }
+		cgp_grid_barrier(g.barrier, bar_expected, G, g.info);
+		if (timing) { const long long t1 = clock64(); tk[2] += t1 - t0; t0 = t1; }
+		const double pq = cgp_grid_sum(part, G, red);
+		const double alpha = (pq != 0.0) ? rr / pq : 0.0;
+		// ---- x += alpha p ; r -= alpha q ; partial of r.r   (owned segments, shared memory)
+		double rr_local = 0.0;
+		for (int e = tid; e < nsl * Cout; e += CGP_THREADS) {
+			if (blockIdx.x + (e / Cout) * G < l) {
+				xs[e] += alpha * ps[e];
+				const double rn = rs[e] - alpha * qs[e];
+				rs[e] = rn;
+				rr_local += rn * rn;
+			}
+		}
+		const double rr_cta = cgp_block_sum(rr_local, red);
+		if (tid == 0) __stcg(part + G + blockIdx.x, rr_cta);
+		if (timing) { const long long t1 = clock64(); tk[3] += t1 - t0; t0 = t1; }
+		cgp_grid_barrier(g.barrier, bar_expected, G, g.info);
+		if (timing) { const long long t1 = clock64(); tk[4] += t1 - t0; t0 = t1; }
+		const double rrn = cgp_grid_sum(part + G, G, red);
+		const double beta = (rr != 0.0) ? rrn / rr : 0.0;
+		for (int e = tid; e < nsl * Cout; e += CGP_THREADS) {
+			const int li = blockIdx.x + (e / Cout) * G;
+			if (li < l) { const double pn = rs[e] + beta * ps[e]; ps[e] = pn; __stcg(g.p + (size_t)li * Cout + (e % Cout), pn); }
+		}
+		rr = rrn;
+		// stopping rules of the host loop (local_solve_cg), evaluated identically by every CTA
+		if (!(rr == rr)) { reason = 4; ++it; break; }
+		if (rr <= g.target) { reason = 1; ++it; break; }
+		if (rr < 0.5 * best) { best = rr; since_best = 0; } else if (++since_best >= 48) { reason = 2; ++it; break; }
+		if (rr < 1e-20 * g.rr_start) { reason = 3; ++it; break; }
+		if (timing) { const long long t1 = clock64(); tk[3] += t1 - t0; t0 = t1; }
+		cgp_grid_barrier(g.barrier, bar_expected, G, g.info);     // the new p is visible to every CTA
+		if (timing) { const long long t1 = clock64(); tk[5] += t1 - t0; t0 = t1; }
+	}
+	__syncthreads();
+	for (int s = 0; s < nsl; ++s) {
+		const int li = blockIdx.x + s * G;
+		if (li < l) for (int e = tid; e < Cout; e += CGP_THREADS) {
+			const size_t o = (size_t)li * Cout + e;
+			g.x[o] = xs[s * Cout + e]; g.r[o] = rs[s * Cout + e];
+		}
+	}
+	if (blockIdx.x == 0 && tid == 0) { g.sc[0] = rr; g.info[0] = (unsigned)it; g.info[1] = reason; }
+	if (timing) { for (int i = 0; i < 6; ++i) g.info[4 + i] = (unsigned)(tk[i] >> 4); }
+}
+
+// launches spd_cg_kernel if the shapes fit; returns false (nothing done) otherwise
+bool spd_cg_persistent(const SpdSiteApply& sa, double* x, double* r, double* p, double* sc, size_t max_it, double target,
+                       double rr_start, size_t& iterations, unsigned& reason, double& rr_out) {
+	Context& c = ctx();
+	if (!c.als_persistent_cg || sa.m != sa.n || sa.a > size_t(CGP_AMAX) || sa.l > 4096 || sa.r > 4096) return false;
+	const size_t KR = sa.b * sa.r, KA = sa.a * sa.n, QA = sa.m * sa.b, Rp = (sa.r + 1) & ~size_t(1), Cout = sa.m * sa.r;
+	const size_t cap = std::min<size_t>(c.max_smem_optin, 227 * 1024) - 1024;
+	auto smem_for = [&](size_t nsl) {
+		return (KR * Rp + ((QA * KA + 1) & ~size_t(1)) + size_t(CGP_AMAX) * sa.l + KA * Rp + ((sa.m * KR + 1) & ~size_t(1)) + 4 * nsl * Cout + 32) * sizeof(double);
+	};
+	// one CTA per slice of the left bond when that many are co-resident, otherwise several slices per CTA
+	size_t nsl = 1, smem = 0;
+	int G = 0;
+	for (;; ++nsl) {
+		smem = smem_for(nsl);
+		if (smem > cap) return false;
+		static size_t attr_smem = 0;
+		if (smem > attr_smem) {
+			XB_CUDA(cudaFuncSetAttribute(spd_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+			attr_smem = smem;
+		}
+		int per_sm = 0;
+		XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spd_cg_kernel, CGP_THREADS, smem));
+		if (per_sm < 1) return false;
+		G = int((sa.l + nsl - 1) / nsl);
+		if (size_t(G) <= size_t(c.num_sms) * per_sm) break;
+	}
+	DBuf partial(size_t(4) * G);
+	unsigned int* info = static_cast<unsigned int*>(dalloc_bytes(16 * sizeof(unsigned int)));
+	const bool timing = getenv("XB_CG_TIMING") != nullptr;
+	{ const unsigned int init[12] = {0, 0, 0, timing ? 0xC10Cu : 0u, 0, 0, 0, 0, 0, 0, 0, 0}; XB_CUDA(cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, c.stream)); }
+	SpdCgArgs g;
+	g.L = sa.L; g.A2 = sa.A2; g.R = sa.R; g.x = x; g.r = r; g.p = p; g.partial = partial; g.sc = sc; g.info = info; g.barrier = info + 11;
+	g.l = int(sa.l); g.a = int(sa.a); g.n = int(sa.n); g.m = int(sa.m); g.b = int(sa.b); g.rr = int(sa.r); g.nsl = int(nsl);
+	g.max_it = int(std::min<size_t>(max_it, 1u << 30)); g.target = target; g.rr_start = rr_start;
+	void* args[] = {&g};
+	{
+		ProfScope prof("als_cg_kernel");
+		XB_CUDA(cudaLaunchCooperativeKernel((void*)spd_cg_kernel, dim3(unsigned(G)), dim3(CGP_THREADS), args, smem, c.stream));
+		c.launches++;
+	}
+	unsigned int* h = reinterpret_cast<unsigned int*>(c.h_scratch + 8);
+	XB_CUDA(cudaMemcpyAsync(c.h_scratch, sc, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaMemcpyAsync(h, info, 10 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaStreamSynchronize(c.stream));
+	dfree(info);
+	rr_out = c.h_scratch[0]; iterations = h[0]; reason = h[1];
+	if (h[2] == 0xDEADu) throw Error(XB_ERR_CUDA, "persistent CG: a grid barrier timed out (internal scheduling error)");
+	if (timing && h[0]) fprintf(stderr, "[cg] G=%d its=%u cycles/it: step1 %u steps2-3 %u barrier1 %u update %u barrier2 %u barrier3 %u\n", G, h[0],
+	                            h[4] * 16 / h[0], h[5] * 16 / h[0], h[6] * 16 / h[0], h[7] * 16 / h[0], h[8] * 16 / h[0], h[9] * 16 / h[0]);
+	return true;
+}
+
 // y = {L, A_1..A_s, R} applied to v, SPD environments: L(l, a, l'), A_p(a, m, n, b), R(r, b, r'), v(l', n_1..n_s, r' [, col])
 // -> y(l, m_1..m_s, r [, col]).  One GEMM per factor, one reshuffle per operator core (als.cpp:383-401 un-contracted).
 DT spd_env_apply(const DT& L, const std::vector<DT>& Acores, const DT& R, const DT& v) {
@@ -482,6 +783,15 @@ struct Als {
 			struct GraphHolder { cudaGraph_t g = nullptr; cudaGraphExec_t e = nullptr;
 				~GraphHolder() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); } } graph;
 			const bool use_graph = site_apply && fused_update && c.als_graph && !c.profile;
+			if (site_apply) {
+				// one cooperative launch per CG run (spd_cg_kernel); the stopping rules below run on the device
+				size_t done = 0; unsigned reason = 0; double rr_new = rr;
+				if (spd_cg_persistent(*site_apply, xv.data(), r.data(), p.data(), sc.p, max_it - it, target, rr_start, done, reason, rr_new)) {
+					it += done; rr = rr_new;
+					if (reason == 4 || !(rr == rr)) throw Error(XB_ERR_NUMERIC, "local CG produced NaN (operator not positive definite?)");
+					continue;
+				}
+			}
 			while (rr > target && it < max_it) {
 				const size_t chunk = std::min<size_t>(8, max_it - it);
 				if (use_graph && chunk == 8) {
@@ -598,11 +908,11 @@ struct Als {
 		double last_e2 = 1e102, last_e = 1e101, e = energy();
 		size_t half_sweeps = 0;
 		for (;;) {
-			local_step();
+			{ ProfScope prof("als_local_step"); local_step(); }
 			// check_for_end_of_sweep (als.cpp:426-475)
 			if ((!increasing && cur == first) || (increasing && cur == last - sites)) {
 				half_sweeps += 1;
-				last_e2 = last_e; last_e = e; e = energy();
+				last_e2 = last_e; last_e = e; { ProfScope prof("als_energy"); e = energy(); }
 				if (half_sweeps == opt.num_half_sweeps || std::fabs(last_e - e) < opt.convergence_epsilon ||
 				    std::fabs(last_e2 - e) < opt.convergence_epsilon || last - first <= sites) {
 					if (canon_end && opt.preserve_core_position) move_core(x, core_end, true);
@@ -611,6 +921,7 @@ struct Als {
 				increasing = !increasing;
 			}
 			// move_to_next_index (als.cpp:340-380)
+			ProfScope prof_move("als_move_to_next");
 			if (increasing) {
 				if (sites == 1) move_core(x, cur + 1, true);
 				if (A) { opR.pop_back(); opL.push_back(op_left(opL.back(), cur)); }

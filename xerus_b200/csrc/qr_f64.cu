@@ -524,7 +524,7 @@ static void apply_block_reflector(double* C, size_t ldc, size_t mp, size_t nc, c
 	XB_LAUNCH_CHECK();
 }
 
-void qr(double* Q, double* R, const double* A, size_t m, size_t n) {
+void qr(double* Q, double* R, const double* A, size_t m, size_t n, bool defer_q) {
 	XB_REQUIRE(m > 0 && n > 0, "Dimension m and n must be larger than zero");    // blasLapackWrapper.cpp:392-393
 	XB_REQUIRE(m <= 0x7fffffffULL && n <= 0x7fffffffULL, "Dimension to large for QR");
 	ProfScope prof("qr");
@@ -569,11 +569,19 @@ void qr(double* Q, double* R, const double* A, size_t m, size_t n) {
 		qr_extract_r_kernel<<<blocks, 256, 0, ctx().stream>>>(R, W, k, n, sc.p + 1);
 		XB_LAUNCH_CHECK();
 	}
-	// Q = H_1 ... H_k [I; 0] : apply the block reflectors in reverse order to the identity
-	set_identity(Q, m, k, k);
-	for (size_t p = npanels; p-- > 0;) {
-		const size_t j0 = p * QR_NB, mp = m - j0;
-		apply_block_reflector(Q + j0 * k + j0, k, mp, k - j0, Vall.p + p * m * QR_NB, Tall.p + p * QR_NB * QR_NB, false, Wp);
+	// Q = H_1 ... H_k [I; 0] : apply the block reflectors in reverse order to the identity.  In a sweep nothing downstream of
+	// R needs Q (it only becomes the new core), so with defer_q it is formed on the side stream, next to the main stream's
+	// push of R and the next factorization; the reflector storage is released on the stream that read it last.
+	const bool defer = defer_q && ctx().qr_defer != 0 && npanels > 1;
+	if (defer) aux_fork();
+	{
+		AuxScope side(defer);
+		set_identity(Q, m, k, k);
+		for (size_t p = npanels; p-- > 0;) {
+			const size_t j0 = p * QR_NB, mp = m - j0;
+			apply_block_reflector(Q + j0 * k + j0, k, mp, k - j0, Vall.p + p * m * QR_NB, Tall.p + p * QR_NB * QR_NB, false, Wp);
+		}
+		Vall.reset(); Tall.reset(); Wp.reset();
 	}
 }
 
@@ -615,10 +623,11 @@ static size_t numerical_rank(const std::vector<double>& S) {
 	return rank;
 }
 
-size_t qc(double* Q, double* C, const double* A, size_t m, size_t n) {
+size_t qc(double* Q, double* C, const double* A, size_t m, size_t n, bool defer_q) {
 	const size_t k = std::min(m, n);
-	qr(Q, C, A, m, n);
+	qr(Q, C, A, m, n, defer_q);
 	if (diag_is_full_rank(C, k, n)) return k;
+	aux_join();
 	// (near) rank deficient: reveal the rank through the SVD of the triangular factor, R = U S Vt:
 	//   A = (Q U_r) (S_r Vt_r)
 	Svd s;

@@ -59,8 +59,8 @@ static void select_worker(int w) {
 		Context* c = new Context();
 		c->initialised = true; c->worker = i; c->device = g_ctx.device; c->pool = g_ctx.pool;
 		c->num_sms = g_ctx.num_sms; c->max_smem_optin = g_ctx.max_smem_optin;
-		c->svd_max_sweeps = g_ctx.svd_max_sweeps; c->gemm_force_small = g_ctx.gemm_force_small; c->gemm_big = g_ctx.gemm_big;
-		c->svd_persistent = g_ctx.svd_persistent; c->svd_polish = g_ctx.svd_polish; c->tt_svd_polish = g_ctx.tt_svd_polish; c->svd_mixed = g_ctx.svd_mixed; c->svd_recursive = g_ctx.svd_recursive; c->svd_flip = g_ctx.svd_flip; c->svd_split = g_ctx.svd_split; c->svd_gram = g_ctx.svd_gram; c->als_graph = g_ctx.als_graph; c->svd_jacc = g_ctx.svd_jacc; c->svd_fast = g_ctx.svd_fast; c->qr_cluster = g_ctx.qr_cluster; c->svd_square_qr = g_ctx.svd_square_qr;
+		c->svd_max_sweeps = g_ctx.svd_max_sweeps; c->gemm_force_small = g_ctx.gemm_force_small; c->gemm_big = g_ctx.gemm_big; c->qr_defer = g_ctx.qr_defer;
+		c->svd_persistent = g_ctx.svd_persistent; c->svd_polish = g_ctx.svd_polish; c->tt_svd_polish = g_ctx.tt_svd_polish; c->svd_mixed = g_ctx.svd_mixed; c->svd_recursive = g_ctx.svd_recursive; c->svd_flip = g_ctx.svd_flip; c->svd_split = g_ctx.svd_split; c->svd_gram = g_ctx.svd_gram; c->als_graph = g_ctx.als_graph; c->als_persistent_cg = g_ctx.als_persistent_cg; c->svd_jacc = g_ctx.svd_jacc; c->svd_fast = g_ctx.svd_fast; c->qr_cluster = g_ctx.qr_cluster; c->svd_square_qr = g_ctx.svd_square_qr;
 		c->svd_mixed_min = g_ctx.svd_mixed_min; c->svd_max_bw = g_ctx.svd_max_bw; c->als_direct_max = g_ctx.als_direct_max;
 		XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 		XB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scratch), c->h_scratch_len * sizeof(double)));
@@ -76,6 +76,39 @@ void* dalloc_bytes(size_t bytes) {
 	XB_CUDA(cudaMallocAsync(&p, bytes, ctx().stream));
 	return p;
 }
+static void ensure_aux(Context& c) {
+	if (c.aux) return;
+	XB_CUDA(cudaStreamCreateWithFlags(&c.aux, cudaStreamNonBlocking));
+	XB_CUDA(cudaEventCreateWithFlags(&c.aux_fork_ev, cudaEventDisableTiming));
+	XB_CUDA(cudaEventCreateWithFlags(&c.aux_join_ev, cudaEventDisableTiming));
+}
+void aux_fork() {
+	Context& c = ctx();
+	ensure_aux(c);
+	XB_CUDA(cudaEventRecord(c.aux_fork_ev, c.stream));
+	XB_CUDA(cudaStreamWaitEvent(c.aux, c.aux_fork_ev, 0));
+}
+void aux_join() {
+	Context& c = ctx();
+	if (!c.aux_pending) return;
+	XB_CUDA(cudaEventRecord(c.aux_join_ev, c.aux));
+	XB_CUDA(cudaStreamWaitEvent(c.stream, c.aux_join_ev, 0));
+	c.aux_pending = false;
+}
+AuxScope::AuxScope(bool enable) : on(enable) {
+	if (!on) return;
+	Context& c = ctx();
+	ensure_aux(c);
+	saved = c.stream;
+	c.stream = c.aux;
+}
+AuxScope::~AuxScope() {
+	if (!on) return;
+	Context& c = ctx();
+	c.stream = saved;
+	c.aux_pending = true;
+}
+
 double* dalloc(size_t n) { return static_cast<double*>(dalloc_bytes(n * sizeof(double))); }
 void dfree(void* p) { if (p) cudaFreeAsync(p, ctx().stream); }
 
@@ -186,6 +219,7 @@ xb_status xb_set_option(const char* key, double value) {
 			if (k == "svd_max_sweeps") c.svd_max_sweeps = int(value);
 			else if (k == "gemm_force_small") c.gemm_force_small = int(value);
 			else if (k == "gemm_big") c.gemm_big = int(value);
+			else if (k == "qr_defer") c.qr_defer = int(value);
 			else if (k == "svd_persistent") c.svd_persistent = int(value);
 			else if (k == "svd_max_bw") c.svd_max_bw = int(value);
 			else if (k == "svd_mixed") c.svd_mixed = int(value);
@@ -194,6 +228,7 @@ xb_status xb_set_option(const char* key, double value) {
 			else if (k == "svd_split") c.svd_split = int(value);
 			else if (k == "svd_gram") c.svd_gram = int(value);
 			else if (k == "als_graph") c.als_graph = int(value);
+			else if (k == "als_persistent_cg") c.als_persistent_cg = int(value);
 			else if (k == "svd_jacc") c.svd_jacc = int(value);
 			else if (k == "svd_fast") c.svd_fast = int(value);
 			else if (k == "qr_cluster") c.qr_cluster = int(value);

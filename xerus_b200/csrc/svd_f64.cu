@@ -1505,8 +1505,10 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	DBuf At, Rr;
 	if (reduced) {
 		Qred.resize(mw * nw); Rr.resize(nw * nw);
-		if (swapped) { At.resize(m * n); transpose(At, A, m, n); qr(Qred, Rr, At, mw, nw); }
-		else qr(Qred, Rr, A, mw, nw);
+		// Qred is not needed before extract(): it is formed on the side stream while the Jacobi kernel runs
+		if (swapped) { At.resize(m * n); transpose(At, A, m, n); qr(Qred, Rr, At, mw, nw, true); }
+		else qr(Qred, Rr, A, mw, nw, true);
+		q_deferred = true;
 		// Jacobi runs on the columns of R^T (the rows of R), not of R: after a QR step the rows of the triangular factor are
 		// far closer to the left singular directions than its columns are to the right ones (Drmac & Veselic's
 		// pre-conditioning), so graded inputs need half the sweeps.  The two vector parts swap roles in extract().
@@ -1691,6 +1693,7 @@ void Svd::extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, 
 	                                                       outV, svc, svr, scale_v, dS, soft_threshold, scale.p);
 	XB_LAUNCH_CHECK();
 	if (reduced) {
+		if (q_deferred) { aux_join(); q_deferred = false; }
 		if (!swapped) gemm(U, k, m, k, 1.0, Qred, nw, false, nw, Xk, k, false, 0.0);          // U = Qred * Xk
 		else gemm(Vt, n, k, n, 1.0, Xk, k, true, nw, Qred, nw, true, 0.0);                    // Vt = Xk^T * Qred^T
 	}

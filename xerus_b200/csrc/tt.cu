@@ -21,8 +21,9 @@ static void transfer_core(xb_tt* t, size_t from, size_t to, bool allow_rank_redu
 		const size_t kmax = std::min(rows, cols);
 		DBuf Q(rows * kmax), R(kmax * cols);
 		size_t k = kmax;
-		if (allow_rank_reduction) k = qc(Q, R, t->core[from], rows, cols);      // :843
-		else qr(Q, R, t->core[from], rows, cols);                              // :845
+		// the explicit Q only becomes the new core: it is formed on the side stream (move_core joins before anything reads it)
+		if (allow_rank_reduction) k = qc(Q, R, t->core[from], rows, cols, true);      // :843
+		else qr(Q, R, t->core[from], rows, cols, true);                              // :845
 		Q.n = rows * k;
 		const size_t ncols = t->ext(to) * t->rank[to + 1];
 		DBuf nt(k * ncols);
@@ -68,9 +69,11 @@ void move_core(xb_tt* t, size_t position, bool keep_rank) {   // ttNetwork.cpp:5
 		for (size_t n = 0; n < position; ++n) transfer_core(t, n, n + 1, arr);
 		for (size_t n = d - 1; n > position; --n) transfer_core(t, n, n - 1, arr);
 	}
+	aux_join();                                                          // every new core is complete on the main stream from here on
 	while (exceeds_maximal_ranks(t)) {                                   // :609-624
 		for (size_t n = position; n > 0; --n) transfer_core(t, n, n - 1, arr);
 		for (size_t n = 0; n + 1 < d; ++n) transfer_core(t, n, n + 1, arr);
+		aux_join();
 		for (size_t n = d - 1; n > position; --n) transfer_core(t, n, n - 1, arr);
 	}
 	t->canonicalized = true;

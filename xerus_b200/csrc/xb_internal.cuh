@@ -42,6 +42,9 @@ struct Context {
 	std::vector<std::pair<std::string, ProfTotal>> prof_totals;
 	int device = -1;
 	cudaStream_t stream = nullptr;
+	cudaStream_t aux = nullptr;      // side stream for work off the critical path of a sweep (explicit Q of a QR), see aux_fork / aux_join
+	cudaEvent_t aux_fork_ev = nullptr, aux_join_ev = nullptr;
+	bool aux_pending = false;
 	cudaMemPool_t pool = nullptr;
 	uint64_t launches = 0;
 	int num_sms = 148;
@@ -53,6 +56,7 @@ struct Context {
 	int svd_max_sweeps = 100;      // graded spectra (kappa ~ 1e14) need ~45 sweeps of the un-preconditioned Jacobi
 	int qr_panel = 32;
 	int gemm_force_small = 0;
+	int qr_defer = 1;              // sweeps: the explicit Q of a QR is formed on the side stream while the main stream carries on with R
 	int gemm_big = 1;              // 128 x 128 cp.async GEMM kernel for outputs of about a wave of such tiles or more
 	bool profile = false;
 	int svd_persistent = 1;
@@ -63,6 +67,7 @@ struct Context {
 	int qr_cluster = 1;            // QR panels of 128..2048 rows on a thread-block cluster (registers + DSMEM reduction)
 	int svd_fast = 1;              // specialised Jacobi kernel (compile-time row length, 128-bit accesses) up to 512 columns
 	int svd_jacc = 1;              // specialised Jacobi kernel: rotations of a block visit accumulated, applied to V once (DMMA)
+	int als_persistent_cg = 1;     // one-site SPD local problems: a whole CG run in one cooperative launch (spd_cg_kernel)
 	int als_graph = 1;             // one-site SPD CG: chunks of 8 iterations replayed as a CUDA graph
 	int svd_gram = 0;              // experimental: Jacobi block visits in Gram space (one Gram matrix, 16 x 16 rounds, one DMMA apply
 	                               // per visit); correct, but not faster than the column-space kernel on one SM per block pair
@@ -138,9 +143,22 @@ double read_scalar(const double* d_value);                                // D2H
 double two_norm(const double* x, size_t n);
 double dot(const double* x, const double* y, size_t n);
 
+// Side stream.  aux_fork(): the side stream waits for everything enqueued on the main stream so far.  aux_join(): the main
+// stream waits for everything enqueued on the side stream so far (no-op when nothing is pending).  AuxScope redirects
+// ctx().stream — and with it every launch, allocation and free of the library — to the side stream for its lifetime.
+void aux_fork();
+void aux_join();
+struct AuxScope {
+	cudaStream_t saved = nullptr; bool on = false;
+	explicit AuxScope(bool enable);
+	~AuxScope();
+};
+
 // factorizations
-// A (m x n packed, destroyed? no: const) -> Q (m x k packed), R (k x n packed), k = min(m,n)
-void qr(double* Q, double* R, const double* A, size_t m, size_t n);
+// A (m x n packed, destroyed? no: const) -> Q (m x k packed), R (k x n packed), k = min(m,n).
+// defer_q: R is complete on the main stream when this returns, Q is formed on the side stream; the caller calls aux_join()
+// before the main stream reads, overwrites or frees Q.
+void qr(double* Q, double* R, const double* A, size_t m, size_t n, bool defer_q = false);
 // A = L * Q : L m x k packed (lower trapezoidal), Q k x n packed, orthonormal rows
 void lq(double* L, double* Q, const double* A, size_t m, size_t n);
 // true RQ with LAPACK's convention (R upper-trapezoidal, bottom-right aligned)
@@ -161,12 +179,14 @@ struct Svd {
 	bool swapped = false, reduced = false, flipped = false;
 	size_t mw = 0, nw = 0, npad = 0, mt = 0, mdot = 0, voff = 0, ld = 0;
 	DBuf GT, Qred, Ssorted, perm, scale;   // scale: [2^-e, 2^e] of the Jacobi input (squares must not overflow)
+	bool q_deferred = false;               // Qred is still being formed on the side stream
+	~Svd() { if (q_deferred) aux_join(); }
 	void factor(const double* A, size_t m, size_t n);
 	void extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, double* dS /* optional device S (k) */);
 };
 
 // rank-revealing QC / CQ on device; returns the rank; Q, C are max-size device buffers that come back packed
-size_t qc(double* Q, double* C, const double* A, size_t m, size_t n);
+size_t qc(double* Q, double* C, const double* A, size_t m, size_t n, bool defer_q = false);   // defer_q as in qr()
 size_t cq(double* C, double* Q, const double* A, size_t m, size_t n);
 
 // dense solves on device (A n x n packed, destroyed; B n x nrhs packed, overwritten with X). Return false if not SPD.
