@@ -124,6 +124,10 @@ xb_status xb_tt_assume_core_position(xb_tt* tt, size_t position);               
 xb_status xb_tt_set_component(xb_tt* tt, size_t idx, const double* host_core, size_t rl, size_t rr);
 xb_status xb_tt_get_component(const xb_tt* tt, size_t idx, double* host_core);
 xb_status xb_tt_component_size(const xb_tt* tt, size_t idx, size_t* rl, size_t* ext, size_t* rr);
+/* all d components at once (copies enqueued back to back, one synchronisation): host_cores[i] row-major as above,
+ * ranks = the d-1 bond ranks the written components have; clears `canonicalized`. */
+xb_status xb_tt_set_components(xb_tt* tt, const double* const* host_cores, const size_t* ranks);
+xb_status xb_tt_get_components(const xb_tt* tt, double* const* host_cores);
 /* TTNetwork::move_core (ttNetwork.cpp:582-628): keep_rank -> plain QR/LQ, otherwise rank-revealing */
 xb_status xb_tt_move_core(xb_tt* tt, size_t position, int keep_rank);
 /* TTNetwork::round (ttNetwork.cpp:644-684): max_ranks has d-1 entries (0 = unlimited), 0 <= eps < 1.

@@ -62,6 +62,7 @@ _SIGS = {
     "xb_tt_core_position": [vp, P(C.c_int), szp], "xb_tt_assume_core_position": [vp, sz],
     "xb_tt_set_component": [vp, sz, dp, sz, sz], "xb_tt_get_component": [vp, sz, dp],
     "xb_tt_component_size": [vp, sz, szp, szp, szp],
+    "xb_tt_set_components": [vp, P(dp), szp], "xb_tt_get_components": [vp, P(dp)],
     "xb_tt_move_core": [vp, sz, C.c_int], "xb_tt_round": [vp, szp, C.c_double],
     "xb_tt_round_svals": [vp, szp, C.c_double, dp, sz], "xb_tt_round_batched": [P(vp), sz, sz, C.c_double],
     "xb_tt_frob_norm": [vp, dp], "xb_tt_inner": [vp, vp, dp], "xb_tt_distance": [vp, vp, dp],

@@ -334,6 +334,40 @@ xb_status xb_tt_get_component(const xb_tt* tt, size_t idx, double* host_core) {
 	});
 }
 
+// All components in one call: the copies are enqueued back to back and the stream is synchronised once (the per-component
+// entry points above synchronise per component, which at 32 components is milliseconds of host latency).
+xb_status xb_tt_set_components(xb_tt* tt, const double* const* host_cores, const size_t* ranks) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(tt && host_cores && (ranks || tt->d == 1), "null");
+		for (size_t i = 0; i + 1 < tt->d; ++i) XB_REQUIRE(ranks[i] > 0, "set_components: bond ranks must be positive");
+		for (size_t i = 0; i < tt->d; ++i) {
+			XB_REQUIRE(host_cores[i], "null component");
+			tt->rank[i] = (i == 0) ? 1 : ranks[i - 1];
+			tt->rank[i + 1] = (i + 1 == tt->d) ? 1 : ranks[i];
+		}
+		for (size_t i = 0; i < tt->d; ++i) {
+			tt->core[i].resize(tt->core_size(i));
+			XB_CUDA(cudaMemcpyAsync(tt->core[i].p, host_cores[i], tt->core_size(i) * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+		}
+		XB_CUDA(cudaStreamSynchronize(ctx().stream));
+		tt->canonicalized = false;                                             // ttNetwork.cpp:491 (more than the core was written)
+	});
+}
+
+xb_status xb_tt_get_components(const xb_tt* tt, double* const* host_cores) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(tt && host_cores, "null");
+		require_correct_format(tt);
+		for (size_t i = 0; i < tt->d; ++i) {
+			XB_REQUIRE(host_cores[i], "null component");
+			XB_CUDA(cudaMemcpyAsync(host_cores[i], tt->core[i].p, tt->core_size(i) * sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+		}
+		XB_CUDA(cudaStreamSynchronize(ctx().stream));
+	});
+}
+
 xb_status xb_tt_component_size(const xb_tt* tt, size_t idx, size_t* rl, size_t* ext, size_t* rr) {
 	return guard([&] { check_idx(tt, idx); if (rl) *rl = tt->rank[idx]; if (ext) *ext = tt->ext(idx); if (rr) *rr = tt->rank[idx + 1]; });
 }

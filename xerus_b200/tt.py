@@ -61,9 +61,12 @@ class TTNetwork:
             dims = [c.shape[1] for c in cores] + [c.shape[2] for c in cores]
         else:
             dims = [c.shape[1] for c in cores]
-        t = cls._create(dims, [c.shape[-1] for c in cores[:-1]])
-        for i, c in enumerate(cores):
-            t.set_component(i, c)
+        ranks = [c.shape[-1] for c in cores[:-1]]
+        t = cls._create(dims, ranks)
+        if cores[0].shape[0] != 1 or cores[-1].shape[-1] != 1:
+            raise XerusError(1, "the outer bonds of a tensor train have dimension one")
+        ptrs = (_lib.dp * len(cores))(*[c.ctypes.data_as(_lib.dp) for c in cores])
+        call("xb_tt_set_components", t._h, ptrs, _sizes(ranks))
         if core_position is not None:
             t.assume_core_position(core_position)
         return t
@@ -183,7 +186,15 @@ class TTNetwork:
         call("xb_tt_set_component", self._h, int(idx), core.ctypes.data_as(_lib.dp), core.shape[0], core.shape[-1])
 
     def cores(self):
-        return [self.get_component(i) for i in range(self.num_components)]
+        """All components as host arrays (one call, one synchronisation)."""
+        d = self.num_components
+        dims = self.dimensions
+        rk = [1] + self.ranks() + [1]
+        out = [np.empty((rk[i], dims[i], dims[d + i], rk[i + 1]) if self.is_operator else (rk[i], dims[i], rk[i + 1]), dtype=np.float64)
+               for i in range(d)]
+        ptrs = (_lib.dp * d)(*[c.ctypes.data_as(_lib.dp) for c in out])
+        call("xb_tt_get_components", self._h, ptrs)
+        return out
 
     # -- hot path ----------------------------------------------------------------------------------------------------
     def move_core(self, position, keepRank=False):
