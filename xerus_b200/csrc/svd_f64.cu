@@ -718,7 +718,38 @@ __global__ void __launch_bounds__(MAXT) jacobi_fast_kernel(double* __restrict__ 
 // JS_DEPTH slots in global memory, with back-pressure), applies it to the v halves with DMMA and hands the travelling block's
 // v half to the next V worker through its own ready flags.  Measured upper bound of the gain (V work deleted): -16 %.
 constexpr int JS_DEPTH = 4;
-template <int EP2>
+// DSMEM helpers of the hand-over (same instructions as the QR panel kernel uses for its reductions)
+__device__ __forceinline__ unsigned jsm_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned jmapa(unsigned addr, unsigned rank) {
+	unsigned r;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+	return r;
+}
+__device__ __forceinline__ void jst_async_v2(unsigned raddr, const double2 v, unsigned rmbar) {
+	asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
+	             :: "r"(raddr), "l"(__double_as_longlong(v.x)), "l"(__double_as_longlong(v.y)), "r"(rmbar) : "memory");
+}
+__device__ __forceinline__ void jst_async_f64(unsigned raddr, const double v, unsigned rmbar) {
+	asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+	             :: "r"(raddr), "l"(__double_as_longlong(v)), "r"(rmbar) : "memory");
+}
+// bounded wait (never hang the GPU): returns false on time-out
+__device__ __forceinline__ bool jmbar_wait(unsigned mbar, unsigned parity) {
+	unsigned done = 0, spins = 0;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+	} while (!done && ++spins < (1u << 22));
+	return done != 0;
+}
+// DS: the X workers form one thread-block cluster (the V workers a second one) and, inside a phase of the tournament, hand the
+// travelling block's x half to the next worker by pushing it straight into that CTA's shared memory (st.async + mbarrier
+// transaction count; a variant with one DSMEM bulk copy per row measured 2 % slower) instead of storing it to global memory, fencing, raising a flag and having the neighbour poll and load
+// it: one SM-to-SM transfer replaces three L2 round trips on the critical path.  The travelling block is double buffered
+// (buffer = step parity); a worker pushes into its neighbour's other buffer only after that neighbour has published (a
+// progress counter in global memory, read off the critical path) that it is done with the step that used it.  Phase changes
+// (both blocks re-dealt) and the V workers keep the global-memory path.
+template <int EP2, bool DS>
 __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ GT, const int nblk, const double tol2, const double big2,
                                                           unsigned int* __restrict__ counters, unsigned int* __restrict__ info,
                                                           const int max_sweeps, unsigned int* flags, double* jlog) {
@@ -730,11 +761,13 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 	constexpr int SLOT = N * N + 8;
 	constexpr int TB = (EP2 % 4 == 0) ? 4 : ((EP2 % 2 == 0) ? 2 : 1);
 	extern __shared__ double S_split[];
-	double* S = S_split;                        // [N][HLS]
-	double* nrm = S + (size_t)N * HLS;          // [N]
-	unsigned short* sched = reinterpret_cast<unsigned short*>(nrm + N);              // [(N-1)][BW]
+	double* S = S_split;                        // [N][HLS] (+ [BW][HLS]: second buffer of the travelling block with DS)
+	double* nrm = S + (size_t)(DS ? N + BW : N) * HLS;   // [N] (+ [BW] with DS)
+	unsigned short* sched = reinterpret_cast<unsigned short*>(nrm + (DS ? N + BW : N));              // [(N-1)][BW]
 	double* Js = reinterpret_cast<double*>(sched + ((N - 1) * BW + 8));              // [N][ldj]   ((N-1)*BW + 8 = 128 shorts)
 	__shared__ unsigned int s_rot, s_big;
+	__shared__ __align__(8) unsigned long long full_bar[2];
+	__shared__ unsigned int prog[16];           // DS: steps completed by every X worker of the cluster (each worker writes its entry in all CTAs)
 	cooperative_groups::grid_group grid = cooperative_groups::this_grid();
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int nw = nblk >> 1;
@@ -746,6 +779,17 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 	unsigned int* jdone = jready + nw;
 	unsigned int* rdy = vrole ? vready : xready;
 	const size_t hoff = vrole ? HL : 0;
+	constexpr unsigned PUSH_BYTES = BW * HL * 8 + BW * 8;
+	unsigned int use0 = 0, use1 = 0;            // completed DSMEM receptions per buffer (mbarrier phase parity)
+	if (DS) {
+		if (threadIdx.x < 16) prog[threadIdx.x] = 0;
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(jsm_u32(&full_bar[0])), "r"(1u) : "memory");
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(jsm_u32(&full_bar[1])), "r"(1u) : "memory");
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		cooperative_groups::this_cluster().sync();  // every CTA of the cluster is resident and its barriers are initialised
+	}
 	for (int e = threadIdx.x; e < (N - 1) * BW; e += blockDim.x) {
 		const int rr = e / BW, pi = e % BW;
 		int a, b;
@@ -781,7 +825,28 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 			const int pb = G * g + j, qb = G * g + h + ((j + t) & (h - 1));
 			const bool loadp = (t == 0), storep = (t == h - 1), full = (g == 2);
 			double* slot = jlog + ((size_t)wid * JS_DEPTH + (ground % JS_DEPTH)) * SLOT;
-			if (threadIdx.x == 0) {
+			// travelling block: rows BW..N-1 of S, or (DS, X workers, odd steps) the second buffer behind S
+			const bool dsx = DS && !vrole;
+			const int buf = dsx ? (ground & 1) : 0;
+			double* Qc = S + (size_t)(buf ? N : BW) * HLS;
+			double* nq = nrm + (buf ? N : BW);
+			const bool by_push = dsx && !loadp;       // this step's travelling block arrives through DSMEM
+			const bool push = dsx && !storep;         // ... and leaves through DSMEM, into the next worker's other buffer
+			const int recv = G * h + ((j + h - 1) & (h - 1));
+			if (by_push) {
+				const unsigned mb = jsm_u32(&full_bar[buf]);
+				if (threadIdx.x == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(PUSH_BYTES) : "memory");
+				if (!jmbar_wait(mb, (buf ? use1 : use0) & 1u)) { if (threadIdx.x == 0) atomicOr(&counters[2 * max_sweeps], 0xDEADu); }
+				if (buf) ++use1; else ++use0;
+			}
+			if (threadIdx.x == 0 && by_push) {
+				// only the ring slot of the rotation-product log has to be free
+				unsigned int spins = 0;
+				volatile unsigned int* jd = jdone;
+				while (jd[wid] + JS_DEPTH < (unsigned)ground + 1u && ++spins < (1u << 27)) {}
+				if (spins >= (1u << 27)) atomicOr(&counters[2 * max_sweeps], 0xDEADu);
+			}
+			if (threadIdx.x == 0 && !by_push) {
 				unsigned int spins = 0;
 				volatile unsigned int* rd = rdy;
 				volatile unsigned int* jr = jready;
@@ -797,10 +862,10 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 			}
 			__syncthreads();
 			if (timing) tk0 = clock64();
-			for (int r = (loadp ? 0 : BW) + warp; r < N; r += 8) {
+			for (int r = (by_push ? N : (loadp ? 0 : BW)) + warp; r < N; r += 8) {
 				const int grow = (r < BW ? pb * BW + r : qb * BW + (r - BW));
 				const double2* src = reinterpret_cast<const double2*>(GT + (size_t)grow * LD + hoff) + lane;
-				double2* dst = reinterpret_cast<double2*>(S + (size_t)r * HLS) + lane;
+				double2* dst = reinterpret_cast<double2*>(r < BW ? S + (size_t)r * HLS : Qc + (size_t)(r - BW) * HLS) + lane;
 				double2 v[EP2];
 #pragma unroll
 				for (int k = 0; k < EP2; ++k) v[k] = __ldcg(src + 32 * k);
@@ -811,7 +876,7 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 					double ss = s0 + s1;
 #pragma unroll
 					for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-					if (lane == 0) nrm[r] = ss;
+					if (lane == 0) { if (r < BW) nrm[r] = ss; else nq[r - BW] = ss; }
 				}
 			}
 			if (vrole) {
@@ -834,8 +899,10 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 					for (int rr = 0; rr < N - 1; ++rr) {
 						const unsigned int ab_ = sched[rr * BW + warp];
 						const int a = ab_ & 255, b = ab_ >> 8;
-						double2* x = reinterpret_cast<double2*>(S + (size_t)a * HLS) + lane;
-						double2* y = reinterpret_cast<double2*>(S + (size_t)b * HLS) + lane;
+						double2* x = reinterpret_cast<double2*>(a < BW ? S + (size_t)a * HLS : Qc + (size_t)(a - BW) * HLS) + lane;
+						double2* y = reinterpret_cast<double2*>(b < BW ? S + (size_t)b * HLS : Qc + (size_t)(b - BW) * HLS) + lane;
+						double* na_p = a < BW ? nrm + a : nq + (a - BW);
+						double* nb_p = b < BW ? nrm + b : nq + (b - BW);
 						double2 xr[EP2], yr[EP2];
 #pragma unroll
 						for (int k = 0; k < EP2; ++k) { xr[k] = x[32 * k]; yr[k] = y[32 * k]; }
@@ -846,7 +913,7 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 							else { g0 += xr[k].x * yr[k].x; g1 += xr[k].y * yr[k].y; }
 						}
 						double gs = (g0 + g1) + (g2 + g3);
-						const double aa = nrm[a], bb = nrm[b];
+						const double aa = *na_p, bb = *nb_p;
 #pragma unroll
 						for (int o = 16; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
 						const double gg = gs * gs, ab = aa * bb;
@@ -876,7 +943,7 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 							}
 							visit_rot = 1;
 							if (lane == 0) {
-								nrm[a] = na; nrm[b] = nb;
+								*na_p = na; *nb_p = nb;
 								my_rot += 1;
 								if (gg > big2 * ab) my_big += 1;
 							}
@@ -893,7 +960,7 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 					double aa = nrm[a], ja = (lane < N) ? Js[a * ldj + lane] : 0.0;
 					for (int rr = 0; rr < BW; ++rr) {
 						const int b = BW + ((warp + rr) & (BW - 1));
-						double2* y = reinterpret_cast<double2*>(S + (size_t)b * HLS) + lane;
+						double2* y = reinterpret_cast<double2*>(Qc + (size_t)(b - BW) * HLS) + lane;
 						double2 yr[EP2];
 #pragma unroll
 						for (int k = 0; k < EP2; ++k) yr[k] = y[32 * k];
@@ -904,7 +971,7 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 							else { g0 += xr[k].x * yr[k].x; g1 += xr[k].y * yr[k].y; }
 						}
 						double gs = (g0 + g1) + (g2 + g3);
-						const double bb = nrm[b];
+						const double bb = nq[b - BW];
 #pragma unroll
 						for (int o = 16; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
 						const double gg = gs * gs, ab = aa * bb;
@@ -915,7 +982,8 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 #pragma unroll
 							for (int k = 0; k < EP2; ++k) {
 								const double2 xn = make_double2(c * xr[k].x - s * yr[k].x, c * xr[k].y - s * yr[k].y);
-								y[32 * k] = make_double2(s * xr[k].x + c * yr[k].x, s * xr[k].y + c * yr[k].y);
+								yr[k] = make_double2(s * xr[k].x + c * yr[k].x, s * xr[k].y + c * yr[k].y);
+								y[32 * k] = yr[k];
 								xr[k] = xn;
 							}
 							if (lane < N) { Js[b * ldj + lane] = s * ja + c * jb; ja = c * ja - s * jb; }
@@ -924,8 +992,7 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 								double sa = 0.0, sb = 0.0;
 #pragma unroll
 								for (int k = 0; k < EP2; ++k) {
-									const double2 yn = y[32 * k];
-									sa += xr[k].x * xr[k].x + xr[k].y * xr[k].y; sb += yn.x * yn.x + yn.y * yn.y;
+									sa += xr[k].x * xr[k].x + xr[k].y * xr[k].y; sb += yr[k].x * yr[k].x + yr[k].y * yr[k].y;
 								}
 #pragma unroll
 								for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
@@ -934,7 +1001,7 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 							aa = na;
 							visit_rot = 1;
 							if (lane == 0) {
-								nrm[b] = nb;
+								nq[b - BW] = nb;
 								my_rot += 1;
 								if (gg > big2 * ab) my_big += 1;
 							}
@@ -955,25 +1022,54 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 			}
 			if (timing) { const long long t1 = clock64(); tk_inner += t1 - tk0; tk0 = t1; }
 			if (lane == 0 && my_rot) { atomicAdd(&s_rot, my_rot); atomicAdd(&s_big, my_big); my_rot = 0; my_big = 0; }
-			for (int r = (storep ? 0 : BW) + warp; r < N; r += 8) {
-				const int grow = (r < BW ? pb * BW + r : qb * BW + (r - BW));
-				double2* dst = reinterpret_cast<double2*>(GT + (size_t)grow * LD + hoff) + lane;
-				const double2* src = reinterpret_cast<const double2*>(S + (size_t)r * HLS) + lane;
+			if (push) {
+				// every thread pushes 16-byte pieces of the travelling block (and lane 0 of each warp a cached norm) into the
+				// receiver's other buffer; completion is counted in bytes on the receiver's mbarrier.  The receiver meets the block
+				// in step ground + 1 in its buffer (ground + 1) & 1, which it used in step ground - 1: prog[] says it has left it.
+				if (threadIdx.x == 0) {
+					unsigned int spins = 0;
+					volatile unsigned int* xp = prog;
+					while (xp[recv] < (unsigned)ground && ++spins < (1u << 27)) {}
+					if (spins >= (1u << 27)) atomicOr(&counters[2 * max_sweeps], 0xDEADu);
+				}
+				__syncthreads();
+				const int nb_ = buf ^ 1;
+				const unsigned rmb = jmapa(jsm_u32(&full_bar[nb_]), (unsigned)recv);
+				const double2* src = reinterpret_cast<const double2*>(Qc + (size_t)warp * HLS) + lane;
+				const unsigned rdst = jmapa(jsm_u32(S + (size_t)((nb_ ? N : BW) + warp) * HLS) + 16u * lane, (unsigned)recv);
 				double2 v[EP2];
 #pragma unroll
 				for (int k = 0; k < EP2; ++k) v[k] = src[32 * k];
 #pragma unroll
-				for (int k = 0; k < EP2; ++k) dst[32 * k] = v[k];
+				for (int k = 0; k < EP2; ++k) jst_async_v2(rdst + 512u * k, v[k], rmb);
+				if (lane == 0) jst_async_f64(jmapa(jsm_u32(nrm + (nb_ ? N : BW) + warp), (unsigned)recv), nq[warp], rmb);
+			} else {
+				for (int r = (storep ? 0 : BW) + warp; r < N; r += 8) {
+					const int grow = (r < BW ? pb * BW + r : qb * BW + (r - BW));
+					double2* dst = reinterpret_cast<double2*>(GT + (size_t)grow * LD + hoff) + lane;
+					const double2* src = reinterpret_cast<const double2*>(r < BW ? S + (size_t)r * HLS : Qc + (size_t)(r - BW) * HLS) + lane;
+					double2 v[EP2];
+#pragma unroll
+					for (int k = 0; k < EP2; ++k) v[k] = src[32 * k];
+#pragma unroll
+					for (int k = 0; k < EP2; ++k) dst[32 * k] = v[k];
+				}
 			}
 			if (timing) { const long long t1 = clock64(); tk_store += t1 - tk0; tk0 = t1; }
 			__syncthreads();
 			if (threadIdx.x == 0) {
-				__threadfence();
-				volatile unsigned int* rd = rdy;
-				if (storep) rd[pb] = (unsigned)ground + 1u;
-				rd[qb] = (unsigned)ground + 1u;
+				if (!push) {
+					__threadfence();
+					volatile unsigned int* rd = rdy;
+					if (storep) rd[pb] = (unsigned)ground + 1u;
+					rd[qb] = (unsigned)ground + 1u;
+				}
 				if (vrole) *((volatile unsigned int*)&jdone[wid]) = (unsigned)ground + 1u;
 			}
+			// this step's buffer has been read out (the pushes took their data from registers): publish the step count in every
+			// X worker's shared memory (plain DSMEM stores)
+			if (dsx && threadIdx.x < nw)
+				asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(jmapa(jsm_u32(&prog[wid]), (unsigned)threadIdx.x)), "r"((unsigned)ground + 1u) : "memory");
 			if (timing) { const long long t1 = clock64(); tk_sync += t1 - tk0; tk0 = t1; }
 		}
 		++sweeps;
@@ -1398,23 +1494,49 @@ static void launch_gram(double* gt, const JacobiPlan& p, double tol2, double big
 	ctx().launches++;
 }
 
+template <int EP2, bool DS>
+static bool launch_split_impl(double* gt, const JacobiPlan& p, double tol2, double big2, unsigned int* d_cnt, unsigned int* d_info, int max_sweeps,
+                              size_t smem_cap) {
+	int nblk = int(p.nblk);
+	const int nw = nblk / 2;
+	const size_t rows = DS ? 24 : 16;
+	const size_t smem = (rows * (64 * EP2 + 4) + rows + 16 * 20) * sizeof(double) + 256 + 64;
+	if (smem > smem_cap) { XB_REQUIRE(DS, "internal: split Jacobi kernel exceeds shared memory"); return false; }
+	static bool attr = false;
+	if (!attr) {
+		XB_CUDA(cudaFuncSetAttribute(jacobi_split_kernel<EP2, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+		if (DS) XB_CUDA(cudaFuncSetAttribute(jacobi_split_kernel<EP2, DS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+		attr = true;
+	}
+	unsigned int* flags = d_cnt + 2 * max_sweeps + 12;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(unsigned(nblk)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = ctx().stream;
+	cudaLaunchAttribute at[2];
+	at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+	unsigned nat = 1;
+	if (DS) {
+		at[1].id = cudaLaunchAttributeClusterDimension;
+		at[1].val.clusterDim.x = unsigned(nw); at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+		nat = 2;
+	}
+	cfg.attrs = at; cfg.numAttrs = nat;
+	if (DS) {
+		// both clusters (X workers, V workers) must be resident at the same time
+		int nclusters = 0;
+		if (cudaOccupancyMaxActiveClusters(&nclusters, jacobi_split_kernel<EP2, DS>, &cfg) != cudaSuccess || nclusters < 2) { cudaGetLastError(); return false; }
+	}
+	DBuf jlog(size_t(nw) * JS_DEPTH * (16 * 16 + 8));
+	double* jl = jlog.p;
+	XB_CUDA(cudaLaunchKernelEx(&cfg, jacobi_split_kernel<EP2, DS>, gt, nblk, tol2, big2, d_cnt, d_info, max_sweeps, flags, jl));
+	ctx().launches++;
+	return true;
+}
 template <int EP2>
 static void launch_split(double* gt, const JacobiPlan& p, double tol2, double big2, unsigned int* d_cnt, unsigned int* d_info, int max_sweeps,
                          size_t smem_cap) {
-	static bool attr = false;
-	if (!attr) {
-		XB_CUDA(cudaFuncSetAttribute(jacobi_split_kernel<EP2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
-		attr = true;
-	}
-	int nblk = int(p.nblk);
-	unsigned int* flags = d_cnt + 2 * max_sweeps + 12;
-	const size_t smem = (size_t(16) * (64 * EP2 + 4) + 16 + 16 * 20) * sizeof(double) + 256 + 64;
-	XB_REQUIRE(smem <= smem_cap, "internal: split Jacobi kernel exceeds shared memory");
-	DBuf jlog(size_t(nblk / 2) * JS_DEPTH * (16 * 16 + 8));
-	double* jl = jlog.p;
-	void* args[] = {&gt, &nblk, &tol2, &big2, &d_cnt, &d_info, &max_sweeps, &flags, &jl};
-	XB_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_split_kernel<EP2>, dim3(unsigned(nblk)), dim3(256), args, smem, ctx().stream));
-	ctx().launches++;
+	const int nw = int(p.nblk) / 2;
+	if (ctx().svd_dsmem && nw >= 2 && nw <= 16 && launch_split_impl<EP2, true>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap)) return;
+	launch_split_impl<EP2, false>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
 }
 
 static void launch_fast_any(double* gt, const JacobiPlan& p, double tol2, double big2, unsigned int* d_cnt, unsigned int* d_info, int max_sweeps,

@@ -71,6 +71,7 @@ struct Context {
 	int als_graph = 1;             // one-site SPD CG: chunks of 8 iterations replayed as a CUDA graph
 	int svd_gram = 0;              // experimental: Jacobi block visits in Gram space (one Gram matrix, 16 x 16 rounds, one DMMA apply
 	                               // per visit); correct, but not faster than the column-space kernel on one SM per block pair
+	int svd_dsmem = 1;             // split Jacobi kernel: X workers in one cluster, travelling block handed over through DSMEM (st.async + mbarrier)
 	int svd_split = 1;             // Jacobi: separate CTAs apply the rotation products to the accumulated-rotation halves
 	int svd_recursive = 1;         // recursive bipartite tournament with point-to-point block flags (power-of-two block counts)
 	int svd_mixed = 0;             // FP32 pre-conditioning sweeps + FP64 finishing sweeps (measured: no gain, kept as an experiment)
