@@ -1,6 +1,7 @@
 // xb200 runtime: device context, stream, stream-ordered memory pool, error state, memory hooks of the C ABI.
 #include "xb_internal.cuh"
 #include <mutex>
+#include <cstdlib>
 
 namespace xb {
 
@@ -14,6 +15,34 @@ static int g_num_workers = 1;
 static thread_local int tl_worker = 0;
 static std::mutex g_ctx_mutex;
 Context& ctx() { return *g_workers[tl_worker]; }
+
+static void apply_option(Context& c, const std::string& k, double value) {
+	if (k == "svd_max_sweeps") c.svd_max_sweeps = int(value);
+	else if (k == "gemm_force_small") c.gemm_force_small = int(value);
+	else if (k == "gemm_big") c.gemm_big = int(value);
+	else if (k == "qr_defer") c.qr_defer = int(value);
+	else if (k == "svd_persistent") c.svd_persistent = int(value);
+	else if (k == "svd_max_bw") c.svd_max_bw = int(value);
+	else if (k == "svd_mixed") c.svd_mixed = int(value);
+	else if (k == "svd_recursive") c.svd_recursive = int(value);
+	else if (k == "svd_flip") c.svd_flip = int(value);
+	else if (k == "svd_split") c.svd_split = int(value);
+	else if (k == "svd_dsmem") c.svd_dsmem = int(value);
+	else if (k == "svd_colsort") c.svd_colsort = int(value);
+	else if (k == "svd_last_sweep_cos") c.svd_last_sweep_cos = value;
+	else if (k == "svd_gram") c.svd_gram = int(value);
+	else if (k == "als_graph") c.als_graph = int(value);
+	else if (k == "als_persistent_cg") c.als_persistent_cg = int(value);
+	else if (k == "svd_jacc") c.svd_jacc = int(value);
+	else if (k == "svd_fast") c.svd_fast = int(value);
+	else if (k == "qr_cluster") c.qr_cluster = int(value);
+	else if (k == "svd_square_qr") c.svd_square_qr = int(value);
+	else if (k == "svd_mixed_min") c.svd_mixed_min = int(value);
+	else if (k == "svd_polish") c.svd_polish = int(value);
+	else if (k == "tt_svd_polish") c.tt_svd_polish = int(value);
+	else if (k == "als_direct_max") c.als_direct_max = int(value);
+	else throw Error(XB_ERR_INVALID, "xb_set_option: unknown key " + k);
+}
 
 static void init_locked(int device) {
 	if (g_ctx.initialised) return;
@@ -39,6 +68,19 @@ static void init_locked(int device) {
 	XB_CUDA(cudaMemPoolSetAttribute(g_ctx.pool, cudaMemPoolAttrReleaseThreshold, &threshold));
 	XB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&g_ctx.h_scratch), g_ctx.h_scratch_len * sizeof(double)));
 	g_ctx.initialised = true;
+	// XB_OPTIONS="key=value,key=value": the knobs of xb_set_option from the environment (A/B runs of any driver)
+	if (const char* env = getenv("XB_OPTIONS")) {
+		std::string all(env);
+		size_t pos = 0;
+		while (pos < all.size()) {
+			size_t end = all.find(',', pos);
+			if (end == std::string::npos) end = all.size();
+			const std::string item = all.substr(pos, end - pos);
+			const size_t eq = item.find('=');
+			if (eq != std::string::npos) apply_option(g_ctx, item.substr(0, eq), atof(item.c_str() + eq + 1));
+			pos = end + 1;
+		}
+	}
 }
 
 void ensure_init() {
@@ -60,7 +102,7 @@ static void select_worker(int w) {
 		c->initialised = true; c->worker = i; c->device = g_ctx.device; c->pool = g_ctx.pool;
 		c->num_sms = g_ctx.num_sms; c->max_smem_optin = g_ctx.max_smem_optin;
 		c->svd_max_sweeps = g_ctx.svd_max_sweeps; c->gemm_force_small = g_ctx.gemm_force_small; c->gemm_big = g_ctx.gemm_big; c->qr_defer = g_ctx.qr_defer;
-		c->svd_persistent = g_ctx.svd_persistent; c->svd_polish = g_ctx.svd_polish; c->tt_svd_polish = g_ctx.tt_svd_polish; c->svd_mixed = g_ctx.svd_mixed; c->svd_recursive = g_ctx.svd_recursive; c->svd_flip = g_ctx.svd_flip; c->svd_split = g_ctx.svd_split; c->svd_dsmem = g_ctx.svd_dsmem; c->svd_gram = g_ctx.svd_gram; c->als_graph = g_ctx.als_graph; c->als_persistent_cg = g_ctx.als_persistent_cg; c->svd_jacc = g_ctx.svd_jacc; c->svd_fast = g_ctx.svd_fast; c->qr_cluster = g_ctx.qr_cluster; c->svd_square_qr = g_ctx.svd_square_qr;
+		c->svd_persistent = g_ctx.svd_persistent; c->svd_polish = g_ctx.svd_polish; c->tt_svd_polish = g_ctx.tt_svd_polish; c->svd_mixed = g_ctx.svd_mixed; c->svd_recursive = g_ctx.svd_recursive; c->svd_flip = g_ctx.svd_flip; c->svd_split = g_ctx.svd_split; c->svd_dsmem = g_ctx.svd_dsmem; c->svd_colsort = g_ctx.svd_colsort; c->svd_last_sweep_cos = g_ctx.svd_last_sweep_cos; c->svd_gram = g_ctx.svd_gram; c->als_graph = g_ctx.als_graph; c->als_persistent_cg = g_ctx.als_persistent_cg; c->svd_jacc = g_ctx.svd_jacc; c->svd_fast = g_ctx.svd_fast; c->qr_cluster = g_ctx.qr_cluster; c->svd_square_qr = g_ctx.svd_square_qr;
 		c->svd_mixed_min = g_ctx.svd_mixed_min; c->svd_max_bw = g_ctx.svd_max_bw; c->als_direct_max = g_ctx.als_direct_max;
 		XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 		XB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scratch), c->h_scratch_len * sizeof(double)));
@@ -214,32 +256,7 @@ xb_status xb_set_option(const char* key, double value) {
 		XB_REQUIRE(key, "null key");
 		const std::string k(key);
 		std::lock_guard<std::mutex> lock(g_ctx_mutex);
-		for (int w = 0; w < g_num_workers; ++w) {
-			Context& c = *g_workers[w];
-			if (k == "svd_max_sweeps") c.svd_max_sweeps = int(value);
-			else if (k == "gemm_force_small") c.gemm_force_small = int(value);
-			else if (k == "gemm_big") c.gemm_big = int(value);
-			else if (k == "qr_defer") c.qr_defer = int(value);
-			else if (k == "svd_persistent") c.svd_persistent = int(value);
-			else if (k == "svd_max_bw") c.svd_max_bw = int(value);
-			else if (k == "svd_mixed") c.svd_mixed = int(value);
-			else if (k == "svd_recursive") c.svd_recursive = int(value);
-			else if (k == "svd_flip") c.svd_flip = int(value);
-			else if (k == "svd_split") c.svd_split = int(value);
-			else if (k == "svd_dsmem") c.svd_dsmem = int(value);
-			else if (k == "svd_gram") c.svd_gram = int(value);
-			else if (k == "als_graph") c.als_graph = int(value);
-			else if (k == "als_persistent_cg") c.als_persistent_cg = int(value);
-			else if (k == "svd_jacc") c.svd_jacc = int(value);
-			else if (k == "svd_fast") c.svd_fast = int(value);
-			else if (k == "qr_cluster") c.qr_cluster = int(value);
-			else if (k == "svd_square_qr") c.svd_square_qr = int(value);
-			else if (k == "svd_mixed_min") c.svd_mixed_min = int(value);
-			else if (k == "svd_polish") c.svd_polish = int(value);
-			else if (k == "tt_svd_polish") c.tt_svd_polish = int(value);
-			else if (k == "als_direct_max") c.als_direct_max = int(value);
-			else throw Error(XB_ERR_INVALID, "xb_set_option: unknown key " + k);
-		}
+		for (int w = 0; w < g_num_workers; ++w) apply_option(*g_workers[w], k, value);
 	});
 }
 

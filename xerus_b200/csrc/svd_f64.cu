@@ -1390,7 +1390,8 @@ __global__ void svd_extract_kernel(const double* __restrict__ GT, const int ldg,
                                    const double* __restrict__ Ssorted, const int* __restrict__ perm,
                                    double* __restrict__ outX, const long long sxi, const long long sxr, const int scale_x,
                                    double* __restrict__ outV, const long long svc, const long long svr, const int scale_v,
-                                   double* __restrict__ dS, const double soft, const double* __restrict__ scale2) {
+                                   double* __restrict__ dS, const double soft, const double* __restrict__ scale2,
+                                   const int* __restrict__ mapX, const int* __restrict__ mapV) {
 	const int r = blockIdx.x;
 	const double sigma = Ssorted[r];                          // unscaled singular value; the X part of GT holds x * scale2[0]
 	const double sigma_eff = fmax(0.0, sigma - soft);        // soft thresholding (tensorNetwork.cpp:766)
@@ -1398,9 +1399,62 @@ __global__ void svd_extract_kernel(const double* __restrict__ GT, const int ldg,
 	const double inv = sigma > 0.0 ? 1.0 / (sigma * scale2[0]) : 0.0;        // 1 / (scaled sigma)
 	const double fx = scale_x ? (soft == 0.0 ? scale2[1] : sigma_eff * inv) : inv;
 	const double fv = scale_v ? sigma_eff : 1.0;
-	for (int i = threadIdx.x; i < mdot; i += blockDim.x) outX[(long long)i * sxi + (long long)r * sxr] = g[i] * fx;
-	for (int c = threadIdx.x; c < nw; c += blockDim.x) outV[(long long)c * svc + (long long)r * svr] = g[voff + c] * fv;
+	// mapX / mapV (optional): the part that holds right vectors of the column-sorted working matrix goes back to the original order
+	for (int i = threadIdx.x; i < mdot; i += blockDim.x) outX[(long long)(mapX ? mapX[i] : i) * sxi + (long long)r * sxr] = g[i] * fx;
+	for (int c = threadIdx.x; c < nw; c += blockDim.x) outV[(long long)(mapV ? mapV[c] : c) * svc + (long long)r * svr] = g[voff + c] * fv;
 	if (dS && threadIdx.x == 0) dS[r] = sigma_eff;
+}
+
+// Column ordering of the QR pre-conditioning (Drmac & Veselic use a pivoted QR; sorting the columns by norm first captures
+// most of its effect): the working matrix Mw(i, j) = A[i * rs + j * cs] (m x n) gets its columns ranked by descending
+// Euclidean norm (ties by index), perm[rank] = column.  Single CTA; squares are taken of the power-of-two scaled entries.
+__global__ void __launch_bounds__(1024) svd_colrank_kernel(const double* __restrict__ A, const int m, const int n, const long long rs,
+                                                            const long long cs, const double* __restrict__ scale, int* __restrict__ perm) {
+	extern __shared__ double cn[];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	const double sc = scale[0];
+	if (cs == 1) {
+		// row-major working matrix: a thread sums every fourth row of one column (neighbouring threads read neighbouring
+		// columns: coalesced), the four partial sums of a column are added in a fixed order
+		double* part = cn + n;                               // [4][n]
+		for (int e = threadIdx.x; e < 4 * n; e += blockDim.x) {
+			const int p4 = e / n, j = e % n;
+			double a0 = 0.0, a1 = 0.0;
+			int i = p4;
+			for (; i + 4 < m; i += 8) {
+				const double v0 = A[(long long)i * rs + j] * sc, v1 = A[(long long)(i + 4) * rs + j] * sc;
+				a0 += v0 * v0; a1 += v1 * v1;
+			}
+			if (i < m) { const double v0 = A[(long long)i * rs + j] * sc; a0 += v0 * v0; }
+			part[e] = a0 + a1;
+		}
+		__syncthreads();
+		for (int j = threadIdx.x; j < n; j += blockDim.x) cn[j] = (part[j] + part[n + j]) + (part[2 * n + j] + part[3 * n + j]);
+	} else {
+		for (int j = warp; j < n; j += nwarps) {
+			double acc = 0.0;
+			for (int i = lane; i < m; i += 32) { const double v = A[(long long)i * rs + (long long)j * cs] * sc; acc += v * v; }
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+			if (lane == 0) cn[j] = acc;
+		}
+	}
+	__syncthreads();
+	for (int j = threadIdx.x; j < n; j += blockDim.x) {
+		const double v = cn[j];
+		int rank = 0;
+		for (int i = 0; i < n; ++i) { const double u = cn[i]; rank += (u > v || (u == v && i < j)) ? 1 : 0; }
+		perm[rank] = j;
+	}
+}
+// out (m x n, packed) = Mw[:, perm]
+__global__ void svd_gather_cols_kernel(double* __restrict__ out, const double* __restrict__ A, const int m, const int n, const long long rs,
+                                       const long long cs, const int* __restrict__ perm) {
+	const size_t total = (size_t)m * n;
+	for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+		const int i = int(e / n), j = int(e % n);
+		out[e] = A[(long long)i * rs + (long long)perm[j] * cs];
+	}
 }
 
 __global__ void add_diag_kernel(double* __restrict__ M, const size_t n, const double v) {
@@ -1628,8 +1682,27 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	if (reduced) {
 		Qred.resize(mw * nw); Rr.resize(nw * nw);
 		// Qred is not needed before extract(): it is formed on the side stream while the Jacobi kernel runs
-		if (swapped) { At.resize(m * n); transpose(At, A, m, n); qr(Qred, Rr, At, mw, nw, true); }
-		else qr(Qred, Rr, A, mw, nw, true);
+		const long long ars = swapped ? 1 : (long long)n, acs = swapped ? (long long)n : 1;     // Mw(i, j) = A[i * ars + j * acs]
+		if (c.svd_colsort && nw >= 16 && nw <= 1200) {
+			// columns of the working matrix in order of descending norm: the poor man's pivoted QR.  The TT sweeps hand over
+			// matrices like [Q1 W, Q2 W] with W = U Sigma, and products of many random cores at the first edges: column norms
+			// spread over up to nine decades in no particular order, on which the unpivoted factor needs 2 - 4 x the sweeps.
+			colperm.resize((nw + 1) / 2 + 1);
+			int* perm_ = reinterpret_cast<int*>(colperm.p);
+			DBuf sc0(2);
+			amax_scale_dev(sc0, A, m * n);
+			svd_colrank_kernel<<<1, 1024, 5 * nw * sizeof(double), c.stream>>>(A, int(mw), int(nw), ars, acs, sc0.p, perm_);
+			XB_LAUNCH_CHECK();
+			At.resize(m * n);
+			svd_gather_cols_kernel<<<unsigned(std::min<size_t>((m * n + 255) / 256, size_t(c.num_sms) * 8)), 256, 0, c.stream>>>(At, A, int(mw), int(nw), ars, acs, perm_);
+			XB_LAUNCH_CHECK();
+			permuted = true;
+			qr(Qred, Rr, At, mw, nw, true);
+		} else {
+			permuted = false;
+			if (swapped) { At.resize(m * n); transpose(At, A, m, n); qr(Qred, Rr, At, mw, nw, true); }
+			else qr(Qred, Rr, A, mw, nw, true);
+		}
 		q_deferred = true;
 		// Jacobi runs on the columns of R^T (the rows of R), not of R: after a QR step the rows of the triangular factor are
 		// far closer to the left singular directions than its columns are to the right ones (Drmac & Veselic's
@@ -1638,7 +1711,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		src = Rr; mdot = nw;
 		if (flipped) { rs = 1; cs = (long long)nw; } else { rs = (long long)nw; cs = 1; }
 	} else {
-		flipped = false;
+		flipped = false; permuted = false;
 		src = A; mdot = mw;
 		if (swapped) { rs = 1; cs = (long long)n; } else { rs = (long long)n; cs = 1; }
 	}
@@ -1722,7 +1795,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		svd_init_kernel<<<init_blocks, 256, 0, c.stream>>>(GT, int(ld), int(npad), int(mdot), int(voff), int(nw), src, rs, cs, scale.p);
 		XB_LAUNCH_CHECK();
 		if (plan.persistent) {
-			converged = run_persistent<double>(GT.p, ld, voff, plan, tol, 1e-7, c.svd_max_sweeps, sweeps, smem_cap, "f64");
+			converged = run_persistent<double>(GT.p, ld, voff, plan, tol, c.svd_last_sweep_cos, c.svd_max_sweeps, sweeps, smem_cap, "f64");
 		} else {
 			// fallback for shapes the cooperative kernel cannot hold: one launch per tournament round
 			const int bw = plan.bw;
@@ -1811,8 +1884,10 @@ void Svd::extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, 
 		// working matrix was R^T: its left vectors (X part) are the right vectors of R and vice versa
 		std::swap(outX, outV); std::swap(sxi, svc); std::swap(sxr, svr); std::swap(scale_x, scale_v);
 	}
+	// with sorted columns the right vectors of the working matrix carry the permuted index: the X part if flipped, else the V part
+	const int* cp = permuted ? reinterpret_cast<const int*>(colperm.p) : nullptr;
 	svd_extract_kernel<<<unsigned(k), 256, 0, c.stream>>>(GT, int(ld), int(mdot), int(voff), int(nw), Ssorted, p, outX, sxi, sxr, scale_x,
-	                                                       outV, svc, svr, scale_v, dS, soft_threshold, scale.p);
+	                                                       outV, svc, svr, scale_v, dS, soft_threshold, scale.p, flipped ? cp : nullptr, flipped ? nullptr : cp);
 	XB_LAUNCH_CHECK();
 	if (reduced) {
 		if (q_deferred) { aux_join(); q_deferred = false; }

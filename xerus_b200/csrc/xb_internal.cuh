@@ -71,6 +71,8 @@ struct Context {
 	int als_graph = 1;             // one-site SPD CG: chunks of 8 iterations replayed as a CUDA graph
 	int svd_gram = 0;              // experimental: Jacobi block visits in Gram space (one Gram matrix, 16 x 16 rounds, one DMMA apply
 	                               // per visit); correct, but not faster than the column-space kernel on one SM per block pair
+	double svd_last_sweep_cos = 1e-7;   // a Jacobi sweep in which no pair had |cos| above this is the last one (quadratic convergence)
+	int svd_colsort = 1;           // QR pre-conditioning of the SVD on the columns sorted by descending norm (surrogate of a pivoted QR)
 	int svd_dsmem = 1;             // split Jacobi kernel: X workers in one cluster, travelling block handed over through DSMEM (st.async + mbarrier)
 	int svd_split = 1;             // Jacobi: separate CTAs apply the rotation products to the accumulated-rotation halves
 	int svd_recursive = 1;         // recursive bipartite tournament with point-to-point block flags (power-of-two block counts)
@@ -177,9 +179,9 @@ struct Svd {
 	                               // factors, per-call layer); 1: without the clean-up sweep (sweep layer: exact projection, left vectors
 	                               // orthogonal to ~1e-12); 0: none
 	// internals
-	bool swapped = false, reduced = false, flipped = false;
+	bool swapped = false, reduced = false, flipped = false, permuted = false;
 	size_t mw = 0, nw = 0, npad = 0, mt = 0, mdot = 0, voff = 0, ld = 0;
-	DBuf GT, Qred, Ssorted, perm, scale;   // scale: [2^-e, 2^e] of the Jacobi input (squares must not overflow)
+	DBuf GT, Qred, Ssorted, perm, colperm, scale;   // scale: [2^-e, 2^e] of the Jacobi input (squares must not overflow)
 	bool q_deferred = false;               // Qred is still being formed on the side stream
 	~Svd() { if (q_deferred) aux_join(); }
 	void factor(const double* A, size_t m, size_t n);
