@@ -320,7 +320,10 @@ def bond_split_workload(args, rank, local_rank, world):
                 "whole_job_tflops": flops / (t * 1e-3) / 1e12,
                 "whole_job_frac_of_peak": flops / (t * 1e-3) / 1e12 / peak,
                 "roofline": {"kernel": "gemm_f64_big_kernel (128x128 tiles, cp.async, DMMA m8n8k4)", "bound": "tensor", "unit": "TFLOP/s",
-                             "achieved": achieved, "peak": peak, "frac": achieved / peak, "traffic": None,
+                             "achieved": achieved, "peak": peak, "frac": achieved / peak,
+                             # dram bytes read + written by the 1024 x 8192 x 512 launch (ncu --set full, profiles/r1_gemm_big.txt);
+                             # its operands and result are 105 MB, part of the result stays in the 126 MB L2
+                             "traffic": (38317056 + 34946304) if world == 1 else None,
                              "peak_source": "cuBLAS DGEMM 8192^3 measured in this run",
                              "algorithmic_flops_per_rank": gemm_flops / world, "gemm_ms_per_apply": gms, "gemm_launches": glaunch},
                 "roofline_mid_apply": {"kernel": "mid_apply_kernel (operator cores, r_A*n = 8)", "bound": "hbm", "unit": "GB/s",
@@ -510,8 +513,10 @@ def main():
     jac_scopes, jac_launches, jac_ms = prof["svd_jacobi"]
     svd_tf = svd_f / (jac_ms * 1e-3) / 1e12 if jac_ms > 0 else 0.0
     roofline = {
-        "kernel": "jacobi_fast_kernel / jacobi_persistent_kernel (one-sided block Jacobi SVD, one cooperative launch per SVD)", "bound": "tensor", "unit": "TFLOP/s",
-        "achieved": svd_tf, "peak": fp64_peak, "frac": svd_tf / fp64_peak if fp64_peak else None, "traffic": None,
+        "kernel": "jacobi_split_kernel (one-sided block Jacobi SVD, X and V workers, one cooperative cluster launch per SVD)", "bound": "tensor", "unit": "TFLOP/s",
+        "achieved": svd_tf, "peak": fp64_peak, "frac": svd_tf / fp64_peak if fp64_peak else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch on a 256-column problem (ncu --set full, profiles/r1_jacobi_split.txt)
+        "traffic": 1087744 + 312576, "traffic_unit": "bytes per launch (256-column SVD; algorithmic: 1.5 MB matrix in + factors out)",
         "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (no FP64 entry in MEASURED_PEAKS.json; nominal ~40)",
         "algorithmic_flops_per_round": svd_f, "accounting": "22*min(m,n)^3 per SVD (SURVEY §8d)",
         "launches_per_round": jac_launches, "kernel_ms_per_round": jac_ms,

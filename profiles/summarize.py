@@ -2,6 +2,7 @@
 
     python profiles/summarize.py launches gpurun_out/launches_r1.csv   > profiles/r1_launches_c3.txt
     python profiles/summarize.py kernel   gpurun_out/prof_jacobi_r1.ncu-rep > profiles/r1_jacobi_persistent.txt
+    python profiles/summarize.py source   gpurun_out/prof_jacobi_split_r1b.ncu-rep [min_share] > profiles/r1_jacobi_split_source.txt
 """
 import collections
 import csv
@@ -54,5 +55,30 @@ def kernel(path):
                 print("%-85s %s %s" % (k, d[k], units[hdr.index(k)]))
 
 
+def source(path, min_share=0.004):
+    """Warp-stall samples per SASS instruction (ncu --set full --import-source on): totals per stall reason and every
+    instruction that holds at least min_share of the samples, in program order."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    print("# kernel:", rows[0][1][:150])
+    hdr, data = rows[1], rows[2:]
+    isrc, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
+    stalls = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+    tot = sum(int(r[isamp]) for r in data)
+    agg = collections.Counter()
+    for r in data:
+        for i, h in stalls:
+            agg[h] += int(r[i])
+    print("# %d SASS instructions, %d warp-stall samples" % (len(data), tot))
+    print("# samples by stall reason:", ", ".join("%s %.1f%%" % (h, 100.0 * v / max(tot, 1)) for h, v in agg.most_common(8)))
+    print("# idx  instruction                                                     samples  share  executed  top stall reasons")
+    for k, r in enumerate(data):
+        n = int(r[isamp])
+        if n >= tot * float(min_share):
+            top = sorted(((int(r[i]), h) for i, h in stalls), reverse=True)[:2]
+            print("%5d  %-64s %7d %5.1f%% %9s  %s" % (k, r[isrc].strip()[:64], n, 100.0 * n / tot, r[iex],
+                                                       ", ".join("%s %d" % (h, v) for v, h in top if v)))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel, "source": source}[sys.argv[1]](*sys.argv[2:])
