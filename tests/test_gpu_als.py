@@ -170,6 +170,31 @@ def test_als_config2_reduced_rank20_cg_runs():
     assert Ax.distance(b) / b.frob_norm() < 1e-5     # iterative local solves: see test_als_spd_golden on conditioning
 
 
+def test_persistent_cg_kernel_agrees_with_launch_per_iteration_path():
+    """One-site SPD local problems above als_direct_max: the whole CG run in one cooperative launch (spd_cg_kernel) against the
+    three-GEMM + vector-kernel path; same energies, same iterates (both stop at the same residual target)."""
+    rng = np.random.default_rng(21)
+    d, n, r = 6, 10, 14                                  # n_loc = 14 * 10 * 14 = 1960 > 1536: matrix-free CG
+    A, b = xb.TTOperator.laplace(d, n), xb.TTTensor.ones([n] * d)
+    x0 = xb.TTTensor.random([n] * d, r, rng)
+    out = {}
+    try:
+        for v in (0, 1):
+            xb.set_option("als_persistent_cg", v)
+            x = x0.copy()
+            alg = xb.ALSVariant(1, 0, True)
+            e = alg(A, x, b, 2)
+            out[v] = (e, x, alg.last_local_iterations)
+    finally:
+        xb.set_option("als_persistent_cg", 1)
+    assert out[0][2] > 0 and out[1][2] > 0                # both went through CG
+    assert abs(out[0][0] - out[1][0]) < 1e-9 * abs(out[0][0])
+    assert out[0][1].distance(out[1][1]) < 1e-8 * out[0][1].frob_norm()
+    res = A.apply(out[1][1]).distance(b) / b.frob_norm()
+    eo = O.ALS_SPD(O.laplace_operator(d, n), O.TT(x0.cores(), core_position=0), O.tt_ones([n] * d), 2)
+    assert abs(out[1][0] - eo) < 1e-8 * abs(eo), (out[1][0], eo, res)
+
+
 @pytest.mark.parametrize("sites", [1, 2])
 def test_env_apply_and_bond_split(sites):
     """Matrix-free local operator (als.cpp:383-401) against einsum, and the bond split: partial applications over

@@ -231,27 +231,70 @@ def test_svd_vs_oracle(m, n):
     assert np.linalg.norm(U.T @ U - np.eye(k)) < 1e-11 and np.linalg.norm(Vt @ Vt.T - np.eye(k)) < 1e-11
 
 
-VARIANT_DEFAULTS = {"svd_fast": 1, "svd_jacc": 1, "svd_recursive": 1, "svd_flip": 1, "qr_cluster": 1, "svd_gram": 0, "svd_split": 1}
+VARIANT_DEFAULTS = {"svd_fast": 1, "svd_jacc": 1, "svd_recursive": 1, "svd_flip": 1, "qr_cluster": 1, "svd_gram": 0, "svd_split": 1,
+                    "svd_dsmem": 1, "svd_colsort": 1, "qr_defer": 1}
 
 
-@pytest.mark.parametrize("option", sorted(VARIANT_DEFAULTS))
-def test_factorization_kernel_variants_agree(option):
-    """Every optimisation of the factorisation kernels can be switched off; both settings must give the same factors."""
+def _variant_matrix(shape):
     rng = np.random.default_rng(11)
-    A = rng.standard_normal((200, 260)) @ np.diag(np.logspace(0, -6, 260)) @ rng.standard_normal((260, 150))
+    if shape == "graded_150":
+        return rng.standard_normal((200, 260)) @ np.diag(np.logspace(0, -6, 260)) @ rng.standard_normal((260, 150))
+    # 150 columns = 19 blocks (generic kernel); 128 / 256 columns = power-of-two block counts: the split kernel with X and V
+    # workers and the DSMEM hand-over (clusters of 8 / 16).  Columns scaled over eight decades in random order: the case
+    # the norm-sorted pre-conditioning is there for.
+    n = 128 if shape == "unsorted_cols_128" else 256
+    return rng.standard_normal((300, n)) * 10.0 ** rng.uniform(-8, 0, n)
+
+
+@pytest.mark.parametrize("shape", ["graded_150", "unsorted_cols_128", "unsorted_cols_256"])
+@pytest.mark.parametrize("option", sorted(VARIANT_DEFAULTS))
+def test_factorization_kernel_variants_agree(option, shape):
+    """Every optimisation of the factorisation kernels can be switched off; both settings must give the same factors."""
+    A = _variant_matrix(shape)
     res = []
     try:
         for v in (0, 1):
             xb.set_option(option, v)
             U, S, Vt = BW.svd(A)
             Q, R = BW.qr(A)
+            k = A.shape[1]
             assert rel((U * S) @ Vt, A) < 1e-12 and rel(Q @ R, A) < 1e-13
-            assert np.linalg.norm(U.T @ U - np.eye(150)) < 1e-11 and np.linalg.norm(Q.T @ Q - np.eye(150)) < 1e-12
+            assert np.linalg.norm(U.T @ U - np.eye(k)) < 1e-11 and np.linalg.norm(Q.T @ Q - np.eye(k)) < 1e-12
+            assert np.linalg.norm(Vt @ Vt.T - np.eye(k)) < 1e-11
             res.append((S, np.abs(R)))
     finally:
         xb.set_option(option, VARIANT_DEFAULTS[option])
     assert np.max(np.abs(res[0][0] - res[1][0])) < 1e-13 * res[0][0][0]
     assert np.allclose(res[0][1], res[1][1], rtol=1e-9, atol=1e-12 * res[0][1].max())
+
+
+def test_svd_unsorted_column_scales_need_few_sweeps():
+    """The matrices a TT sweep hands to the SVD have column norms spread over many decades in no particular order (products of
+    cores at the first edges, [Q1 W, Q2 W] later).  With the columns sorted by norm before the QR pre-conditioning the Jacobi
+    iteration needs a third of the sweeps, and the singular values keep their relative accuracy."""
+    import ctypes as C
+    import torch
+    from xerus_b200._lib import call
+    rng = np.random.default_rng(3)
+    n = 256
+    A = rng.standard_normal((n, n)) * 10.0 ** rng.uniform(-9, 0, n)
+    dA = torch.from_numpy(A).cuda()
+    U, Vt = (torch.empty(n, n, dtype=torch.float64, device="cuda") for _ in range(2))
+    S = torch.empty(n, dtype=torch.float64, device="cuda")
+    sweeps = {}
+    try:
+        for v in (0, 1):
+            xb.set_option("svd_colsort", v)
+            sw = C.c_int()
+            call("xb_dev_svd", U.data_ptr(), S.data_ptr(), Vt.data_ptr(), dA.data_ptr(), n, n, n, 0, 0, C.byref(sw))
+            xb.synchronize()
+            sweeps[v] = sw.value
+            s_ref = np.linalg.svd(A, compute_uv=False)
+            assert np.max(np.abs(S.cpu().numpy() - s_ref) / s_ref[0]) < 1e-13
+            assert rel((U.cpu().numpy() * S.cpu().numpy()) @ Vt.cpu().numpy(), A) < 1e-12
+    finally:
+        xb.set_option("svd_colsort", 1)
+    assert sweeps[1] + 4 <= sweeps[0], sweeps
 
 
 @pytest.mark.parametrize("tag", ["svd.tall", "svd.wide"])

@@ -308,3 +308,43 @@ def test_round_large_magnitudes():
     o = to_oracle(t)
     t.round(5); o.round(5)
     assert t.ranks() == o.ranks() and O.tt_distance_rel(to_oracle(t), o) < 1e-9
+
+
+@pytest.mark.parametrize("option", ["svd_colsort", "svd_dsmem", "qr_defer"])
+def test_round_sweep_variants_agree(option):
+    """round() with the sweep-level optimisations switched off gives the same tensor: sorted-column pre-conditioning, DSMEM
+    hand-over in the Jacobi kernel, Q formed on the side stream.  Degree 14, n = 2, rank 64 -> 32: interior SVDs of 64 columns
+    (split kernel, clusters of 4) and first edges with column norms spread over decades."""
+    rng = np.random.default_rng(8)
+    base = xb.TTTensor.random([2] * 14, 64, rng)
+    out = []
+    try:
+        for v in (0, 1):
+            xb.set_option(option, v)
+            t = base.copy()
+            t.round(32)
+            out.append(t)
+    finally:
+        xb.set_option(option, 1)
+    assert out[0].ranks() == out[1].ranks()
+    assert out[0].distance(out[1]) < 1e-12 * out[1].frob_norm()
+    ref = O.TT(base.cores(), core_position=0)
+    ref.round(32)
+    assert O.tt_distance_rel(O.TT(out[1].cores(), core_position=out[1].corePosition), ref) < 1e-9
+
+
+def test_components_in_one_call_roundtrip():
+    """from_cores / cores() move all components with one synchronisation (xb_tt_set_components / xb_tt_get_components)."""
+    rng = np.random.default_rng(2)
+    cores = [rng.standard_normal(s) for s in [(1, 3, 5), (5, 2, 7), (7, 4, 2), (2, 3, 1)]]
+    t = xb.TTTensor.from_cores(cores)
+    assert t.ranks() == [5, 7, 2] and not t.canonicalized
+    for a, b in zip(t.cores(), cores):
+        assert np.array_equal(a, b)
+    for i, c in enumerate(cores):
+        assert np.array_equal(t.get_component(i), c)
+    ops = [rng.standard_normal(s) for s in [(1, 2, 3, 4), (4, 3, 2, 1)]]
+    A = xb.TTOperator.from_cores(ops)
+    assert A.ranks() == [4] and all(np.array_equal(a, b) for a, b in zip(A.cores(), ops))
+    with pytest.raises(xb.XerusError):
+        xb.TTTensor.from_cores([np.zeros((2, 3, 1))])
