@@ -258,32 +258,53 @@ def bond_split_workload(args, rank, local_rank, world):
     torch.cuda.synchronize()
     flops = 2 * (r * a) * r * (n * n * r) + 2 * 2 * (r * n * r) * (a * n) * (n * a) + 2 * (r * n * n) * (a * r) * r
 
-    def step():
+    # N > 1: the reduction is fused into the application over peer memory (xb_env_apply_fused: the last GEMM's epilogue writes
+    # each rank's row block into that rank's buffer over NVLink, a reduce kernel sums the blocks); --collective nccl times the
+    # plain xb_env_apply + ncclAllReduce for comparison.  Both are measured, the fused one is the line's value.
+    px = parallel.PeerExchange(r * n * n, r, rank, world, dist=dist) if world > 1 else None
+    state = {"y": y}
+
+    def step(fused):
         with torch.cuda.stream(stream):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            parallel.bond_split_apply(L, [A1, A2], R, v, rank, world, out=y)
+            if fused:
+                state["y"] = parallel.bond_split_apply_fused(L, [A1, A2], R, v, px)
+            else:
+                state["y"] = parallel.bond_split_apply(L, [A1, A2], R, v, rank, world, out=y)
             e1.record(stream)
         return e0, e1
 
-    for _ in range(args.warmup):
-        step()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize(); xb.synchronize()
-    launches0 = xb.kernel_launch_count()
-    events = []
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        events.append(step())
-    torch.cuda.synchronize(); xb.synchronize()
-    if dist is not None:
-        dist.barrier()
-    launches = xb.kernel_launch_count() - launches0
-    ms = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in events) / args.steps], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    def timed(fused):
+        for _ in range(args.warmup):
+            step(fused)
+            if dist is not None:
+                xb.synchronize(); dist.barrier()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(); xb.synchronize()
+        l0 = xb.kernel_launch_count()
+        events = []
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()                          # the ranks enter a step together (the fused path has no collective to align them)
+            events.append(step(fused))
+        torch.cuda.synchronize(); xb.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in events) / args.steps], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t, xb.kernel_launch_count() - l0
+
+    use_fused = world > 1 and args.collective == "fused"
+    ms_other = None
+    if world > 1:
+        ms_other, _ = timed(not use_fused)
+    ms, launches = timed(use_fused)
+    y = state["y"]
     # check against the unsplit application on this rank
     ref = parallel.env_apply(L, [A1, A2], R, v)
     xb.synchronize()
@@ -315,7 +336,11 @@ def bond_split_workload(args, rank, local_rank, world):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic (i.i.d. N(0,1) environments, operator cores and vector)",
                 "config": {"workload": "two-site DMRG local apply, bond rank %d, n=4, operator rank 2 (BASELINE configs[3]); "
                                        "environment contraction split along the right bond over %d GPU(s) + NCCL all-reduce" % (r, world),
-                           "l2": "flushed between timed iterations", "allreduce_bytes": int(y.numel() * 8) if world > 1 else 0},
+                           "l2": "flushed between timed iterations",
+                           "collective": ("none" if world == 1 else ("fused: GEMM epilogue writes row blocks into the peers' buffers over NVLink + reduce kernel (xb_env_apply_fused)"
+                                                                     if use_fused else "xb_env_apply + ncclAllReduce")),
+                           "exchanged_bytes_per_rank": int(y.numel() * 8 * 2 * (world - 1) / world) if world > 1 else 0},
+                "other_collective_ms": (float(ms_other.item()) if ms_other is not None else None),
                 "gpu_launches": launches, "check": {"rel_err_vs_unsplit": err},
                 "whole_job_tflops": flops / (t * 1e-3) / 1e12,
                 "whole_job_frac_of_peak": flops / (t * 1e-3) / 1e12 / peak,
@@ -373,6 +398,7 @@ def main():
     ap.add_argument("--impl", default="xb200", choices=["xb200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c4", "c5"])
     ap.add_argument("--bond", type=int, default=512, help="bond rank for --workload c4")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"], help="--workload c4 at N > 1: reduction fused over peer memory, or NCCL all-reduce")
     ap.add_argument("--items", type=int, default=8, help="items per GPU per step for --workload c5")
     ap.add_argument("--workers", type=int, default=8, help="host threads / library workers (CUDA streams) per GPU for --workload c5")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -170,6 +170,22 @@ xb_status xb_als_solve(const xb_tt* A, xb_tt* x, const xb_tt* b, const xb_als_op
 xb_status xb_env_apply(double* y, const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims,
                        size_t sites, const double* R, size_t r, size_t a_right, const double* v, size_t slab_begin, size_t slab_end);
 
+/* Bond-split application fused with its reduction over peer memory (BASELINE config 4, the GPUs of one box; replaces
+ * xb_env_apply + ncclAllReduce).  Every rank creates one symmetric buffer of xb_peer_buffer_bytes(rows, cols, world) bytes
+ * (rows = l * m_1..m_s, cols = r), exports its CUDA IPC handle (64 bytes) and opens the handles of the other ranks; `sym`
+ * holds the world device pointers in rank order (sym[rank] = the rank's own buffer).  The last contraction writes each
+ * rank's row block of the partial result straight into that rank's buffer over NVLink, a reduce kernel sums the blocks in
+ * rank order and writes the sum into every rank's result area; *y_out points at this rank's copy of the full result, valid
+ * in stream order.  `epoch` counts the calls on these buffers from 1 and must agree on all ranks. */
+xb_status xb_peer_buffer_bytes(size_t rows, size_t cols, int world, size_t* bytes);
+xb_status xb_peer_buffer_create(size_t bytes, void** dptr, unsigned char* handle64);
+xb_status xb_peer_buffer_open(const unsigned char* handle64, void** dptr);
+xb_status xb_peer_buffer_close(void* dptr);
+xb_status xb_peer_buffer_destroy(void* dptr);
+xb_status xb_env_apply_fused(const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims, size_t sites,
+                             const double* R, size_t r, size_t a_right, const double* v, size_t slab_begin, size_t slab_end,
+                             int rank, int world, void* const* sym, unsigned int epoch, double** y_out);
+
 /* ---- 4. data files: the reference's own save_to_file / load_from_file format, Binary and TSV ------------------------
  * (misc::save_to_file / load_from_file, include/xerus/misc/fileIO.h:102-164; stream_writer / stream_reader of Tensor,
  * src/xerus/tensor.cpp:1781-1845, of TensorNetwork, src/xerus/tensorNetwork.cpp:1429-1505, and of TTNetwork,

@@ -224,3 +224,55 @@ def test_env_apply_and_bond_split(sites):
             acc += part
         torch.cuda.synchronize()
         assert np.linalg.norm(acc.cpu().numpy() - ref) < 1e-12 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_fused_bond_split_apply_on_one_device(world):
+    """xb_env_apply_fused with the "ranks" as host threads on library workers of one device (same kernels, same flag protocol,
+    plain device pointers instead of IPC mappings): every rank ends with the full application, bit-identical across ranks, equal
+    to the unsplit one up to summation order; a second call (epoch 2) on the same buffers works."""
+    import threading
+    import torch
+    from xerus_b200 import parallel
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(9)
+    r, n, a = 48, 4, 2
+    rnd = lambda *shape: torch.randn(*shape, dtype=torch.float64, generator=g).to(dev)
+    L, R, A1, A2 = rnd(r, a, r), rnd(r, a, r), rnd(a, n, n, a), rnd(a, n, n, a)
+    vs = [rnd(r, n, n, r), rnd(r, n, n, r)]
+    torch.cuda.synchronize()
+    rows, cols = r * n * n, r
+    bufs = parallel.PeerExchange.allocate_local(rows, cols, world)
+    results = [[None, None] for _ in range(world)]
+    errors = []
+
+    def run(rank):
+        try:
+            xb.worker_select(rank + 1)
+            px = parallel.PeerExchange(rows, cols, rank, world, local_buffers=bufs)
+            for it, v in enumerate(vs):
+                y = parallel.bond_split_apply_fused(L, [A1, A2], R, v, px)
+                xb.synchronize()
+                results[rank][it] = y.clone()
+                barrier.wait()                              # nobody starts epoch 2 before everybody has read epoch 1
+        except Exception as ex:                             # noqa: BLE001
+            errors.append(ex)
+            barrier.abort()
+
+    barrier = threading.Barrier(world)
+    threads = [threading.Thread(target=run, args=(k,)) for k in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    xb.worker_select(0)
+    for it, v in enumerate(vs):
+        ref = parallel.env_apply(L, [A1, A2], R, v)
+        xb.synchronize()
+        for k in range(world):
+            assert float((results[k][it] - ref).norm() / ref.norm()) < 1e-13
+            assert torch.equal(results[k][it], results[0][it])
+    from xerus_b200._lib import call
+    for q in bufs:
+        call("xb_peer_buffer_destroy", q)

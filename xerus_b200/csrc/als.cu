@@ -483,7 +483,7 @@ bool spd_cg_persistent(const SpdSiteApply& sa, double* x, double* r, double* p, 
 
 // y = {L, A_1..A_s, R} applied to v, SPD environments: L(l, a, l'), A_p(a, m, n, b), R(r, b, r'), v(l', n_1..n_s, r' [, col])
 // -> y(l, m_1..m_s, r [, col]).  One GEMM per factor, one reshuffle per operator core (als.cpp:383-401 un-contracted).
-DT spd_env_apply(const DT& L, const std::vector<DT>& Acores, const DT& R, const DT& v) {
+DT spd_env_apply(const DT& L, const std::vector<DT>& Acores, const DT& R, const DT& v, const GemmScatter* scatter = nullptr) {
 	const int s = int(Acores.size());
 	const bool batched = int(v.dims.size()) == s + 3;            // trailing column mode: (l, n.., r, col)
 	DT t = dt_contract(L, {2}, v, {0});                           // (l, a, n_1..n_s, r'[, col])
@@ -513,6 +513,14 @@ DT spd_env_apply(const DT& L, const std::vector<DT>& Acores, const DT& R, const 
 		o.push_back(nu - 2); o.push_back(nu - 1);
 		for (int i = p + 1; i < nu - 2; ++i) o.push_back(i);
 		t = dt_permute(u, o);
+	}
+	if (scatter) {
+		// last contraction with its row blocks written to the given destinations (peer receive buffers): y(rows | r) = t(rows | b r') R(r | b r')^T
+		XB_REQUIRE(!batched, "scattered output: single vector only");
+		const size_t K = R.dims[1] * R.dims[2], N = R.dims[0], M = t.size() / K;
+		XB_REQUIRE(t.dims[1 + s] == R.dims[1] && t.dims[2 + s] == R.dims[2], "Index dimensions do not coincide");
+		gemm_scatter(*scatter, N, M, N, 1.0, t.p, K, false, K, R.p, K, true);
+		return DT();
 	}
 	DT y = dt_contract(t, {1 + s, 2 + s}, R, {1, 2});             // (l, m_1..m_s, [col,] r)
 	if (!batched) return y;
@@ -993,6 +1001,144 @@ xb_status xb_env_apply(double* y, const double* L, size_t l, size_t a_left, cons
 			res = spd_env_apply(Lv, ac, Rs, vs);
 		}
 		copy(y, res.p, res.size());
+	});
+}
+
+// ---- bond-split application fused with its reduction over peer memory (BASELINE config 4, N GPUs of one box) -----------------
+// Every rank owns a symmetric buffer that all ranks map (CUDA IPC):  [ flags 256 B | receive slots: world x (M/world x N) | y: M x N ].
+//  1. the rank contracts its slab of the right bond; the epilogue of the last GEMM writes row block p of the partial result straight
+//     into rank p's receive slot [rank] (remote stores over NVLink while the remaining tiles are multiplied), then a one-warp kernel
+//     fences at system scope and bumps flag 0 of every peer;
+//  2. after a one-thread wait for world - 1 bumps the reduce kernel sums the slots of its own row block in rank order (deterministic, identical on
+//     all ranks) and writes the sum into the y area of EVERY rank; the last CTA to finish fences and bumps flag 1 everywhere;
+//  3. a one-warp kernel waits for world bumps of flag 1: the y area of this rank is complete.
+// Flags count monotonically (epoch = number of the call, same on all ranks), so nothing is ever reset; all waits are bounded.
+constexpr size_t PEER_FLAG_BYTES = 256;
+__global__ void peer_signal_kernel(unsigned int* const* flags, const int rank, const int world, const int which) {
+	__threadfence_system();
+	if (int(threadIdx.x) < world && int(threadIdx.x) != rank) atomicAdd_system(flags[threadIdx.x] + which, 1u);
+}
+struct PeerPtrs { unsigned int* flags[8]; double* y[8]; };
+__global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerPtrs pp, const double* __restrict__ recv, const size_t block_elems, const int rank,
+                                                           const int world, const unsigned int epoch) {
+	unsigned int* myflags = pp.flags[rank];
+	const size_t nv = block_elems / 2;                   // block_elems is even (checked on the host)
+	const double2* rv = reinterpret_cast<const double2*>(recv);
+	for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < nv; e += (size_t)gridDim.x * blockDim.x) {
+		double2 acc = __ldcg(rv + e);
+		for (int s = 1; s < world; ++s) { const double2 t = __ldcg(rv + (size_t)s * nv + e); acc.x += t.x; acc.y += t.y; }
+		for (int p = 0; p < world; ++p) reinterpret_cast<double2*>(pp.y[p] + (size_t)rank * block_elems)[e] = acc;
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned int done = atomicInc(myflags + 2, gridDim.x - 1);
+		if (done == gridDim.x - 1) {
+			__threadfence_system();
+			for (int p = 0; p < world; ++p) atomicAdd_system(pp.flags[p] + 1, 1u);
+		}
+	}
+}
+// one thread of one CTA polls (the waiting must not occupy the SMs the peers' kernels may need when "ranks" share a device)
+__global__ void peer_wait_kernel(unsigned int* myflags, const int which, const unsigned int expected) {
+	if (threadIdx.x == 0) {
+		unsigned int spins = 0;
+		while (*((volatile unsigned int*)(myflags + which)) < expected && ++spins < (1u << 28)) {}
+		if (spins >= (1u << 28)) myflags[3] = 0xDEADu;
+		__threadfence_system();
+	}
+}
+
+xb_status xb_peer_buffer_create(size_t bytes, void** dptr, unsigned char* handle64) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(dptr && handle64 && bytes > 0, "null");
+		static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+		XB_CUDA(cudaMalloc(dptr, bytes));
+		XB_CUDA(cudaMemset(*dptr, 0, bytes));
+		cudaIpcMemHandle_t h;
+		XB_CUDA(cudaIpcGetMemHandle(&h, *dptr));
+		std::memcpy(handle64, &h, 64);
+	});
+}
+xb_status xb_peer_buffer_open(const unsigned char* handle64, void** dptr) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(dptr && handle64, "null");
+		cudaIpcMemHandle_t h;
+		std::memcpy(&h, handle64, 64);
+		XB_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+	});
+}
+xb_status xb_peer_buffer_close(void* dptr) { return guard([&] { if (dptr) XB_CUDA(cudaIpcCloseMemHandle(dptr)); }); }
+xb_status xb_peer_buffer_destroy(void* dptr) { return guard([&] { if (dptr) XB_CUDA(cudaFree(dptr)); }); }
+xb_status xb_peer_buffer_bytes(size_t rows, size_t cols, int world, size_t* bytes) {
+	return guard([&] {
+		XB_REQUIRE(bytes && world >= 1 && world <= 8, "1 to 8 ranks");
+		XB_REQUIRE(rows % size_t(world) == 0 && (rows / world * cols) % 2 == 0, "the rows of the result must split evenly over the ranks");
+		*bytes = PEER_FLAG_BYTES + 2 * rows * cols * sizeof(double);
+	});
+}
+
+xb_status xb_env_apply_fused(const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims, size_t sites,
+                             const double* R, size_t r, size_t a_right, const double* v, size_t slab_begin, size_t slab_end,
+                             int rank, int world, void* const* sym, unsigned int epoch, double** y_out) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(L && A_cores && A_dims && R && v && sym && y_out, "null");
+		XB_REQUIRE(sites >= 1 && sites <= 4, "1 to 4 sites");
+		XB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world && epoch >= 1, "illegal rank / world / epoch");
+		XB_REQUIRE(slab_begin < slab_end && slab_end <= r, "illegal bond slab");
+		std::vector<DT> ac;
+		std::vector<size_t> vd = {l};
+		size_t rows = l;
+		for (size_t p = 0; p < sites; ++p) {
+			const size_t* d = A_dims + 4 * p;
+			XB_REQUIRE(d[0] == (p == 0 ? a_left : A_dims[4 * (p - 1) + 3]), "operator bond dimensions do not coincide");
+			ac.push_back(dt_view(A_cores[p], {d[0], d[1], d[2], d[3]}));
+			vd.push_back(d[2]);
+			rows *= d[1];
+		}
+		XB_REQUIRE(A_dims[4 * (sites - 1) + 3] == a_right, "operator bond dimensions do not coincide");
+		XB_REQUIRE(rows % size_t(world) == 0 && (rows / world * r) % 2 == 0, "the rows of the result must split evenly over the ranks");
+		const size_t rpb = rows / world, block_elems = rpb * r;
+		size_t rows_v = l;
+		for (size_t p = 0; p < sites; ++p) rows_v *= A_dims[4 * p + 2];
+		auto flags_of = [&](int p) { return reinterpret_cast<unsigned int*>(sym[p]); };
+		auto recv_of = [&](int p) { return reinterpret_cast<double*>(static_cast<char*>(sym[p]) + PEER_FLAG_BYTES); };
+		auto y_of = [&](int p) { return recv_of(p) + rows * r; };
+		GemmScatter sc;
+		for (int i = 0; i < 8; ++i) sc.blk[i] = (i < world) ? recv_of(i) + size_t(rank) * block_elems : nullptr;
+		sc.rows_per_block = rpb;
+		const size_t slab = slab_end - slab_begin;
+		DT Lv = dt_view(L, {l, a_left, l});
+		if (slab == r) {
+			vd.push_back(r);
+			spd_env_apply(Lv, ac, dt_view(R, {r, a_right, r}), dt_view(v, vd), &sc);
+		} else {
+			vd.push_back(slab);
+			DT vs = dt_alloc(vd);
+			copy2d(vs.data(), slab, v + slab_begin, r, rows_v, slab);
+			DT Rs = dt_alloc({r, a_right, slab});
+			copy2d(Rs.data(), slab, R + slab_begin, r, r * a_right, slab);
+			spd_env_apply(Lv, ac, Rs, vs, &sc);
+		}
+		Context& c = ctx();
+		// device-side tables of the peers' flag words and result areas
+		PeerPtrs pp;
+		for (int p = 0; p < 8; ++p) { pp.flags[p] = (p < world) ? flags_of(p) : nullptr; pp.y[p] = (p < world) ? y_of(p) : nullptr; }
+		DBuf table(8);
+		XB_CUDA(cudaMemcpyAsync(table.p, pp.flags, 8 * sizeof(void*), cudaMemcpyHostToDevice, c.stream));
+		peer_signal_kernel<<<1, 32, 0, c.stream>>>(reinterpret_cast<unsigned int* const*>(table.p), rank, world, 0);
+		XB_LAUNCH_CHECK();
+		const unsigned grid = unsigned(std::min<size_t>((block_elems / 2 + 255) / 256, size_t(c.num_sms) * 4));
+		peer_wait_kernel<<<1, 32, 0, c.stream>>>(flags_of(rank), 0, epoch * unsigned(world - 1));      // every peer's partial block has landed
+		XB_LAUNCH_CHECK();
+		peer_reduce_kernel<<<grid, 256, 0, c.stream>>>(pp, recv_of(rank), block_elems, rank, world, epoch);
+		XB_LAUNCH_CHECK();
+		peer_wait_kernel<<<1, 32, 0, c.stream>>>(flags_of(rank), 1, epoch * unsigned(world));
+		XB_LAUNCH_CHECK();
+		*y_out = y_of(rank);
 	});
 }
 

@@ -23,7 +23,15 @@ struct GemmArgs {
 	int m, n, k;
 	int transA, transB;
 	double alpha, beta;
+	// optional scattered output (beta = 0): row i goes to Cblk[i / rpb] + (i % rpb) * ldc.  The blocks may live on peer GPUs
+	// (bond-split application: the epilogue of the last contraction writes each rank's row block straight into that rank's
+	// receive buffer over NVLink, so the transfer runs while the remaining tiles are still being multiplied).
+	double* Cblk[8];
+	int rpb;
 };
+__device__ __forceinline__ double* gemm_out_row(const GemmArgs& g, double* C, const int row) {
+	return g.rpb ? g.Cblk[row / g.rpb] + (long long)(row % g.rpb) * g.ldc : C + (long long)row * g.ldc;
+}
 
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_THREADS = 128;
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g
 #pragma unroll
 			for (int c = 0; c < 2; ++c) {
 				if (col + c < g.n) {
-					double* p = C + (long long)row * g.ldc + col + c;
+					double* p = gemm_out_row(g, C, row) + col + c;
 					double v = g.alpha * acc[i][j][c];
 					if (g.beta != 0.0) v += g.beta * (*p);
 					*p = v;
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(BIG_THREADS, 1) gemm_f64_big_kernel(const Gemm
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
 			const int col = n0 + wn * 32 + j * 8 + tig * 2;
-			double* p = C + (long long)row * g.ldc + col;
+			double* p = gemm_out_row(g, C, row) + col;
 			if (vec_store && col + 1 < g.n) {
 				double2 v = make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
 				if (g.beta != 0.0) { const double2 o = *reinterpret_cast<const double2*>(p); v.x += g.beta * o.x; v.y += g.beta * o.y; }
@@ -277,6 +285,8 @@ static void launch_big(const GemmArgs& g, const dim3 grid, const int vec_store) 
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static thread_local const GemmScatter* tl_scatter = nullptr;
+
 void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, double alpha, const double* A, size_t lda,
                   size_t strideA, bool transA, size_t k, const double* B, size_t ldb, size_t strideB, bool transB,
                   double beta, size_t batch) {
@@ -290,6 +300,16 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
 	g.strideC = (long long)strideC; g.strideA = (long long)strideA; g.strideB = (long long)strideB;
 	g.m = int(m); g.n = int(n); g.k = int(k);
 	g.transA = transA; g.transB = transB; g.alpha = alpha; g.beta = beta;
+	g.rpb = 0;
+	for (int i = 0; i < 8; ++i) g.Cblk[i] = nullptr;
+	bool blocks_aligned = true;
+	if (tl_scatter) {
+		XB_REQUIRE(beta == 0.0 && batch == 1 && tl_scatter->rows_per_block > 0 && (m + tl_scatter->rows_per_block - 1) / tl_scatter->rows_per_block <= 8,
+		           "scattered GEMM output: beta = 0, one problem, at most 8 row blocks");
+		g.rpb = int(tl_scatter->rows_per_block);
+		for (int i = 0; i < 8; ++i) { g.Cblk[i] = tl_scatter->blk[i]; if (g.Cblk[i] && (reinterpret_cast<uintptr_t>(g.Cblk[i]) & 15)) blocks_aligned = false; }
+		C = g.Cblk[0]; g.C = C;
+	}
 	// large-tile path: at least ~0.8 waves of 128 x 128 tiles, and every 16-byte cp.async chunk aligned and either fully
 	// inside or fully outside its operand (the choice never changes the bits of the result, see gemm_f64_big_kernel)
 	const size_t tiles128 = ((m + 127) / 128) * ((n + 127) / 128) * batch;
@@ -298,7 +318,7 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
 	    (!transA || m % 2 == 0) && (transB || n % 2 == 0)) {
 		dim3 grid(unsigned((n + 127) / 128), unsigned((m + 127) / 128), unsigned(batch));
 		XB_REQUIRE(grid.y <= 65535, "m too large for the GEMM grid");
-		const int vec_store = (ldc % 2 == 0 && strideC % 2 == 0 && aligned16(C)) ? 1 : 0;
+		const int vec_store = (ldc % 2 == 0 && strideC % 2 == 0 && aligned16(C) && blocks_aligned) ? 1 : 0;
 		if (transA) { if (transB) launch_big<true, true>(g, grid, vec_store); else launch_big<true, false>(g, grid, vec_store); }
 		else { if (transB) launch_big<false, true>(g, grid, vec_store); else launch_big<false, false>(g, grid, vec_store); }
 		XB_LAUNCH_CHECK();
@@ -316,6 +336,13 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
 		gemm_f64_kernel<4, 4><<<grid, GEMM_THREADS, 0, ctx().stream>>>(g);
 	}
 	XB_LAUNCH_CHECK();
+}
+
+void gemm_scatter(const GemmScatter& sc, size_t ldc, size_t m, size_t n, double alpha, const double* A, size_t lda, bool transA, size_t k,
+                  const double* B, size_t ldb, bool transB) {
+	struct Reset { ~Reset() { tl_scatter = nullptr; } } reset;
+	tl_scatter = &sc;
+	gemm_batched(sc.blk[0], ldc, 0, m, n, alpha, A, lda, 0, transA, k, B, ldb, 0, transB, 0.0, 1);
 }
 
 void gemm(double* C, size_t ldc, size_t m, size_t n, double alpha, const double* A, size_t lda, bool transA, size_t k,

@@ -122,6 +122,11 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
                   size_t strideA, bool transA, size_t k, const double* B, size_t ldb, size_t strideB, bool transB,
                   double beta, size_t batch);
 
+// C row i -> blk[i / rows_per_block] + (i % rows_per_block) * ldc (beta = 0): the row blocks may be buffers of peer GPUs
+struct GemmScatter { double* blk[8]; size_t rows_per_block; };
+void gemm_scatter(const GemmScatter& sc, size_t ldc, size_t m, size_t n, double alpha, const double* A, size_t lda, bool transA, size_t k,
+                  const double* B, size_t ldb, bool transB);
+
 // elementwise / movement
 void copy(double* dst, const double* src, size_t n);
 void copy2d(double* dst, size_t ldd, const double* src, size_t lds, size_t rows, size_t cols);

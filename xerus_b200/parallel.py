@@ -123,3 +123,94 @@ def bond_split_apply(L, A_cores, R, v, rank, world, out=None, group=None):
     if world > 1:
         dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
     return y
+
+
+class PeerExchange:
+    """Symmetric peer-memory buffers for bond_split_apply_fused: every rank allocates one buffer, exports its CUDA IPC handle,
+    and maps the buffers of the other ranks of the box (handles travel through torch.distributed).  With `group_size` ranks in
+    ONE process (tests: the "ranks" are host threads on library workers of the same device) no IPC is involved."""
+
+    def __init__(self, rows, cols, rank, world, dist=None, local_buffers=None):
+        import ctypes as C
+        from ._lib import call
+        self.rank, self.world, self.epoch = rank, world, 0
+        self.rows, self.cols = rows, cols
+        nbytes = C.c_size_t()
+        call("xb_peer_buffer_bytes", rows, cols, world, C.byref(nbytes))
+        self._opened = []
+        if local_buffers is not None:                     # same process: pointers are shared as they are
+            self.mine = None
+            self.ptrs = list(local_buffers)
+        else:
+            mine, handle = C.c_void_p(), C.create_string_buffer(64)
+            call("xb_peer_buffer_create", nbytes.value, C.byref(mine), handle)
+            self.mine = mine
+            handles = [handle.raw]
+            if world > 1:
+                handles = [None] * world
+                dist.all_gather_object(handles, handle.raw)
+            self.ptrs = []
+            for p in range(world):
+                if p == rank:
+                    self.ptrs.append(mine.value)
+                else:
+                    q = C.c_void_p()
+                    call("xb_peer_buffer_open", handles[p], C.byref(q))
+                    self._opened.append(q)
+                    self.ptrs.append(q.value)
+            if world > 1:
+                dist.barrier()                            # every buffer is zeroed and mapped before the first remote store
+
+    @staticmethod
+    def allocate_local(rows, cols, world):
+        """`world` buffers in this process (for the single-device emulation); returns the list of device pointers."""
+        import ctypes as C
+        from ._lib import call
+        nbytes = C.c_size_t()
+        call("xb_peer_buffer_bytes", rows, cols, world, C.byref(nbytes))
+        out = []
+        for _ in range(world):
+            q, h = C.c_void_p(), C.create_string_buffer(64)
+            call("xb_peer_buffer_create", nbytes.value, C.byref(q), h)
+            out.append(q.value)
+        return out
+
+    def close(self, dist=None):
+        from ._lib import call
+        import ctypes as C
+        if dist is not None and self.world > 1:
+            dist.barrier()
+        for q in self._opened:
+            call("xb_peer_buffer_close", q)
+        self._opened = []
+        if self.mine is not None:
+            call("xb_peer_buffer_destroy", self.mine)
+            self.mine = None
+
+
+def bond_split_apply_fused(L, A_cores, R, v, px):
+    """bond_split_apply with the reduction fused into the application over peer memory (xb_env_apply_fused): the last GEMM's
+    epilogue writes each rank's row block into that rank's buffer over NVLink, a reduce kernel sums the blocks in rank order and
+    writes the sum to every rank.  Returns a torch view of this rank's copy of y (valid in the library stream's order; it is
+    overwritten by the next call on `px`)."""
+    import ctypes as C
+    import torch
+    from ._lib import call
+    s = len(A_cores)
+    l, r = L.shape[0], R.shape[0]
+    begin, end = slab_range(r, px.rank, px.world)
+    ptrs = (C.c_void_p * s)(*[a.data_ptr() for a in A_cores])
+    dims = (C.c_size_t * (4 * s))(*[int(x) for a in A_cores for x in a.shape])
+    sym = (C.c_void_p * px.world)(*px.ptrs)
+    px.epoch += 1
+    y = C.c_void_p()
+    call("xb_env_apply_fused", L.data_ptr(), l, L.shape[1], ptrs, dims, s, R.data_ptr(), r, R.shape[1], v.data_ptr(), begin, end,
+         px.rank, px.world, sym, px.epoch, C.byref(y))
+    shape = (l,) + tuple(a.shape[1] for a in A_cores) + (r,)
+    n = 1
+    for d in shape:
+        n *= d
+
+    class _Arr:                                              # __cuda_array_interface__ view of the result area (no copy)
+        __cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (y.value, False), "version": 3, "strides": None}
+    return torch.as_tensor(_Arr(), device=v.device)
