@@ -1634,9 +1634,30 @@ static void launch_fast_any(float*, const JacobiPlan&, float, float, unsigned in
 }
 
 // Runs sweeps until convergence (or max_sweeps) in one cooperative launch; returns {converged, sweeps}.
+struct JacobiPending {          // convergence record of a launch whose read-back was left to the caller's next synchronisation
+	bool active = false; std::string tag; size_t ld = 0, nblk = 0; int bw = 0;
+};
+// evaluates the record once the stream has been synchronised (it sits in the last 16 doubles of the pinned scratch)
+static bool jacobi_finish(const JacobiPending& pend, int& sweeps_out) {
+	Context& c = ctx();
+	unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch + c.h_scratch_len - 16);
+	const bool dead = h_info[0] == 0xDEADu;
+	h_info += 4;
+	sweeps_out = int(h_info[1]);
+	const bool converged = h_info[2] == 0;
+	if (dead) throw Error(XB_ERR_CUDA, "Jacobi SVD: a block hand-over flag was never raised (internal scheduling error)");
+	if (getenv("XB_JACOBI_TIMING") != nullptr) {
+		if (h_info[-3]) fprintf(stderr, "[jacobi %s] inner = gram %u + rounds on G %u + apply %u kcycles\n", pend.tag.c_str(), h_info[-3], h_info[-2], h_info[-1]);
+		fprintf(stderr, "[jacobi %s] ld=%zu bw=%d ctas=%zu sweeps=%d kcycles: load %u inner %u store %u sync %u\n", pend.tag.c_str(), pend.ld, pend.bw,
+		        pend.nblk / 2, sweeps_out, h_info[4], h_info[5], h_info[6], h_info[7]);
+	}
+	return converged;
+}
+// pending != nullptr: the kernel and the read-back of its convergence record are enqueued, nothing is waited for; the caller calls
+// jacobi_finish() after its next synchronisation of the stream (one host round trip per SVD instead of two)
 template <typename T>
 static bool run_persistent(T* gt, size_t ld, size_t voff, const JacobiPlan& p, double tol, double big, int max_sweeps, int& sweeps_out,
-                           size_t smem_cap, const char* tag) {
+                           size_t smem_cap, const char* tag, JacobiPending* pending = nullptr) {
 	Context& c = ctx();
 	const size_t n_u32 = 2 * max_sweeps + 12 + 4 * p.nblk;  // sweep counters | info | ready flags (x blocks, v blocks, product log)
 	unsigned int* d_cnt = static_cast<unsigned int*>(dalloc_bytes(n_u32 * sizeof(unsigned int)));
@@ -1650,19 +1671,15 @@ static bool run_persistent(T* gt, size_t ld, size_t voff, const JacobiPlan& p, d
 	else if (p.EH == 4) launch_persistent<T, 4, 512>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
 	else if (p.EH == 8) launch_persistent<T, 8, 512>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
 	else launch_persistent<T, 16, 256>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
-	unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch);
+	unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch + c.h_scratch_len - 16);
 	XB_CUDA(cudaMemcpyAsync(h_info, d_info - 4, 12 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
-	XB_CUDA(cudaStreamSynchronize(c.stream));
-	const bool dead = h_info[0] == 0xDEADu;
-	h_info += 4;
-	sweeps_out = int(h_info[1]);
-	const bool converged = h_info[2] == 0;
-	if (dead) { dfree(d_cnt); throw Error(XB_ERR_CUDA, "Jacobi SVD: a block hand-over flag was never raised (internal scheduling error)"); }
-	if (timing && h_info[-3]) fprintf(stderr, "[jacobi %s] inner = gram %u + rounds on G %u + apply %u kcycles\n", tag, h_info[-3], h_info[-2], h_info[-1]);
-	if (timing) fprintf(stderr, "[jacobi %s] ld=%zu bw=%d ctas=%zu sweeps=%d kcycles: load %u inner %u store %u sync %u\n", tag, ld, p.bw,
-	                    p.nblk / 2, sweeps_out, h_info[4], h_info[5], h_info[6], h_info[7]);
 	dfree(d_cnt);
-	return converged;
+	JacobiPending local;
+	JacobiPending& pend = pending ? *pending : local;
+	pend.active = true; pend.tag = tag; pend.ld = ld; pend.nblk = p.nblk; pend.bw = p.bw;
+	if (pending) return true;
+	XB_CUDA(cudaStreamSynchronize(c.stream));
+	return jacobi_finish(pend, sweeps_out);
 }
 
 void Svd::factor(const double* A, size_t m_, size_t n_) {
@@ -1683,7 +1700,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		Qred.resize(mw * nw); Rr.resize(nw * nw);
 		// Qred is not needed before extract(): it is formed on the side stream while the Jacobi kernel runs
 		const long long ars = swapped ? 1 : (long long)n, acs = swapped ? (long long)n : 1;     // Mw(i, j) = A[i * ars + j * acs]
-		if (c.svd_colsort && nw >= 16 && nw <= 1200) {
+		if (c.svd_colsort && nw >= 32 && nw <= 1200) {
 			// columns of the working matrix in order of descending norm: the poor man's pivoted QR.  The TT sweeps hand over
 			// matrices like [Q1 W, Q2 W] with W = U Sigma, and products of many random cores at the first edges: column norms
 			// spread over up to nine decades in no particular order, on which the unpivoted factor needs 2 - 4 x the sweeps.
@@ -1758,6 +1775,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 
 	sweeps = 0;
 	bool converged = false;
+	JacobiPending pending;
 	ProfScope* prof_jacobi = new ProfScope("svd_jacobi");
 	const bool mixed = plan.persistent && c.svd_mixed && nw >= size_t(c.svd_mixed_min);
 	if (mixed) {
@@ -1795,7 +1813,10 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		svd_init_kernel<<<init_blocks, 256, 0, c.stream>>>(GT, int(ld), int(npad), int(mdot), int(voff), int(nw), src, rs, cs, scale.p);
 		XB_LAUNCH_CHECK();
 		if (plan.persistent) {
-			converged = run_persistent<double>(GT.p, ld, voff, plan, tol, c.svd_last_sweep_cos, c.svd_max_sweeps, sweeps, smem_cap, "f64");
+			// without a clean-up run (sweep layer) the convergence record is read back together with the singular values below
+			const bool defer = !(c.svd_polish && polish > 1);
+			converged = run_persistent<double>(GT.p, ld, voff, plan, tol, c.svd_last_sweep_cos, c.svd_max_sweeps, sweeps, smem_cap, "f64",
+			                                   defer ? &pending : nullptr);
 		} else {
 			// fallback for shapes the cooperative kernel cannot hold: one launch per tournament round
 			const int bw = plan.bw;
@@ -1851,7 +1872,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		XB_LAUNCH_CHECK();
 	}
 	S.resize(nw);
-	if (nw <= c.h_scratch_len) {
+	if (nw + 16 <= c.h_scratch_len) {
 		XB_CUDA(cudaMemcpyAsync(c.h_scratch, Ssorted.p, nw * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
 		XB_CUDA(cudaStreamSynchronize(c.stream));
 		std::copy(c.h_scratch, c.h_scratch + nw, S.begin());
@@ -1859,6 +1880,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		XB_CUDA(cudaMemcpyAsync(S.data(), Ssorted.p, nw * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
 		XB_CUDA(cudaStreamSynchronize(c.stream));
 	}
+	if (pending.active && !jacobi_finish(pending, sweeps)) throw Error(XB_ERR_NUMERIC, "Jacobi SVD did not converge within svd_max_sweeps sweeps");
 }
 
 void Svd::extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, double* dS) {
