@@ -1581,7 +1581,9 @@ static bool launch_split_impl(double* gt, const JacobiPlan& p, double tol2, doub
 	}
 	DBuf jlog(size_t(nw) * JS_DEPTH * (16 * 16 + 8));
 	double* jl = jlog.p;
-	XB_CUDA(cudaLaunchKernelEx(&cfg, jacobi_split_kernel<EP2, DS>, gt, nblk, tol2, big2, d_cnt, d_info, max_sweeps, flags, jl));
+	const cudaError_t le = cudaLaunchKernelEx(&cfg, jacobi_split_kernel<EP2, DS>, gt, nblk, tol2, big2, d_cnt, d_info, max_sweeps, flags, jl);
+	if (le != cudaSuccess && DS) { cudaGetLastError(); return false; }        // the caller falls back to the global-memory hand-over
+	XB_CUDA(le);
 	ctx().launches++;
 	return true;
 }
@@ -1589,7 +1591,11 @@ template <int EP2>
 static void launch_split(double* gt, const JacobiPlan& p, double tol2, double big2, unsigned int* d_cnt, unsigned int* d_info, int max_sweeps,
                          size_t smem_cap) {
 	const int nw = int(p.nblk) / 2;
-	if (ctx().svd_dsmem && nw >= 2 && nw <= 16 && launch_split_impl<EP2, true>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap)) return;
+	// Nsight Compute cannot launch the cluster + cooperative variant (it aborts the process with LaunchFailed): under the
+	// profiler (its injection variables are in the environment) the hand-over goes through global memory
+	static const bool profiler_attached = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr;
+	if (ctx().svd_dsmem && !profiler_attached && nw >= 2 && nw <= 16 &&
+	    launch_split_impl<EP2, true>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap)) return;
 	launch_split_impl<EP2, false>(gt, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
 }
 
