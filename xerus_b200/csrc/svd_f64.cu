@@ -977,6 +977,11 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 						const double gg = gs * gs, ab = aa * bb;
 						if (gg > tol2 * ab) {
 							const double jb = (lane < N) ? Js[b * ldj + lane] : 0.0;
+							// bookkeeping first (every lane counts, lane 0's counters are the ones flushed): it then overlaps the latency of
+							// the rotation parameters instead of trailing the stores in front of the barrier
+							my_rot += 1;
+							my_big += (gg > big2 * ab) ? 1u : 0u;
+							visit_rot = 1;
 							double c, s, tt;
 							rotation(aa, bb, gs, gg, c, s, tt);
 #pragma unroll
@@ -999,12 +1004,7 @@ __global__ void __launch_bounds__(256) jacobi_split_kernel(double* __restrict__ 
 								na = sa; nb = sb;
 							}
 							aa = na;
-							visit_rot = 1;
-							if (lane == 0) {
-								nq[b - BW] = nb;
-								my_rot += 1;
-								if (gg > big2 * ab) my_big += 1;
-							}
+							if (lane == 0) nq[b - BW] = nb;
 						}
 						__syncthreads();
 					}
