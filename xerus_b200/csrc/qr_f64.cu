@@ -316,7 +316,7 @@ qr_panel_cluster_kernel(double* __restrict__ W, const long long ldw, const int m
 }
 
 static bool launch_panel_cluster(double* Wpanel, long long ldw, size_t mp, size_t nbe, double* Vp, double* Tp) {
-	if (!ctx().qr_cluster || mp < 128 || mp > size_t(QRC_CS * QRC_WARPS * 32)) return false;
+	if (!ctx().qr_cluster || mp < size_t(ctx().qr_cluster_min_rows) || mp > size_t(QRC_CS * QRC_WARPS * 32)) return false;
 	const size_t rpt = (mp + QRC_CS * QRC_WARPS - 1) / (QRC_CS * QRC_WARPS);
 	cudaStream_t st = ctx().stream;
 	static const bool timing = getenv("XB_QR_TIMING") != nullptr;

@@ -65,6 +65,7 @@ struct Context {
 	int svd_flip = 1;              // Jacobi on the rows of the triangular factor after a QR reduction (pre-conditioning)
 	int svd_square_qr = 1;         // square inputs also go through the QR reduction (needed for svd_flip)
 	int qr_cluster = 1;            // QR panels of 128..2048 rows on a thread-block cluster (registers + DSMEM reduction)
+	int qr_cluster_min_rows = 64;  // smallest panel height for the cluster panel kernel (below: one CTA, panel in shared memory)
 	int svd_fast = 1;              // specialised Jacobi kernel (compile-time row length, 128-bit accesses) up to 512 columns
 	int svd_jacc = 1;              // specialised Jacobi kernel: rotations of a block visit accumulated, applied to V once (DMMA)
 	int als_persistent_cg = 1;     // one-site SPD local problems: a whole CG run in one cooperative launch (spd_cg_kernel)
