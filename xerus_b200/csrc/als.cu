@@ -193,11 +193,12 @@ struct SpdSiteApply {
 // device; the host reads one status record per launch.
 struct SpdCgArgs {
 	const double* L; const double* A2; const double* R;
-	double* x; double* r; double* p; double* partial; double* sc; unsigned int* info; unsigned int* barrier;
+	const double* rhs;               // right-hand side of the local problem
+	double* x; double* p; double* partial; double* sc; unsigned int* info; unsigned int* barrier;
 	int l, a, n, m, b, rr;           // L (l, a, l), A2 (m b | a n), R (rr, b, rr); vectors (l, n, rr) with m == n
 	int nsl;                         // slices per CTA (1 whenever l <= number of co-resident CTAs)
 	int max_it;
-	double target, rr_start;
+	double target, bnorm2;
 };
 constexpr int CGP_THREADS = 256;
 constexpr int CGP_AMAX = 4;          // operator bond dimension handled by the register accumulators of step 1
@@ -258,7 +259,8 @@ __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) 
 	double* rs = xs + (size_t)nsl * Cout;
 	double* ps = rs + (size_t)nsl * Cout;
 	double* qs = ps + (size_t)nsl * Cout;
-	double* red = qs + (size_t)nsl * Cout;         // [32]
+	double* bs = qs + (size_t)nsl * Cout;          //            ... and of the right-hand side
+	double* red = bs + (size_t)nsl * Cout;         // [32]
 	const int tid = threadIdx.x, G = gridDim.x;
 	for (int e = tid; e < KR * R; e += CGP_THREADS) { const int ro = e / KR, k = e % KR; Rt[k * Rp + ro] = g.R[e]; }
 	if (Rp != R) for (int k = tid; k < KR; k += CGP_THREADS) Rt[k * Rp + R] = 0.0;
@@ -267,24 +269,21 @@ __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) 
 		const int li = blockIdx.x + s * G;
 		if (li < l) for (int e = tid; e < Cout; e += CGP_THREADS) {
 			const size_t o = (size_t)li * Cout + e;
-			xs[s * Cout + e] = g.x[o]; rs[s * Cout + e] = g.r[o]; ps[s * Cout + e] = g.p[o];
+			xs[s * Cout + e] = g.x[o]; bs[s * Cout + e] = g.rhs[o];
 		}
 	}
 	__syncthreads();
 
-	double rr = g.sc[0];                           // r.r of the start residual (written by the host path before the launch)
-	double best = rr;
+	double rr = 0.0, rr0 = -1.0, best = 0.0;
 	int since_best = 0, it = 0;
 	unsigned int reason = 0;                       // 1 target, 2 stagnation, 3 re-anchor, 4 NaN, 0 iteration budget
 	unsigned int bar_expected = 0;
 	const bool timing = g.info[3] == 0xC10C && blockIdx.x == 0 && tid == 0;
 	long long tk[6] = {0, 0, 0, 0, 0, 0}, t0 = 0;  // step 1 | steps 2-3 | barrier 1 | update | barrier 2 | barrier 3
 	const bool vec_ok = (Cin & 1) == 0;
-	for (; it < g.max_it; ++it) {
-		double* part = g.partial + (size_t)(it & 1) * 2 * G;
-		if (timing) t0 = clock64();
-		// ---- q = A p on the owned slices, and the partial of p.q
-		double pq_local = 0.0;
+	// qs <- (A src) on the owned slices; dot_local += <wsm, qs> with wsm the shared-memory copy of src's owned segments.
+	// src is read through L2 (every CTA needs all of it, and other CTAs wrote it).
+	auto apply_owned = [&](const double* __restrict__ src, const double* __restrict__ wsm, double& dot_local) {
 		for (int s = 0; s < nsl; ++s) {
 			const int li = blockIdx.x + s * G;
 			if (li >= l) break;                      // uniform per CTA
@@ -298,7 +297,7 @@ __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) 
 					double acc[CGP_AMAX][2];
 #pragma unroll
 					for (int aa = 0; aa < CGP_AMAX; ++aa) { acc[aa][0] = 0.0; acc[aa][1] = 0.0; }
-					const double2* pj = reinterpret_cast<const double2*>(g.p) + j2;
+					const double2* pj = reinterpret_cast<const double2*>(src) + j2;
 					for (int base = 0; base < l; base += CGP_ROWS) {
 						double2 pv[CGP_ROWS];
 #pragma unroll
@@ -326,7 +325,7 @@ __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) 
 			} else {
 				for (int j = tid; j < Cin; j += CGP_THREADS) {
 					double acc[CGP_AMAX] = {0.0, 0.0, 0.0, 0.0};
-					const double* pj = g.p + j;
+					const double* pj = src + j;
 #pragma unroll 8
 					for (int lp = 0; lp < l; ++lp) {
 						const double pv = __ldcg(pj + (size_t)lp * Cin);
@@ -369,15 +368,58 @@ __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) 
 					y00 += ua * rv.x; y01 += ua * rv.y; y10 += ub * rv.x; y11 += ub * rv.y;
 				}
 				const int o0 = s * Cout + m0 * R + ro;
-				qs[o0] = y00; pq_local += ps[o0] * y00;
-				if (ro + 1 < R) { qs[o0 + 1] = y01; pq_local += ps[o0 + 1] * y01; }
+				qs[o0] = y00; dot_local += wsm[o0] * y00;
+				if (ro + 1 < R) { qs[o0 + 1] = y01; dot_local += wsm[o0 + 1] * y01; }
 				if (m1 != m0) {
-					qs[o0 + R] = y10; pq_local += ps[o0 + R] * y10;
-					if (ro + 1 < R) { qs[o0 + R + 1] = y11; pq_local += ps[o0 + R + 1] * y11; }
+					qs[o0 + R] = y10; dot_local += wsm[o0 + R] * y10;
+					if (ro + 1 < R) { qs[o0 + R + 1] = y11; dot_local += wsm[o0 + R + 1] * y11; }
 				}
 			}
 			__syncthreads();
 		}
+	};
+
+	// The host loop of local_solve_cg, on the device: true residual of the current x, CG from it until the recurrence residual
+	// meets the target / stagnates / has dropped 20 decades, re-anchor at the true residual, at most six times.
+	for (int restart = 0; restart < 6; ++restart) {
+		if (restart > 0) {
+			for (int e = tid; e < nsl * Cout; e += CGP_THREADS) {
+				const int li = blockIdx.x + (e / Cout) * G;
+				if (li < l) __stcg(g.x + (size_t)li * Cout + (e % Cout), xs[e]);
+			}
+			cgp_grid_barrier(g.barrier, bar_expected, G, g.info);
+		}
+		double dummy = 0.0, rl = 0.0;
+		apply_owned(g.x, xs, dummy);
+		for (int e = tid; e < nsl * Cout; e += CGP_THREADS) {
+			if (blockIdx.x + (e / Cout) * G < l) { const double rn = bs[e] - qs[e]; rs[e] = rn; rl += rn * rn; }
+		}
+		double* rpart = g.partial + (size_t)(4 + (restart & 1)) * G;
+		const double rl_cta = cgp_block_sum(rl, red);
+		if (tid == 0) __stcg(rpart + blockIdx.x, rl_cta);
+		cgp_grid_barrier(g.barrier, bar_expected, G, g.info);
+		rr = cgp_grid_sum(rpart, G, red);
+		if (rr0 < 0.0) rr0 = rr;
+		if (!(rr == rr)) { reason = 4; break; }
+		if (rr <= g.target) { reason = 1; break; }
+		if (it >= g.max_it) { reason = 0; break; }
+		if (restart == 0 && rr > 1e4 * g.bnorm2) {       // useless warm start: begin from zero instead
+			for (int e = tid; e < nsl * Cout; e += CGP_THREADS) { xs[e] = 0.0; rs[e] = bs[e]; }
+			rr = g.bnorm2;
+		}
+		for (int e = tid; e < nsl * Cout; e += CGP_THREADS) {
+			const int li = blockIdx.x + (e / Cout) * G;
+			if (li < l) { ps[e] = rs[e]; __stcg(g.p + (size_t)li * Cout + (e % Cout), rs[e]); }
+		}
+		cgp_grid_barrier(g.barrier, bar_expected, G, g.info);
+		best = rr; since_best = 0; reason = 0;
+		const double rr_start = rr;
+	for (; it < g.max_it; ++it) {
+		double* part = g.partial + (size_t)(it & 1) * 2 * G;
+		if (timing) t0 = clock64();
+		// ---- q = A p on the owned slices, and the partial of p.q
+		double pq_local = 0.0;
+		apply_owned(g.p, ps, pq_local);
 		const double pq_cta = cgp_block_sum(pq_local, red);
 		if (tid == 0) __stcg(part + blockIdx.x, pq_cta);
 		if (timing) { const long long t1 = clock64(); tk[1] += t1 - t0; t0 = t1; }
@@ -411,32 +453,36 @@ __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) 
 		if (!(rr == rr)) { reason = 4; ++it; break; }
 		if (rr <= g.target) { reason = 1; ++it; break; }
 		if (rr < 0.5 * best) { best = rr; since_best = 0; } else if (++since_best >= 48) { reason = 2; ++it; break; }
-		if (rr < 1e-20 * g.rr_start) { reason = 3; ++it; break; }
+		if (rr < 1e-20 * rr_start) { reason = 3; ++it; break; }
 		if (timing) { const long long t1 = clock64(); tk[3] += t1 - t0; t0 = t1; }
 		cgp_grid_barrier(g.barrier, bar_expected, G, g.info);     // the new p is visible to every CTA
 		if (timing) { const long long t1 = clock64(); tk[5] += t1 - t0; t0 = t1; }
+	}
+		if (reason == 4) break;
+		// (leaving the CG loop through a stopping rule skips its last barrier; the next residual starts with one after publishing x)
 	}
 	__syncthreads();
 	for (int s = 0; s < nsl; ++s) {
 		const int li = blockIdx.x + s * G;
 		if (li < l) for (int e = tid; e < Cout; e += CGP_THREADS) {
 			const size_t o = (size_t)li * Cout + e;
-			g.x[o] = xs[s * Cout + e]; g.r[o] = rs[s * Cout + e];
+			g.x[o] = xs[s * Cout + e];
 		}
 	}
-	if (blockIdx.x == 0 && tid == 0) { g.sc[0] = rr; g.info[0] = (unsigned)it; g.info[1] = reason; }
+	if (blockIdx.x == 0 && tid == 0) { g.sc[0] = rr; g.sc[1] = rr0; g.info[0] = (unsigned)it; g.info[1] = reason; }
 	if (timing) { for (int i = 0; i < 6; ++i) g.info[4 + i] = (unsigned)(tk[i] >> 4); }
 }
 
 // launches spd_cg_kernel if the shapes fit; returns false (nothing done) otherwise
-bool spd_cg_persistent(const SpdSiteApply& sa, double* x, double* r, double* p, double* sc, size_t max_it, double target,
-                       double rr_start, size_t& iterations, unsigned& reason, double& rr_out) {
+// (x: warm start in, solution out; b: right-hand side; p: work vector; rr0_out: squared norm of the first true residual)
+bool spd_cg_persistent(const SpdSiteApply& sa, double* x, const double* b, double* p, double* sc, size_t max_it, double target,
+                       double bnorm2, size_t& iterations, unsigned& reason, double& rr_out, double& rr0_out) {
 	Context& c = ctx();
 	if (!c.als_persistent_cg || sa.m != sa.n || sa.a > size_t(CGP_AMAX) || sa.l > 4096 || sa.r > 4096) return false;
 	const size_t KR = sa.b * sa.r, KA = sa.a * sa.n, QA = sa.m * sa.b, Rp = (sa.r + 1) & ~size_t(1), Cout = sa.m * sa.r;
 	const size_t cap = std::min<size_t>(c.max_smem_optin, 227 * 1024) - 1024;
 	auto smem_for = [&](size_t nsl) {
-		return (KR * Rp + ((QA * KA + 1) & ~size_t(1)) + size_t(CGP_AMAX) * sa.l + KA * Rp + ((sa.m * KR + 1) & ~size_t(1)) + 4 * nsl * Cout + 32) * sizeof(double);
+		return (KR * Rp + ((QA * KA + 1) & ~size_t(1)) + size_t(CGP_AMAX) * sa.l + KA * Rp + ((sa.m * KR + 1) & ~size_t(1)) + 5 * nsl * Cout + 32) * sizeof(double);
 	};
 	// one CTA per slice of the left bond when that many are co-resident, otherwise several slices per CTA
 	size_t nsl = 1, smem = 0;
@@ -455,14 +501,14 @@ bool spd_cg_persistent(const SpdSiteApply& sa, double* x, double* r, double* p, 
 		G = int((sa.l + nsl - 1) / nsl);
 		if (size_t(G) <= size_t(c.num_sms) * per_sm) break;
 	}
-	DBuf partial(size_t(4) * G);
+	DBuf partial(size_t(6) * G);
 	unsigned int* info = static_cast<unsigned int*>(dalloc_bytes(16 * sizeof(unsigned int)));
 	const bool timing = getenv("XB_CG_TIMING") != nullptr;
 	{ const unsigned int init[12] = {0, 0, 0, timing ? 0xC10Cu : 0u, 0, 0, 0, 0, 0, 0, 0, 0}; XB_CUDA(cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, c.stream)); }
 	SpdCgArgs g;
-	g.L = sa.L; g.A2 = sa.A2; g.R = sa.R; g.x = x; g.r = r; g.p = p; g.partial = partial; g.sc = sc; g.info = info; g.barrier = info + 11;
+	g.L = sa.L; g.A2 = sa.A2; g.R = sa.R; g.x = x; g.rhs = b; g.p = p; g.partial = partial; g.sc = sc; g.info = info; g.barrier = info + 11;
 	g.l = int(sa.l); g.a = int(sa.a); g.n = int(sa.n); g.m = int(sa.m); g.b = int(sa.b); g.rr = int(sa.r); g.nsl = int(nsl);
-	g.max_it = int(std::min<size_t>(max_it, 1u << 30)); g.target = target; g.rr_start = rr_start;
+	g.max_it = int(std::min<size_t>(max_it, 1u << 30)); g.target = target; g.bnorm2 = bnorm2;
 	void* args[] = {&g};
 	{
 		ProfScope prof("als_cg_kernel");
@@ -470,11 +516,11 @@ bool spd_cg_persistent(const SpdSiteApply& sa, double* x, double* r, double* p, 
 		c.launches++;
 	}
 	unsigned int* h = reinterpret_cast<unsigned int*>(c.h_scratch + 8);
-	XB_CUDA(cudaMemcpyAsync(c.h_scratch, sc, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaMemcpyAsync(c.h_scratch, sc, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
 	XB_CUDA(cudaMemcpyAsync(h, info, 10 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
 	XB_CUDA(cudaStreamSynchronize(c.stream));
 	dfree(info);
-	rr_out = c.h_scratch[0]; iterations = h[0]; reason = h[1];
+	rr_out = c.h_scratch[0]; rr0_out = c.h_scratch[1]; iterations = h[0]; reason = h[1];
 	if (h[2] == 0xDEADu) throw Error(XB_ERR_CUDA, "persistent CG: a grid barrier timed out (internal scheduling error)");
 	if (timing && h[0]) fprintf(stderr, "[cg] G=%d its=%u cycles/it: step1 %u steps2-3 %u barrier1 %u update %u barrier2 %u barrier3 %u\n", G, h[0],
 	                            h[4] * 16 / h[0], h[5] * 16 / h[0], h[6] * 16 / h[0], h[7] * 16 / h[0], h[8] * 16 / h[0], h[9] * 16 / h[0]);
@@ -768,6 +814,17 @@ struct Als {
 		const unsigned grid = vec_grid(n);
 		size_t it = 0;
 		double rr = 0.0, rr0 = -1.0;
+		if (site_apply) {
+			// one cooperative launch for the whole solve: true residual, CG, re-anchoring at the true residual (spd_cg_kernel)
+			DT pw = dt_alloc(rhs.dims);
+			size_t done = 0; unsigned reason = 0;
+			if (spd_cg_persistent(*site_apply, xv.data(), rhs.p, pw.data(), sc.p, max_it, target, bnorm2, done, reason, rr, rr0)) {
+				if (reason == 4 || !(rr == rr)) throw Error(XB_ERR_NUMERIC, "local CG produced NaN (operator not positive definite?)");
+				cg_iterations += done;
+				if (getenv("XB_DEBUG_ALS")) fprintf(stderr, "[als] site %zu n=%zu cg its=%zu rel res=%.3e (start %.3e) [one launch]\n", cur, n, done, std::sqrt(rr / bnorm2), std::sqrt(rr0 / bnorm2));
+				return xv;
+			}
+		}
 		for (int restart = 0; restart < 6 && it < max_it; ++restart) {
 			DT r = dt_copy(rhs);
 			if (site_apply) { site_apply->apply(xv.p, qbuf.data()); axpy(r.data(), -1.0, qbuf.p, n); }
@@ -791,15 +848,6 @@ struct Als {
 			struct GraphHolder { cudaGraph_t g = nullptr; cudaGraphExec_t e = nullptr;
 				~GraphHolder() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); } } graph;
 			const bool use_graph = site_apply && fused_update && c.als_graph && !c.profile;
-			if (site_apply) {
-				// one cooperative launch per CG run (spd_cg_kernel); the stopping rules below run on the device
-				size_t done = 0; unsigned reason = 0; double rr_new = rr;
-				if (spd_cg_persistent(*site_apply, xv.data(), r.data(), p.data(), sc.p, max_it - it, target, rr_start, done, reason, rr_new)) {
-					it += done; rr = rr_new;
-					if (reason == 4 || !(rr == rr)) throw Error(XB_ERR_NUMERIC, "local CG produced NaN (operator not positive definite?)");
-					continue;
-				}
-			}
 			while (rr > target && it < max_it) {
 				const size_t chunk = std::min<size_t>(8, max_it - it);
 				if (use_graph && chunk == 8) {
