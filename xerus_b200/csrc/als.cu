@@ -245,6 +245,18 @@ __device__ __forceinline__ void cgp_grid_barrier(unsigned int* counter, unsigned
 	__syncthreads();
 }
 
+__device__ __forceinline__ unsigned cgp_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned cgp_mapa(unsigned addr, unsigned rank) {
+	unsigned r;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+	return r;
+}
+// CSZ > 1: the CTAs form clusters of CSZ.  Step 1 of an application (t1 = L(li) src, which needs ALL of src in every CTA and is
+// bound by L2 latency: 40 % of an iteration) is shared inside a cluster: a CTA reads only its 1/CSZ of the rows of src, forms
+// the partial t1 of all CSZ slices of its cluster from them, and the partials are exchanged through DSMEM — one bulk copy
+// (cp.async.bulk shared::cta -> shared::cluster, 8 KB at config 2) per destination, completion counted on the destination's
+// mbarrier — and summed in member order.  L2 traffic and load latency per CTA drop by CSZ, the arithmetic per CTA is unchanged.
+template <int CSZ>
 __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) {
 	extern __shared__ double cgp_smem[];
 	const int l = g.l, a = g.a, n = g.n, m = g.m, b = g.b, R = g.rr, nsl = g.nsl;
@@ -261,6 +273,20 @@ __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) 
 	double* qs = ps + (size_t)nsl * Cout;
 	double* bs = qs + (size_t)nsl * Cout;          //            ... and of the right-hand side
 	double* red = bs + (size_t)nsl * Cout;         // [32]
+	// cluster variant: weights of all slices of the cluster over this CTA's rows, staged partials, received partials
+	const int crows = (l + CSZ - 1) / CSZ + 1;
+	double* Lc = red + 32;                         // [CSZ][crows][2]
+	double* stage = Lc + ((CSZ * crows * 2 + 1) & ~1);   // [CSZ][KA * Rp]
+	double* recvp = stage + (size_t)CSZ * KA * Rp; // [CSZ][KA * Rp]
+	__shared__ __align__(8) unsigned long long xbar;
+	unsigned int applies = 0;
+	if (CSZ > 1) {
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(cgp_smem_u32(&xbar)), "r"(1u) : "memory");
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		cooperative_groups::this_cluster().sync();
+	}
 	const int tid = threadIdx.x, G = gridDim.x;
 	for (int e = tid; e < KR * R; e += CGP_THREADS) { const int ro = e / KR, k = e % KR; Rt[k * Rp + ro] = g.R[e]; }
 	if (Rp != R) for (int k = tid; k < KR; k += CGP_THREADS) Rt[k * Rp + R] = 0.0;
@@ -284,9 +310,80 @@ __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) 
 	// qs <- (A src) on the owned slices; dot_local += <wsm, qs> with wsm the shared-memory copy of src's owned segments.
 	// src is read through L2 (every CTA needs all of it, and other CTAs wrote it).
 	auto apply_owned = [&](const double* __restrict__ src, const double* __restrict__ wsm, double& dot_local) {
+		if (timing) t0 = clock64();
 		for (int s = 0; s < nsl; ++s) {
 			const int li = blockIdx.x + s * G;
 			if (li >= l) break;                      // uniform per CTA
+			if (CSZ > 1) {
+				// ---- step 1 shared inside the cluster (host guarantees nsl == 1, a <= 2, Cin even, G % CSZ == 0)
+				const int cr = blockIdx.x % CSZ, cbase = blockIdx.x - cr;
+				const int lr0 = (cr * l) / CSZ, lr1 = ((cr + 1) * l) / CSZ, nr = lr1 - lr0;
+				const int TS = KA * Rp;                                   // doubles of one partial t1
+				if (tid < CSZ) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // last application's copies have read `stage`
+				for (int e = tid; e < CSZ * nr * 2; e += CGP_THREADS) {
+					const int c = e / (nr * 2), i = (e / 2) % nr, aa = e & 1;
+					Lc[(c * crows + i) * 2 + aa] = (aa < a) ? g.L[((size_t)(cbase + c) * a + aa) * l + lr0 + i] : 0.0;
+				}
+				__syncthreads();
+				for (int j2 = tid; j2 < (Cin >> 1); j2 += CGP_THREADS) {
+					double acc[CSZ][2][2];
+#pragma unroll
+					for (int c = 0; c < CSZ; ++c) { acc[c][0][0] = 0.0; acc[c][0][1] = 0.0; acc[c][1][0] = 0.0; acc[c][1][1] = 0.0; }
+					const double2* pj = reinterpret_cast<const double2*>(src) + j2;
+					for (int base = 0; base < nr; base += CGP_ROWS) {
+						double2 pv[CGP_ROWS];
+#pragma unroll
+						for (int i = 0; i < CGP_ROWS; ++i) pv[i] = (base + i < nr) ? __ldcg(pj + (size_t)(lr0 + base + i) * (Cin >> 1)) : make_double2(0.0, 0.0);
+#pragma unroll
+						for (int i = 0; i < CGP_ROWS; ++i) {
+							if (base + i < nr) {
+#pragma unroll
+								for (int c = 0; c < CSZ; ++c) {
+									const double2 w = *reinterpret_cast<const double2*>(Lc + (c * crows + base + i) * 2);
+									acc[c][0][0] += w.x * pv[i].x; acc[c][0][1] += w.x * pv[i].y;
+									acc[c][1][0] += w.y * pv[i].x; acc[c][1][1] += w.y * pv[i].y;
+								}
+							}
+						}
+					}
+					const int j = 2 * j2, n0 = j / R, r0 = j - n0 * R;
+					const int n1 = (r0 + 1 < R) ? n0 : n0 + 1, r1 = (r0 + 1 < R) ? r0 + 1 : 0;
+#pragma unroll
+					for (int c = 0; c < CSZ; ++c)
+#pragma unroll
+						for (int aa = 0; aa < 2; ++aa) if (aa < a) {
+							stage[(size_t)c * TS + (aa * n + n0) * Rp + r0] = acc[c][aa][0];
+							stage[(size_t)c * TS + (aa * n + n1) * Rp + r1] = acc[c][aa][1];
+						}
+				}
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				__syncthreads();
+				const unsigned mb = cgp_smem_u32(&xbar);
+				if (tid < CSZ && tid != cr) {
+					asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+					             :: "r"(cgp_mapa(cgp_smem_u32(recvp + (size_t)cr * TS), (unsigned)tid)), "r"(cgp_smem_u32(stage + (size_t)tid * TS)),
+					                "r"((unsigned)(TS * 8)), "r"(cgp_mapa(mb, (unsigned)tid)) : "memory");
+					asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+				}
+				if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"((unsigned)((CSZ - 1) * TS * 8)) : "memory");
+				{
+					unsigned done = 0, spins = 0;
+					const unsigned parity = applies & 1u;
+					do {
+						asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+						             : "=r"(done) : "r"(mb), "r"(parity) : "memory");
+					} while (!done && ++spins < (1u << 24));
+					if (!done && tid == 0) g.info[2] = 0xDEADu;
+				}
+				++applies;
+				// t1 = sum of the partials in member order (the own one from `stage`)
+				for (int e = tid; e < TS; e += CGP_THREADS) {
+					double t = 0.0;
+#pragma unroll
+					for (int c = 0; c < CSZ; ++c) t += (c == cr) ? stage[(size_t)cr * TS + e] : recvp[(size_t)c * TS + e];
+					t1s[e] = t;
+				}
+			} else {
 			// weights of the slice, transposed and zero padded to CGP_AMAX per row: Ls[lp][aa] = L(li, aa, lp)
 			for (int e = tid; e < CGP_AMAX * l; e += CGP_THREADS) { const int lp = e / CGP_AMAX, aa = e % CGP_AMAX; Ls[e] = (aa < a) ? g.L[((size_t)li * a + aa) * l + lp] : 0.0; }
 			__syncthreads();
@@ -335,6 +432,7 @@ __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) 
 #pragma unroll
 					for (int aa = 0; aa < CGP_AMAX; ++aa) if (aa < a) t1s[(aa * n + j / R) * Rp + j % R] = acc[aa];
 				}
+			}
 			}
 			__syncthreads();
 			if (timing) { const long long t1 = clock64(); tk[0] += t1 - t0; t0 = t1; }
@@ -481,38 +579,75 @@ bool spd_cg_persistent(const SpdSiteApply& sa, double* x, const double* b, doubl
 	if (!c.als_persistent_cg || sa.m != sa.n || sa.a > size_t(CGP_AMAX) || sa.l > 4096 || sa.r > 4096) return false;
 	const size_t KR = sa.b * sa.r, KA = sa.a * sa.n, QA = sa.m * sa.b, Rp = (sa.r + 1) & ~size_t(1), Cout = sa.m * sa.r;
 	const size_t cap = std::min<size_t>(c.max_smem_optin, 227 * 1024) - 1024;
-	auto smem_for = [&](size_t nsl) {
-		return (KR * Rp + ((QA * KA + 1) & ~size_t(1)) + size_t(CGP_AMAX) * sa.l + KA * Rp + ((sa.m * KR + 1) & ~size_t(1)) + 5 * nsl * Cout + 32) * sizeof(double);
+	auto smem_for = [&](size_t nsl, size_t csz) {
+		const size_t crows = (sa.l + csz - 1) / csz + 1;
+		const size_t cluster_part = csz > 1 ? ((csz * crows * 2 + 1) & ~size_t(1)) + 2 * csz * KA * Rp : 2;
+		return (KR * Rp + ((QA * KA + 1) & ~size_t(1)) + size_t(CGP_AMAX) * sa.l + KA * Rp + ((sa.m * KR + 1) & ~size_t(1)) + 5 * nsl * Cout + 32 +
+		        cluster_part) * sizeof(double);
 	};
-	// one CTA per slice of the left bond when that many are co-resident, otherwise several slices per CTA
-	size_t nsl = 1, smem = 0;
-	int G = 0;
-	for (;; ++nsl) {
-		smem = smem_for(nsl);
-		if (smem > cap) return false;
-		static size_t attr_smem = 0;
-		if (smem > attr_smem) {
-			XB_CUDA(cudaFuncSetAttribute(spd_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-			attr_smem = smem;
-		}
-		int per_sm = 0;
-		XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spd_cg_kernel, CGP_THREADS, smem));
-		if (per_sm < 1) return false;
-		G = int((sa.l + nsl - 1) / nsl);
-		if (size_t(G) <= size_t(c.num_sms) * per_sm) break;
-	}
-	DBuf partial(size_t(6) * G);
+	struct Variant { const void* fn; int csz; };
+	const Variant variants[4] = {{(const void*)spd_cg_kernel<8>, 8}, {(const void*)spd_cg_kernel<5>, 5}, {(const void*)spd_cg_kernel<4>, 4}, {(const void*)spd_cg_kernel<2>, 2}};
+	static const bool profiler_attached = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("NV_NSIGHT_INJECTION_PORT_BASE") != nullptr;
+	DBuf partial;
 	unsigned int* info = static_cast<unsigned int*>(dalloc_bytes(16 * sizeof(unsigned int)));
 	const bool timing = getenv("XB_CG_TIMING") != nullptr;
 	{ const unsigned int init[12] = {0, 0, 0, timing ? 0xC10Cu : 0u, 0, 0, 0, 0, 0, 0, 0, 0}; XB_CUDA(cudaMemcpyAsync(info, init, sizeof(init), cudaMemcpyHostToDevice, c.stream)); }
 	SpdCgArgs g;
-	g.L = sa.L; g.A2 = sa.A2; g.R = sa.R; g.x = x; g.rhs = b; g.p = p; g.partial = partial; g.sc = sc; g.info = info; g.barrier = info + 11;
-	g.l = int(sa.l); g.a = int(sa.a); g.n = int(sa.n); g.m = int(sa.m); g.b = int(sa.b); g.rr = int(sa.r); g.nsl = int(nsl);
+	g.L = sa.L; g.A2 = sa.A2; g.R = sa.R; g.x = x; g.rhs = b; g.p = p; g.sc = sc; g.info = info; g.barrier = info + 11;
+	g.l = int(sa.l); g.a = int(sa.a); g.n = int(sa.n); g.m = int(sa.m); g.b = int(sa.b); g.rr = int(sa.r);
 	g.max_it = int(std::min<size_t>(max_it, 1u << 30)); g.target = target; g.bnorm2 = bnorm2;
-	void* args[] = {&g};
-	{
+	int G = 0;
+	bool launched = false;
+	// cluster variant: one slice per CTA, operator bond <= 2, even row length, 16-byte multiples for the bulk copies, and the
+	// whole grid co-resident as clusters of csz (largest cluster size that divides the number of slices)
+	if (c.als_cg_cluster && !profiler_attached && sa.a <= 2 && (sa.n * sa.r) % 2 == 0 && (KA * Rp) % 2 == 0 && sa.l <= size_t(c.num_sms)) {
+		for (const Variant& v : variants) {
+			if (sa.l % size_t(v.csz) != 0) continue;
+			const size_t smem = smem_for(1, size_t(v.csz));
+			if (smem > cap) continue;
+			if (cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) { cudaGetLastError(); continue; }
+			G = int(sa.l);
+			cudaLaunchConfig_t cfg = {};
+			cfg.gridDim = dim3(unsigned(G)); cfg.blockDim = dim3(CGP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = c.stream;
+			cudaLaunchAttribute at[2];
+			at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+			at[1].id = cudaLaunchAttributeClusterDimension;
+			at[1].val.clusterDim.x = unsigned(v.csz); at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+			cfg.attrs = at; cfg.numAttrs = 2;
+			int nclusters = 0;
+			if (cudaOccupancyMaxActiveClusters(&nclusters, v.fn, &cfg) != cudaSuccess || nclusters * v.csz < G) { cudaGetLastError(); continue; }
+			partial.resize(size_t(6) * G);
+			g.partial = partial; g.nsl = 1;
+			void* args[] = {&g};
+			ProfScope prof("als_cg_kernel");
+			if (cudaLaunchKernelExC(&cfg, v.fn, args) != cudaSuccess) { cudaGetLastError(); continue; }
+			c.launches++;
+			launched = true;
+			break;
+		}
+	}
+	if (!launched) {
+		// one CTA per slice of the left bond when that many are co-resident, otherwise several slices per CTA
+		size_t nsl = 1, smem = 0;
+		for (;; ++nsl) {
+			smem = smem_for(nsl, 1);
+			if (smem > cap) { dfree(info); return false; }
+			static size_t attr_smem = 0;
+			if (smem > attr_smem) {
+				XB_CUDA(cudaFuncSetAttribute(spd_cg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+				attr_smem = smem;
+			}
+			int per_sm = 0;
+			XB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spd_cg_kernel<1>, CGP_THREADS, smem));
+			if (per_sm < 1) { dfree(info); return false; }
+			G = int((sa.l + nsl - 1) / nsl);
+			if (size_t(G) <= size_t(c.num_sms) * per_sm) break;
+		}
+		partial.resize(size_t(6) * G);
+		g.partial = partial; g.nsl = int(nsl);
+		void* args[] = {&g};
 		ProfScope prof("als_cg_kernel");
-		XB_CUDA(cudaLaunchCooperativeKernel((void*)spd_cg_kernel, dim3(unsigned(G)), dim3(CGP_THREADS), args, smem, c.stream));
+		XB_CUDA(cudaLaunchCooperativeKernel((void*)spd_cg_kernel<1>, dim3(unsigned(G)), dim3(CGP_THREADS), args, smem, c.stream));
 		c.launches++;
 	}
 	unsigned int* h = reinterpret_cast<unsigned int*>(c.h_scratch + 8);
