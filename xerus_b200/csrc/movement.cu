@@ -101,8 +101,10 @@ constexpr int RED_MAX_BLOCKS = 296;
 
 // MODE 0: sum x*y   1: sum |x|   2: max |x|   3: sum (x * *y)^2  (y points to a device scalar: overflow-safe 2-norm)
 template <int MODE>
-__global__ void reduce_stage1(double* __restrict__ partial, const double* __restrict__ x, const double* __restrict__ y, size_t n) {
+__global__ void reduce_kernel(double* __restrict__ result, double* __restrict__ partial, unsigned int* __restrict__ counter,
+                              const double* __restrict__ x, const double* __restrict__ y, size_t n) {
 	__shared__ double sh[RED_THREADS / 32];
+	__shared__ bool last;
 	double acc = 0.0;
 	const double sc = (MODE == 3) ? y[0] : 1.0;
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -122,20 +124,22 @@ __global__ void reduce_stage1(double* __restrict__ partial, const double* __rest
 		double s = 0.0;
 		for (int w = 0; w < RED_THREADS / 32; ++w) s = (MODE == 2) ? fmax(s, sh[w]) : s + sh[w];
 		partial[blockIdx.x] = s;
+		// the last block to arrive finishes the reduction (one launch instead of two); the counter wraps back to zero
+		__threadfence();
+		last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
 	}
-}
-// MODE as above; for MODE 2 the result is turned into an exact power-of-two scaling pair
-//   result[0] = s with amax * s in [0.5, 1)   result[1] = 1 / s          (s = 1 for an all-zero input)
-template <int MODE>
-__global__ void reduce_stage2(double* __restrict__ result, const double* __restrict__ partial, int nblocks) {
-	if (threadIdx.x == 0 && blockIdx.x == 0) {
+	__syncthreads();
+	if (last && threadIdx.x == 0) {
+		__threadfence();
+		// fixed order over the block partials: deterministic.  MODE 2: the result is turned into an exact power-of-two scaling
+		// pair  result[0] = s with amax * s in [0.5, 1)   result[1] = 1 / s          (s = 1 for an all-zero input)
 		double s = 0.0;
-		for (int i = 0; i < nblocks; ++i) s = (MODE == 2) ? fmax(s, partial[i]) : s + partial[i];
+		for (unsigned i = 0; i < gridDim.x; ++i) { const double v = __ldcg(partial + i); s = (MODE == 2) ? fmax(s, v) : s + v; }
 		if (MODE == 2) {
 			int e = 0;
-			double sc = 1.0, inv = 1.0;
-			if (s > 0.0 && s < HUGE_VAL) { frexp(s, &e); sc = ldexp(1.0, -e); inv = ldexp(1.0, e); }
-			result[0] = sc; result[1] = inv;
+			double scl = 1.0, inv = 1.0;
+			if (s > 0.0 && s < HUGE_VAL) { frexp(s, &e); scl = ldexp(1.0, -e); inv = ldexp(1.0, e); }
+			result[0] = scl; result[1] = inv;
 		} else {
 			*result = s;
 		}
@@ -153,15 +157,16 @@ __global__ void scale_block_by_dev_kernel(double* __restrict__ A, size_t ld, siz
 
 static void reduce(double* d_result, const double* x, const double* y, size_t n, int mode) {
 	double*& partial = ctx().red_partial;
-	if (!partial) partial = dalloc(RED_MAX_BLOCKS);
+	if (!partial) {
+		partial = dalloc(RED_MAX_BLOCKS + 2);                 // block partials | arrival counter
+		XB_CUDA(cudaMemsetAsync(partial + RED_MAX_BLOCKS, 0, 2 * sizeof(double), ctx().stream));
+	}
+	unsigned int* counter = reinterpret_cast<unsigned int*>(partial + RED_MAX_BLOCKS);
 	unsigned blocks = unsigned(std::min<size_t>(RED_MAX_BLOCKS, std::max<size_t>(1, (n + RED_THREADS * 4 - 1) / (RED_THREADS * 4))));
-	if (mode == 0) reduce_stage1<0><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);
-	else if (mode == 1) reduce_stage1<1><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);
-	else if (mode == 2) reduce_stage1<2><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);
-	else reduce_stage1<3><<<blocks, RED_THREADS, 0, ctx().stream>>>(partial, x, y, n);
-	XB_LAUNCH_CHECK();
-	if (mode == 2) reduce_stage2<2><<<1, 32, 0, ctx().stream>>>(d_result, partial, int(blocks));
-	else reduce_stage2<0><<<1, 32, 0, ctx().stream>>>(d_result, partial, int(blocks));
+	if (mode == 0) reduce_kernel<0><<<blocks, RED_THREADS, 0, ctx().stream>>>(d_result, partial, counter, x, y, n);
+	else if (mode == 1) reduce_kernel<1><<<blocks, RED_THREADS, 0, ctx().stream>>>(d_result, partial, counter, x, y, n);
+	else if (mode == 2) reduce_kernel<2><<<blocks, RED_THREADS, 0, ctx().stream>>>(d_result, partial, counter, x, y, n);
+	else reduce_kernel<3><<<blocks, RED_THREADS, 0, ctx().stream>>>(d_result, partial, counter, x, y, n);
 	XB_LAUNCH_CHECK();
 }
 
