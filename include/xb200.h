@@ -63,6 +63,11 @@ xb_status xb_alloc_host(void** hptr, size_t bytes);      /* pinned host memory *
 xb_status xb_free_host(void* hptr);
 xb_status xb_upload(void* dst_dev, const void* src_host, size_t bytes);    /* async on the library stream */
 xb_status xb_download(void* dst_host, const void* src_dev, size_t bytes);  /* async + stream synchronise */
+/* xb_prefetch pins an existing host range in place (cudaHostRegister) so that the per-call layer's transfers of arrays that
+ * live inside it are direct DMA instead of staged copies — for Tensor data that was allocated with new[] and cannot move
+ * (the 15 allocation sites of tensor.cpp); xb_release undoes it.  Both are no-ops on a range that is already in that state. */
+xb_status xb_prefetch(const void* host_ptr, size_t bytes);
+xb_status xb_release(const void* host_ptr);
 
 /* ---- 1. per-call layer: host pointers, mirrors xerus::blasWrapper one to one ----------------------------------- */
 /* blasLapackWrapper.h:41-47 */

@@ -101,6 +101,22 @@ def test_gemm_large_tile_beta_and_odd_shapes():
         assert rel(dC.cpu().numpy(), want.numpy()) < 1e-13
 
 
+def test_prefetch_pins_host_operands_in_place():
+    """xb_prefetch / xb_release (memory hooks): an existing host array is pinned where it lies; results do not change."""
+    from xerus_b200._lib import call
+    rng = np.random.default_rng(4)
+    A, B = rng.standard_normal((300, 200)), rng.standard_normal((200, 150))
+    want = BW.matrix_matrix_product(1.0, A, False, B, False)
+    call("xb_prefetch", A.ctypes.data, A.nbytes)
+    call("xb_prefetch", A.ctypes.data, A.nbytes)          # idempotent
+    try:
+        assert np.array_equal(BW.matrix_matrix_product(1.0, A, False, B, False), want)
+    finally:
+        call("xb_release", A.ctypes.data)
+        call("xb_release", A.ctypes.data)                 # idempotent
+    assert np.array_equal(BW.matrix_matrix_product(1.0, A, False, B, False), want)
+
+
 def test_gemv_ger_level1(golden):
     rng = np.random.default_rng(3)
     A, y = rng.standard_normal((37, 23)), rng.standard_normal(23)

@@ -43,7 +43,7 @@ _SIGS = {
     "xb_kernel_launch_count": [P(C.c_uint64)], "xb_set_option": [C.c_char_p, C.c_double],
     "xb_profile_enable": [C.c_int], "xb_profile_get": [C.c_char_p, P(C.c_uint64), P(C.c_uint64), dp],
     "xb_alloc": [P(vp), sz], "xb_free": [vp], "xb_alloc_host": [P(vp), sz], "xb_free_host": [vp],
-    "xb_upload": [vp, vp, sz], "xb_download": [vp, vp, sz],
+    "xb_upload": [vp, vp, sz], "xb_download": [vp, vp, sz], "xb_prefetch": [vp, sz], "xb_release": [vp],
     "xb_one_norm": [dp, sz, dp], "xb_two_norm": [dp, sz, dp], "xb_dot_product": [dp, sz, dp, dp],
     "xb_matrix_vector_product": [dp, sz, C.c_double, dp, sz, C.c_int, dp],
     "xb_dyadic_vector_product": [dp, sz, sz, C.c_double, dp, dp],

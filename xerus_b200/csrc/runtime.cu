@@ -292,6 +292,26 @@ xb_status xb_alloc_host(void** hptr, size_t bytes) {
 	return guard([&] { ensure_init(); XB_REQUIRE(hptr, "null"); XB_CUDA(cudaMallocHost(hptr, bytes ? bytes : 8)); });
 }
 xb_status xb_free_host(void* hptr) { return guard([&] { if (hptr) XB_CUDA(cudaFreeHost(hptr)); }); }
+xb_status xb_prefetch(const void* host_ptr, size_t bytes) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(host_ptr && bytes > 0, "null");
+		cudaPointerAttributes at;
+		if (cudaPointerGetAttributes(&at, host_ptr) == cudaSuccess && at.type == cudaMemoryTypeHost) return;      // already pinned
+		cudaGetLastError();
+		const cudaError_t e = cudaHostRegister(const_cast<void*>(host_ptr), bytes, cudaHostRegisterDefault);
+		if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return; }
+		XB_CUDA(e);
+	});
+}
+xb_status xb_release(const void* host_ptr) {
+	return guard([&] {
+		if (!host_ptr) return;
+		const cudaError_t e = cudaHostUnregister(const_cast<void*>(host_ptr));
+		if (e == cudaErrorHostMemoryNotRegistered) { cudaGetLastError(); return; }
+		XB_CUDA(e);
+	});
+}
 xb_status xb_upload(void* dst, const void* src, size_t bytes) {
 	return guard([&] { ensure_init(); if (bytes) XB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx().stream)); });
 }
