@@ -139,6 +139,10 @@ xb_status xb_tt_move_core(xb_tt* tt, size_t position, int keep_rank);
  * svals (optional, may be NULL): receives the kept singular values per edge, edge e at svals[e*stride ..]. */
 xb_status xb_tt_round(xb_tt* tt, const size_t* max_ranks, double eps);
 xb_status xb_tt_round_svals(xb_tt* tt, const size_t* max_ranks, double eps, double* svals, size_t stride);
+/* TTNetwork::soft_threshold (ttNetwork.cpp:688-713): the sweep of round() without rank cap and with eps = 0, every singular
+ * value replaced by max(0, sigma - tau) (tensorNetwork.cpp:766); ranks do not change.  taus has d-1 entries and — as in the
+ * reference, :700 — taus[i] belongs to the i-th edge *from the right*.  prevent_zero is accepted and ignored, as there. */
+xb_status xb_tt_soft_threshold(xb_tt* tt, const double* taus, int prevent_zero);
 /* batch of independent roundings (BASELINE config 5): tts[b] rounded to max_rank */
 xb_status xb_tt_round_batched(xb_tt** tts, size_t batch, size_t max_rank, double eps);
 xb_status xb_tt_frob_norm(const xb_tt* tt, double* result);                        /* ttNetwork.cpp:782-789 */
@@ -148,6 +152,9 @@ xb_status xb_tt_scale(xb_tt* tt, double factor);                                
 xb_status xb_tt_add(xb_tt** out, const xb_tt* a, const xb_tt* b);                  /* operator+  (ttNetwork.cpp:797-847) */
 xb_status xb_tt_apply(xb_tt** out, const xb_tt* A, const xb_tt* x);               /* y(i&0)=A(i/2,j/2)*x(j&0), ttStack.cpp:197-300 */
 xb_status xb_tt_from_dense(xb_tt** out, const double* host, size_t d, const size_t* dims, double eps, size_t max_rank); /* ttNetwork.cpp:112-160 */
+/* the same constructor with per-bond rank caps (max_ranks: d-1 entries, NULL = unlimited) and for TTOperators: dims then has
+ * 2d entries (m_1..m_d, n_1..n_d), the dense operator is reshuffled to (m_1,n_1,m_2,n_2,...) first (ttNetwork.cpp:129-135) */
+xb_status xb_tt_from_dense_ex(xb_tt** out, const double* host, size_t d, const size_t* dims, int is_operator, double eps, const size_t* max_ranks);
 xb_status xb_tt_to_dense(const xb_tt* tt, double* host);                           /* tensorNetwork.cpp:287-306 */
 
 /* ALS / DMRG (src/xerus/algorithms/als.cpp:483-553).  A may be NULL (projection of b, als.cpp:541-545).
@@ -160,8 +167,11 @@ typedef struct {
 	size_t   num_half_sweeps;        /* 0 = until convergence */
 	double   convergence_epsilon;    /* als.h:137 default 1e-6 */
 	int      preserve_core_position; /* als.h:120 default true */
-	double   local_tolerance;        /* relative residual of the local solves (0 -> 1e-13) */
+	double   local_tolerance;        /* relative residual of the iterative local solves (0 -> 1e-15, i.e. down to the rounding
+	                                    floor: the solver stops by itself when the residual stagnates there) */
 	size_t   local_max_iterations;   /* 0 -> 4 * local size, capped */
+	int      local_solver;           /* 0: ALSVariant::lapack_solver semantics (als.cpp:43-71; dense or matrix-free CG);
+	                                    1: ALSVariant::ASD_solver (als.cpp:73-103), one exact-line-search gradient step per site */
 } xb_als_options;
 xb_status xb_als_default_options(xb_als_options* opt, uint32_t sites, int assume_spd);
 xb_status xb_als_solve(const xb_tt* A, xb_tt* x, const xb_tt* b, const xb_als_options* opt, double* energy,

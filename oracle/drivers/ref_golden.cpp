@@ -304,9 +304,57 @@ static void als_section(Writer& w) {
 	}
 }
 
+// Second container (tests/golden/xerus_ref_v2.npz, `ref_golden <out.bin> v2`): rows a11 / a12 / a19 of SURVEY.md 8 that the first
+// file does not cover — soft_threshold, the TT-SVD constructor for TTOperators and with per-bond rank caps, ASD / ASD_SPD.
+static void v2_section(Writer& w) {
+	// ---------- TTNetwork::soft_threshold (ttNetwork.cpp:688-713): scalar tau and per-edge taus (taus[i]: i-th edge from the right)
+	misc::randomEngine.seed(0xBAADF00D);
+	TTTensor A = TTTensor::random(std::vector<size_t>(8, 4), std::vector<size_t>(7, 32));
+	w.tt("st.in", A);
+	{ TTTensor T = A; T.soft_threshold(2.0e4); w.tt("st.scalar", T); w.sizes("st.scalar.ranks", T.ranks()); w.scalar("st.scalar.norm", frob_norm(T)); }
+	{
+		const std::vector<double> taus = {1.0e4, 3.0e4, 0.0, 6.0e4, 2.5e4, 5.0e3, 4.0e4};
+		w.vec("st.taus", taus);
+		TTTensor T = A; T.soft_threshold(taus);
+		w.tt("st.vector", T); w.sizes("st.vector.ranks", T.ranks()); w.scalar("st.vector.norm", frob_norm(T));
+	}
+	{ TTTensor T = A; T.move_core(5); T.soft_threshold(1.5e6); w.tt("st.core5", T); w.sizes("st.core5.ranks", T.ranks()); }   // thresholds whole spectra to 0
+	// ---------- TT-SVD constructor: TTOperator (reshuffle branch, ttNetwork.cpp:129-135) and per-bond rank caps
+	misc::randomEngine.seed(0xBAADF00D);
+	{
+		Tensor full = randn({3, 4, 2, 3, 2, 5, 3, 2});         // (m_1..m_4, n_1..n_4)
+		w.tensor("opsvd.full", full);
+		TTOperator T(full, 1e-14);
+		w.tt("opsvd.tt", T); w.sizes("opsvd.ranks", T.ranks());
+		TTOperator T2(full, 0.0, std::vector<size_t>{4, 7, 3});
+		w.tt("opsvd.tt_caps", T2); w.sizes("opsvd.caps.ranks", T2.ranks()); w.tensor("opsvd.tt_caps.dense", Tensor(T2));
+		Tensor f2 = randn({4, 3, 5, 2, 4});
+		w.tensor("ttsvd2.full", f2);
+		TTTensor T3(f2, 0.0, std::vector<size_t>{2, 5, 6, 3});
+		w.tt("ttsvd2.tt_caps", T3); w.sizes("ttsvd2.caps.ranks", T3.ranks()); w.tensor("ttsvd2.tt_caps.dense", Tensor(T3));
+	}
+	// ---------- ASD / ASD_SPD (als.cpp:73-103, :562-563): fixed numbers of half-sweeps from the same start as the ALS goldens
+	struct Case { const char* tag; size_t d, n, r; };
+	for (const Case& c : {Case{"asd_small", 6, 4, 3}, Case{"asd_mid", 8, 5, 6}}) {
+		misc::randomEngine.seed(0xBAADF00D);
+		const std::string tag = c.tag;
+		TTOperator Aop = laplace_operator(c.d, c.n);
+		TTTensor b = TTTensor::ones(std::vector<size_t>(c.d, c.n));
+		TTTensor x0 = TTTensor::random(std::vector<size_t>(c.d, c.n), std::vector<size_t>(c.d - 1, c.r));
+		x0 /= frob_norm(x0);                                   // a start of norm one: gradient steps are sensitive to scale
+		w.tt(tag + ".x0", x0);
+		for (size_t hs : {size_t(1), size_t(2), size_t(6)}) {
+			{ TTTensor x = x0; const double e = ASD_SPD(Aop, x, b, hs); w.tt(tag + ".spd_hs" + std::to_string(hs) + ".x", x); w.scalar(tag + ".spd_hs" + std::to_string(hs) + ".energy", e); }
+			// the reference's non-SPD step (ratio of norms, als.cpp:97) diverges on this operator: only the first steps are comparable
+			if (hs <= 2) { TTTensor x = x0; const double e = ASD(Aop, x, b, hs); w.tt(tag + ".gen_hs" + std::to_string(hs) + ".x", x); w.scalar(tag + ".gen_hs" + std::to_string(hs) + ".energy", e); }
+		}
+	}
+}
+
 int main(int argc, char** argv) {
-	if (argc < 2) { std::fprintf(stderr, "usage: %s <out.bin>\n", argv[0]); return 2; }
+	if (argc < 2) { std::fprintf(stderr, "usage: %s <out.bin> [v2]\n", argv[0]); return 2; }
 	Writer w(argv[1]);
+	if (argc > 2 && std::string(argv[2]) == "v2") { v2_section(w); return 0; }
 	blas_section(w);
 	tensor_section(w);
 	tt_section(w);

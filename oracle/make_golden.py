@@ -43,15 +43,18 @@ def main():
     exe = os.path.join(HERE, "_ref", "ref_golden")
     if not os.path.exists(exe):
         sys.exit("build it first: make -C oracle")
-    with tempfile.TemporaryDirectory() as td:
-        dump = os.path.join(td, "golden.bin")
-        subprocess.check_call([exe, dump])
-        rec = read_container(dump)
     dst = os.path.join(ROOT, "tests", "golden")
     os.makedirs(dst, exist_ok=True)
-    np.savez_compressed(os.path.join(dst, "xerus_ref_v1.npz"), **rec)
-    print("wrote %d records (%.1f KB raw) to tests/golden/xerus_ref_v1.npz"
-          % (len(rec), sum(v.nbytes for v in rec.values()) / 1024))
+    # `python oracle/make_golden.py v2` regenerates only the second file (soft_threshold, operator TT-SVD, ASD)
+    for name, extra in [("xerus_ref_v1.npz", []), ("xerus_ref_v2.npz", ["v2"])]:
+        if sys.argv[1:] and sys.argv[1:] != extra:
+            continue
+        with tempfile.TemporaryDirectory() as td:
+            dump = os.path.join(td, "golden.bin")
+            subprocess.check_call([exe, dump] + extra)
+            rec = read_container(dump)
+        np.savez_compressed(os.path.join(dst, name), **rec)
+        print("wrote %d records (%.1f KB raw) to tests/golden/%s" % (len(rec), sum(v.nbytes for v in rec.values()) / 1024, name))
 
 
 if __name__ == "__main__":

@@ -304,6 +304,21 @@ class TT:
             self.move_core(initial_core, False, signed_quirk)                 # (:662-664)
         return svals
 
+    def soft_threshold(self, taus, signed_quirk=True):
+        """TTNetwork::soft_threshold (ttNetwork.cpp:688-713): the sweep of round() with no rank cap, eps = 0 and every singular
+        value replaced by max(0, sigma - tau); taus[i] belongs to the i-th edge from the right (:700)."""
+        d = self.d
+        if np.isscalar(taus):
+            taus = [float(taus)] * (d - 1)
+        assert len(taus) == d - 1
+        initial_canon, initial_core = self.canonicalized, self.core_position
+        self.move_core(d - 1, False, signed_quirk)
+        for i in range(d - 1):
+            self.round_edge(d - 1 - i, d - 2 - i, 0, 0.0, taus[i], signed_quirk)
+        self.canonicalized, self.core_position = True, 0
+        if initial_canon:
+            self.move_core(initial_core, False, signed_quirk)
+
     # -- values --------------------------------------------------------------------------------------------------
     def to_dense(self):
         """operator Tensor() (tensorNetwork.cpp:287-306) for a chain; operators come out as (m_1..m_d, n_1..n_d)."""
@@ -431,15 +446,23 @@ def tt_apply(A, x):
     return TT(cores)
 
 
-def tt_svd(full, eps=EPSILON, max_rank=0):
-    """TT-SVD constructor TTTensor(Tensor, eps, maxRank) (ttNetwork.cpp:112-160): successive SVDs from the right,
-    Sigma pushed to the left remainder (:151-155)."""
+def tt_svd(full, eps=EPSILON, max_rank=0, is_operator=False):
+    """TT-SVD constructor TTNetwork(Tensor, eps, maxRanks) (ttNetwork.cpp:112-160): successive SVDs from the right,
+    Sigma pushed to the left remainder (:151-155).  max_rank: 0 = no cap, an int, or one cap per bond.  Operators: `full` has
+    modes (m_1..m_d, n_1..n_d) and is reshuffled to (m_1,n_1,m_2,n_2,...) first (:129-135)."""
+    N = 2 if is_operator else 1
+    d = full.ndim // N
+    if is_operator:
+        shuffle = [0] * full.ndim
+        for i in range(d):
+            shuffle[i], shuffle[d + i] = 2 * i, 2 * i + 1
+        full = reshuffle(full, shuffle)
     dims = full.shape
-    d = len(dims)
+    caps = [int(max_rank)] * (d - 1) if np.isscalar(max_rank) else [int(r) for r in max_rank]
     cores = [None] * d
     remains = full.reshape(dims + (1,))
     for pos in range(d - 1, 0, -1):
-        U, S, Vt = calculate_svd(remains, pos, max_rank, eps)
+        U, S, Vt = calculate_svd(remains, pos * N, caps[pos - 1], eps)
         cores[pos] = Vt
         remains = U * S
     cores[0] = remains.reshape((1,) + remains.shape)
@@ -475,7 +498,8 @@ class ALSVariant:
 
     sites = 1 (ALS) or 2 (DMRG); assume_spd selects x^T A x (SPD) or x^T A^T A x environments."""
 
-    def __init__(self, sites=1, assume_spd=True, convergence_epsilon=1e-6, fix_dmrg_turn=False):
+    def __init__(self, sites=1, assume_spd=True, convergence_epsilon=1e-6, fix_dmrg_turn=False, solver="lapack"):
+        self.solver = solver          # "lapack": ALSVariant::lapack_solver (als.cpp:43-71); "ASD": ALSVariant::ASD_solver (:73-103)
         self.sites = sites
         self.assume_spd = assume_spd
         self.convergence_epsilon = convergence_epsilon
@@ -575,7 +599,7 @@ class ALSVariant:
         half_sweeps = 0
         while True:
             if A is not None:
-                xs = self._local_solve(opL[-1], opR[-1], rhL[-1], rhR[-1], Ac, b.cores, cur, increasing, target_rank)
+                xs = self._local_solve(opL[-1], opR[-1], rhL[-1], rhR[-1], Ac, b.cores, cur, increasing, target_rank, x.cores[cur])
                 for p in range(sites):
                     x.cores[cur + p] = xs[p]
                 if sites > 1:   # set_component on a non-core index clears the flag (ttNetwork.cpp:491)
@@ -707,9 +731,19 @@ class ALSVariant:
             T = np.einsum("...cd,cdr->...r", T, envR)                     # envR (rb, a, r)
         return T
 
-    def _local_solve(self, envL, envR, rhsL, rhsR, Acores, bcores, cur, increasing, target_rank):
+    def _local_solve(self, envL, envR, rhsL, rhsR, Acores, bcores, cur, increasing, target_rank, xcur=None):
         Aloc, shape = self.local_operator(envL, envR, Acores, cur)
         bloc = self.local_rhs(rhsL, rhsR, Acores, bcores, cur)
+        if self.solver == "ASD":                                                # (:73-103)
+            assert self.sites == 1, "ASD only defined for single site alternation at the moment"
+            xv = xcur.reshape(-1)
+            grad = bloc.reshape(-1) - Aloc @ xv                                 # (:81)
+            if self.assume_spd:
+                alpha = float(grad @ grad) / float(grad @ (Aloc @ grad))        # (:85)
+            else:
+                grad = Aloc.T @ grad                                            # (:87)
+                alpha = float(np.linalg.norm(grad)) / float(np.linalg.norm(Aloc @ grad))   # (:89): norms, not their squares
+            return [(xv + alpha * grad).reshape(shape)]
         xloc = solve(Aloc, bloc.reshape(-1)).reshape(shape)
         sites = self.sites
         out = [None] * sites
@@ -732,6 +766,8 @@ ALS = ALSVariant(1, False)
 ALS_SPD = ALSVariant(1, True)
 DMRG = ALSVariant(2, False)
 DMRG_SPD = ALSVariant(2, True)
+ASD = ALSVariant(1, False, solver="ASD")
+ASD_SPD = ALSVariant(1, True, solver="ASD")
 
 
 def residual(A, x, b):

@@ -300,3 +300,61 @@ def test_als_projection_without_operator(golden):
     assert abs(d(X) - float(golden["proj.projNorm"])) < 1e-7 * float(golden["proj.projNorm"])
     assert d(X) < d(X0)                                  # als.cxx:100  TEST(projNorm < roundNorm)
     assert O.tt_distance_rel(X, load_tt(golden, "proj.x")) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------------------- v2 --------
+# second golden file (oracle/drivers/ref_golden.cpp v2_section): soft_threshold, operator TT-SVD / rank caps, ASD
+@pytest.fixture(scope="module")
+def golden2():
+    import os
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "xerus_ref_v2.npz")))
+
+
+@pytest.mark.parametrize("name", ["scalar", "vector", "core5"])
+def test_soft_threshold(golden2, name):
+    t = load_tt(golden2, "st.in")
+    if name == "scalar":
+        t.soft_threshold(2.0e4)
+    elif name == "vector":
+        t.soft_threshold(list(golden2["st.taus"]))
+    else:
+        t.move_core(5)
+        t.soft_threshold(1.5e6)                      # every spectrum goes to zero: the ranks collapse edge by edge
+    ref = load_tt(golden2, "st." + name)
+    assert t.ranks() == [int(v) for v in golden2["st.%s.ranks" % name]]
+    if name == "core5":
+        assert t.core_position == 5
+        assert float(np.linalg.norm(t.to_dense())) == 0.0 and float(np.linalg.norm(ref.to_dense())) == 0.0
+    else:
+        assert abs(t.frob_norm() - float(golden2["st.%s.norm" % name])) < 1e-12 * t.frob_norm()
+        assert O.tt_distance_rel(t, ref) < 1e-12
+
+
+def test_tt_svd_operator_and_rank_caps(golden2):
+    full = golden2["opsvd.full"]                                   # (m_1..m_4, n_1..n_4)
+    t = O.tt_svd(full, 1e-14, is_operator=True)
+    assert t.ranks() == [int(v) for v in golden2["opsvd.ranks"]]
+    assert np.linalg.norm(t.to_dense() - full) < 1e-12 * np.linalg.norm(full)
+    t2 = O.tt_svd(full, 0.0, [4, 7, 3], is_operator=True)
+    assert t2.ranks() == [int(v) for v in golden2["opsvd.caps.ranks"]]
+    assert np.linalg.norm(t2.to_dense() - golden2["opsvd.tt_caps.dense"]) < 1e-11 * np.linalg.norm(full)
+    t3 = O.tt_svd(golden2["ttsvd2.full"], 0.0, [2, 5, 6, 3])
+    assert t3.ranks() == [int(v) for v in golden2["ttsvd2.caps.ranks"]]
+    assert np.linalg.norm(t3.to_dense() - golden2["ttsvd2.tt_caps.dense"]) < 1e-11 * np.linalg.norm(golden2["ttsvd2.full"])
+
+
+@pytest.mark.parametrize("tag,d,n", [("asd_small", 6, 4), ("asd_mid", 8, 5)])
+@pytest.mark.parametrize("hs", [1, 2, 6])
+def test_asd(golden2, tag, d, n, hs):
+    A, b = O.laplace_operator(d, n), O.tt_ones([n] * d)
+    x = load_tt(golden2, tag + ".x0")
+    e = O.ASD_SPD(A, x, b, hs)
+    e_ref = float(golden2["%s.spd_hs%d.energy" % (tag, hs)])
+    assert abs(e - e_ref) < 1e-10 * abs(e_ref)
+    assert O.tt_distance_rel(x, load_tt(golden2, "%s.spd_hs%d.x" % (tag, hs))) < 1e-9
+    if hs <= 2:
+        x = load_tt(golden2, tag + ".x0")
+        e = O.ASD(A, x, b, hs)
+        e_ref = float(golden2["%s.gen_hs%d.energy" % (tag, hs)])
+        assert abs(e - e_ref) < 1e-8 * abs(e_ref)
+        assert O.tt_distance_rel(x, load_tt(golden2, "%s.gen_hs%d.x" % (tag, hs))) < 1e-7

@@ -23,7 +23,7 @@ class XerusError(RuntimeError):
 class ALSOptions(C.Structure):
     _fields_ = [("sites", C.c_uint32), ("assume_spd", C.c_int), ("num_half_sweeps", C.c_size_t),
                 ("convergence_epsilon", C.c_double), ("preserve_core_position", C.c_int),
-                ("local_tolerance", C.c_double), ("local_max_iterations", C.c_size_t)]
+                ("local_tolerance", C.c_double), ("local_max_iterations", C.c_size_t), ("local_solver", C.c_int)]
 
 
 def declared_symbols():
@@ -68,6 +68,7 @@ _SIGS = {
     "xb_tt_frob_norm": [vp, dp], "xb_tt_inner": [vp, vp, dp], "xb_tt_distance": [vp, vp, dp],
     "xb_tt_scale": [vp, C.c_double], "xb_tt_add": [P(vp), vp, vp], "xb_tt_apply": [P(vp), vp, vp],
     "xb_tt_from_dense": [P(vp), dp, sz, szp, C.c_double, sz], "xb_tt_to_dense": [vp, dp],
+    "xb_tt_from_dense_ex": [P(vp), dp, sz, szp, C.c_int, C.c_double, szp], "xb_tt_soft_threshold": [vp, dp, C.c_int],
     "xb_als_default_options": [P(ALSOptions), C.c_uint32, C.c_int],
     "xb_als_solve": [vp, vp, vp, P(ALSOptions), dp, szp],
     "xb_env_apply": [vp, vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz],

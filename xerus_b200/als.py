@@ -10,7 +10,7 @@ from .tt import TTOperator, TTTensor
 
 
 class ALSVariant:
-    def __init__(self, sites, numHalfSweeps, assumeSPD, localTolerance=0.0, localMaxIterations=0):
+    def __init__(self, sites, numHalfSweeps, assumeSPD, localTolerance=0.0, localMaxIterations=0, localSolver="lapack"):
         if sites <= 0:
             raise XerusError(1, "sites must be positive")          # als.h:141
         self.sites = int(sites)
@@ -20,6 +20,9 @@ class ALSVariant:
         self.assumeSPD = bool(assumeSPD)
         self.localTolerance = float(localTolerance)
         self.localMaxIterations = int(localMaxIterations)
+        if localSolver not in ("lapack", "ASD"):
+            raise XerusError(1, "localSolver must be 'lapack' (ALSVariant::lapack_solver) or 'ASD' (ALSVariant::ASD_solver)")
+        self.localSolver = localSolver                             # als.h:123-124: the reference takes a std::function here
         self.last_local_iterations = 0
 
     def __call__(self, *args):
@@ -45,6 +48,7 @@ class ALSVariant:
         opt.preserve_core_position = int(self.preserveCorePosition)
         opt.local_tolerance = self.localTolerance
         opt.local_max_iterations = self.localMaxIterations
+        opt.local_solver = 1 if self.localSolver == "ASD" else 0
         energy = C.c_double()
         iters = C.c_size_t()
         call("xb_als_solve", A._h if A is not None else None, x._h, b._h, C.byref(opt), C.byref(energy), C.byref(iters))
@@ -56,3 +60,5 @@ ALS = ALSVariant(1, 0, False)        # als.cpp:556-563
 ALS_SPD = ALSVariant(1, 0, True)
 DMRG = ALSVariant(2, 0, False)
 DMRG_SPD = ALSVariant(2, 0, True)
+ASD = ALSVariant(1, 0, False, localSolver="ASD")
+ASD_SPD = ALSVariant(1, 0, True, localSolver="ASD")

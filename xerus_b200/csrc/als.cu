@@ -927,7 +927,7 @@ struct Als {
 	// CG is restarted from the current iterate until it meets the tolerance (residual replacement).
 	DT local_solve_cg(const DT& rhs, const DT& v0) {
 		const size_t n = rhs.size();
-		const double tol = opt.local_tolerance > 0 ? opt.local_tolerance : 1e-12;
+		const double tol = opt.local_tolerance > 0 ? opt.local_tolerance : 1e-15;
 		const size_t max_it = opt.local_max_iterations ? opt.local_max_iterations : std::min<size_t>(std::max<size_t>(4 * n, 64), 4000);
 		DT xv = dt_copy(v0);
 		xv.dims = rhs.dims;
@@ -1043,6 +1043,25 @@ struct Als {
 		DT rhs = local_rhs();
 		// warm start: the current component(s) contracted to one tensor (l, n_1..n_s, r)
 		DT v0 = dt_view(x->core[cur], {x->rank[cur], x->dim_m[cur], x->rank[cur + 1]});
+		if (opt.local_solver == 1) {
+			// ALSVariant::ASD_solver (als.cpp:73-103): x += alpha * grad with grad = b~ - A~ x and the step the reference takes:
+			// SPD: <g,g>/<g,A~g>; otherwise g <- A~^T g first and alpha = ||g|| / ||A~ g|| (norms, not their squares, :97)
+			XB_REQUIRE(sites == 1, "ASD only defined for single site alternation at the moment");   // :78
+			const size_t n = rhs.size();
+			DT g = dt_copy(rhs);
+			{ DT Ax = local_apply(v0); axpy(g.data(), -1.0, Ax.p, n); }
+			double alpha;
+			if (opt.assume_spd) {
+				DT Ag = local_apply(g);
+				alpha = dt_dot(g, g) / dt_dot(g, Ag);
+			} else {
+				g = local_apply(g);                                      // the projected A^T A is symmetric
+				DT Ag = local_apply(g);
+				alpha = std::sqrt(dt_dot(g, g)) / std::sqrt(dt_dot(Ag, Ag));
+			}
+			if (alpha == alpha && std::isfinite(alpha)) axpy(x->core[cur].p, alpha, g.p, n);   // zero gradient: nothing to do
+			return;
+		}
 		DT v0own;
 		if (sites == 2) {
 			v0own = dt_contract(v0, {2}, xcore(cur + 1), {0});
@@ -1062,7 +1081,7 @@ struct Als {
 		svd.factor(sol.p, l * n1, n2 * r);
 		// the reference truncates the split with eps = EPSILON (als.cpp:55,:65); below the accuracy of an iterative
 		// local solve singular values are noise, so the CG path cuts at its own tolerance instead
-		const double tol_cg = opt.local_tolerance > 0 ? opt.local_tolerance : 1e-12;
+		const double tol_cg = opt.local_tolerance > 0 ? opt.local_tolerance : 1e-15;
 		const size_t k = truncation_rank(svd.S, target_rank[cur], direct ? EPSILON : std::max(EPSILON, 10.0 * tol_cg));
 		DBuf U(l * n1 * k), Vt(k * n2 * r);
 		svd.extract(U, Vt, k, !increasing, increasing, nullptr);
@@ -1144,6 +1163,7 @@ xb_status xb_als_default_options(xb_als_options* opt, uint32_t sites, int assume
 		opt->preserve_core_position = 1;                           // als.h:138
 		opt->local_tolerance = 0.0;
 		opt->local_max_iterations = 0;
+		opt->local_solver = 0;
 	});
 }
 

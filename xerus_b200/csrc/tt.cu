@@ -122,7 +122,9 @@ static void round_edge(xb_tt* t, size_t from, size_t max_rank, double eps, doubl
 	}
 }
 
-static void round_tt(xb_tt* t, const size_t* max_ranks, double eps, double* svals, size_t stride) {   // ttNetwork.cpp:644-665
+// taus != nullptr: TTNetwork::soft_threshold (ttNetwork.cpp:688-713) — same sweep, no rank cap, eps = 0, taus[i] for the i-th
+// edge from the right (:700)
+static void round_tt(xb_tt* t, const size_t* max_ranks, double eps, double* svals, size_t stride, const double* taus = nullptr) {   // ttNetwork.cpp:644-665
 	XB_REQUIRE(eps >= 0.0 && eps < 1.0, "_eps must be smaller than one.");
 	const size_t d = t->d;
 	const bool initial_canon = t->canonicalized;
@@ -131,7 +133,8 @@ static void round_tt(xb_tt* t, const size_t* max_ranks, double eps, double* sval
 	std::vector<double> sv;
 	for (size_t i = 0; i + 1 < d; ++i) {                                 // :656-658
 		const size_t from = d - 1 - i, edge = from - 1;
-		round_edge(t, from, max_ranks[edge], eps, 0.0, true, svals ? &sv : nullptr);
+		if (taus) round_edge(t, from, 0, 0.0, taus[i], true, nullptr);
+		else round_edge(t, from, max_ranks[edge], eps, 0.0, true, svals ? &sv : nullptr);
 		if (svals) {
 			XB_REQUIRE(sv.size() <= stride, "svals stride too small");
 			std::copy(sv.begin(), sv.end(), svals + edge * stride);
@@ -391,6 +394,16 @@ xb_status xb_tt_round_svals(xb_tt* tt, const size_t* max_ranks, double eps, doub
 }
 xb_status xb_tt_round(xb_tt* tt, const size_t* max_ranks, double eps) { return xb_tt_round_svals(tt, max_ranks, eps, nullptr, 0); }
 
+xb_status xb_tt_soft_threshold(xb_tt* tt, const double* taus, int /*prevent_zero*/) {
+	return guard([&] {
+		ensure_init();
+		require_correct_format(tt);
+		XB_REQUIRE(taus || tt->d == 1, "There must be exactly degree/N-1 taus.");
+		static const double none = 0.0;                                  // d == 1: no edge, nothing is read
+		round_tt(tt, nullptr, 0.0, nullptr, 0, taus ? taus : &none);
+	});
+}
+
 xb_status xb_tt_round_batched(xb_tt** tts, size_t batch, size_t max_rank, double eps) {
 	return guard([&] {
 		ensure_init();
@@ -446,31 +459,47 @@ xb_status xb_tt_to_dense(const xb_tt* tt, double* host) {
 	});
 }
 
-// TT-SVD constructor TTTensor(Tensor, eps, maxRank) (ttNetwork.cpp:112-160): successive SVDs from the right, Sigma
+// TT-SVD constructor TTNetwork(Tensor, eps, maxRanks) (ttNetwork.cpp:112-160): successive SVDs from the right, Sigma
 // pushed into the left remainder (:151-155).  Result is canonicalised with the core at position 0.
-xb_status xb_tt_from_dense(xb_tt** out, const double* host, size_t d, const size_t* dims, double eps, size_t max_rank) {
+xb_status xb_tt_from_dense_ex(xb_tt** out, const double* host, size_t d, const size_t* dims, int is_operator, double eps, const size_t* max_ranks) {
 	return guard([&] {
 		ensure_init();
 		XB_REQUIRE(out && host && dims && d > 0, "xb_tt_from_dense: bad arguments");
-		XB_REQUIRE(eps >= 0.0 && eps < 1.0, "eps must be in [0,1)");
+		XB_REQUIRE(eps >= 0.0 && eps < 1.0, "_eps must be positive and smaller than one.");       // ttNetwork.cpp:114
+		const bool op = is_operator != 0;
+		std::vector<size_t> ext(d);
 		size_t total = 1;
-		for (size_t i = 0; i < d; ++i) { XB_REQUIRE(dims[i] > 0, "dimension 0"); total *= dims[i]; }
+		for (size_t i = 0; i < d; ++i) {
+			XB_REQUIRE(dims[i] > 0 && (!op || dims[d + i] > 0), "dimension 0");
+			ext[i] = dims[i] * (op ? dims[d + i] : 1);
+			total *= ext[i];
+		}
+		for (size_t i = 0; max_ranks && i + 1 < d; ++i) XB_REQUIRE(max_ranks[i] > 0, "Maximal ranks must be strictly positive.");   // :116
 		xb_tt* t = new xb_tt();
 		try {
-			t->d = d; t->is_operator = false; t->dim_m.assign(dims, dims + d); t->dim_n.assign(d, 1);
+			t->d = d; t->is_operator = op; t->dim_m.assign(dims, dims + d);
+			if (op) t->dim_n.assign(dims + d, dims + 2 * d); else t->dim_n.assign(d, 1);
 			t->rank.assign(d + 1, 1);
 			t->core.resize(d);
 			DBuf remains(total);
 			XB_CUDA(cudaMemcpyAsync(remains.p, host, total * sizeof(double), cudaMemcpyHostToDevice, ctx().stream));
+			if (op && d > 1) {                                 // (m_1..m_d, n_1..n_d) -> (m_1,n_1,m_2,n_2,...)   (:129-135)
+				XB_REQUIRE(2 * d <= 16, "operator too long to reshuffle (at most 8 sites)");
+				std::vector<size_t> sh(2 * d);
+				for (size_t i = 0; i < d; ++i) { sh[i] = 2 * i; sh[d + i] = 2 * i + 1; }
+				DBuf p(total);
+				permute(p, remains, dims, sh.data(), 2 * d);
+				remains = std::move(p);
+			}
 			std::vector<size_t> prefix(d + 1, 1);
-			for (size_t i = 0; i < d; ++i) prefix[i + 1] = prefix[i] * dims[i];
-			size_t r = 1;                                     // remains is (n_0...n_pos-1) x (n_pos * r)
+			for (size_t i = 0; i < d; ++i) prefix[i + 1] = prefix[i] * ext[i];
+			size_t r = 1;                                     // remains is (e_0...e_pos-1) x (e_pos * r)
 			for (size_t pos = d - 1; pos > 0; --pos) {
-				const size_t lrows = prefix[pos], cols = dims[pos] * r;
+				const size_t lrows = prefix[pos], cols = ext[pos] * r;
 				Svd svd;
 				svd.polish = ctx().tt_svd_polish;
 				svd.factor(remains, lrows, cols);
-				const size_t k = truncation_rank(svd.S, max_rank, eps);
+				const size_t k = truncation_rank(svd.S, max_ranks ? max_ranks[pos - 1] : 0, eps);
 				DBuf US(lrows * k), Vt(k * cols);
 				svd.extract(US, Vt, k, true, false, nullptr);
 				t->core[pos] = std::move(Vt);
@@ -484,6 +513,11 @@ xb_status xb_tt_from_dense(xb_tt** out, const double* host, size_t d, const size
 		} catch (...) { delete t; throw; }
 		*out = t;
 	});
+}
+
+xb_status xb_tt_from_dense(xb_tt** out, const double* host, size_t d, const size_t* dims, double eps, size_t max_rank) {
+	std::vector<size_t> mr(d > 1 ? d - 1 : 1, max_rank);
+	return xb_tt_from_dense_ex(out, host, d, dims, 0, eps, max_rank ? mr.data() : nullptr);
 }
 
 } // extern "C"

@@ -232,6 +232,16 @@ class TTNetwork:
             return [sv[i, :rk[i]].copy() for i in range(d - 1)]
         call("xb_tt_round", self._h, _sizes(max_ranks), e)
 
+    def soft_threshold(self, tau, preventZero=False):
+        """TTNetwork::soft_threshold (src/xerus/ttNetwork.cpp:688-713): scalar tau, or one tau per edge — taus[i] belongs to the
+        i-th edge from the right, as in the reference (:700)."""
+        d = self.num_components
+        taus = [float(tau)] * (d - 1) if np.isscalar(tau) else [float(t) for t in tau]
+        if len(taus) + 1 != d:
+            raise XerusError(1, "There must be exactly degree/N-1 taus.")          # ttNetwork.cpp:690
+        arr = (C.c_double * max(1, d - 1))(*taus)
+        call("xb_tt_soft_threshold", self._h, arr, int(bool(preventZero)))
+
     def frob_norm(self):
         r = C.c_double()
         call("xb_tt_frob_norm", self._h, C.byref(r))
@@ -274,20 +284,42 @@ class TTNetwork:
         return out
 
 
+def _from_dense(cls, full, eps, max_ranks):
+    """TT-SVD constructor TTNetwork(Tensor, eps, maxRanks) (src/xerus/ttNetwork.cpp:112-160); max_ranks: 0 / None = unlimited,
+    an int for every bond, or one entry per bond."""
+    full = np.ascontiguousarray(full, dtype=np.float64)
+    N = 2 if cls.is_operator else 1
+    if full.ndim % N:
+        raise XerusError(1, "Number of indicis must be even for TTOperator")           # ttNetwork.cpp:113
+    d = full.ndim // N
+    if max_ranks is None or (np.isscalar(max_ranks) and int(max_ranks) == 0):
+        mr = None
+    elif np.isscalar(max_ranks):
+        mr = _sizes([int(max_ranks)] * max(1, d - 1))
+    else:
+        if len(max_ranks) != d - 1:
+            raise XerusError(1, "We need %d ranks but %d where given" % (d - 1, len(max_ranks)))   # :115
+        mr = _sizes([int(r) for r in max_ranks] or [1])
+    h = C.c_void_p()
+    call("xb_tt_from_dense_ex", C.byref(h), full.ctypes.data_as(_lib.dp), d, _sizes(full.shape), int(cls.is_operator), float(eps), mr)
+    return cls(h)
+
+
 class TTTensor(TTNetwork):
     is_operator = False
 
     @classmethod
     def from_dense(cls, full, eps=EPSILON, max_rank=0):
-        """TT-SVD constructor TTTensor(Tensor, eps, maxRank) (src/xerus/ttNetwork.cpp:112-160)."""
-        full = np.ascontiguousarray(full, dtype=np.float64)
-        h = C.c_void_p()
-        call("xb_tt_from_dense", C.byref(h), full.ctypes.data_as(_lib.dp), full.ndim, _sizes(full.shape), float(eps), int(max_rank))
-        return cls(h)
+        return _from_dense(cls, full, eps, max_rank)
 
 
 class TTOperator(TTNetwork):
     is_operator = True
+
+    @classmethod
+    def from_dense(cls, full, eps=EPSILON, max_rank=0):
+        """TTOperator(Tensor, eps, maxRanks): `full` has modes (m_1..m_d, n_1..n_d) (ttNetwork.cpp:129-135)."""
+        return _from_dense(cls, full, eps, max_rank)
 
     def apply(self, x):
         """y(i&0) = A(i/2, j/2) * x(j&0)  (src/xerus/ttNetwork.cpp:889-967, src/xerus/ttStack.cpp:197-300)."""
