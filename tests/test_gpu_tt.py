@@ -348,3 +348,39 @@ def test_components_in_one_call_roundtrip():
     assert A.ranks() == [4] and all(np.array_equal(a, b) for a, b in zip(A.cores(), ops))
     with pytest.raises(xb.XerusError):
         xb.TTTensor.from_cores([np.zeros((2, 3, 1))])
+
+
+# ---- round plans (captured CUDA graph of a whole sweep, speculative ranks) ---------------------------------------------
+def test_round_plan_replay_is_bit_identical_and_falls_back():
+    """The third round() of a shape replays the graph captured at the second: same kernels in the same order on the same data,
+    so the result is bit for bit the one of the ordinary path; data that break the speculation (a rank-deficient TT of the same
+    shape) raise the device flag and take the ordinary path."""
+    rng = np.random.default_rng(77)
+    dims, r = [3, 4, 5, 4, 3], 7
+    inputs = [xb.TTTensor.random(dims, r, rng) for _ in range(4)]
+    assert all(t.ranks() == inputs[0].ranks() for t in inputs)
+    xb.set_option("round_plans", 0)
+    plain = []
+    for t in inputs:
+        c = t.copy(); c.round(4); plain.append(c.cores())
+    xb.set_option("round_plans", 1)
+    l0 = xb.kernel_launch_count()
+    for t, ref in zip(inputs, plain):
+        c = t.copy(); c.round(4)
+        assert c.ranks() == [3, 4, 4, 3] and c.canonicalized and c.corePosition == 0
+        for a, b in zip(c.cores(), ref):
+            assert np.array_equal(a, b)
+    assert xb.kernel_launch_count() > l0
+    # same shape, but numerically rank deficient at bond 2: the reference (and the ordinary path) cut that bond to 2
+    low = xb.TTTensor.random(dims, [3, 2, 7, 3], rng)
+    cores = low.cores()
+    pad = [np.zeros(s.shape) for s in inputs[0].cores()]
+    for p, c in zip(pad, cores):
+        p[:c.shape[0], :, :c.shape[2]] = c
+    deficient = xb.TTTensor.from_cores(pad, core_position=None)
+    deficient.move_core(0, True)                       # keepRank: same ranks and canonical form as the planned shape
+    assert deficient.ranks() == inputs[0].ranks()
+    ref = to_oracle(deficient); ref.round(4)
+    deficient.round(4)
+    assert deficient.ranks() == ref.ranks()
+    assert O.tt_distance_rel(to_oracle(deficient), ref) < 1e-9

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libxb200.so")
-SOURCES = ["runtime.cu", "gemm_f64.cu", "movement.cu", "qr_f64.cu", "svd_f64.cu", "solve_f64.cu", "blas_api.cu", "tt.cu", "als.cu", "fileio.cu"]
+SOURCES = ["runtime.cu", "gemm_f64.cu", "movement.cu", "qr_f64.cu", "small_f64.cu", "svd_f64.cu", "solve_f64.cu", "blas_api.cu", "tt.cu", "als.cu", "fileio.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]
 

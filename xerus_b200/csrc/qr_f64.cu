@@ -529,6 +529,10 @@ void qr(double* Q, double* R, const double* A, size_t m, size_t n, bool defer_q)
 	XB_REQUIRE(m <= 0x7fffffffULL && n <= 0x7fffffffULL, "Dimension to large for QR");
 	ProfScope prof("qr");
 	const size_t k = std::min(m, n);
+	if (qr_small_fits(m, n)) {           // rank ramps: factor + explicit Q in one single-CTA launch (small_f64.cu)
+		qr_small(Q, (long long)k, 1, R, (long long)n, 1, A, (long long)n, 1, m, n);
+		return;
+	}
 	const size_t npanels = (k + QR_NB - 1) / QR_NB;
 	DBuf W(m * n), Vall(npanels * m * QR_NB), Tall(npanels * QR_NB * QR_NB);
 	const size_t nch_max = (m + QR_CHUNK - 1) / QR_CHUNK;
@@ -587,6 +591,11 @@ void qr(double* Q, double* R, const double* A, size_t m, size_t n, bool defer_q)
 
 void lq(double* L, double* Q, const double* A, size_t m, size_t n) {
 	const size_t k = std::min(m, n);
+	if (qr_small_fits(n, m)) {           // QR of A^T through strides: Q = Qt^T (k x n), L = Rt^T (m x k); no transposed copies
+		ProfScope prof("qr");
+		qr_small(Q, 1, (long long)n, L, 1, (long long)k, A, 1, (long long)n, n, m);
+		return;
+	}
 	DBuf At(m * n), Qt(n * k), Rt(k * m);
 	transpose(At, A, m, n);            // n x m
 	qr(Qt, Rt, At, n, m);              // A^T = Qt * Rt
@@ -606,7 +615,20 @@ void rq(double* R, double* Q, const double* A, size_t m, size_t n) {
 }
 
 // ---- rank revealing variants ------------------------------------------------------------------------------------
+// speculative variant: raises the flag instead of reporting to the host
+__global__ void diag_spec_kernel(const double* __restrict__ A, const size_t k, const size_t ld, unsigned int* __restrict__ flag) {
+	double mn = HUGE_VAL, mx = 0.0;
+	for (size_t i = threadIdx.x; i < k; i += 32) { const double v = fabs(A[i * ld + i]); mn = fmin(mn, v); mx = fmax(mx, v); }
+	for (int o = 16; o > 0; o >>= 1) { mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+	if (threadIdx.x == 0 && !(mx > 0.0 && mn >= 16.0 * 2.220446049250313e-16 * mx)) *flag = 1u;
+}
+
 static bool diag_is_full_rank(const double* M, size_t k, size_t ld) {
+	if (ctx().speculate) {
+		diag_spec_kernel<<<1, 32, 0, ctx().stream>>>(M, k, ld, ctx().spec_flag);
+		XB_LAUNCH_CHECK();
+		return true;
+	}
 	DBuf mm(2);
 	diag_minmax_kernel<<<1, 32, 0, ctx().stream>>>(M, k, ld, mm);
 	XB_LAUNCH_CHECK();

@@ -1,0 +1,318 @@
+// Small-matrix factorisations: one CTA, one launch, everything in shared memory.
+//
+// The ends of every tensor train are rank ramps (2, 4, 8, ... in config 3; 4, 16 in configs 1 and 5) and config 1 is nothing
+// but ramps: matrices of at most a few dozen columns.  On those the general path (cluster QR panels, multi-CTA cooperative
+// Jacobi, pre-conditioning QR, Newton-Schulz polish: ~8 launches per QR, ~25 per SVD, 3-25 us each) is pure launch latency —
+// a config-1 round() was 190 launches for 7 MFLOP.  Here a thin QR (Householder, explicit Q) and a one-sided Jacobi SVD of a
+// matrix with min(m, n) <= 32 columns and max(m, n) <= 256 rows are one launch each:
+//
+//   qr_small   replaces dgeqrf + dorgqr (blasLapackWrapper.cpp:374-437) / their transposed use for LQ on these shapes
+//   svd_small  replaces dgesdd (blasLapackWrapper.cpp:201-232); it leaves the factor in the layout Svd::extract() reads
+//
+// Both work on A * 2^-e (exact power of two; TT cores carry norms like 1e33 .. 1e150 and the kernels sum squares).
+#include "xb_internal.cuh"
+
+namespace xb {
+
+constexpr int SM_WARPS = 16;
+constexpr int SM_THREADS = SM_WARPS * 32;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+	return v;
+}
+
+// max |a| over the CTA -> power-of-two scale (scl = 2^-e with max * scl in [0.5, 1), inv = 2^e); zero / non-finite input: 1
+__device__ void cta_pow2_scale(const double amax_local, double* red /* SM_WARPS + 2 */, double& scl, double& inv) {
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const double w = warp_max(amax_local);
+	if (lane == 0) red[warp] = w;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double s = 0.0;
+		for (int i = 0; i < SM_WARPS; ++i) s = fmax(s, red[i]);
+		double a = 1.0, b = 1.0;
+		if (s > 0.0 && s < HUGE_VAL) { int e; frexp(s, &e); a = ldexp(1.0, -e); b = ldexp(1.0, e); }
+		red[SM_WARPS] = a; red[SM_WARPS + 1] = b;
+	}
+	__syncthreads();
+	scl = red[SM_WARPS]; inv = red[SM_WARPS + 1];
+}
+
+// ---- thin QR --------------------------------------------------------------------------------------------------------------
+// G(i, j) = A[i * ars + j * acs] (m x n), G = Q R with Q (m x k) -> Qo[i * qrs + c * qcs], R (k x n) -> Ro[c * rrs + j * rcs],
+// k = min(m, n).  Strides make the transposed uses (LQ: A = L Q') free.  Shared memory: W[n][ldw] (columns of G, reflectors
+// below the diagonal as in LAPACK), Qs[k][ldw] (columns of Q), tau[k].
+// Schedule: one warp per column and look-ahead — while the other warps apply reflector j to their columns, warp 0 applies it to
+// column j+1 and turns that column into reflector j+1 straight away, so a step costs one block barrier and the reflector
+// arithmetic (reduction, rsqrt, reciprocal) is off the other warps' critical path.
+constexpr int QS_WARPS = 32;
+constexpr int QS_THREADS = QS_WARPS * 32;
+
+__device__ __forceinline__ void qs_make_reflector(double* x, const int j, const int m, const int lane, double* tau) {
+	// dlarfg on x[j..m): beta = -sign(alpha) |x|, v = x / (alpha - beta) below the diagonal, tau = (beta - alpha) / beta
+	double s = 0.0;
+	for (int i = j + 1 + lane; i < m; i += 32) s += x[i] * x[i];
+	s = warp_sum(s);
+	const double alpha = x[j];
+	double t = 0.0, beta = alpha, f = 0.0;
+	if (s > 0.0) {
+		const double n2 = alpha * alpha + s, r = rsqrt(n2), nrm = n2 * r;     // |x| = n2 / sqrt(n2)
+		beta = -copysign(nrm, alpha);
+		t = 1.0 + fabs(alpha) * r;                                            // (beta - alpha) / beta
+		f = copysign(__drcp_rn(fabs(alpha) + nrm), alpha);                    // 1 / (alpha - beta)
+	}
+	__syncwarp();
+	for (int i = j + 1 + lane; i < m; i += 32) x[i] *= f;
+	if (lane == 0) { x[j] = beta; tau[j] = t; }
+	__syncwarp();
+}
+// a -= tau (v' a) v with v = [1; x[j+1..m)]
+__device__ __forceinline__ void qs_apply(const double* x, const double t, double* a, const int j, const int m, const int lane) {
+	double w = 0.0;
+	for (int i = j + 1 + lane; i < m; i += 32) w += x[i] * a[i];
+	const double aj = a[j];
+	w = (warp_sum(w) + aj) * t;
+	for (int i = j + 1 + lane; i < m; i += 32) a[i] -= w * x[i];
+	if (lane == 0) a[j] = aj - w;
+}
+
+__global__ void __launch_bounds__(QS_THREADS, 1) qr_small_kernel(const double* __restrict__ A, const long long ars, const long long acs, const int m, const int n,
+                                                              double* __restrict__ Qo, const long long qrs, const long long qcs,
+                                                              double* __restrict__ Ro, const long long rrs, const long long rcs) {
+	extern __shared__ __align__(16) double sm[];
+	const int k = min(m, n), ldw = m + 1;
+	double* W = sm;                        // n * ldw
+	double* Qs = W + (size_t)n * ldw;      // k * ldw
+	double* tau = Qs + (size_t)k * ldw;    // k
+	double* red = tau + k;                 // QS_WARPS + 2
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+	double amax = 0.0;
+	if (acs == 1) {      // row-major source: neighbouring threads read neighbouring columns
+		for (int e = threadIdx.x; e < m * n; e += QS_THREADS) { const int i = e / n, j = e - i * n; const double v = A[i * ars + j]; W[(size_t)j * ldw + i] = v; amax = fmax(amax, fabs(v)); }
+	} else {
+		for (int e = threadIdx.x; e < m * n; e += QS_THREADS) { const int j = e / m, i = e - j * m; const double v = A[i * ars + j * acs]; W[(size_t)j * ldw + i] = v; amax = fmax(amax, fabs(v)); }
+	}
+	// power-of-two scale from the block maximum
+	{
+		const double w = warp_max(amax);
+		if (lane == 0) red[warp] = w;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			double s = 0.0;
+			for (int i = 0; i < QS_WARPS; ++i) s = fmax(s, red[i]);
+			double a = 1.0, b = 1.0;
+			if (s > 0.0 && s < HUGE_VAL) { int e; frexp(s, &e); a = ldexp(1.0, -e); b = ldexp(1.0, e); }
+			red[QS_WARPS] = a; red[QS_WARPS + 1] = b;
+		}
+		__syncthreads();
+	}
+	const double scl = red[QS_WARPS], inv = red[QS_WARPS + 1];
+	for (int e = threadIdx.x; e < m * n; e += QS_THREADS) { const int j = e / m, i = e - j * m; W[(size_t)j * ldw + i] *= scl; }
+	for (int e = threadIdx.x; e < m * k; e += QS_THREADS) { const int c = e / m, i = e - c * m; Qs[(size_t)c * ldw + i] = (i == c) ? 1.0 : 0.0; }
+	__syncthreads();
+	if (warp == 0) qs_make_reflector(W, 0, m, lane, tau);
+	__syncthreads();
+
+	for (int j = 0; j < k; ++j) {
+		const double* x = W + (size_t)j * ldw;
+		const double t = tau[j];
+		if (warp == 0) {
+			if (j + 1 < n) {
+				double* a = W + (size_t)(j + 1) * ldw;
+				if (t != 0.0) qs_apply(x, t, a, j, m, lane);
+				__syncwarp();
+				if (j + 1 < k) qs_make_reflector(a, j + 1, m, lane, tau);
+			}
+		} else if (t != 0.0) {
+			for (int c = j + 1 + warp; c < n; c += QS_WARPS - 1) qs_apply(x, t, W + (size_t)c * ldw, j, m, lane);
+		}
+		__syncthreads();
+	}
+	// R: upper trapezoid, unscaled
+	for (int e = threadIdx.x; e < k * n; e += QS_THREADS) {
+		const int c = e / n, j = e - c * n;
+		Ro[c * rrs + j * rcs] = (j >= c) ? W[(size_t)j * ldw + c] * inv : 0.0;
+	}
+	// Q = H_0 ... H_{k-1} [I; 0]: reflectors in reverse order; H_j only touches rows >= j, and columns < j of the
+	// partially formed Q are still unit vectors e_c with c < j: untouched
+	for (int j = k - 1; j >= 0; --j) {
+		const double t = tau[j];
+		const double* x = W + (size_t)j * ldw;
+		if (t != 0.0) for (int c = j + warp; c < k; c += QS_WARPS) qs_apply(x, t, Qs + (size_t)c * ldw, j, m, lane);
+		__syncthreads();
+	}
+	if (qcs == 1) {
+		for (int e = threadIdx.x; e < m * k; e += QS_THREADS) { const int i = e / k, c = e - i * k; Qo[i * qrs + c] = Qs[(size_t)c * ldw + i]; }
+	} else {
+		for (int e = threadIdx.x; e < m * k; e += QS_THREADS) { const int c = e / m, i = e - c * m; Qo[i * qrs + c * qcs] = Qs[(size_t)c * ldw + i]; }
+	}
+}
+
+static size_t qr_small_smem(size_t m, size_t n) {
+	const size_t k = std::min(m, n);
+	return ((n + k) * (m + 1) + k + QS_WARPS + 2) * sizeof(double);
+}
+
+bool qr_small_fits(size_t m, size_t n) {
+	if (!ctx().small_kernels) return false;
+	if (std::min(m, n) > 32 || std::max(m, n) > 512) return false;
+	return qr_small_smem(m, n) <= 200 * 1024;
+}
+
+void qr_small(double* Q, long long qrs, long long qcs, double* R, long long rrs, long long rcs, const double* A, long long ars, long long acs, size_t m, size_t n) {
+	static bool attr_set = false;
+	if (!attr_set) {
+		XB_CUDA(cudaFuncSetAttribute(qr_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		attr_set = true;
+	}
+	qr_small_kernel<<<1, QS_THREADS, qr_small_smem(m, n), ctx().stream>>>(A, ars, acs, int(m), int(n), Q, qrs, qcs, R, rrs, rcs);
+	XB_LAUNCH_CHECK();
+}
+
+// ---- one-sided Jacobi SVD ---------------------------------------------------------------------------------------------------
+// Working matrix G (mw x nw, nw <= mw): G(i, j) = A[i * rs + j * cs].  Columns are rotated pairwise (Hestenes) in a round-robin
+// tournament, one warp per pair, squared norms cached and refreshed every sweep; V accumulates the rotations.  A sweep in which
+// no pair had |cos| above `last_cos` is the last one (quadratic convergence), as in the multi-CTA kernels (svd_f64.cu).
+// Output, in the layout Svd::extract() reads: GT row j = [ x_j (mw) ... | v_j (nw) ... ] with leading dimension ld and the V part
+// at voff; Ssorted (descending, unscaled) and perm (rank -> row); scale2 = {2^-e, 2^e}; info = {0, sweeps, not converged}.
+__global__ void __launch_bounds__(SM_THREADS) svd_small_kernel(const double* __restrict__ A, const long long rs, const long long cs, const int mw, const int nw,
+                                                               double* __restrict__ GT, const int ld, const int voff,
+                                                               double* __restrict__ Ssorted, int* __restrict__ perm, double* __restrict__ scale2,
+                                                               unsigned int* __restrict__ info, const double tol, const double last_cos, const int max_sweeps) {
+	extern __shared__ __align__(16) double sm[];
+	const int np = (nw + 1) & ~1;                      // even number of columns (a zero column pads odd ones)
+	const int ldx = mw + 1, ldv = nw + 1;
+	double* X = sm;                                    // np * ldx
+	double* V = X + (size_t)np * ldx;                  // np * ldv
+	double* nrm = V + (size_t)np * ldv;                // np : squared norms
+	double* red = nrm + np;                            // SM_WARPS + 2
+	__shared__ double sweep_max[SM_WARPS];
+	__shared__ int stop_flag;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+	double amax = 0.0;
+	if (cs == 1) {
+		for (int e = threadIdx.x; e < mw * nw; e += SM_THREADS) { const int i = e / nw, j = e - i * nw; const double v = A[i * rs + j]; X[(size_t)j * ldx + i] = v; amax = fmax(amax, fabs(v)); }
+	} else {
+		for (int e = threadIdx.x; e < mw * nw; e += SM_THREADS) { const int j = e / mw, i = e - j * mw; const double v = A[i * rs + j * cs]; X[(size_t)j * ldx + i] = v; amax = fmax(amax, fabs(v)); }
+	}
+	if (np > nw) for (int i = threadIdx.x; i < mw; i += SM_THREADS) X[(size_t)nw * ldx + i] = 0.0;
+	for (int e = threadIdx.x; e < np * nw; e += SM_THREADS) { const int j = e / nw, c = e - j * nw; V[(size_t)j * ldv + c] = (j == c) ? 1.0 : 0.0; }
+	double scl, inv;
+	cta_pow2_scale(amax, red, scl, inv);
+	for (int e = threadIdx.x; e < mw * nw; e += SM_THREADS) { const int j = e / mw, i = e - j * mw; X[(size_t)j * ldx + i] *= scl; }
+	__syncthreads();
+
+	const int npairs = np / 2;
+	const double tol2 = tol * tol;
+	int sweeps = 0;
+	bool converged = (nw == 1);
+	while (!converged && sweeps < max_sweeps) {
+		for (int j = warp; j < np; j += SM_WARPS) {      // refresh the cached squared norms
+			const double* x = X + (size_t)j * ldx;
+			double s = 0.0;
+			for (int i = lane; i < mw; i += 32) s += x[i] * x[i];
+			s = warp_sum(s);
+			if (lane == 0) nrm[j] = s;
+		}
+		if (lane == 0) sweep_max[warp] = 0.0;
+		__syncthreads();
+		double my_max = 0.0;                       // largest cos^2 met in this sweep
+		for (int round = 0; round < np - 1; ++round) {
+			for (int pi = warp; pi < npairs; pi += SM_WARPS) {
+				// circle method: slot 0 is fixed, slots 1 .. np-1 rotate; pair pi = (slot pi, slot np-1-pi)
+				int p = 0, q = np - 2 - pi + round;
+				if (pi != 0) { p = pi - 1 + round; if (p >= np - 1) p -= np - 1; p += 1; }
+				if (q >= np - 1) q -= np - 1;
+				q += 1;
+				if (p > q) { const int t = p; p = q; q = t; }
+				double* xp = X + (size_t)p * ldx; double* xq = X + (size_t)q * ldx;
+				const double a = nrm[p], b = nrm[q];
+				if (a == 0.0 || b == 0.0) continue;
+				double c = 0.0;
+				for (int i = lane; i < mw; i += 32) c += xp[i] * xq[i];
+				c = warp_sum(c);
+				const double c2 = c * c, ab = a * b;
+				if (c2 > my_max * ab) my_max = c2 / ab;       // rare after the first sweeps: the maximum only ever grows
+				if (!(c2 > tol2 * ab)) continue;
+				// rotation that annihilates c in [[a, c], [c, b]], two rsqrt and no division: with d = b - a, h = sqrt(d^2 + 4 c^2):
+				// cos^2 = (1 + |d| / h) / 2, sin cos = sign(d) c / h
+				const double d = b - a;
+				const double r1 = rsqrt(d * d + 4.0 * c2);
+				const double cs2 = 0.5 + 0.5 * fabs(d) * r1;
+				const double r2 = rsqrt(cs2);
+				const double csr = cs2 * r2;
+				const double snr = copysign(c * r1 * r2, d * c);
+				const double tc = copysign(c2 * r1 * r2 * r2, d);      // tan * c
+				double* vp = V + (size_t)p * ldv; double* vq = V + (size_t)q * ldv;
+				for (int i = lane; i < mw; i += 32) { const double u = xp[i], w = xq[i]; xp[i] = csr * u - snr * w; xq[i] = snr * u + csr * w; }
+				for (int i = lane; i < nw; i += 32) { const double u = vp[i], w = vq[i]; vp[i] = csr * u - snr * w; vq[i] = snr * u + csr * w; }
+				if (lane == 0) { nrm[p] = fmax(0.0, a - tc); nrm[q] = b + tc; }
+			}
+			__syncthreads();
+		}
+		if (lane == 0) sweep_max[warp] = my_max;
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			double mx = 0.0;
+			for (int i = 0; i < SM_WARPS; ++i) mx = fmax(mx, sweep_max[i]);
+			stop_flag = (mx <= last_cos * last_cos) ? 1 : 0;
+		}
+		__syncthreads();
+		++sweeps;
+		converged = stop_flag != 0;
+		__syncthreads();
+	}
+	// singular values = column norms (recomputed), ranked in descending order
+	for (int j = warp; j < nw; j += SM_WARPS) {
+		const double* x = X + (size_t)j * ldx;
+		double s = 0.0;
+		for (int i = lane; i < mw; i += 32) s += x[i] * x[i];
+		s = warp_sum(s);
+		if (lane == 0) nrm[j] = sqrt(s);
+	}
+	__syncthreads();
+	for (int j = threadIdx.x; j < nw; j += SM_THREADS) {
+		const double v = nrm[j];
+		int rank = 0;
+		for (int i = 0; i < nw; ++i) { const double u = nrm[i]; rank += (u > v || (u == v && i < j)) ? 1 : 0; }
+		Ssorted[rank] = v * inv;
+		perm[rank] = j;
+	}
+	for (int e = threadIdx.x; e < nw * mw; e += SM_THREADS) { const int j = e / mw, i = e - j * mw; GT[(size_t)j * ld + i] = X[(size_t)j * ldx + i]; }
+	for (int e = threadIdx.x; e < nw * nw; e += SM_THREADS) { const int j = e / nw, c = e - j * nw; GT[(size_t)j * ld + voff + c] = V[(size_t)j * ldv + c]; }
+	if (threadIdx.x == 0) { scale2[0] = scl; scale2[1] = inv; info[0] = 0u; info[1] = unsigned(sweeps); info[2] = converged ? 0u : 1u; }
+}
+
+static size_t svd_small_smem(size_t mw, size_t nw) {
+	const size_t np = (nw + 1) & ~size_t(1);
+	return (np * (mw + 1) + np * (nw + 1) + np + SM_WARPS + 2) * sizeof(double);
+}
+
+bool svd_small_fits(size_t mw, size_t nw) {
+	if (!ctx().small_kernels) return false;
+	if (nw > 32 || mw > 512) return false;
+	return svd_small_smem(mw, nw) <= 200 * 1024;
+}
+
+void svd_small(const double* A, long long rs, long long cs, size_t mw, size_t nw, double* GT, size_t ld, size_t voff, double* Ssorted, int* perm,
+               double* scale2, unsigned int* info, double tol, double last_cos, int max_sweeps) {
+	static bool attr_set = false;
+	if (!attr_set) {
+		XB_CUDA(cudaFuncSetAttribute(svd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		attr_set = true;
+	}
+	svd_small_kernel<<<1, SM_THREADS, svd_small_smem(mw, nw), ctx().stream>>>(A, rs, cs, int(mw), int(nw), GT, int(ld), int(voff), Ssorted, perm, scale2, info,
+	                                                                         tol, last_cos, max_sweeps);
+	XB_LAUNCH_CHECK();
+}
+
+} // namespace xb

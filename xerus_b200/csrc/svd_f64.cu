@@ -1659,6 +1659,20 @@ static bool jacobi_finish(const JacobiPending& pend, int& sweeps_out) {
 	}
 	return converged;
 }
+// speculative execution: the convergence record is checked on the device
+__global__ void jacobi_spec_kernel(const unsigned int* __restrict__ rec, unsigned int* __restrict__ flag) {
+	if (threadIdx.x == 0 && (rec[0] == 0xDEADu || rec[4 + 2] != 0u)) *flag = 2u;
+}
+__global__ void small_spec_kernel(const unsigned int* __restrict__ info, unsigned int* __restrict__ flag) {
+	if (threadIdx.x == 0 && info[2] != 0u) *flag = 2u;
+}
+// raises the flag if the eps rule (tensor.cpp:1468-1473) would cut inside the first k singular values
+__global__ void svd_spec_rank_kernel(const double* __restrict__ S, const int k, const double eps, unsigned int* __restrict__ flag) {
+	const double s0 = S[0];
+	bool bad = !(s0 == s0);
+	for (int j = 1 + threadIdx.x; j < k; j += blockDim.x) if (S[j] <= eps * s0) bad = true;
+	if (bad) *flag = 3u;
+}
 // pending != nullptr: the kernel and the read-back of its convergence record are enqueued, nothing is waited for; the caller calls
 // jacobi_finish() after its next synchronisation of the stream (one host round trip per SVD instead of two)
 template <typename T>
@@ -1677,6 +1691,13 @@ static bool run_persistent(T* gt, size_t ld, size_t voff, const JacobiPlan& p, d
 	else if (p.EH == 4) launch_persistent<T, 4, 512>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
 	else if (p.EH == 8) launch_persistent<T, 8, 512>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
 	else launch_persistent<T, 16, 256>(gt, int(ld), epl_x, epl_v, p, tol2, big2, d_cnt, d_info, max_sweeps, smem_cap);
+	if (c.speculate) {
+		jacobi_spec_kernel<<<1, 32, 0, c.stream>>>(d_info - 4, c.spec_flag);
+		XB_LAUNCH_CHECK();
+		dfree(d_cnt);
+		sweeps_out = 0;
+		return true;
+	}
 	unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch + c.h_scratch_len - 16);
 	XB_CUDA(cudaMemcpyAsync(h_info, d_info - 4, 12 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
 	dfree(d_cnt);
@@ -1699,6 +1720,39 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	// square inputs take the QR step too (from 64 columns on): it is what makes the flipped orientation below possible
 	reduced = (mw > 32) && (mw > nw || (c.svd_flip != 0 && c.svd_square_qr != 0 && nw >= 64));
 	const size_t smem_cap = std::min<size_t>(c.max_smem_optin, 227 * 1024) - 1024;
+
+	if (svd_small_fits(mw, nw)) {
+		// rank ramps: scaling, Jacobi sweeps and the ranking of the singular values in one single-CTA launch (small_f64.cu);
+		// the factor is left in the layout extract() reads
+		reduced = false; flipped = false; permuted = false; q_deferred = false;
+		mdot = mw;
+		voff = (mw + 3) / 4 * 4; ld = voff + (nw + 3) / 4 * 4; mt = ld; npad = nw;
+		GT.resize(nw * ld); Ssorted.resize(nw); perm.resize((nw + 1) / 2 + 1); scale.resize(2);
+		unsigned int* d_info = static_cast<unsigned int*>(dalloc_bytes(4 * sizeof(unsigned int)));
+		const long long srs = swapped ? 1 : (long long)n, scs = swapped ? (long long)n : 1;     // Gw(i, j) = A[i * srs + j * scs]
+		{
+			ProfScope prof_jacobi("svd_jacobi");
+			svd_small(A, srs, scs, mw, nw, GT, ld, voff, Ssorted, reinterpret_cast<int*>(perm.p), scale, d_info,
+			          std::sqrt(double(mdot)) * DBL_EPS, c.svd_last_sweep_cos, c.svd_max_sweeps);
+		}
+		S.resize(nw);
+		if (c.speculate) {
+			small_spec_kernel<<<1, 32, 0, c.stream>>>(d_info, c.spec_flag);
+			XB_LAUNCH_CHECK();
+			dfree(d_info);
+			S.clear();
+			return;
+		}
+		unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch + c.h_scratch_len - 16);
+		XB_CUDA(cudaMemcpyAsync(h_info, d_info, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+		XB_CUDA(cudaMemcpyAsync(c.h_scratch, Ssorted.p, nw * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+		dfree(d_info);
+		XB_CUDA(cudaStreamSynchronize(c.stream));
+		std::copy(c.h_scratch, c.h_scratch + nw, S.begin());
+		sweeps = int(h_info[1]);
+		if (h_info[2] != 0) throw Error(XB_ERR_NUMERIC, "Jacobi SVD did not converge within svd_max_sweeps sweeps");
+		return;
+	}
 
 	const double* src; long long rs, cs;
 	DBuf At, Rr;
@@ -1784,6 +1838,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	JacobiPending pending;
 	ProfScope* prof_jacobi = new ProfScope("svd_jacobi");
 	const bool mixed = plan.persistent && c.svd_mixed && nw >= size_t(c.svd_mixed_min);
+	if (mixed && c.speculate) { delete prof_jacobi; throw SpecUnsupported("mixed-precision Jacobi"); }
 	if (mixed) {
 		// Mixed precision: the bulk of the sweeps run in FP32 on a scaled copy (FP32 issues 4x faster than FP64 here and
 		// halves the shared-memory traffic); its V (orthogonal to ~1e-6) is re-orthogonalised in FP64 by two Newton-Schulz
@@ -1825,6 +1880,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 			                                   defer ? &pending : nullptr);
 		} else {
 			// fallback for shapes the cooperative kernel cannot hold: one launch per tournament round
+			if (c.speculate) { delete prof_jacobi; throw SpecUnsupported("launch-per-round Jacobi needs the host between sweeps"); }
 			const int bw = plan.bw;
 			const size_t nblk = plan.nblk;
 			const size_t smem = size_t(2 * bw) * ld * sizeof(double);
@@ -1878,6 +1934,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		XB_LAUNCH_CHECK();
 	}
 	S.resize(nw);
+	if (c.speculate) { S.clear(); return; }                    // rank_for() checks the values on the device
 	if (nw + 16 <= c.h_scratch_len) {
 		XB_CUDA(cudaMemcpyAsync(c.h_scratch, Ssorted.p, nw * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
 		XB_CUDA(cudaStreamSynchronize(c.stream));
@@ -1887,6 +1944,15 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		XB_CUDA(cudaStreamSynchronize(c.stream));
 	}
 	if (pending.active && !jacobi_finish(pending, sweeps)) throw Error(XB_ERR_NUMERIC, "Jacobi SVD did not converge within svd_max_sweeps sweeps");
+}
+
+size_t Svd::rank_for(size_t max_rank, double eps) {
+	Context& c = ctx();
+	if (!c.speculate) return truncation_rank(S, max_rank, eps);
+	const size_t k = max_rank ? std::min(kmax, max_rank) : kmax;
+	svd_spec_rank_kernel<<<1, 256, 0, c.stream>>>(Ssorted, int(k), eps, c.spec_flag);
+	XB_LAUNCH_CHECK();
+	return k;
 }
 
 void Svd::extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, double* dS) {

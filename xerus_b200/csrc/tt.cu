@@ -96,14 +96,14 @@ static void round_edge(xb_tt* t, size_t from, size_t max_rank, double eps, doubl
 	svd.polish = ctx().tt_svd_polish;
 	if (to_orthonormal) {
 		svd.factor(t->core[from], r, fcols);
-		const size_t k = truncation_rank(svd.S, max_rank, eps);               // tensor.cpp:1464-1474
+		const size_t k = svd.rank_for(max_rank, eps);                         // tensor.cpp:1464-1474
 		DBuf US(r * k), nf(k * fcols), nt(trows * k);
 		svd.extract(US, nf, k, true, false, nullptr);                         // from = Vt_k ; U_k S_k
 		gemm(nt, k, trows, k, 1.0, t->core[to], r, false, r, US, k, false, 0.0);   // to = to * U_k S_k   (:779)
 		t->core[from] = std::move(nf);
 		t->core[to] = std::move(nt);
 		t->rank[from] = k;
-		if (svals_out) svals_out->assign(svd.S.begin(), svd.S.begin() + k);
+		if (svals_out) { XB_REQUIRE(!ctx().speculate, "internal: singular values are not available on the speculative path"); svals_out->assign(svd.S.begin(), svd.S.begin() + k); }
 	} else {
 		// general case: to = Tq * B, M = B * from, M = U S Vt  ->  to = Tq * U_k S_k, from = Vt_k
 		const size_t kb = std::min(trows, r);
@@ -111,7 +111,7 @@ static void round_edge(xb_tt* t, size_t from, size_t max_rank, double eps, doubl
 		qr(Tq, B, t->core[to], trows, r);
 		gemm(M, fcols, kb, fcols, 1.0, B, r, false, r, t->core[from], fcols, false, 0.0);
 		svd.factor(M, kb, fcols);
-		const size_t k = truncation_rank(svd.S, max_rank, eps);
+		const size_t k = svd.rank_for(max_rank, eps);
 		DBuf US(kb * k), nf(k * fcols), nt(trows * k);
 		svd.extract(US, nf, k, true, false, nullptr);
 		gemm(nt, k, trows, k, 1.0, Tq, kb, false, kb, US, k, false, 0.0);
@@ -144,6 +144,188 @@ static void round_tt(xb_tt* t, const size_t* max_ranks, double eps, double* sval
 	t->canonicalized = true;                                             // assume_core_position(0) (:660)
 	t->core_position = 0;
 	if (initial_canon) move_core(t, initial_core, false);                // :662-664
+}
+
+
+// ---- round plans -----------------------------------------------------------------------------------------------------
+// A round() is ~250 (config 1) to ~1 600 (config 3) small launches with a host read-back per edge (the rank decision).  For a
+// shape that comes back — batches of equal TTs (config 5), repeated roundings inside an iteration — the whole sweep is
+// captured once into a CUDA graph and replayed: every rank decision is *speculated* to come out as it did when the plan was
+// recorded (ranks = min(cap, incoming rank), no eps cut, no rank deficiency, Jacobi converged) and checked on the device
+// (ctx().spec_flag); one word is read back at the end, and a raised flag sends the call down the ordinary path on the
+// untouched input.  The graph owns its temporaries and its result cores (stream-ordered allocations inside the capture,
+// cudaGraphInstantiateFlagAutoFreeOnLaunch); the caller's cores are copied in and the result cores copied out by one
+// kernel each, so a replay is 3 launches + 1 graph launch from the host's point of view.
+struct CopyJobs { const double* src[48]; double* dst[48]; unsigned long long n[48]; int count; };
+__global__ void copy_many_kernel(const CopyJobs jobs) {
+	for (int j = blockIdx.y; j < jobs.count; j += gridDim.y) {
+		const double* __restrict__ s = jobs.src[j]; double* __restrict__ d = jobs.dst[j];
+		const unsigned long long n = jobs.n[j];
+		for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) d[i] = s[i];
+	}
+}
+static void copy_many(const std::vector<const double*>& src, const std::vector<double*>& dst, const std::vector<size_t>& n) {
+	for (size_t base = 0; base < src.size(); base += 48) {
+		CopyJobs jobs;
+		jobs.count = int(std::min<size_t>(48, src.size() - base));
+		size_t mx = 1;
+		for (int j = 0; j < jobs.count; ++j) { jobs.src[j] = src[base + j]; jobs.dst[j] = dst[base + j]; jobs.n[j] = n[base + j]; mx = std::max(mx, n[base + j]); }
+		const unsigned bx = unsigned(std::min<size_t>((mx + 255) / 256, 64));
+		copy_many_kernel<<<dim3(bx, unsigned(jobs.count)), 256, 0, ctx().stream>>>(jobs);
+		XB_LAUNCH_CHECK();
+	}
+}
+
+struct RoundPlan {
+	std::string key;
+	uint64_t uses = 0, stamp = 0;
+	bool unplannable = false;
+	std::vector<size_t> ranks_out;              // d + 1 entries, as recorded by the first (ordinary) run
+	bool canon_out = false; size_t core_out = 0;
+	cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+	std::vector<DBuf> staging;                  // the graph's view of the caller's cores (persistent, outside the graph)
+	std::vector<double*> out;                   // result cores inside the graph's memory, valid after a launch until the next one
+	unsigned int* flag = nullptr;
+	uint64_t nodes = 0;
+	~RoundPlan() {
+		if (exec) cudaGraphExecDestroy(exec);
+		if (graph) cudaGraphDestroy(graph);
+		if (flag) cudaFree(flag);
+	}
+};
+
+static std::string plan_key(const xb_tt* t, const size_t* max_ranks, double eps) {
+	std::string k;
+	auto put = [&](const void* p, size_t n) { k.append(reinterpret_cast<const char*>(p), n); };
+	const size_t head[4] = {t->d, size_t(t->is_operator), size_t(t->canonicalized), t->canonicalized ? t->core_position : 0};
+	put(head, sizeof head);
+	put(t->dim_m.data(), t->d * sizeof(size_t)); put(t->dim_n.data(), t->d * sizeof(size_t));
+	put(t->rank.data(), (t->d + 1) * sizeof(size_t));
+	if (t->d > 1) put(max_ranks, (t->d - 1) * sizeof(size_t));
+	put(&eps, sizeof eps);
+	put(&ctx().options_epoch, sizeof(uint64_t));
+	return k;
+}
+
+static void capture_plan(RoundPlan& pl, const xb_tt* t, const size_t* max_ranks, double eps) {
+	Context& c = ctx();
+	const size_t d = t->d;
+	pl.staging.resize(d);
+	for (size_t i = 0; i < d; ++i) pl.staging[i].resize(t->core_size(i));
+	XB_CUDA(cudaMalloc(reinterpret_cast<void**>(&pl.flag), 4 * sizeof(unsigned int)));
+	XB_CUDA(cudaStreamSynchronize(c.stream));
+	xb_tt proto;
+	proto.d = d; proto.is_operator = t->is_operator; proto.dim_m = t->dim_m; proto.dim_n = t->dim_n; proto.rank = t->rank;
+	proto.canonicalized = t->canonicalized; proto.core_position = t->core_position;
+	proto.core.resize(d);
+	const uint64_t launches0 = c.launches;
+	bool ok = false;
+	std::string why;
+	XB_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
+	c.speculate = true; c.spec_flag = pl.flag;
+	try {
+		XB_CUDA(cudaMemsetAsync(pl.flag, 0, 4 * sizeof(unsigned int), c.stream));
+		std::vector<const double*> src; std::vector<double*> dst; std::vector<size_t> n;
+		for (size_t i = 0; i < d; ++i) {
+			proto.core[i].resize(t->core_size(i));                       // allocated inside the capture: the sweep may free it
+			src.push_back(pl.staging[i].p); dst.push_back(proto.core[i].p); n.push_back(t->core_size(i));
+		}
+		copy_many(src, dst, n);
+		round_tt(&proto, max_ranks, eps, nullptr, 0);
+		aux_join();
+		ok = true;
+	} catch (const std::exception& e) { why = e.what(); }
+	c.speculate = false; c.spec_flag = nullptr;
+	// the result cores stay allocated inside the graph (freed by the next launch, AutoFreeOnLaunch): detach them from their DBufs
+	pl.out.clear();
+	for (size_t i = 0; i < d; ++i) { pl.out.push_back(proto.core[i].p); if (ok) { proto.core[i].p = nullptr; proto.core[i].n = 0; } }
+	cudaGraph_t g = nullptr;
+	const cudaError_t e_end = cudaStreamEndCapture(c.stream, &g);
+	pl.nodes = c.launches - launches0;
+	c.launches = launches0;
+	if (!ok || e_end != cudaSuccess || !g) {
+		for (size_t i = 0; i < d; ++i) { proto.core[i].p = nullptr; proto.core[i].n = 0; }   // whatever they were, the capture is void
+		if (g) cudaGraphDestroy(g);
+		cudaGetLastError();
+		pl.unplannable = true; pl.staging.clear();
+		if (getenv("XB_DEBUG_PLAN")) fprintf(stderr, "[plan] capture failed: %s %s\n", why.c_str(), e_end != cudaSuccess ? cudaGetErrorString(e_end) : "");
+		return;
+	}
+	pl.graph = g;
+	const cudaError_t e_inst = cudaGraphInstantiateWithFlags(&pl.exec, pl.graph, cudaGraphInstantiateFlagAutoFreeOnLaunch);
+	if (e_inst != cudaSuccess) {
+		cudaGetLastError();
+		pl.exec = nullptr; pl.unplannable = true; pl.staging.clear();
+		if (getenv("XB_DEBUG_PLAN")) fprintf(stderr, "[plan] instantiate failed: %s\n", cudaGetErrorString(e_inst));
+		return;
+	}
+	bool same = proto.rank == pl.ranks_out && proto.canonicalized == pl.canon_out && (!pl.canon_out || proto.core_position == pl.core_out);
+	if (!same) { pl.unplannable = true; if (getenv("XB_DEBUG_PLAN")) fprintf(stderr, "[plan] speculated ranks differ from the recorded ones\n"); }
+	if (getenv("XB_DEBUG_PLAN")) fprintf(stderr, "[plan] captured: %llu kernels\n", (unsigned long long)pl.nodes);
+}
+
+// returns true if the round was carried out by a plan
+static bool round_planned(xb_tt* t, const size_t* max_ranks, double eps) {
+	Context& c = ctx();
+	if (!c.round_plans || c.profile || c.speculate || t->d < 2 || t->d > 96) return false;
+	const std::string key = plan_key(t, max_ranks, eps);
+	RoundPlan* pl = nullptr;
+	static thread_local uint64_t clock = 0;
+	for (RoundPlan* q : c.plans) if (q->key == key) pl = q;
+	if (!pl) {
+		if (c.plans.size() >= 6) {                                    // evict the least recently used plan
+			size_t lru = 0;
+			for (size_t i = 1; i < c.plans.size(); ++i) if (c.plans[i]->stamp < c.plans[lru]->stamp) lru = i;
+			XB_CUDA(cudaStreamSynchronize(c.stream));
+			delete c.plans[lru];
+			c.plans.erase(c.plans.begin() + lru);
+		}
+		pl = new RoundPlan();
+		pl->key = key;
+		c.plans.push_back(pl);
+	}
+	pl->stamp = ++clock;
+	pl->uses += 1;
+	if (pl->unplannable) return false;
+	if (pl->uses == 1) {
+		// first sight of this shape: ordinary path, and the outcome is what the plan will speculate on
+		round_tt(t, max_ranks, eps, nullptr, 0);
+		pl->ranks_out = t->rank; pl->canon_out = t->canonicalized; pl->core_out = t->core_position;
+		return true;
+	}
+	if (!pl->exec) {
+		capture_plan(*pl, t, max_ranks, eps);
+		if (pl->unplannable || !pl->exec) return false;
+	}
+	const size_t d = t->d;
+	{
+		std::vector<const double*> src; std::vector<double*> dst; std::vector<size_t> n;
+		for (size_t i = 0; i < d; ++i) { src.push_back(t->core[i].p); dst.push_back(pl->staging[i].p); n.push_back(t->core_size(i)); }
+		copy_many(src, dst, n);
+	}
+	XB_CUDA(cudaGraphLaunch(pl->exec, c.stream));
+	c.launches += pl->nodes;
+	unsigned int* h_flag = reinterpret_cast<unsigned int*>(c.h_scratch);
+	XB_CUDA(cudaMemcpyAsync(h_flag, pl->flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+	// result cores: sized by the recorded ranks; copied out of the graph's memory (valid until the next launch of this plan)
+	std::vector<DBuf> fresh(d);
+	{
+		std::vector<const double*> src; std::vector<double*> dst; std::vector<size_t> n;
+		for (size_t i = 0; i < d; ++i) {
+			const size_t sz = pl->ranks_out[i] * t->ext(i) * pl->ranks_out[i + 1];
+			fresh[i].resize(sz);
+			src.push_back(pl->out[i]); dst.push_back(fresh[i].p); n.push_back(sz);
+		}
+		copy_many(src, dst, n);
+	}
+	XB_CUDA(cudaStreamSynchronize(c.stream));
+	if (*h_flag != 0) {
+		if (getenv("XB_DEBUG_PLAN")) fprintf(stderr, "[plan] speculation failed (reason %u): ordinary path\n", *h_flag);
+		return false;                                               // the caller's TT is untouched
+	}
+	for (size_t i = 0; i < d; ++i) t->core[i] = std::move(fresh[i]);
+	t->rank = pl->ranks_out; t->canonicalized = pl->canon_out; t->core_position = pl->core_out;
+	return true;
 }
 
 double tt_inner(const xb_tt* a, const xb_tt* b) {
@@ -389,6 +571,8 @@ xb_status xb_tt_round_svals(xb_tt* tt, const size_t* max_ranks, double eps, doub
 		ensure_init();
 		require_correct_format(tt);
 		XB_REQUIRE(max_ranks || tt->d == 1, "There must be exactly degree-1 maxRanks");
+		XB_REQUIRE(eps >= 0.0 && eps < 1.0, "_eps must be smaller than one.");
+		if (!svals && round_planned(tt, max_ranks, eps)) return;
 		round_tt(tt, max_ranks, eps, svals, stride);
 	});
 }
@@ -411,7 +595,7 @@ xb_status xb_tt_round_batched(xb_tt** tts, size_t batch, size_t max_rank, double
 		for (size_t b = 0; b < batch; ++b) {
 			require_correct_format(tts[b]);
 			std::vector<size_t> mr(tts[b]->d > 1 ? tts[b]->d - 1 : 1, max_rank);
-			round_tt(tts[b], mr.data(), eps, nullptr, 0);
+			if (!round_planned(tts[b], mr.data(), eps)) round_tt(tts[b], mr.data(), eps, nullptr, 0);
 		}
 	});
 }

@@ -82,6 +82,15 @@ struct Context {
 	int svd_mixed_min = 64;        // smallest column count for the mixed path
 	int svd_max_bw = 0;            // 0 = automatic block width of the Jacobi kernel
 	int als_direct_max = 1536;     // local problems up to this size are solved densely (reference semantics), larger ones by CG
+	int small_kernels = 1;         // min(m,n) <= 32: QR and Jacobi SVD as one single-CTA launch each (small_f64.cu)
+	int round_plans = 1;           // round(): repeated shapes replay a captured CUDA graph of the whole sweep (speculative ranks, tt.cu)
+	// Speculative execution (round plans): rank decisions are not read back; every decision point assumes the outcome the
+	// plan was recorded with and raises *spec_flag on the device when the data disagree (the caller then repeats the
+	// operation on the synchronising path).
+	bool speculate = false;
+	unsigned int* spec_flag = nullptr;
+	std::vector<struct RoundPlan*> plans;
+	uint64_t options_epoch = 0;    // bumped by xb_set_option: plans recorded under other options are not replayed
 };
 Context& ctx();               // the calling thread's current worker
 void ensure_init();
@@ -174,6 +183,16 @@ void lq(double* L, double* Q, const double* A, size_t m, size_t n);
 // true RQ with LAPACK's convention (R upper-trapezoidal, bottom-right aligned)
 void rq(double* R, double* Q, const double* A, size_t m, size_t n);
 
+// thrown by a decision point that cannot run without a host read-back while ctx().speculate is set
+struct SpecUnsupported : Error { explicit SpecUnsupported(const std::string& m) : Error(XB_ERR_UNSUPPORTED, m) {} };
+
+// single-CTA kernels for min(m, n) <= 32 (small_f64.cu); G(i, j) = A[i * ars + j * acs], outputs through strides
+bool qr_small_fits(size_t m, size_t n);
+void qr_small(double* Q, long long qrs, long long qcs, double* R, long long rrs, long long rcs, const double* A, long long ars, long long acs, size_t m, size_t n);
+bool svd_small_fits(size_t mw, size_t nw);
+void svd_small(const double* A, long long rs, long long cs, size_t mw, size_t nw, double* GT, size_t ld, size_t voff, double* Ssorted, int* perm,
+               double* scale2, unsigned int* info, double tol, double last_cos, int max_sweeps);
+
 struct SvdWork;   // opaque between svd_factor and svd_extract
 // Jacobi SVD of A (m x n packed).  Returns singular values (descending) on the host, keeps vectors on device.
 // Then extract() writes the first k triplets: U (m x k), Vt (k x n); Sigma optionally folded into U or Vt.
@@ -192,6 +211,9 @@ struct Svd {
 	bool q_deferred = false;               // Qred is still being formed on the side stream
 	~Svd() { if (q_deferred) aux_join(); }
 	void factor(const double* A, size_t m, size_t n);
+	// rank of the truncation rule (tensor.cpp:1464-1474).  Normally evaluated on the host copy of S; while ctx().speculate is set
+	// it returns min(max_rank, kmax) and enqueues a check that raises the speculation flag if the eps rule would cut earlier.
+	size_t rank_for(size_t max_rank, double eps);
 	void extract(double* U, double* Vt, size_t k, bool scale_u, bool scale_vt, double* dS /* optional device S (k) */);
 };
 
