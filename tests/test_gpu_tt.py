@@ -384,3 +384,26 @@ def test_round_plan_replay_is_bit_identical_and_falls_back():
     deficient.round(4)
     assert deficient.ranks() == ref.ranks()
     assert O.tt_distance_rel(to_oracle(deficient), ref) < 1e-9
+
+
+def test_batched_items_match_the_single_calls():
+    """xb_tt_apply_round_batched / xb_tt_round_batched (library threads + streams, round plans) against one call per item."""
+    rng = np.random.default_rng(55)
+    d, n, r = 6, 4, 12
+    A = xb.TTOperator.laplace(d, n)
+    xs = [xb.TTTensor.random([n] * d, r, rng) for _ in range(13)]
+    single = []
+    for x in xs:
+        y = A.apply(x); y.round(r); single.append(y)
+    ys = xb.apply_round_batched(A, xs, r)
+    assert len(ys) == len(xs)
+    for y, ref in zip(ys, single):
+        assert y.ranks() == ref.ranks() and y.canonicalized and y.corePosition == 0
+        assert y.distance(ref) < 1e-12 * ref.frob_norm()
+    raw = [A.apply(x) for x in xs]
+    xb.round_batched(raw, r)
+    for y, ref in zip(raw, single):
+        assert y.ranks() == ref.ranks() and y.distance(ref) < 1e-12 * ref.frob_norm()
+    assert xb.apply_round_batched(A, [], r) == []
+    with pytest.raises(xb.XerusError):
+        xb.apply_round_batched(A, [xb.TTTensor.ones([n] * (d - 1))], r)

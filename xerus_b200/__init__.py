@@ -5,7 +5,7 @@ Host-side mirror of the reference interface for that path; all arithmetic runs i
 from ._lib import XerusError, lib, declared_symbols, LIB_PATH      # noqa: F401
 from . import blas_wrapper as blasWrapper                          # noqa: F401
 from .blas_wrapper import contract, reshuffle, calculate_svd, EPSILON   # noqa: F401
-from .tt import TTTensor, TTOperator, TTNetwork, round_batched, reduce_to_maximal_ranks   # noqa: F401
+from .tt import TTTensor, TTOperator, TTNetwork, round_batched, apply_round_batched, reduce_to_maximal_ranks   # noqa: F401
 from .als import ALSVariant, ALS, ALS_SPD, DMRG, DMRG_SPD, ASD, ASD_SPD   # noqa: F401
 from .file_io import FileFormat, save_to_file, load_from_file, read_file, write_tt_file, write_tensor_file   # noqa: F401
 

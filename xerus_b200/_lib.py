@@ -65,6 +65,7 @@ _SIGS = {
     "xb_tt_set_components": [vp, P(dp), szp], "xb_tt_get_components": [vp, P(dp)],
     "xb_tt_move_core": [vp, sz, C.c_int], "xb_tt_round": [vp, szp, C.c_double],
     "xb_tt_round_svals": [vp, szp, C.c_double, dp, sz], "xb_tt_round_batched": [P(vp), sz, sz, C.c_double],
+    "xb_tt_apply_round_batched": [P(vp), vp, P(vp), sz, sz, C.c_double],
     "xb_tt_frob_norm": [vp, dp], "xb_tt_inner": [vp, vp, dp], "xb_tt_distance": [vp, vp, dp],
     "xb_tt_scale": [vp, C.c_double], "xb_tt_add": [P(vp), vp, vp], "xb_tt_apply": [P(vp), vp, vp],
     "xb_tt_from_dense": [P(vp), dp, sz, szp, C.c_double, sz], "xb_tt_to_dense": [vp, dp],

@@ -46,6 +46,7 @@ static void apply_option(Context& c, const std::string& k, double value) {
 	else if (k == "als_direct_max") c.als_direct_max = int(value);
 	else if (k == "round_plans") c.round_plans = int(value);
 	else if (k == "small_kernels") c.small_kernels = int(value);
+	else if (k == "batch_workers") c.batch_workers = int(value);
 	else throw Error(XB_ERR_INVALID, "xb_set_option: unknown key " + k);
 }
 
@@ -108,9 +109,21 @@ static void select_worker(int w) {
 		c->num_sms = g_ctx.num_sms; c->max_smem_optin = g_ctx.max_smem_optin;
 		c->svd_max_sweeps = g_ctx.svd_max_sweeps; c->gemm_force_small = g_ctx.gemm_force_small; c->gemm_big = g_ctx.gemm_big; c->qr_defer = g_ctx.qr_defer;
 		c->svd_persistent = g_ctx.svd_persistent; c->svd_polish = g_ctx.svd_polish; c->tt_svd_polish = g_ctx.tt_svd_polish; c->svd_mixed = g_ctx.svd_mixed; c->svd_recursive = g_ctx.svd_recursive; c->svd_flip = g_ctx.svd_flip; c->svd_split = g_ctx.svd_split; c->svd_dsmem = g_ctx.svd_dsmem; c->svd_colsort = g_ctx.svd_colsort; c->svd_last_sweep_cos = g_ctx.svd_last_sweep_cos; c->svd_gram = g_ctx.svd_gram; c->als_graph = g_ctx.als_graph; c->als_persistent_cg = g_ctx.als_persistent_cg; c->als_cg_cluster = g_ctx.als_cg_cluster; c->svd_jacc = g_ctx.svd_jacc; c->svd_fast = g_ctx.svd_fast; c->qr_cluster = g_ctx.qr_cluster; c->qr_cluster_min_rows = g_ctx.qr_cluster_min_rows; c->svd_square_qr = g_ctx.svd_square_qr;
-		c->svd_mixed_min = g_ctx.svd_mixed_min; c->svd_max_bw = g_ctx.svd_max_bw; c->als_direct_max = g_ctx.als_direct_max; c->round_plans = g_ctx.round_plans; c->small_kernels = g_ctx.small_kernels;
+		c->svd_mixed_min = g_ctx.svd_mixed_min; c->svd_max_bw = g_ctx.svd_max_bw; c->als_direct_max = g_ctx.als_direct_max; c->round_plans = g_ctx.round_plans; c->small_kernels = g_ctx.small_kernels; c->batch_workers = g_ctx.batch_workers;
 		XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 		XB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scratch), c->h_scratch_len * sizeof(double)));
+		{
+			// a memory pool per worker: with one shared pool a block freed on one worker's stream and reused on another's makes the
+			// second stream wait for the first (the pool inserts the dependency), which serialises workers that should overlap
+			cudaMemPoolProps props = {};
+			props.allocType = cudaMemAllocationTypePinned;
+			props.handleTypes = cudaMemHandleTypeNone;
+			props.location.type = cudaMemLocationTypeDevice;
+			props.location.id = g_ctx.device;
+			XB_CUDA(cudaMemPoolCreate(&c->pool, &props));
+			uint64_t threshold = UINT64_MAX;
+			XB_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+		}
 		g_workers[i] = c;
 		g_num_workers = i + 1;
 	}
@@ -120,7 +133,16 @@ static void select_worker(int w) {
 void* dalloc_bytes(size_t bytes) {
 	void* p = nullptr;
 	if (bytes == 0) bytes = 8;
-	XB_CUDA(cudaMallocAsync(&p, bytes, ctx().stream));
+	Context& c = ctx();
+	if (c.arena_on) {
+		const size_t b = (bytes + 255) / 256 * 256;
+		if (c.arena_off + b > c.arena_size) throw SpecUnsupported("capture arena exhausted");
+		p = c.arena + c.arena_off;
+		c.arena_off += b;
+		return p;
+	}
+	if (c.count_allocs) c.alloc_counter += (bytes + 255) / 256 * 256;
+	XB_CUDA(cudaMallocFromPoolAsync(&p, bytes, c.pool, c.stream));
 	return p;
 }
 static void ensure_aux(Context& c) {
@@ -157,7 +179,12 @@ AuxScope::~AuxScope() {
 }
 
 double* dalloc(size_t n) { return static_cast<double*>(dalloc_bytes(n * sizeof(double))); }
-void dfree(void* p) { if (p) cudaFreeAsync(p, ctx().stream); }
+void dfree(void* p) {
+	if (!p) return;
+	Context& c = ctx();
+	if (c.arena_on) return;                       // arena memory lives as long as the plan
+	cudaFreeAsync(p, c.stream);
+}
 
 double read_scalar(const double* d_value) {
 	Context& c = ctx();

@@ -7,6 +7,9 @@
 // transfer_core / round_edge (src/xerus/tensorNetwork.cpp:678-909); nothing leaves the device during a sweep except
 // the per-edge rank decision (singular values / one min-max pair), which the host needs to size the next launches.
 #include "tt_internal.cuh"
+#include <atomic>
+#include <mutex>
+#include <thread>
 
 using namespace xb;
 
@@ -153,9 +156,11 @@ static void round_tt(xb_tt* t, const size_t* max_ranks, double eps, double* sval
 // captured once into a CUDA graph and replayed: every rank decision is *speculated* to come out as it did when the plan was
 // recorded (ranks = min(cap, incoming rank), no eps cut, no rank deficiency, Jacobi converged) and checked on the device
 // (ctx().spec_flag); one word is read back at the end, and a raised flag sends the call down the ordinary path on the
-// untouched input.  The graph owns its temporaries and its result cores (stream-ordered allocations inside the capture,
-// cudaGraphInstantiateFlagAutoFreeOnLaunch); the caller's cores are copied in and the result cores copied out by one
-// kernel each, so a replay is 3 launches + 1 graph launch from the host's point of view.
+// untouched input.  Temporaries and result cores of the captured sweep are bump-allocated from an arena the plan owns (sized
+// by the first, ordinary run of the shape; never reused inside a sweep, so the side stream needs no extra ordering): the graph
+// holds kernel nodes only — with stream-ordered allocations inside the capture the graphs of different workers did not
+// overlap on the device.  The caller's cores are copied in and the result cores copied out by one kernel each, so a replay
+// is 3 launches + 1 graph launch from the host's point of view.
 struct CopyJobs { const double* src[48]; double* dst[48]; unsigned long long n[48]; int count; };
 __global__ void copy_many_kernel(const CopyJobs jobs) {
 	for (int j = blockIdx.y; j < jobs.count; j += gridDim.y) {
@@ -184,13 +189,15 @@ struct RoundPlan {
 	bool canon_out = false; size_t core_out = 0;
 	cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
 	std::vector<DBuf> staging;                  // the graph's view of the caller's cores (persistent, outside the graph)
-	std::vector<double*> out;                   // result cores inside the graph's memory, valid after a launch until the next one
+	std::vector<double*> out;                   // result cores inside the plan's arena, valid after a launch until the next one
+	char* arena = nullptr; size_t arena_size = 0;   // every temporary and result of the captured sweep (bump-allocated, never reused)
 	unsigned int* flag = nullptr;
 	uint64_t nodes = 0;
 	~RoundPlan() {
 		if (exec) cudaGraphExecDestroy(exec);
 		if (graph) cudaGraphDestroy(graph);
 		if (flag) cudaFree(flag);
+		if (arena) cudaFree(arena);
 	}
 };
 
@@ -213,6 +220,7 @@ static void capture_plan(RoundPlan& pl, const xb_tt* t, const size_t* max_ranks,
 	pl.staging.resize(d);
 	for (size_t i = 0; i < d; ++i) pl.staging[i].resize(t->core_size(i));
 	XB_CUDA(cudaMalloc(reinterpret_cast<void**>(&pl.flag), 4 * sizeof(unsigned int)));
+	XB_CUDA(cudaMalloc(reinterpret_cast<void**>(&pl.arena), pl.arena_size));
 	XB_CUDA(cudaStreamSynchronize(c.stream));
 	xb_tt proto;
 	proto.d = d; proto.is_operator = t->is_operator; proto.dim_m = t->dim_m; proto.dim_n = t->dim_n; proto.rank = t->rank;
@@ -223,6 +231,7 @@ static void capture_plan(RoundPlan& pl, const xb_tt* t, const size_t* max_ranks,
 	std::string why;
 	XB_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
 	c.speculate = true; c.spec_flag = pl.flag;
+	c.arena = pl.arena; c.arena_size = pl.arena_size; c.arena_off = 0; c.arena_on = true;
 	try {
 		XB_CUDA(cudaMemsetAsync(pl.flag, 0, 4 * sizeof(unsigned int), c.stream));
 		std::vector<const double*> src; std::vector<double*> dst; std::vector<size_t> n;
@@ -235,16 +244,16 @@ static void capture_plan(RoundPlan& pl, const xb_tt* t, const size_t* max_ranks,
 		aux_join();
 		ok = true;
 	} catch (const std::exception& e) { why = e.what(); }
-	c.speculate = false; c.spec_flag = nullptr;
-	// the result cores stay allocated inside the graph (freed by the next launch, AutoFreeOnLaunch): detach them from their DBufs
+	// the result cores live in the arena: detach them from their DBufs (arena_on is still set: nothing below reaches cudaFreeAsync)
 	pl.out.clear();
-	for (size_t i = 0; i < d; ++i) { pl.out.push_back(proto.core[i].p); if (ok) { proto.core[i].p = nullptr; proto.core[i].n = 0; } }
+	for (size_t i = 0; i < d; ++i) { pl.out.push_back(proto.core[i].p); proto.core[i].p = nullptr; proto.core[i].n = 0; }
+	c.speculate = false; c.spec_flag = nullptr;
+	c.arena_on = false; c.arena = nullptr;
 	cudaGraph_t g = nullptr;
 	const cudaError_t e_end = cudaStreamEndCapture(c.stream, &g);
 	pl.nodes = c.launches - launches0;
 	c.launches = launches0;
 	if (!ok || e_end != cudaSuccess || !g) {
-		for (size_t i = 0; i < d; ++i) { proto.core[i].p = nullptr; proto.core[i].n = 0; }   // whatever they were, the capture is void
 		if (g) cudaGraphDestroy(g);
 		cudaGetLastError();
 		pl.unplannable = true; pl.staging.clear();
@@ -252,7 +261,7 @@ static void capture_plan(RoundPlan& pl, const xb_tt* t, const size_t* max_ranks,
 		return;
 	}
 	pl.graph = g;
-	const cudaError_t e_inst = cudaGraphInstantiateWithFlags(&pl.exec, pl.graph, cudaGraphInstantiateFlagAutoFreeOnLaunch);
+	const cudaError_t e_inst = cudaGraphInstantiate(&pl.exec, pl.graph, 0);
 	if (e_inst != cudaSuccess) {
 		cudaGetLastError();
 		pl.exec = nullptr; pl.unplannable = true; pl.staging.clear();
@@ -288,8 +297,14 @@ static bool round_planned(xb_tt* t, const size_t* max_ranks, double eps) {
 	pl->uses += 1;
 	if (pl->unplannable) return false;
 	if (pl->uses == 1) {
-		// first sight of this shape: ordinary path, and the outcome is what the plan will speculate on
-		round_tt(t, max_ranks, eps, nullptr, 0);
+		// first sight of this shape: ordinary path; the outcome is what the plan will speculate on, the bytes it allocates
+		// size the plan's arena
+		size_t in_bytes = 0;
+		for (size_t i = 0; i < t->d; ++i) in_bytes += (t->core_size(i) * sizeof(double) + 255) / 256 * 256;
+		c.count_allocs = true; c.alloc_counter = 0;
+		try { round_tt(t, max_ranks, eps, nullptr, 0); } catch (...) { c.count_allocs = false; throw; }
+		c.count_allocs = false;
+		pl->arena_size = c.alloc_counter + in_bytes + (1u << 20);
 		pl->ranks_out = t->rank; pl->canon_out = t->canonicalized; pl->core_out = t->core_position;
 		return true;
 	}
@@ -326,6 +341,52 @@ static bool round_planned(xb_tt* t, const size_t* max_ranks, double eps) {
 	for (size_t i = 0; i < d; ++i) t->core[i] = std::move(fresh[i]);
 	t->rank = pl->ranks_out; t->canonicalized = pl->canon_out; t->core_position = pl->core_out;
 	return true;
+}
+
+// ---- batches of independent items (BASELINE config 5) -------------------------------------------------------------------
+// The items of a batch run on library-owned host threads, one library worker (CUDA stream, scratch, plan cache) each: no
+// interpreter and no caller-side threading on the hot path.  Items are dealt round-robin; the workers' streams first wait for
+// everything the caller has enqueued (the items were produced on the caller's stream) and the caller's stream waits for all of
+// them at the end, so the call composes with stream-ordered code on either side.  Repeated shapes replay their round plan: an
+// item is then a handful of launches, which is what lets several items be in flight at once instead of queueing behind the
+// host's launch rate (~4 us per launch, 800 launches per item on the ordinary path).
+constexpr int XB_BATCH_WORKER_BASE = 40;     // workers 40 .. 40 + batch_workers - 1 belong to the batch executor
+template <class F> static void run_batch(size_t batch, F&& fn) {
+	if (batch == 0) return;
+	Context& caller = ctx();
+	const int nthreads = int(std::min<size_t>(batch, size_t(std::max(1, std::min(caller.batch_workers, 24)))));
+	if (nthreads == 1) { for (size_t b = 0; b < batch; ++b) fn(b); return; }
+	cudaEvent_t start;
+	XB_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+	XB_CUDA(cudaEventRecord(start, caller.stream));
+	std::vector<cudaEvent_t> done(nthreads, nullptr);
+	std::mutex err_mutex;
+	std::string err; xb_status err_code = XB_OK;
+	std::vector<std::thread> threads;
+	for (int t = 0; t < nthreads; ++t) {
+		threads.emplace_back([&, t] {
+			try {
+				if (xb_worker_select(XB_BATCH_WORKER_BASE + t) != XB_OK) throw Error(XB_ERR_CUDA, xb_last_error());
+				Context& c = ctx();
+				XB_CUDA(cudaSetDevice(c.device));
+				XB_CUDA(cudaStreamWaitEvent(c.stream, start, 0));
+				for (size_t b = size_t(t); b < batch; b += size_t(nthreads)) fn(b);
+				aux_join();
+				XB_CUDA(cudaEventCreateWithFlags(&done[t], cudaEventDisableTiming));
+				XB_CUDA(cudaEventRecord(done[t], c.stream));
+			} catch (const Error& e) {
+				std::lock_guard<std::mutex> lock(err_mutex);
+				if (err.empty()) { err = e.what(); err_code = e.code; }
+			} catch (const std::exception& e) {
+				std::lock_guard<std::mutex> lock(err_mutex);
+				if (err.empty()) { err = e.what(); err_code = XB_ERR_INVALID; }
+			}
+		});
+	}
+	for (auto& th : threads) th.join();
+	for (int t = 0; t < nthreads; ++t) if (done[t]) { cudaStreamWaitEvent(caller.stream, done[t], 0); cudaEventDestroy(done[t]); }
+	cudaEventDestroy(start);
+	if (!err.empty()) throw Error(err_code, err);
 }
 
 double tt_inner(const xb_tt* a, const xb_tt* b) {
@@ -592,10 +653,32 @@ xb_status xb_tt_round_batched(xb_tt** tts, size_t batch, size_t max_rank, double
 	return guard([&] {
 		ensure_init();
 		XB_REQUIRE(tts || batch == 0, "null");
-		for (size_t b = 0; b < batch; ++b) {
-			require_correct_format(tts[b]);
+		XB_REQUIRE(eps >= 0.0 && eps < 1.0, "_eps must be smaller than one.");
+		for (size_t b = 0; b < batch; ++b) require_correct_format(tts[b]);
+		run_batch(batch, [&](size_t b) {
 			std::vector<size_t> mr(tts[b]->d > 1 ? tts[b]->d - 1 : 1, max_rank);
 			if (!round_planned(tts[b], mr.data(), eps)) round_tt(tts[b], mr.data(), eps, nullptr, 0);
+		});
+	});
+}
+
+xb_status xb_tt_apply_round_batched(xb_tt** out, const xb_tt* A, xb_tt* const* xs, size_t batch, size_t max_rank, double eps) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE((out && xs) || batch == 0, "null");
+		XB_REQUIRE(eps >= 0.0 && eps < 1.0, "_eps must be smaller than one.");
+		require_correct_format(A);
+		for (size_t b = 0; b < batch; ++b) { require_correct_format(xs[b]); out[b] = nullptr; }
+		try {
+			run_batch(batch, [&](size_t b) {
+				xb_tt* y = tt_apply(A, xs[b]);
+				out[b] = y;
+				std::vector<size_t> mr(y->d > 1 ? y->d - 1 : 1, max_rank);
+				if (!round_planned(y, mr.data(), eps)) round_tt(y, mr.data(), eps, nullptr, 0);
+			});
+		} catch (...) {
+			for (size_t b = 0; b < batch; ++b) { delete out[b]; out[b] = nullptr; }
+			throw;
 		}
 	});
 }

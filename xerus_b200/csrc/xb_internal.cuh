@@ -83,6 +83,7 @@ struct Context {
 	int svd_max_bw = 0;            // 0 = automatic block width of the Jacobi kernel
 	int als_direct_max = 1536;     // local problems up to this size are solved densely (reference semantics), larger ones by CG
 	int small_kernels = 1;         // min(m,n) <= 32: QR and Jacobi SVD as one single-CTA launch each (small_f64.cu)
+	int batch_workers = 8;         // host threads / library workers of the batched entry points (xb_tt_round_batched, ...)
 	int round_plans = 1;           // round(): repeated shapes replay a captured CUDA graph of the whole sweep (speculative ranks, tt.cu)
 	// Speculative execution (round plans): rank decisions are not read back; every decision point assumes the outcome the
 	// plan was recorded with and raises *spec_flag on the device when the data disagree (the caller then repeats the
@@ -90,6 +91,11 @@ struct Context {
 	bool speculate = false;
 	unsigned int* spec_flag = nullptr;
 	std::vector<struct RoundPlan*> plans;
+	// Capture arena: while a plan is being captured every device allocation is a bump allocation from the plan's persistent
+	// arena and frees are no-ops, so the graph holds kernel nodes only (graphs with memory nodes do not overlap across streams).
+	// alloc_counter measures the arena a shape needs during its first, ordinary run.
+	char* arena = nullptr; size_t arena_size = 0, arena_off = 0; bool arena_on = false;
+	bool count_allocs = false; size_t alloc_counter = 0;
 	uint64_t options_epoch = 0;    // bumped by xb_set_option: plans recorded under other options are not replayed
 };
 Context& ctx();               // the calling thread's current worker

@@ -355,3 +355,13 @@ def round_batched(tts, max_rank, eps=EPSILON):
     """Batch of independent roundings (BASELINE config 5)."""
     arr = (C.c_void_p * len(tts))(*[t._h for t in tts])
     call("xb_tt_round_batched", arr, len(tts), int(max_rank), float(eps))
+
+
+def apply_round_batched(A, xs, max_rank, eps=EPSILON):
+    """The item of BASELINE config 5 for a whole batch in one call: [round(A x, max_rank) for x in xs]; the items run concurrently
+    on library-owned threads / streams."""
+    n = len(xs)
+    out = (C.c_void_p * n)()
+    arr = (C.c_void_p * n)(*[x._h for x in xs])
+    call("xb_tt_apply_round_batched", out, A._h, arr, n, int(max_rank), float(eps))
+    return [TTTensor(C.c_void_p(h)) for h in out]
