@@ -101,6 +101,54 @@ def run_ref_bench(w, reps, threads=None, dump=None):
     return json.loads(out.strip().splitlines()[-1])
 
 
+def reference_dump(w):
+    """Runs the unmodified reference once on this box (`ref_bench round ... dump`: TTTensor::random with seed 0xBAADF00D, then
+    round(target)) and returns its input cores, its result cores and its own summary — the checker for the timed path."""
+    import tempfile
+    import numpy as np
+    import struct
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "dump.bin")
+        info = run_ref_bench(w, 1, dump=path)
+        rec = {}
+        with open(path, "rb") as f:                       # record container of oracle/drivers/common.h
+            assert f.read(8) == b"XBGOLD01"
+            while True:
+                hdr = f.read(8)
+                if not hdr:
+                    break
+                name = f.read(struct.unpack("<Q", hdr)[0]).decode()
+                nd = struct.unpack("<Q", f.read(8))[0]
+                dims = struct.unpack("<%dQ" % nd, f.read(8 * nd)) if nd else ()
+                n = int(np.prod(dims)) if nd else 1
+                rec[name] = np.frombuffer(f.read(8 * n), dtype="<f8").copy().reshape(dims)
+    d = int(rec["in.d"])
+    return {"in": [rec["in.c%d" % i] for i in range(d)], "out": [rec["out.c%d" % i] for i in range(d)],
+            "ranks": [int(v) for v in rec["out.ranks"]], "info": info}
+
+
+def check_against_reference(xb, np, out_t, ref_dump, target):
+    """`check` of the bench line: the result of the timed path against the reference's result for the same input."""
+    if not ref_dump:
+        return {"reference": "not available in this snapshot (oracle/_ref/ref_bench missing or --no-cpu-baseline)"}
+    if "error" in ref_dump:
+        return {"reference": "failed: " + ref_dump["error"]}
+    ref = xb.TTTensor.from_cores(ref_dump["out"], core_position=0)
+    norm_ref = ref.frob_norm()
+    bond = out_t.num_components // 2
+    a, b = out_t.copy(), ref.copy()
+    a.move_core(bond, True); b.move_core(bond, True)
+    ca, cb = a.get_component(bond), b.get_component(bond)
+    sa = np.linalg.svd(ca.reshape(ca.shape[0], -1), compute_uv=False)
+    sb = np.linalg.svd(cb.reshape(cb.shape[0], -1), compute_uv=False)
+    return {"against": "unmodified reference (oracle/_ref/ref_bench, same input cores, seed 0xBAADF00D)",
+            "ranks_equal": out_t.ranks() == ref_dump["ranks"],
+            "rel_dist_vs_reference": out_t.distance(ref) / norm_ref,
+            "norm_rel": abs(out_t.frob_norm() - ref_dump["info"]["norm_out"]) / ref_dump["info"]["norm_out"],
+            "sigma_rel": float(np.max(np.abs(sa - sb)) / sb[0]), "sigma_bond": bond,
+            "tolerance": "ranks equal; reconstructed TT and singular values <= 1e-9 relative (north_star)"}
+
+
 def oracle_port_ms(w, reps):
     """Fallback CPU baseline: the numpy restatement (only when the compiled reference is not in the snapshot)."""
     import numpy as np
@@ -116,7 +164,7 @@ def oracle_port_ms(w, reps):
     return times
 
 
-def als_sweep_numbers(xb, np, torch, stream, args):
+def als_sweep_numbers(xb, np, torch, stream, args, fp64_peak=None):
     """ALS_SPD(A, x, b, 2) = one full sweep, device resident, matrix-free CG local solves."""
     d, n, r = 16, 10, 50
     rng = np.random.default_rng(16)
@@ -136,10 +184,26 @@ def als_sweep_numbers(xb, np, torch, stream, args):
             times.append(e0.elapsed_time(e1))
     residual = A.apply(x).distance(b) / b.frob_norm()
     apply_flops = 2 * 2 * (2 * n * r ** 3) + 2 * 2 * 2 * n * n * r * r          # 5 + 2 + 5 MFLOP at C2
+    # time inside the local solves (CUDA events inside the library around every local step: one persistent spd_cg_kernel launch
+    # per site plus the local right-hand side)
+    xb.profile_enable(True)
+    xp = x0.copy()
+    variant(A, xp, b, 2)
+    xb.synchronize()
+    _, solve_launches, solve_ms = xb.profile_get("als_local_step")
+    _, _, move_ms = xb.profile_get("als_move_to_next")
+    xb.profile_enable(False)
     out = {"workload": "ALS_SPD, Laplace-like TTOperator d=16 n=10 (TT-rank 2), b = ones, solution rank 50, one full sweep",
            "ms_per_sweep": sum(times) / len(times), "energy": energy, "residual": residual,
            "local_solver": "matrix-free CG, %d operator applications per sweep" % variant.last_local_iterations,
            "algorithmic_flops_per_sweep": variant.last_local_iterations * apply_flops,
+           "roofline": {"kernel": "spd_cg_kernel (one-site SPD local solve: a whole CG run in one cooperative cluster launch)", "bound": "tensor",
+                        "unit": "TFLOP/s", "achieved": (variant.last_local_iterations * apply_flops / (solve_ms * 1e-3) / 1e12) if solve_ms > 0 else None,
+                        "peak": fp64_peak, "frac": (variant.last_local_iterations * apply_flops / (solve_ms * 1e-3) / 1e12 / fp64_peak) if solve_ms > 0 and fp64_peak else None,
+                        "accounting": "operator applications x (2 x 2 r_A n r^3 + 2 r_A^2 n^2 r^2) flop (SURVEY 8d: 12 MFLOP per apply at config 2)",
+                        "kernel_ms_per_sweep": solve_ms, "launches_per_sweep": solve_launches, "move_and_environment_ms_per_sweep": move_ms,
+                        "traffic": None,
+                        "note": "latency bound: 50 CTAs, three grid barriers per CG iteration on 12 MFLOP of work (profiles/r1_cg.txt)"},
            "reference_cpu": "not runnable inside a bench run at r=50: ~1 h per sweep extrapolated (BASELINE.md section 2)"}
     if os.path.exists(REF_BENCH) and not args.no_cpu_baseline:
         try:
@@ -162,20 +226,37 @@ def als_sweep_numbers(xb, np, torch, stream, args):
     return out
 
 
+_SETUP = {}
+
+
+def setup(local_rank, world):
+    """One process per GPU: device, library, NCCL process group (N > 1), the library stream as a torch stream.  Idempotent."""
+    if not _SETUP:
+        import torch
+        import xerus_b200 as xb
+        torch.cuda.set_device(local_rank)
+        xb.init(local_rank)
+        dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        _SETUP.update(torch=torch, xb=xb, dist=dist, stream=torch.cuda.ExternalStream(xb.stream_handle(), device=local_rank))
+    return _SETUP["torch"], _SETUP["xb"], _SETUP["dist"], _SETUP["stream"]
+
+
+def teardown():
+    if _SETUP.get("dist") is not None:
+        _SETUP["dist"].destroy_process_group()
+    _SETUP.clear()
+
+
 def batch_workload(args, rank, local_rank, world):
     """--workload c5: BASELINE configs[4], reduced per step: every rank processes `items` independent items
-    (y_b = A x_b with x_b = random({4}x12, 64), then y_b.round(64)); items shard by index, no data-path collective."""
+    (y_b = A x_b with x_b = random({4}x12, 64), then y_b.round(64)); items shard by index, no data-path collective.
+    Returns the JSON line (rank 0) or None."""
     import numpy as np
-    import torch
-    import xerus_b200 as xb
     from xerus_b200 import parallel
-    torch.cuda.set_device(local_rank)
-    xb.init(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.ExternalStream(xb.stream_handle(), device=local_rank)
+    torch, xb, dist, stream = setup(local_rank, world)
     d, n, r, per_rank = 12, 4, 64, args.items
     n_items = per_rank * world
     A = xb.TTOperator.laplace(d, n)
@@ -217,9 +298,8 @@ def batch_workload(args, rank, local_rank, world):
                            "parallelism": "items sharded b mod %d, no data-path collective; one xb_tt_apply_round_batched call per GPU, %d library workers (threads + streams)" % (world, args.workers)},
                 "gpu_launches": xb.kernel_launch_count() - launches0,
                 "check": {"ranks_item0": list(summaries[0][0]), "algorithmic_flops_per_item": 1.0e9}}
-        print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 def measured_peaks():
@@ -234,18 +314,10 @@ def measured_peaks():
 def bond_split_workload(args, rank, local_rank, world):
     """--workload c4: BASELINE configs[3], the two-site DMRG local-operator application at bond rank 512 (n = 4,
     operator rank 2), contraction split along the right bond index across the GPUs + one NCCL sum all-reduce.
-    Strong scaling: the total work (17.45 GFLOP per application) is fixed."""
+    Strong scaling: the total work (17.45 GFLOP per application) is fixed.  Returns the JSON line (rank 0) or None."""
     import numpy as np
-    import torch
-    import xerus_b200 as xb
     from xerus_b200 import parallel
-    torch.cuda.set_device(local_rank)
-    xb.init(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.ExternalStream(xb.stream_handle(), device=local_rank)
+    torch, xb, dist, stream = setup(local_rank, world)
     r, n, a = args.bond, 4, 2
     g = torch.Generator(device="cuda").manual_seed(4)                  # same inputs on every rank (replicated operands)
     rnd = lambda *shape: torch.randn(*shape, dtype=torch.float64, device="cuda", generator=g)
@@ -340,7 +412,7 @@ def bond_split_workload(args, rank, local_rank, world):
                 "other_collective_ms": (float(ms_other.item()) if ms_other is not None else None),
                 "gpu_launches": launches, "check": {"rel_err_vs_unsplit": err},
                 "whole_job_tflops": flops / (t * 1e-3) / 1e12,
-                "whole_job_frac_of_peak": flops / (t * 1e-3) / 1e12 / peak,
+                "whole_job_frac_of_peak": flops / (t * 1e-3) / 1e12 / (peak * world),      # of the N GPUs' combined peak
                 "roofline": {"kernel": "gemm_f64_big_kernel (128x128 tiles, cp.async, DMMA m8n8k4)", "bound": "tensor", "unit": "TFLOP/s",
                              "achieved": achieved, "peak": peak, "frac": achieved / peak,
                              # dram bytes read + written by the 1024 x 8192 x 512 launch (ncu --set full, profiles/r1_gemm_big.txt);
@@ -352,9 +424,22 @@ def bond_split_workload(args, rank, local_rank, world):
                                        "achieved": (mid_bytes / world / (mms * 1e-3) / 1e9) if mms > 0 else 0.0, "peak": hbm_peak,
                                        "frac": (mid_bytes / world / (mms * 1e-3) / 1e9 / hbm_peak) if mms > 0 else 0.0,
                                        "algorithmic_bytes_per_rank": mid_bytes / world, "ms_per_apply": mms, "launches": mlaunch}}
-        print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+        return line
+    return None
+
+
+def expected_ranks(w):
+    """Ranks of TTTensor::random({n}^d, r) (reduce_to_maximal_ranks, ttNetwork.cpp:370-402) capped at the target."""
+    d, n, r = w["d"], w["n"], w["r"]
+    return [min(r, n ** (i + 1), n ** (d - 1 - i), w["target"]) for i in range(d - 1)]
+
+
+def bench_config(w, world):
+    """The `config` object, identical in both arms (the driver compares them)."""
+    return {"workload": w["name"], "d": w["d"], "n": w["n"], "rank_in": w["r"], "rank_out": w["target"],
+            "ranks_out": expected_ranks(w),
+            "l2": "xb200 arm: flushed between timed iterations (512 MB write); reference arm: host caches as the reference leaves them",
+            "parallelism": "replicas x%d (no data-path collective); reference arm: rank 0 only, host threads" % world}
 
 
 def reference_arm(args, w, rank, world):
@@ -378,7 +463,7 @@ def reference_arm(args, w, rank, world):
         "impl": "reference", "metric": "TT-round ms (FP64)", "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (TTTensor::random, seed 0xBAADF00D)",
-        "config": {"workload": w["name"], "d": w["d"], "n": w["n"], "rank_in": w["r"], "rank_out": w["target"]},
+        "config": bench_config(w, world),
         "cpu_baseline": {"value": ms, "unit": "ms", "cores": threads_used, "kind": kind,
                          "sample": "%d x TTTensor::round(%d), unmodified xerus + OpenBLAS; faster of {1, %d} BLAS threads on %d host cores"
                                    % (len(times), w["target"], cores, cores)},
@@ -400,39 +485,42 @@ def main():
     ap.add_argument("--workers", type=int, default=8, help="host threads / library workers (CUDA streams) per GPU for --workload c5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-als", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the c4 / c5 sub-records of the default run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "xb200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
-    if args.workload == "c5":
-        batch_workload(args, rank, int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
-        return
-    if args.workload == "c4":
-        bond_split_workload(args, rank, int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
-        return
-    w = WORKLOADS[args.workload]
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload in ("c4", "c5") and args.impl == "xb200":
+        line = (batch_workload if args.workload == "c5" else bond_split_workload)(args, rank, local_rank, world)
+        if line is not None:
+            print(json.dumps(line))
+        teardown()
+        return
+    w = WORKLOADS[args.workload if args.workload in WORKLOADS else "c3"]
 
     if args.impl == "reference":
         reference_arm(args, w, rank, world)
         return
 
     import numpy as np
-    import torch
-    import xerus_b200 as xb
+    torch, xb, dist, stream = setup(local_rank, world)
 
-    torch.cuda.set_device(local_rank)
-    xb.init(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    stream = torch.cuda.ExternalStream(xb.stream_handle(), device=local_rank)
-
-    # ---- input: ranks of TTTensor::random({n}^d, r); i.i.d. N(0,1) cores, canonicalised on the device (move_core(0))
-    rng = np.random.default_rng(0xBAADF00D + rank)
+    # ---- input.  Rank 0 rounds the very TT the reference rounds: `ref_bench ... dump` (the unmodified reference, seed 0xBAADF00D)
+    # writes TTTensor::random({n}^d, r) and its own round(target); the result of the timed path is checked against it below
+    # (`check`).  Without the compiled reference in the snapshot, and on the other ranks (replicas): i.i.d. N(0,1) cores with the
+    # ranks of TTTensor::random, canonicalised on the device (move_core(0)).
     dims = [w["n"]] * w["d"]
-    base = xb.TTTensor.random(dims, w["r"], rng)
+    ref_dump = None
+    if rank == 0 and os.path.exists(REF_BENCH) and not args.no_cpu_baseline:
+        try:
+            ref_dump = reference_dump(w)
+        except Exception as ex:                                    # reported in `check`, never fatal
+            ref_dump = {"error": repr(ex)}
+    if ref_dump and "in" in ref_dump:
+        base = xb.TTTensor.from_cores(ref_dump["in"], core_position=0)
+    else:
+        base = xb.TTTensor.random(dims, w["r"], np.random.default_rng(0xBAADF00D + rank))
     ranks_in = base.ranks()
     host_cores = [torch.from_numpy(c).pin_memory() for c in base.cores()]     # pinned host copy for the e2e leg
     h2d_bytes = sum(c.numel() * 8 for c in host_cores)
@@ -478,6 +566,7 @@ def main():
     ms_per_step = float(total_ms.item()) / args.steps
     out_t = clones[-1]
     ranks_out = out_t.ranks()
+    assert ranks_out == expected_ranks(w), (ranks_out, expected_ranks(w))
 
     # ---- end to end through the host-pointer API --------------------------------------------------------------------
     def e2e_step():
@@ -496,6 +585,36 @@ def main():
     e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    # the same from pageable host arrays (what the reference's Tensor hands out: plain new[] memory, tensor.cpp:58)
+    pageable = [c.numpy().copy() for c in host_cores]
+
+    def e2e_pageable_step():
+        t = xb.TTTensor.from_cores(pageable, core_position=0)
+        t.round(w["target"])
+        return t.cores()
+
+    e2e_pageable_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_pageable_step()
+    barrier()
+    e2e_pageable_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    # ---- the partitioned workloads in the same run (BASELINE configs[3] and [4]): all ranks take part ------------------------
+    sub = {}
+    if not args.no_sub:
+        import copy
+        for name, fn, over in (("c4", bond_split_workload, dict(steps=max(3, min(args.steps, 10)), warmup=3)),
+                               ("c5", batch_workload, dict(steps=2, warmup=3, items=48))):
+            a2 = copy.copy(args)
+            for k, v in over.items():
+                setattr(a2, k, v)
+            try:
+                sub[name] = fn(a2, rank, local_rank, world)
+            except Exception as ex:                                # reported, never fatal for the headline line
+                sub[name] = {"error": repr(ex)}
+            barrier()
 
     # ---- roofline of the dominant kernel class (extra profiled pass, CUDA events inside the library) ----------------
     total_f, svd_f, qr_f, gemm_f, min_bytes = algorithmic_counts(dims, ranks_in, ranks_out)
@@ -524,15 +643,15 @@ def main():
     als = None
     if rank == 0 and not args.no_als:
         try:
-            als = als_sweep_numbers(xb, np, torch, stream, args)
+            als = als_sweep_numbers(xb, np, torch, stream, args, fp64_peak)
         except Exception as ex:       # reported, never fatal for the bench line
             als = {"error": repr(ex)}
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        teardown()
         return
 
+    check = check_against_reference(xb, np, out_t, ref_dump, w["target"])
     jac_scopes, jac_launches, jac_ms = prof["svd_jacobi"]
     svd_tf = svd_f / (jac_ms * 1e-3) / 1e12 if jac_ms > 0 else 0.0
     roofline = {
@@ -570,16 +689,15 @@ def main():
         "metric": "TT-round ms (FP64)", "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic (i.i.d. N(0,1) cores, ranks of TTTensor::random)",
-        "config": {"workload": w["name"], "d": w["d"], "n": w["n"], "rank_in": w["r"], "rank_out": w["target"],
-                   "ranks_out": ranks_out, "l2": "flushed between timed iterations (512 MB write)",
-                   "parallelism": "replicas x%d (no data-path collective)" % world},
-        "e2e": {"value": float(e2e_ms.item()), "unit": "ms", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+        "config": bench_config(w, world),
+        "e2e": {"value": float(e2e_ms.item()), "unit": "ms", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "host_buffers": "pinned", "pageable_value": e2e_pageable_ms},
         "gpu_launches": launches, "wall_ms_timed_region": wall_ms, "step_ms": step_ms,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "als": als,
+        "clocks": clocks, "check": check, "roofline": roofline, "cpu_baseline": cpu, "als": als,
+        "c4": sub.get("c4"), "c5": sub.get("c5"),
     }
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    teardown()
 
 
 if __name__ == "__main__":
