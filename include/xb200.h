@@ -200,6 +200,9 @@ xb_status xb_peer_buffer_bytes(size_t rows, size_t cols, int world, size_t* byte
 xb_status xb_peer_buffer_create(size_t bytes, void** dptr, unsigned char* handle64);
 xb_status xb_peer_buffer_open(const unsigned char* handle64, void** dptr);
 xb_status xb_peer_buffer_close(void* dptr);
+/* the waits inside xb_env_apply_fused are bounded; this synchronises the calling worker's stream and returns XB_ERR_CUDA if a
+ * wait on this rank's own buffer gave up (a peer lagged or died: the result of that call and of all later ones is not valid) */
+xb_status xb_peer_buffer_check(void* dptr);
 xb_status xb_peer_buffer_destroy(void* dptr);
 xb_status xb_env_apply_fused(const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims, size_t sites,
                              const double* R, size_t r, size_t a_right, const double* v, size_t slab_begin, size_t slab_end,

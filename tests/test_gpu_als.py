@@ -276,3 +276,28 @@ def test_fused_bond_split_apply_on_one_device(world):
     from xerus_b200._lib import call
     for q in bufs:
         call("xb_peer_buffer_destroy", q)
+
+
+def test_fused_bond_split_reports_a_missing_peer():
+    """A rank whose peer never shows up: the bounded wait gives up, the reduce kernel publishes nothing, and
+    PeerExchange.check() raises instead of handing out a partial sum."""
+    import torch
+    from xerus_b200 import parallel
+    from xerus_b200._lib import call
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(3)
+    r, n, a = 16, 2, 2
+    rnd = lambda *shape: torch.randn(*shape, dtype=torch.float64, generator=g).to(dev)
+    L, R, A1, v = rnd(r, a, r), rnd(r, a, r), rnd(a, n, n, a), rnd(r, n, r)
+    torch.cuda.synchronize()
+    bufs = parallel.PeerExchange.allocate_local(r * n, r, 2)
+    px = parallel.PeerExchange(r * n, r, 0, 2, local_buffers=bufs)       # rank 1 never calls
+    xb.set_option("peer_wait_spins", 1 << 16)                            # the default bound is about a minute of polling
+    try:
+        parallel.bond_split_apply_fused(L, [A1], R, v, px)
+        with pytest.raises(xb.XerusError):
+            px.check()
+    finally:
+        xb.set_option("peer_wait_spins", 1 << 28)
+    for q in bufs:
+        call("xb_peer_buffer_destroy", q)

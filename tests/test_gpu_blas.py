@@ -397,3 +397,26 @@ def test_error_behaviour():
         BW.matrix_matrix_product(1.0, np.ones((3, 4)), False, np.ones((5, 2)), False)
     with pytest.raises(xb.XerusError):
         BW.qr(np.ones((0, 3)))
+
+
+def test_unfoldings_taller_than_the_grid_y_limit():
+    """TT unfoldings have millions of rows: to_dense / from_dense of a 2^23 tensor multiply and transpose matrices whose row tiles
+    exceed the 65535 limit of grid.y (the m tiles go on grid.x then)."""
+    rng = np.random.default_rng(8)
+    d = 23
+    t = xb.TTTensor.random([2] * d, 2, rng)
+    full = t.to_dense()                                   # last product: (2^22 x 2) * (2 x 2): 131072 row tiles of 32
+    assert full.shape == (2,) * d
+    cores = t.cores()
+    ref = cores[0].reshape(2, -1)
+    for c in cores[1:]:
+        ref = (ref @ c.reshape(c.shape[0], -1)).reshape(-1, c.shape[-1])
+    assert np.linalg.norm(full.reshape(-1) - ref.reshape(-1)) < 1e-12 * np.linalg.norm(ref)
+    back = xb.TTTensor.from_dense(full, 1e-12)            # first SVD sees a (2^22 x 2) matrix
+    assert back.ranks() == t.ranks()
+    assert back.distance(t) < 1e-10 * t.frob_norm()
+    # transpose with more than 65535 row tiles, and a GEMM with that many m tiles, directly
+    A = rng.standard_normal((2_200_000, 3))
+    assert np.array_equal(xb.reshuffle(A, [1, 0]), A.T)
+    B = rng.standard_normal((3, 5))
+    assert rel(xb.blasWrapper.matrix_matrix_product(1.0, A, False, B, False), A @ B) < 1e-13

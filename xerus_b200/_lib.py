@@ -74,7 +74,7 @@ _SIGS = {
     "xb_als_solve": [vp, vp, vp, P(ALSOptions), dp, szp],
     "xb_env_apply": [vp, vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz],
     "xb_peer_buffer_bytes": [sz, sz, C.c_int, szp], "xb_peer_buffer_create": [sz, P(vp), C.c_char_p],
-    "xb_peer_buffer_open": [C.c_char_p, P(vp)], "xb_peer_buffer_close": [vp], "xb_peer_buffer_destroy": [vp],
+    "xb_peer_buffer_open": [C.c_char_p, P(vp)], "xb_peer_buffer_close": [vp], "xb_peer_buffer_check": [vp], "xb_peer_buffer_destroy": [vp],
     "xb_env_apply_fused": [vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz, C.c_int, C.c_int, P(vp), C.c_uint, P(vp)],
     "xb_file_open": [P(vp), C.c_char_p], "xb_file_close": [vp],
     "xb_file_info": [vp, P(C.c_int), szp, P(C.c_int), szp], "xb_file_dims": [vp, szp], "xb_file_ranks": [vp, szp],

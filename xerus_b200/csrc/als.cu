@@ -1225,6 +1225,9 @@ struct PeerPtrs { unsigned int* flags[8]; double* y[8]; };
 __global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerPtrs pp, const double* __restrict__ recv, const size_t block_elems, const int rank,
                                                            const int world, const unsigned int epoch) {
 	unsigned int* myflags = pp.flags[rank];
+	// a wait on this buffer has timed out (a peer lagged or died): the receive slots may be incomplete — sum nothing, publish
+	// nothing, bump nothing; the peers' waits then time out as well and xb_peer_buffer_check() reports it on every rank
+	if (*((volatile unsigned int*)(myflags + 3)) == 0xDEADu) return;
 	const size_t nv = block_elems / 2;                   // block_elems is even (checked on the host)
 	const double2* rv = reinterpret_cast<const double2*>(recv);
 	for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < nv; e += (size_t)gridDim.x * blockDim.x) {
@@ -1243,11 +1246,11 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerPtrs pp, con
 	}
 }
 // one thread of one CTA polls (the waiting must not occupy the SMs the peers' kernels may need when "ranks" share a device)
-__global__ void peer_wait_kernel(unsigned int* myflags, const int which, const unsigned int expected) {
+__global__ void peer_wait_kernel(unsigned int* myflags, const int which, const unsigned int expected, const unsigned int max_spins) {
 	if (threadIdx.x == 0) {
 		unsigned int spins = 0;
-		while (*((volatile unsigned int*)(myflags + which)) < expected && ++spins < (1u << 28)) {}
-		if (spins >= (1u << 28)) myflags[3] = 0xDEADu;
+		while (*((volatile unsigned int*)(myflags + which)) < expected && ++spins < max_spins) {}
+		if (spins >= max_spins) myflags[3] = 0xDEADu;
 		__threadfence_system();
 	}
 }
@@ -1271,6 +1274,19 @@ xb_status xb_peer_buffer_open(const unsigned char* handle64, void** dptr) {
 		cudaIpcMemHandle_t h;
 		std::memcpy(&h, handle64, 64);
 		XB_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+	});
+}
+// The waits of xb_env_apply_fused are bounded (2^28 polls); one that gives up poisons word 3 of the rank's flag block, the reduce
+// kernel then publishes nothing.  This is the host-side check: synchronises the calling worker's stream and reports the poison.
+xb_status xb_peer_buffer_check(void* dptr) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(dptr, "null");
+		Context& c = ctx();
+		unsigned int* h = reinterpret_cast<unsigned int*>(c.h_scratch);
+		XB_CUDA(cudaMemcpyAsync(h, static_cast<unsigned int*>(dptr) + 3, sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+		XB_CUDA(cudaStreamSynchronize(c.stream));
+		if (*h == 0xDEADu) throw Error(XB_ERR_CUDA, "bond-split exchange: a wait for the peers timed out (a rank lagged by more than the bounded wait or died); the result is not valid");
 	});
 }
 xb_status xb_peer_buffer_close(void* dptr) { return guard([&] { if (dptr) XB_CUDA(cudaIpcCloseMemHandle(dptr)); }); }
@@ -1335,11 +1351,12 @@ xb_status xb_env_apply_fused(const double* L, size_t l, size_t a_left, const dou
 		peer_signal_kernel<<<1, 32, 0, c.stream>>>(reinterpret_cast<unsigned int* const*>(table.p), rank, world, 0);
 		XB_LAUNCH_CHECK();
 		const unsigned grid = unsigned(std::min<size_t>((block_elems / 2 + 255) / 256, size_t(c.num_sms) * 4));
-		peer_wait_kernel<<<1, 32, 0, c.stream>>>(flags_of(rank), 0, epoch * unsigned(world - 1));      // every peer's partial block has landed
+		const unsigned int max_spins = unsigned(std::max(1024.0, c.peer_wait_spins));
+		peer_wait_kernel<<<1, 32, 0, c.stream>>>(flags_of(rank), 0, epoch * unsigned(world - 1), max_spins);      // every peer's partial block has landed
 		XB_LAUNCH_CHECK();
 		peer_reduce_kernel<<<grid, 256, 0, c.stream>>>(pp, recv_of(rank), block_elems, rank, world, epoch);
 		XB_LAUNCH_CHECK();
-		peer_wait_kernel<<<1, 32, 0, c.stream>>>(flags_of(rank), 1, epoch * unsigned(world));
+		peer_wait_kernel<<<1, 32, 0, c.stream>>>(flags_of(rank), 1, epoch * unsigned(world), max_spins);
 		XB_LAUNCH_CHECK();
 		*y_out = y_of(rank);
 	});

@@ -28,6 +28,9 @@ struct GemmArgs {
 	// receive buffer over NVLink, so the transfer runs while the remaining tiles are still being multiplied).
 	double* Cblk[8];
 	int rpb;
+	// tall outputs (TT unfoldings: m = prod n_i reaches millions of rows): the m tiles go on grid.x, whose limit is 2^31 - 1
+	// (grid.y stops at 65535), the n tiles on grid.y
+	int swap_xy;
 };
 __device__ __forceinline__ double* gemm_out_row(const GemmArgs& g, double* C, const int row) {
 	return g.rpb ? g.Cblk[row / g.rpb] + (long long)(row % g.rpb) * g.ldc : C + (long long)row * g.ldc;
@@ -47,7 +50,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int wm = warp >> 1, wn = warp & 1;
 	const int grp = lane >> 2, tig = lane & 3;
-	const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+	const int m0 = (g.swap_xy ? blockIdx.x : blockIdx.y) * BM, n0 = (g.swap_xy ? blockIdx.y : blockIdx.x) * BN;
 	const double* __restrict__ A = g.A + (long long)blockIdx.z * g.strideA;
 	const double* __restrict__ B = g.B + (long long)blockIdx.z * g.strideB;
 	double* __restrict__ C = g.C + (long long)blockIdx.z * g.strideC;
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(BIG_THREADS, 1) gemm_f64_big_kernel(const Gemm
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int wm = warp >> 2, wn = warp & 3;             // 2 x 4 warps, warp tile 64 x 32
 	const int grp = lane >> 2, tig = lane & 3;
-	const int m0 = blockIdx.y * BIG_BM, n0 = blockIdx.x * BIG_BN;
+	const int m0 = (g.swap_xy ? blockIdx.x : blockIdx.y) * BIG_BM, n0 = (g.swap_xy ? blockIdx.y : blockIdx.x) * BIG_BN;
 	const double* __restrict__ A = g.A + (long long)blockIdx.z * g.strideA;
 	const double* __restrict__ B = g.B + (long long)blockIdx.z * g.strideB;
 	double* __restrict__ C = g.C + (long long)blockIdx.z * g.strideC;
@@ -300,8 +303,14 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
 	g.strideC = (long long)strideC; g.strideA = (long long)strideA; g.strideB = (long long)strideB;
 	g.m = int(m); g.n = int(n); g.k = int(k);
 	g.transA = transA; g.transB = transB; g.alpha = alpha; g.beta = beta;
-	g.rpb = 0;
+	g.rpb = 0; g.swap_xy = 0;
 	for (int i = 0; i < 8; ++i) g.Cblk[i] = nullptr;
+	auto make_grid = [&](size_t tile) {
+		const size_t tn = (n + tile - 1) / tile, tm = (m + tile - 1) / tile;
+		g.swap_xy = tm > 65535 ? 1 : 0;
+		XB_REQUIRE((g.swap_xy ? tn : tm) <= 65535, "both dimensions of the GEMM output are too large for the launch grid");
+		return g.swap_xy ? dim3(unsigned(tm), unsigned(tn), unsigned(batch)) : dim3(unsigned(tn), unsigned(tm), unsigned(batch));
+	};
 	bool blocks_aligned = true;
 	if (tl_scatter) {
 		XB_REQUIRE(beta == 0.0 && batch == 1 && tl_scatter->rows_per_block > 0 && (m + tl_scatter->rows_per_block - 1) / tl_scatter->rows_per_block <= 8,
@@ -316,8 +325,7 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
 	if (ctx().gemm_big && !ctx().gemm_force_small && tiles128 * 5 >= size_t(ctx().num_sms) * 4 && k >= 64 && k % 2 == 0 &&
 	    lda % 2 == 0 && ldb % 2 == 0 && strideA % 2 == 0 && strideB % 2 == 0 && aligned16(A) && aligned16(B) &&
 	    (!transA || m % 2 == 0) && (transB || n % 2 == 0)) {
-		dim3 grid(unsigned((n + 127) / 128), unsigned((m + 127) / 128), unsigned(batch));
-		XB_REQUIRE(grid.y <= 65535, "m too large for the GEMM grid");
+		const dim3 grid = make_grid(128);
 		const int vec_store = (ldc % 2 == 0 && strideC % 2 == 0 && aligned16(C) && blocks_aligned) ? 1 : 0;
 		if (transA) { if (transB) launch_big<true, true>(g, grid, vec_store); else launch_big<true, false>(g, grid, vec_store); }
 		else { if (transB) launch_big<false, true>(g, grid, vec_store); else launch_big<false, false>(g, grid, vec_store); }
@@ -327,12 +335,10 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
 	const size_t tiles64 = ((m + 63) / 64) * ((n + 63) / 64) * batch;
 	const bool small = ctx().gemm_force_small || tiles64 < size_t(ctx().num_sms);
 	if (small) {
-		dim3 grid(unsigned((n + 31) / 32), unsigned((m + 31) / 32), unsigned(batch));
-		XB_REQUIRE(grid.y <= 65535, "m too large for the small-tile GEMM");
+		const dim3 grid = make_grid(32);
 		gemm_f64_kernel<2, 2><<<grid, GEMM_THREADS, 0, ctx().stream>>>(g);
 	} else {
-		dim3 grid(unsigned((n + 63) / 64), unsigned((m + 63) / 64), unsigned(batch));
-		XB_REQUIRE(grid.y <= 65535, "m too large for the GEMM grid");
+		const dim3 grid = make_grid(64);
 		gemm_f64_kernel<4, 4><<<grid, GEMM_THREADS, 0, ctx().stream>>>(g);
 	}
 	XB_LAUNCH_CHECK();

@@ -59,9 +59,10 @@ __global__ void scale_cols_kernel(double* __restrict__ A, const double* __restri
 // out (cols x rows) = in^T ; 32x32 tiles through shared memory, both sides coalesced.  REVERSE additionally flips
 // both index ranges (used to express RQ through QR: out(j,i) = in(rows-1-i, cols-1-j)).
 template <bool REVERSE>
-__global__ void transpose_kernel(double* __restrict__ out, const double* __restrict__ in, size_t rows, size_t cols) {
+__global__ void transpose_kernel(double* __restrict__ out, const double* __restrict__ in, size_t rows, size_t cols, const int swap_xy) {
 	__shared__ double tile[32][33];
-	const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
+	// swap_xy: the row tiles of a very tall input sit on grid.x (limit 2^31 - 1; grid.y stops at 65535)
+	const size_t c0 = (size_t)(swap_xy ? blockIdx.y : blockIdx.x) * 32, r0 = (size_t)(swap_xy ? blockIdx.x : blockIdx.y) * 32;
 	for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
 		const size_t r = r0 + dy, c = c0 + threadIdx.x;
 		if (r < rows && c < cols) tile[dy][threadIdx.x] = in[r * cols + c];
@@ -156,8 +157,12 @@ __global__ void scale_block_by_dev_kernel(double* __restrict__ A, size_t ld, siz
 }
 
 static void reduce(double* d_result, const double* x, const double* y, size_t n, int mode) {
-	double*& partial = ctx().red_partial;
+	// the side stream (AuxScope) has its own scratch: block partials and the arrival counter of two reductions in flight on the
+	// two streams of a worker must not be shared
+	Context& c = ctx();
+	double*& partial = (c.aux && c.stream == c.aux) ? c.red_partial_aux : c.red_partial;
 	if (!partial) {
+		if (c.arena_on) throw SpecUnsupported("reduction scratch must exist before a plan is captured");
 		partial = dalloc(RED_MAX_BLOCKS + 2);                 // block partials | arrival counter
 		XB_CUDA(cudaMemsetAsync(partial + RED_MAX_BLOCKS, 0, 2 * sizeof(double), ctx().stream));
 	}
@@ -213,16 +218,20 @@ void scale_cols(double* A, const double* s, size_t rows, size_t cols, size_t ld)
 void transpose(double* out, const double* in, size_t rows, size_t cols) {
 	if (!rows || !cols) return;
 	if (rows == 1 || cols == 1) { copy(out, in, rows * cols); return; }
-	dim3 grid(unsigned((cols + 31) / 32), unsigned((rows + 31) / 32)), block(32, 8);
-	XB_REQUIRE(grid.y <= 65535, "matrix too tall for the transpose grid");
-	transpose_kernel<false><<<grid, block, 0, ctx().stream>>>(out, in, rows, cols);
+	const size_t tc = (cols + 31) / 32, tr = (rows + 31) / 32;
+	const int swap_xy = tr > 65535 ? 1 : 0;
+	XB_REQUIRE((swap_xy ? tc : tr) <= 65535, "both dimensions are too large for the transpose grid");
+	dim3 grid(unsigned(swap_xy ? tr : tc), unsigned(swap_xy ? tc : tr)), block(32, 8);
+	transpose_kernel<false><<<grid, block, 0, ctx().stream>>>(out, in, rows, cols, swap_xy);
 	XB_LAUNCH_CHECK();
 }
 void transpose_reverse(double* out, const double* in, size_t rows, size_t cols) {
 	if (!rows || !cols) return;
-	dim3 grid(unsigned((cols + 31) / 32), unsigned((rows + 31) / 32)), block(32, 8);
-	XB_REQUIRE(grid.y <= 65535, "matrix too tall for the transpose grid");
-	transpose_kernel<true><<<grid, block, 0, ctx().stream>>>(out, in, rows, cols);
+	const size_t tc = (cols + 31) / 32, tr = (rows + 31) / 32;
+	const int swap_xy = tr > 65535 ? 1 : 0;
+	XB_REQUIRE((swap_xy ? tc : tr) <= 65535, "both dimensions are too large for the transpose grid");
+	dim3 grid(unsigned(swap_xy ? tr : tc), unsigned(swap_xy ? tc : tr)), block(32, 8);
+	transpose_kernel<true><<<grid, block, 0, ctx().stream>>>(out, in, rows, cols, swap_xy);
 	XB_LAUNCH_CHECK();
 }
 

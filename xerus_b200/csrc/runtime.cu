@@ -1,5 +1,6 @@
 // xb200 runtime: device context, stream, stream-ordered memory pool, error state, memory hooks of the C ABI.
 #include "xb_internal.cuh"
+#include <atomic>
 #include <mutex>
 #include <cstdlib>
 
@@ -14,6 +15,7 @@ static Context* g_workers[XB_MAX_WORKERS] = {&g_ctx};
 static int g_num_workers = 1;
 static thread_local int tl_worker = 0;
 static std::mutex g_ctx_mutex;
+static std::atomic<bool> g_ready{false};        // set once worker 0 is fully initialised (read without the mutex by every entry point)
 Context& ctx() { return *g_workers[tl_worker]; }
 
 static void apply_option(Context& c, const std::string& k, double value) {
@@ -46,6 +48,7 @@ static void apply_option(Context& c, const std::string& k, double value) {
 	else if (k == "als_direct_max") c.als_direct_max = int(value);
 	else if (k == "round_plans") c.round_plans = int(value);
 	else if (k == "small_kernels") c.small_kernels = int(value);
+	else if (k == "peer_wait_spins") c.peer_wait_spins = value;
 	else if (k == "batch_workers") c.batch_workers = int(value);
 	else throw Error(XB_ERR_INVALID, "xb_set_option: unknown key " + k);
 }
@@ -74,6 +77,7 @@ static void init_locked(int device) {
 	XB_CUDA(cudaMemPoolSetAttribute(g_ctx.pool, cudaMemPoolAttrReleaseThreshold, &threshold));
 	XB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&g_ctx.h_scratch), g_ctx.h_scratch_len * sizeof(double)));
 	g_ctx.initialised = true;
+	g_ready.store(true, std::memory_order_release);
 	// XB_OPTIONS="key=value,key=value": the knobs of xb_set_option from the environment (A/B runs of any driver)
 	if (const char* env = getenv("XB_OPTIONS")) {
 		std::string all(env);
@@ -90,7 +94,7 @@ static void init_locked(int device) {
 }
 
 void ensure_init() {
-	if (g_ctx.initialised) {
+	if (g_ready.load(std::memory_order_acquire)) {
 		// the caller may be a different host thread (ctypes); make the library device current
 		cudaSetDevice(g_ctx.device);
 		return;
@@ -109,7 +113,7 @@ static void select_worker(int w) {
 		c->num_sms = g_ctx.num_sms; c->max_smem_optin = g_ctx.max_smem_optin;
 		c->svd_max_sweeps = g_ctx.svd_max_sweeps; c->gemm_force_small = g_ctx.gemm_force_small; c->gemm_big = g_ctx.gemm_big; c->qr_defer = g_ctx.qr_defer;
 		c->svd_persistent = g_ctx.svd_persistent; c->svd_polish = g_ctx.svd_polish; c->tt_svd_polish = g_ctx.tt_svd_polish; c->svd_mixed = g_ctx.svd_mixed; c->svd_recursive = g_ctx.svd_recursive; c->svd_flip = g_ctx.svd_flip; c->svd_split = g_ctx.svd_split; c->svd_dsmem = g_ctx.svd_dsmem; c->svd_colsort = g_ctx.svd_colsort; c->svd_last_sweep_cos = g_ctx.svd_last_sweep_cos; c->svd_gram = g_ctx.svd_gram; c->als_graph = g_ctx.als_graph; c->als_persistent_cg = g_ctx.als_persistent_cg; c->als_cg_cluster = g_ctx.als_cg_cluster; c->svd_jacc = g_ctx.svd_jacc; c->svd_fast = g_ctx.svd_fast; c->qr_cluster = g_ctx.qr_cluster; c->qr_cluster_min_rows = g_ctx.qr_cluster_min_rows; c->svd_square_qr = g_ctx.svd_square_qr;
-		c->svd_mixed_min = g_ctx.svd_mixed_min; c->svd_max_bw = g_ctx.svd_max_bw; c->als_direct_max = g_ctx.als_direct_max; c->round_plans = g_ctx.round_plans; c->small_kernels = g_ctx.small_kernels; c->batch_workers = g_ctx.batch_workers;
+		c->svd_mixed_min = g_ctx.svd_mixed_min; c->svd_max_bw = g_ctx.svd_max_bw; c->als_direct_max = g_ctx.als_direct_max; c->round_plans = g_ctx.round_plans; c->small_kernels = g_ctx.small_kernels; c->peer_wait_spins = g_ctx.peer_wait_spins; c->batch_workers = g_ctx.batch_workers;
 		XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 		XB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scratch), c->h_scratch_len * sizeof(double)));
 		{
@@ -254,9 +258,23 @@ xb_status xb_shutdown(void) {
 	return guard([&] {
 		std::lock_guard<std::mutex> lock(g_ctx_mutex);
 		if (!g_ctx.initialised) return;
-		cudaStreamSynchronize(g_ctx.stream);
-		cudaFreeHost(g_ctx.h_scratch);
-		cudaStreamDestroy(g_ctx.stream);
+		g_ready.store(false, std::memory_order_release);
+		// every worker: streams, events, pinned scratch, reduction scratch, its memory pool (worker 0 uses the device's default pool)
+		for (int w = 0; w < g_num_workers; ++w) {
+			Context* c = g_workers[w];
+			cudaStreamSynchronize(c->stream);
+			if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
+			if (c->aux_fork_ev) cudaEventDestroy(c->aux_fork_ev);
+			if (c->aux_join_ev) cudaEventDestroy(c->aux_join_ev);
+			release_plans(*c);
+			if (c->red_partial) cudaFree(c->red_partial);
+			if (c->red_partial_aux) cudaFree(c->red_partial_aux);
+			if (c->h_scratch) cudaFreeHost(c->h_scratch);
+			cudaStreamDestroy(c->stream);
+			if (w > 0) { if (c->pool) cudaMemPoolDestroy(c->pool); delete c; g_workers[w] = nullptr; }
+		}
+		g_num_workers = 1;
+		tl_worker = 0;
 		g_ctx = Context();
 	});
 }

@@ -186,7 +186,8 @@ void qr_small(double* Q, long long qrs, long long qcs, double* R, long long rrs,
 __global__ void __launch_bounds__(SM_THREADS) svd_small_kernel(const double* __restrict__ A, const long long rs, const long long cs, const int mw, const int nw,
                                                                double* __restrict__ GT, const int ld, const int voff,
                                                                double* __restrict__ Ssorted, int* __restrict__ perm, double* __restrict__ scale2,
-                                                               unsigned int* __restrict__ info, const double tol, const double last_cos, const int max_sweeps) {
+                                                               unsigned int* __restrict__ info, const double tol, const double last_cos, const int max_sweeps,
+                                                               const int polish) {
 	extern __shared__ __align__(16) double sm[];
 	const int np = (nw + 1) & ~1;                      // even number of columns (a zero column pads odd ones)
 	const int ldx = mw + 1, ldv = nw + 1;
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(SM_THREADS) svd_small_kernel(const double* __r
 	double* V = X + (size_t)np * ldx;                  // np * ldv
 	double* nrm = V + (size_t)np * ldv;                // np : squared norms
 	double* red = nrm + np;                            // SM_WARPS + 2
+	double* T = red + SM_WARPS + 2;                    // nw * ldv : Newton-Schulz factor, then the polished V
 	__shared__ double sweep_max[SM_WARPS];
 	__shared__ int stop_flag;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -271,6 +273,41 @@ __global__ void __launch_bounds__(SM_THREADS) svd_small_kernel(const double* __r
 		converged = stop_flag != 0;
 		__syncthreads();
 	}
+	if (polish && nw > 1) {
+		// Polish (as Svd::factor does after the multi-CTA kernels): hundreds of plane rotations leave V orthogonal to ~eps * sqrt(#rotations)
+		// and X = G V with the same drift.  One Newton-Schulz step V <- V (1.5 I - 0.5 V'V) makes V orthogonal to eps^2-level, and the
+		// left part is recomputed from the untouched input, X = G0 V: backward error back at the eps * sqrt(n) of LAPACK.
+		for (int e = threadIdx.x; e < nw * nw; e += SM_THREADS) {
+			const int j = e / nw, l = e - j * nw;
+			const double* vj = V + (size_t)j * ldv; const double* vl = V + (size_t)l * ldv;
+			double g = 0.0;
+			for (int c = 0; c < nw; ++c) g += vj[c] * vl[c];
+			T[(size_t)j * ldv + l] = (j == l ? 1.5 : 0.0) - 0.5 * g;
+		}
+		__syncthreads();
+		// Vnew[j][c] = sum_l T[l][j] V[l][c]  (T symmetric); staged through X's first rows?  no: X is still needed -> use registers
+		double vnew[2];
+		int cnt = 0;
+		for (int e = threadIdx.x; e < nw * nw; e += SM_THREADS, ++cnt) {
+			const int j = e / nw, c = e - j * nw;
+			double a = 0.0;
+			for (int l = 0; l < nw; ++l) a += T[(size_t)l * ldv + j] * V[(size_t)l * ldv + c];
+			vnew[cnt] = a;                          // nw <= 32: at most two entries per thread
+		}
+		__syncthreads();
+		cnt = 0;
+		for (int e = threadIdx.x; e < nw * nw; e += SM_THREADS, ++cnt) { const int j = e / nw, c = e - j * nw; V[(size_t)j * ldv + c] = vnew[cnt]; }
+		__syncthreads();
+		// X[j][i] = sum_c G0(i, c) V[j][c], G0 = scl * A
+		for (int e = threadIdx.x; e < nw * mw; e += SM_THREADS) {
+			const int j = e / mw, i = e - j * mw;
+			const double* vj = V + (size_t)j * ldv;
+			double a = 0.0;
+			for (int c = 0; c < nw; ++c) a += A[i * rs + c * cs] * vj[c];
+			X[(size_t)j * ldx + i] = a * scl;
+		}
+		__syncthreads();
+	}
 	// singular values = column norms (recomputed), ranked in descending order
 	for (int j = warp; j < nw; j += SM_WARPS) {
 		const double* x = X + (size_t)j * ldx;
@@ -294,7 +331,7 @@ __global__ void __launch_bounds__(SM_THREADS) svd_small_kernel(const double* __r
 
 static size_t svd_small_smem(size_t mw, size_t nw) {
 	const size_t np = (nw + 1) & ~size_t(1);
-	return (np * (mw + 1) + np * (nw + 1) + np + SM_WARPS + 2) * sizeof(double);
+	return (np * (mw + 1) + np * (nw + 1) + np + SM_WARPS + 2 + nw * (nw + 1)) * sizeof(double);
 }
 
 bool svd_small_fits(size_t mw, size_t nw) {
@@ -304,14 +341,14 @@ bool svd_small_fits(size_t mw, size_t nw) {
 }
 
 void svd_small(const double* A, long long rs, long long cs, size_t mw, size_t nw, double* GT, size_t ld, size_t voff, double* Ssorted, int* perm,
-               double* scale2, unsigned int* info, double tol, double last_cos, int max_sweeps) {
+               double* scale2, unsigned int* info, double tol, double last_cos, int max_sweeps, int polish) {
 	static bool attr_set = false;
 	if (!attr_set) {
 		XB_CUDA(cudaFuncSetAttribute(svd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		attr_set = true;
 	}
 	svd_small_kernel<<<1, SM_THREADS, svd_small_smem(mw, nw), ctx().stream>>>(A, rs, cs, int(mw), int(nw), GT, int(ld), int(voff), Ssorted, perm, scale2, info,
-	                                                                         tol, last_cos, max_sweeps);
+	                                                                         tol, last_cos, max_sweeps, polish);
 	XB_LAUNCH_CHECK();
 }
 

@@ -1733,7 +1733,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 		{
 			ProfScope prof_jacobi("svd_jacobi");
 			svd_small(A, srs, scs, mw, nw, GT, ld, voff, Ssorted, reinterpret_cast<int*>(perm.p), scale, d_info,
-			          std::sqrt(double(mdot)) * DBL_EPS, c.svd_last_sweep_cos, c.svd_max_sweeps);
+			          std::sqrt(double(mdot)) * DBL_EPS, c.svd_last_sweep_cos, c.svd_max_sweeps, (c.svd_polish && polish > 0) ? 1 : 0);
 		}
 		S.resize(nw);
 		if (c.speculate) {

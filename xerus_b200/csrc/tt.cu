@@ -201,6 +201,13 @@ struct RoundPlan {
 	}
 };
 
+}  // namespace xb
+void xb::release_plans(Context& c) {
+	for (RoundPlan* p : c.plans) delete p;
+	c.plans.clear();
+}
+namespace xb {
+
 static std::string plan_key(const xb_tt* t, const size_t* max_ranks, double eps) {
 	std::string k;
 	auto put = [&](const void* p, size_t n) { k.append(reinterpret_cast<const char*>(p), n); };

@@ -38,6 +38,7 @@ struct Context {
 	bool initialised = false;
 	int worker = 0;
 	double* red_partial = nullptr;   // scratch of the two-stage reductions
+	double* red_partial_aux = nullptr;   // the same for reductions issued on the side stream
 	std::vector<ProfRecord> prof_pending;
 	std::vector<std::pair<std::string, ProfTotal>> prof_totals;
 	int device = -1;
@@ -82,6 +83,7 @@ struct Context {
 	int svd_mixed_min = 64;        // smallest column count for the mixed path
 	int svd_max_bw = 0;            // 0 = automatic block width of the Jacobi kernel
 	int als_direct_max = 1536;     // local problems up to this size are solved densely (reference semantics), larger ones by CG
+	double peer_wait_spins = 268435456.0;   // bound of the polling loops of the fused bond-split exchange (2^28 polls, about a minute)
 	int small_kernels = 1;         // min(m,n) <= 32: QR and Jacobi SVD as one single-CTA launch each (small_f64.cu)
 	int batch_workers = 8;         // host threads / library workers of the batched entry points (xb_tt_round_batched, ...)
 	int round_plans = 1;           // round(): repeated shapes replay a captured CUDA graph of the whole sweep (speculative ranks, tt.cu)
@@ -99,6 +101,7 @@ struct Context {
 	uint64_t options_epoch = 0;    // bumped by xb_set_option: plans recorded under other options are not replayed
 };
 Context& ctx();               // the calling thread's current worker
+void release_plans(Context& c);   // destroys the round plans of a worker (tt.cu)
 void ensure_init();
 
 // Optional CUDA-event timing of a kernel class (bench/roofline only; no-op unless xb_profile_enable(1)).
@@ -197,7 +200,7 @@ bool qr_small_fits(size_t m, size_t n);
 void qr_small(double* Q, long long qrs, long long qcs, double* R, long long rrs, long long rcs, const double* A, long long ars, long long acs, size_t m, size_t n);
 bool svd_small_fits(size_t mw, size_t nw);
 void svd_small(const double* A, long long rs, long long cs, size_t mw, size_t nw, double* GT, size_t ld, size_t voff, double* Ssorted, int* perm,
-               double* scale2, unsigned int* info, double tol, double last_cos, int max_sweeps);
+               double* scale2, unsigned int* info, double tol, double last_cos, int max_sweeps, int polish);
 
 struct SvdWork;   // opaque between svd_factor and svd_extract
 // Jacobi SVD of A (m x n packed).  Returns singular values (descending) on the host, keeps vectors on device.

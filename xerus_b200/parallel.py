@@ -175,6 +175,12 @@ class PeerExchange:
             out.append(q.value)
         return out
 
+    def check(self):
+        """Synchronises this worker's stream and raises XerusError if a bounded wait of the fused exchange gave up on this rank
+        (a peer lagged by more than the wait or died): results since then are not valid (xb_peer_buffer_check)."""
+        from ._lib import call
+        call("xb_peer_buffer_check", self.ptrs[self.rank])
+
     def close(self, dist=None):
         from ._lib import call
         import ctypes as C
