@@ -36,13 +36,25 @@ def exe(name):
 
 
 def run_tests(binary, names, env=None):
-    """One process per group of tests (a test that dies takes only its group along); returns {name: passed}."""
-    result = {}
+    """All tests in one process first (the runner takes several names); whatever has no verdict afterwards — the process died in an
+    earlier test — is run again one process per test.  Returns {name: passed}."""
     e = dict(os.environ, **(env or {}))
-    for name in names:
-        p = subprocess.run([binary, name], capture_output=True, text=True, timeout=600, env=e)
+
+    def verdicts(args):
+        p = subprocess.run([binary] + args, capture_output=True, text=True, timeout=1200, env=e)
         out = re.sub(r"\x1b\[[0-9;]*m", "", p.stdout + p.stderr)
-        result[name] = p.returncode == 0 and (name + ": passed!") in out and "FAILED" not in out
+        res = {}
+        for n in args:
+            if (n + ": passed!") in out:
+                res[n] = True
+            elif (n + ": FAILED!") in out:
+                res[n] = False
+        return res
+
+    result = verdicts(list(names))
+    for n in names:
+        if n not in result:
+            result[n] = verdicts([n]).get(n, False)
     return result
 
 
