@@ -420,3 +420,15 @@ def test_unfoldings_taller_than_the_grid_y_limit():
     assert np.array_equal(xb.reshuffle(A, [1, 0]), A.T)
     B = rng.standard_normal((3, 5))
     assert rel(xb.blasWrapper.matrix_matrix_product(1.0, A, False, B, False), A @ B) < 1e-13
+
+
+def test_svd_beyond_the_persistent_kernels():
+    """More than 512 rows per working column after the reduction / more block pairs than SMs: the launch-per-round Jacobi kernel
+    (jacobi_block_kernel), the fallback of Svd::factor that the cooperative kernels leave to large matrices."""
+    rng = np.random.default_rng(12)
+    A = rng.standard_normal((1100, 1100))
+    U, S, Vt = BW.svd(A)
+    s_ref = np.linalg.svd(A, compute_uv=False)
+    assert np.max(np.abs(S - s_ref)) < 1e-12 * s_ref[0]
+    assert rel((U * S) @ Vt, A) < 1e-12
+    assert np.linalg.norm(U.T @ U - np.eye(1100)) < 1e-10 and np.linalg.norm(Vt @ Vt.T - np.eye(1100)) < 1e-10

@@ -132,10 +132,9 @@ __global__ void jacobi_block_kernel(double* __restrict__ GT, const int ldg, cons
 //  * a sweep in which no pair had |cos| > 1e-9 is the last one (cyclic Jacobi converges quadratically), so no
 //    verification sweep is spent.
 // Rows of GT are [ x (mdot, zero padded to a multiple of 32) | v (nw, zero padded to a multiple of 32) ].
-__device__ __forceinline__ float xb_rsqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double xb_rsqrt(double x) { return rsqrt(x); }
 
-// T = double, or float for the pre-conditioning sweeps of the mixed-precision path (see Svd::factor).
+// T = double (the kernel is generic in the element type; an FP32 pre-sweep variant was measured in round 1, gave nothing and is gone).
 // EH >= max(voff, ld - voff) / 32 : elements per lane of one column part (register tile of a warp = one column pair).
 template <typename T, int EH, int MAXT>
 __global__ void __launch_bounds__(MAXT) jacobi_persistent_kernel(T* __restrict__ GT, const int ld, const int epl_x, const int epl_v,
@@ -1329,38 +1328,6 @@ __global__ void __launch_bounds__(256) jacobi_gram_kernel(double* __restrict__ G
 	}
 }
 
-// mixed-precision helpers: scaled double -> float working copy, float V -> double V
-__global__ void svd_init_f32_kernel(float* __restrict__ GT, const int ld, const int npad, const int mdot, const int voff, const int nw,
-                                    const double* __restrict__ src, const long long rs, const long long cs, const double* __restrict__ amax) {
-	const double scale = (*amax > 0.0) ? 1.0 / *amax : 1.0;
-	const size_t total = (size_t)npad * ld;
-	for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-		const int j = int(e / ld), i = int(e % ld);
-		float v = 0.f;
-		if (j < nw) {
-			if (i < mdot) v = float(src[(long long)i * rs + (long long)j * cs] * scale);
-			else if (i - voff == j) v = 1.f;
-		}
-		GT[e] = v;
-	}
-}
-__global__ void svd_v32_to_f64_kernel(double* __restrict__ GT, const float* __restrict__ GT32, const int ld, const int voff, const int nw) {
-	const size_t total = (size_t)nw * nw;
-	for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-		const size_t j = e / nw, cidx = e % nw;
-		GT[j * ld + voff + cidx] = double(GT32[j * ld + voff + cidx]);
-	}
-}
-__global__ void amax_kernel(const double* __restrict__ x, const size_t n, double* __restrict__ out) {   // single CTA
-	__shared__ double sh[32];
-	double m = 0.0;
-	for (size_t i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(x[i]));
-	for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-	if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
-	__syncthreads();
-	if (threadIdx.x == 0) { for (int w = 1; w < int(blockDim.x >> 5); ++w) m = fmax(m, sh[w]); *out = m; }
-}
-
 // singular values = column norms; rank them (descending, ties by index) -> Ssorted, perm.   single CTA
 __global__ void svd_sort_kernel(const double* __restrict__ GT, const int ldg, const int mdot, const int nw,
                                 double* __restrict__ Ssorted, int* __restrict__ perm, const double* __restrict__ unscale) {
@@ -1635,9 +1602,6 @@ static void launch_fast_any(double* gt, const JacobiPlan& p, double tol2, double
 		default: throw Error(XB_ERR_UNSUPPORTED, "internal: no specialised Jacobi kernel for this row length");
 	}
 }
-static void launch_fast_any(float*, const JacobiPlan&, float, float, unsigned int*, unsigned int*, int, size_t) {
-	throw Error(XB_ERR_UNSUPPORTED, "internal: the specialised Jacobi kernel is FP64 only");
-}
 
 // Runs sweeps until convergence (or max_sweeps) in one cooperative launch; returns {converged, sweeps}.
 struct JacobiPending {          // convergence record of a launch whose read-back was left to the caller's next synchronisation
@@ -1797,7 +1761,7 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	voff = (mdot + 31) / 32 * 32;
 	ld = voff + (nw + 31) / 32 * 32;
 	int ep2 = 0;
-	if (c.svd_fast && std::max(mdot, nw) <= 512 && !(c.svd_mixed && nw >= size_t(c.svd_mixed_min))) {
+	if (c.svd_fast && std::max(mdot, nw) <= 512) {
 		ep2 = int((std::max(mdot, nw) + 63) / 64);
 		if (ep2 == 5) ep2 = 6;
 		if (ep2 == 7) ep2 = 8;
@@ -1837,88 +1801,53 @@ void Svd::factor(const double* A, size_t m_, size_t n_) {
 	bool converged = false;
 	JacobiPending pending;
 	ProfScope* prof_jacobi = new ProfScope("svd_jacobi");
-	const bool mixed = plan.persistent && c.svd_mixed && nw >= size_t(c.svd_mixed_min);
-	if (mixed && c.speculate) { delete prof_jacobi; throw SpecUnsupported("mixed-precision Jacobi"); }
-	if (mixed) {
-		// Mixed precision: the bulk of the sweeps run in FP32 on a scaled copy (FP32 issues 4x faster than FP64 here and
-		// halves the shared-memory traffic); its V (orthogonal to ~1e-6) is re-orthogonalised in FP64 by two Newton-Schulz
-		// steps, X = G0 V is formed in FP64, and FP64 sweeps finish the job from |cos| ~ 1e-6 (quadratic: 2-3 sweeps).
-		const JacobiPlan plan32 = plan_jacobi(ld, nw, voff, sizeof(float), smem_cap);
-		const size_t npad32 = plan32.npad;
-		float* GT32 = static_cast<float*>(dalloc_bytes(npad32 * ld * sizeof(float)));
-		DBuf amax(1);
-		{
-			// max |entry| of the Jacobi input (source matrix is contiguous in all three cases)
-			const size_t count = reduced ? nw * nw : m * n;
-			amax_kernel<<<1, 1024, 0, c.stream>>>(src, count, amax);
-			XB_LAUNCH_CHECK();
-			const unsigned blocks32 = unsigned(std::min<size_t>((npad32 * ld + 255) / 256, size_t(c.num_sms) * 8));
-			svd_init_f32_kernel<<<blocks32, 256, 0, c.stream>>>(GT32, int(ld), int(npad32), int(mdot), int(voff), int(nw), src, rs, cs, amax);
-			XB_LAUNCH_CHECK();
-		}
-		int sw32 = 0;
-		const double tol32 = std::sqrt(double(mdot)) * 6e-8;
-		run_persistent<float>(GT32, ld, voff, plan32, tol32, std::max(1e-3, 4 * tol32), c.svd_max_sweeps, sw32, smem_cap, "f32");
-		// FP64 working matrix: V from the FP32 run, X recomputed
-		XB_CUDA(cudaMemsetAsync(GT.p, 0, npad * ld * sizeof(double), c.stream));
-		svd_v32_to_f64_kernel<<<unsigned(std::min<size_t>((nw * nw + 255) / 256, size_t(c.num_sms) * 8)), 256, 0, c.stream>>>(GT, GT32, int(ld), int(voff), int(nw));
-		XB_LAUNCH_CHECK();
-		dfree(GT32);
-		newton_schulz();
-		newton_schulz();
-		recompute_left();
-		int sw64 = 0;
-		converged = run_persistent<double>(GT.p, ld, voff, plan, tol, 1e-7, c.svd_max_sweeps, sw64, smem_cap, "f64");
-		sweeps = sw32 + sw64;
+	svd_init_kernel<<<init_blocks, 256, 0, c.stream>>>(GT, int(ld), int(npad), int(mdot), int(voff), int(nw), src, rs, cs, scale.p);
+	XB_LAUNCH_CHECK();
+	if (plan.persistent) {
+		// without a clean-up run (sweep layer) the convergence record is read back together with the singular values below
+		const bool defer = !(c.svd_polish && polish > 1);
+		converged = run_persistent<double>(GT.p, ld, voff, plan, tol, c.svd_last_sweep_cos, c.svd_max_sweeps, sweeps, smem_cap, "f64",
+		                                   defer ? &pending : nullptr);
 	} else {
-		svd_init_kernel<<<init_blocks, 256, 0, c.stream>>>(GT, int(ld), int(npad), int(mdot), int(voff), int(nw), src, rs, cs, scale.p);
-		XB_LAUNCH_CHECK();
-		if (plan.persistent) {
-			// without a clean-up run (sweep layer) the convergence record is read back together with the singular values below
-			const bool defer = !(c.svd_polish && polish > 1);
-			converged = run_persistent<double>(GT.p, ld, voff, plan, tol, c.svd_last_sweep_cos, c.svd_max_sweeps, sweeps, smem_cap, "f64",
-			                                   defer ? &pending : nullptr);
-		} else {
-			// fallback for shapes the cooperative kernel cannot hold: one launch per tournament round
-			if (c.speculate) { delete prof_jacobi; throw SpecUnsupported("launch-per-round Jacobi needs the host between sweeps"); }
-			const int bw = plan.bw;
-			const size_t nblk = plan.nblk;
-			const size_t smem = size_t(2 * bw) * ld * sizeof(double);
-			static bool attr_set = false;
-			if (!attr_set) {
-				XB_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
-				attr_set = true;
-			}
-			unsigned int* d_info = static_cast<unsigned int*>(dalloc_bytes(8 * sizeof(unsigned int)));
-			unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch);
-			const int threads = std::max(64, std::min(1024, 32 * bw));
-			for (int sw = 0; sw < c.svd_max_sweeps && !converged; ++sw) {
-				XB_CUDA(cudaMemsetAsync(d_info, 0, 8 * sizeof(unsigned int), c.stream));
-				if (nblk == 2) {
-					jacobi_block_kernel<<<1, threads, smem, c.stream>>>(GT, int(ld), int(ld), int(voff), bw, 2, 0, 1, tol, d_info, 0, 1);
-					XB_LAUNCH_CHECK();
-				} else {
-					for (size_t round = 0; round + 1 < nblk; ++round) {
-						jacobi_block_kernel<<<unsigned(nblk / 2), threads, smem, c.stream>>>(GT, int(ld), int(ld), int(voff), bw, int(nblk),
-						                                                                     int(round), round == 0 ? 1 : 0, tol, d_info, 0, 1);
-						XB_LAUNCH_CHECK();
-					}
-				}
-				XB_CUDA(cudaMemcpyAsync(h_info, d_info, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
-				XB_CUDA(cudaStreamSynchronize(c.stream));
-				++sweeps;
-				converged = (h_info[0] == 0);
-			}
-			dfree(d_info);
+		// fallback for shapes the cooperative kernel cannot hold: one launch per tournament round
+		if (c.speculate) { delete prof_jacobi; throw SpecUnsupported("launch-per-round Jacobi needs the host between sweeps"); }
+		const int bw = plan.bw;
+		const size_t nblk = plan.nblk;
+		const size_t smem = size_t(2 * bw) * ld * sizeof(double);
+		static bool attr_set = false;
+		if (!attr_set) {
+			XB_CUDA(cudaFuncSetAttribute(jacobi_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+			attr_set = true;
 		}
+		unsigned int* d_info = static_cast<unsigned int*>(dalloc_bytes(8 * sizeof(unsigned int)));
+		unsigned int* h_info = reinterpret_cast<unsigned int*>(c.h_scratch);
+		const int threads = std::max(64, std::min(1024, 32 * bw));
+		for (int sw = 0; sw < c.svd_max_sweeps && !converged; ++sw) {
+			XB_CUDA(cudaMemsetAsync(d_info, 0, 8 * sizeof(unsigned int), c.stream));
+			if (nblk == 2) {
+				jacobi_block_kernel<<<1, threads, smem, c.stream>>>(GT, int(ld), int(ld), int(voff), bw, 2, 0, 1, tol, d_info, 0, 1);
+				XB_LAUNCH_CHECK();
+			} else {
+				for (size_t round = 0; round + 1 < nblk; ++round) {
+					jacobi_block_kernel<<<unsigned(nblk / 2), threads, smem, c.stream>>>(GT, int(ld), int(ld), int(voff), bw, int(nblk),
+					                                                                     int(round), round == 0 ? 1 : 0, tol, d_info, 0, 1);
+					XB_LAUNCH_CHECK();
+				}
+			}
+			XB_CUDA(cudaMemcpyAsync(h_info, d_info, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+			XB_CUDA(cudaStreamSynchronize(c.stream));
+			++sweeps;
+			converged = (h_info[0] == 0);
+		}
+		dfree(d_info);
 	}
 	if (!converged) { delete prof_jacobi; throw Error(XB_ERR_NUMERIC, "Jacobi SVD did not converge within svd_max_sweeps sweeps"); }
 
-	if (c.svd_polish && polish > 0 && !mixed) {
+	if (c.svd_polish && polish > 0) {
 		// Polish: thousands of plane rotations leave V orthogonal only to ~eps*sqrt(#rotations) and X = G V with the same
 		// drift.  One Newton-Schulz step re-orthogonalises V, the left part is recomputed from the untouched input, and one
 		// clean-up sweep of tiny rotations restores |cos| <= tol between the left vectors: backward error back at the
-		// eps*sqrt(n) level of LAPACK.  (The mixed path ends with 2-3 FP64 sweeps from a re-orthogonalised V: not needed.)
+		// eps*sqrt(n) level of LAPACK.
 		newton_schulz();
 		recompute_left();
 		if (polish > 1 && plan.persistent && nw > 1) { int extra = 0; run_persistent<double>(GT.p, ld, voff, plan, tol, 1e-7, 2, extra, smem_cap, "clean"); sweeps += extra; }

@@ -79,8 +79,6 @@ struct Context {
 	int svd_dsmem = 1;             // split Jacobi kernel: X workers in one cluster, travelling block handed over through DSMEM (st.async + mbarrier)
 	int svd_split = 1;             // Jacobi: separate CTAs apply the rotation products to the accumulated-rotation halves
 	int svd_recursive = 1;         // recursive bipartite tournament with point-to-point block flags (power-of-two block counts)
-	int svd_mixed = 0;             // FP32 pre-conditioning sweeps + FP64 finishing sweeps (measured: no gain, kept as an experiment)
-	int svd_mixed_min = 64;        // smallest column count for the mixed path
 	int svd_max_bw = 0;            // 0 = automatic block width of the Jacobi kernel
 	int als_direct_max = 1536;     // local problems up to this size are solved densely (reference semantics), larger ones by CG
 	double peer_wait_spins = 268435456.0;   // bound of the polling loops of the fused bond-split exchange (2^28 polls, about a minute)
