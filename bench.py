@@ -23,6 +23,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# Hardware work queues of the CUDA context (read when the context is created, so before torch touches the device): the default
+# of 8 maps the library's worker streams onto 8 queues and serialises independent TTs behind each other (config 5: 400 items/s
+# with 8 queues, 1200 with 32 — see DESIGN.md, batches).  xerus_b200 sets the same default when it is imported first.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 WORKLOADS = {
     "c3": dict(d=32, n=2, r=256, target=128, name="TT rounding degree 32, n=2, rank 256 -> 128 (BASELINE configs[2])"),
@@ -482,7 +486,7 @@ def main():
     ap.add_argument("--bond", type=int, default=512, help="bond rank for --workload c4")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl"], help="--workload c4 at N > 1: reduction fused over peer memory, or NCCL all-reduce")
     ap.add_argument("--items", type=int, default=8, help="items per GPU per step for --workload c5")
-    ap.add_argument("--workers", type=int, default=8, help="host threads / library workers (CUDA streams) per GPU for --workload c5")
+    ap.add_argument("--workers", type=int, default=16, help="library workers (host threads + CUDA streams) per GPU for --workload c5")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-als", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the c4 / c5 sub-records of the default run")
@@ -606,7 +610,7 @@ def main():
     if not args.no_sub:
         import copy
         for name, fn, over in (("c4", bond_split_workload, dict(steps=max(3, min(args.steps, 10)), warmup=3)),
-                               ("c5", batch_workload, dict(steps=2, warmup=3, items=48))):
+                               ("c5", batch_workload, dict(steps=2, warmup=3, items=96))):
             a2 = copy.copy(args)
             for k, v in over.items():
                 setattr(a2, k, v)

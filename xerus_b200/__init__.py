@@ -2,7 +2,14 @@
 
 Host-side mirror of the reference interface for that path; all arithmetic runs in libxb200.so (hand-written CUDA).
 """
-from ._lib import XerusError, lib, declared_symbols, LIB_PATH      # noqa: F401
+import os as _os
+
+# hardware work queues of the CUDA context (read once, when the context is created): with the default of 8 the worker streams of
+# the batched entry points share queues and independent TTs serialise behind each other (DESIGN.md, batches).  xb_init() does
+# the same for C callers; a process that has already created its context keeps what it had.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+from ._lib import XerusError, lib, declared_symbols, LIB_PATH      # noqa: F401,E402
 from . import blas_wrapper as blasWrapper                          # noqa: F401
 from .blas_wrapper import contract, reshuffle, calculate_svd, EPSILON   # noqa: F401
 from .tt import TTTensor, TTOperator, TTNetwork, round_batched, apply_round_batched, reduce_to_maximal_ranks   # noqa: F401
