@@ -48,6 +48,7 @@ static void apply_option(Context& c, const std::string& k, double value) {
 	else if (k == "small_kernels") c.small_kernels = int(value);
 	else if (k == "peer_wait_spins") c.peer_wait_spins = value;
 	else if (k == "batch_workers") c.batch_workers = int(value);
+	else if (k == "batch_threads") c.batch_threads = int(value);
 	else throw Error(XB_ERR_INVALID, "xb_set_option: unknown key " + k);
 }
 
@@ -116,7 +117,7 @@ static void select_worker(int w) {
 		c->num_sms = g_ctx.num_sms; c->max_smem_optin = g_ctx.max_smem_optin;
 		c->svd_max_sweeps = g_ctx.svd_max_sweeps; c->gemm_force_small = g_ctx.gemm_force_small; c->gemm_big = g_ctx.gemm_big; c->qr_defer = g_ctx.qr_defer;
 		c->svd_persistent = g_ctx.svd_persistent; c->svd_polish = g_ctx.svd_polish; c->tt_svd_polish = g_ctx.tt_svd_polish; c->svd_recursive = g_ctx.svd_recursive; c->svd_flip = g_ctx.svd_flip; c->svd_split = g_ctx.svd_split; c->svd_dsmem = g_ctx.svd_dsmem; c->svd_colsort = g_ctx.svd_colsort; c->svd_last_sweep_cos = g_ctx.svd_last_sweep_cos; c->svd_gram = g_ctx.svd_gram; c->als_graph = g_ctx.als_graph; c->als_persistent_cg = g_ctx.als_persistent_cg; c->als_cg_cluster = g_ctx.als_cg_cluster; c->svd_jacc = g_ctx.svd_jacc; c->svd_fast = g_ctx.svd_fast; c->qr_cluster = g_ctx.qr_cluster; c->qr_cluster_min_rows = g_ctx.qr_cluster_min_rows; c->svd_square_qr = g_ctx.svd_square_qr;
-		c->svd_max_bw = g_ctx.svd_max_bw; c->als_direct_max = g_ctx.als_direct_max; c->round_plans = g_ctx.round_plans; c->small_kernels = g_ctx.small_kernels; c->peer_wait_spins = g_ctx.peer_wait_spins; c->batch_workers = g_ctx.batch_workers;
+		c->svd_max_bw = g_ctx.svd_max_bw; c->als_direct_max = g_ctx.als_direct_max; c->round_plans = g_ctx.round_plans; c->small_kernels = g_ctx.small_kernels; c->peer_wait_spins = g_ctx.peer_wait_spins; c->batch_workers = g_ctx.batch_workers; c->batch_threads = g_ctx.batch_threads;
 		XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 		XB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scratch), c->h_scratch_len * sizeof(double)));
 		{
@@ -273,6 +274,7 @@ xb_status xb_shutdown(void) {
 			if (c->red_partial) cudaFree(c->red_partial);
 			if (c->red_partial_aux) cudaFree(c->red_partial_aux);
 			if (c->h_scratch) cudaFreeHost(c->h_scratch);
+			if (c->h_flags) cudaFreeHost(c->h_flags);
 			cudaStreamDestroy(c->stream);
 			if (w > 0) { if (c->pool) cudaMemPoolDestroy(c->pool); delete c; g_workers[w] = nullptr; }
 		}

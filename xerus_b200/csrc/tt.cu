@@ -280,10 +280,19 @@ static void capture_plan(RoundPlan& pl, const xb_tt* t, const size_t* max_ranks,
 	if (getenv("XB_DEBUG_PLAN")) fprintf(stderr, "[plan] captured: %llu kernels\n", (unsigned long long)pl.nodes);
 }
 
-// returns true if the round was carried out by a plan
-static bool round_planned(xb_tt* t, const size_t* max_ranks, double eps) {
+// A replay whose outcome has not been looked at yet: the graph, the read-back of the flag and the copy of the result cores are
+// enqueued; finish() runs after the worker's stream has been synchronised.
+struct PendingRound {
+	xb_tt* t = nullptr;
+	std::vector<size_t> ranks_out; bool canon_out = false; size_t core_out = 0;   // copied from the plan (which may be evicted meanwhile)
+	std::vector<DBuf> fresh;
+	unsigned int* h_flag = nullptr;
+	std::vector<size_t> max_ranks; double eps = 0.0;
+};
+constexpr size_t XB_PENDING_SLOTS = 512;       // pinned flag words per worker = replays in flight per worker
+
+static RoundPlan* plan_lookup(const xb_tt* t, const size_t* max_ranks, double eps) {
 	Context& c = ctx();
-	if (!c.round_plans || c.profile || c.speculate || t->d < 2 || t->d > 96) return false;
 	const std::string key = plan_key(t, max_ranks, eps);
 	RoundPlan* pl = nullptr;
 	static thread_local uint64_t clock = 0;
@@ -302,10 +311,18 @@ static bool round_planned(xb_tt* t, const size_t* max_ranks, double eps) {
 	}
 	pl->stamp = ++clock;
 	pl->uses += 1;
-	if (pl->unplannable) return false;
+	return pl;
+}
+
+// 0: not plannable (the caller takes the ordinary path); 1: done, synchronously (first sight of the shape: ordinary path that
+// records what the plan will speculate on); 2: a replay has been enqueued, `out` must be finished after a synchronisation
+static int round_plan_enqueue(xb_tt* t, const size_t* max_ranks, double eps, PendingRound& out, size_t slot) {
+	Context& c = ctx();
+	if (!c.round_plans || c.profile || c.speculate || t->d < 2 || t->d > 96) return 0;
+	RoundPlan* pl = plan_lookup(t, max_ranks, eps);
+	if (pl->unplannable) return 0;
 	if (pl->uses == 1) {
-		// first sight of this shape: ordinary path; the outcome is what the plan will speculate on, the bytes it allocates
-		// size the plan's arena
+		// the bytes the ordinary path allocates size the plan's arena
 		size_t in_bytes = 0;
 		for (size_t i = 0; i < t->d; ++i) in_bytes += (t->core_size(i) * sizeof(double) + 255) / 256 * 256;
 		c.count_allocs = true; c.alloc_counter = 0;
@@ -313,11 +330,11 @@ static bool round_planned(xb_tt* t, const size_t* max_ranks, double eps) {
 		c.count_allocs = false;
 		pl->arena_size = c.alloc_counter + in_bytes + (1u << 20);
 		pl->ranks_out = t->rank; pl->canon_out = t->canonicalized; pl->core_out = t->core_position;
-		return true;
+		return 1;
 	}
 	if (!pl->exec) {
 		capture_plan(*pl, t, max_ranks, eps);
-		if (pl->unplannable || !pl->exec) return false;
+		if (pl->unplannable || !pl->exec) return 0;
 	}
 	const size_t d = t->d;
 	{
@@ -327,71 +344,120 @@ static bool round_planned(xb_tt* t, const size_t* max_ranks, double eps) {
 	}
 	XB_CUDA(cudaGraphLaunch(pl->exec, c.stream));
 	c.launches += pl->nodes;
-	unsigned int* h_flag = reinterpret_cast<unsigned int*>(c.h_scratch);
-	XB_CUDA(cudaMemcpyAsync(h_flag, pl->flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
-	// result cores: sized by the recorded ranks; copied out of the graph's memory (valid until the next launch of this plan)
-	std::vector<DBuf> fresh(d);
+	if (!c.h_flags) XB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c.h_flags), XB_PENDING_SLOTS * sizeof(unsigned int)));
+	out.h_flag = c.h_flags + (slot % XB_PENDING_SLOTS);
+	*out.h_flag = 0xFFFFFFFFu;
+	XB_CUDA(cudaMemcpyAsync(out.h_flag, pl->flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, c.stream));
+	// result cores: sized by the recorded ranks; copied out of the plan's arena (valid until the next launch of this plan, which
+	// is ordered behind this copy on the same stream)
+	out.fresh.clear(); out.fresh.resize(d);
 	{
 		std::vector<const double*> src; std::vector<double*> dst; std::vector<size_t> n;
 		for (size_t i = 0; i < d; ++i) {
 			const size_t sz = pl->ranks_out[i] * t->ext(i) * pl->ranks_out[i + 1];
-			fresh[i].resize(sz);
-			src.push_back(pl->out[i]); dst.push_back(fresh[i].p); n.push_back(sz);
+			out.fresh[i].resize(sz);
+			src.push_back(pl->out[i]); dst.push_back(out.fresh[i].p); n.push_back(sz);
 		}
 		copy_many(src, dst, n);
 	}
-	XB_CUDA(cudaStreamSynchronize(c.stream));
-	if (*h_flag != 0) {
-		if (getenv("XB_DEBUG_PLAN")) fprintf(stderr, "[plan] speculation failed (reason %u): ordinary path\n", *h_flag);
-		return false;                                               // the caller's TT is untouched
+	out.t = t; out.eps = eps;
+	out.ranks_out = pl->ranks_out; out.canon_out = pl->canon_out; out.core_out = pl->core_out;
+	out.max_ranks.assign(max_ranks, max_ranks + (d - 1));
+	return 2;
+}
+
+// after the stream has been synchronised: install the result, or — speculation failed — round the untouched TT the ordinary way
+static void round_plan_finish(PendingRound& p) {
+	if (*p.h_flag != 0) {
+		if (getenv("XB_DEBUG_PLAN")) fprintf(stderr, "[plan] speculation failed (reason %u): ordinary path\n", *p.h_flag);
+		p.fresh.clear();
+		round_tt(p.t, p.max_ranks.data(), p.eps, nullptr, 0);
+		return;
 	}
-	for (size_t i = 0; i < d; ++i) t->core[i] = std::move(fresh[i]);
-	t->rank = pl->ranks_out; t->canonicalized = pl->canon_out; t->core_position = pl->core_out;
+	for (size_t i = 0; i < p.t->d; ++i) p.t->core[i] = std::move(p.fresh[i]);
+	p.t->rank = p.ranks_out; p.t->canonicalized = p.canon_out; p.t->core_position = p.core_out;
+}
+
+// round() through a plan where there is one; false: the caller takes the ordinary path
+static bool round_planned(xb_tt* t, const size_t* max_ranks, double eps) {
+	PendingRound p;
+	const int how = round_plan_enqueue(t, max_ranks, eps, p, 0);
+	if (how == 0) return false;
+	if (how == 2) {
+		XB_CUDA(cudaStreamSynchronize(ctx().stream));
+		round_plan_finish(p);
+	}
 	return true;
 }
 
 // ---- batches of independent items (BASELINE config 5) -------------------------------------------------------------------
-// The items of a batch run on library-owned host threads, one library worker (CUDA stream, scratch, plan cache) each: no
-// interpreter and no caller-side threading on the hot path.  Items are dealt round-robin; the workers' streams first wait for
-// everything the caller has enqueued (the items were produced on the caller's stream) and the caller's stream waits for all of
-// them at the end, so the call composes with stream-ordered code on either side.  Repeated shapes replay their round plan: an
-// item is then a handful of launches, which is what lets several items be in flight at once instead of queueing behind the
-// host's launch rate (~4 us per launch, 800 launches per item on the ordinary path).
+// The items of a batch run on W library workers (CUDA stream, memory pool, plan cache each; option "batch_workers") that are
+// driven by a few library-owned host threads (option "batch_threads", default min(W, 2); measured: 1 to 8 threads give the same
+// 1 290 items/s at config 5): no interpreter and no caller-side
+// threading on the hot path.  Item b goes to worker b mod W; a host thread owns every T-th worker and deals with its items in
+// order.  Repeated shapes replay their round plan *asynchronously*: copy-in, graph, flag read-back and copy-out are enqueued
+// and the thread moves on to the next item (of another worker), so the number of items in flight on the GPU is W, not the
+// number of host threads — on a box with 4 cores per GPU 16 threads that each block in a synchronisation starve each other.
+// The flags are looked at once per worker at the end; an item whose speculation failed is redone on the ordinary path.
+// The workers' streams first wait for everything the caller has enqueued (the items were produced on the caller's stream)
+// and the caller's stream waits for all of them at the end, so the call composes with stream-ordered code on either side.
 constexpr int XB_BATCH_WORKER_BASE = 40;     // workers 40 .. 40 + batch_workers - 1 belong to the batch executor
-template <class F> static void run_batch(size_t batch, F&& fn) {
+struct BatchItem { xb_tt* t; size_t max_rank; double eps; };
+// make(b) produces the TT of item b on the calling thread's current worker (may enqueue work), the executor rounds it
+template <class F> static void run_batch(size_t batch, size_t max_rank, double eps, F&& make) {
 	if (batch == 0) return;
 	Context& caller = ctx();
-	const int nthreads = int(std::min<size_t>(batch, size_t(std::max(1, std::min(caller.batch_workers, 24)))));
-	if (nthreads == 1) { for (size_t b = 0; b < batch; ++b) fn(b); return; }
+	const int W = int(std::min<size_t>(batch, size_t(std::max(1, std::min(caller.batch_workers, 24)))));
+	const int T = std::max(1, std::min(W, caller.batch_threads > 0 ? caller.batch_threads : 2));
 	cudaEvent_t start;
 	XB_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
 	XB_CUDA(cudaEventRecord(start, caller.stream));
-	std::vector<cudaEvent_t> done(nthreads, nullptr);
+	std::vector<cudaEvent_t> done(W, nullptr);
 	std::mutex err_mutex;
 	std::string err; xb_status err_code = XB_OK;
-	std::vector<std::thread> threads;
-	for (int t = 0; t < nthreads; ++t) {
-		threads.emplace_back([&, t] {
-			try {
-				if (xb_worker_select(XB_BATCH_WORKER_BASE + t) != XB_OK) throw Error(XB_ERR_CUDA, xb_last_error());
+	auto body = [&](int th) {
+		try {
+			std::vector<std::vector<PendingRound>> pending(W);
+			std::vector<char> started(W, 0);
+			auto drain = [&](int w) {
+				if (xb_worker_select(XB_BATCH_WORKER_BASE + w) != XB_OK) throw Error(XB_ERR_CUDA, xb_last_error());
+				XB_CUDA(cudaStreamSynchronize(ctx().stream));
+				for (PendingRound& p : pending[w]) round_plan_finish(p);
+				pending[w].clear();
+			};
+			for (size_t b = 0; b < batch; ++b) {
+				const int w = int(b % size_t(W));
+				if (w % T != th) continue;
+				if (xb_worker_select(XB_BATCH_WORKER_BASE + w) != XB_OK) throw Error(XB_ERR_CUDA, xb_last_error());
 				Context& c = ctx();
-				XB_CUDA(cudaSetDevice(c.device));
-				XB_CUDA(cudaStreamWaitEvent(c.stream, start, 0));
-				for (size_t b = size_t(t); b < batch; b += size_t(nthreads)) fn(b);
-				aux_join();
-				XB_CUDA(cudaEventCreateWithFlags(&done[t], cudaEventDisableTiming));
-				XB_CUDA(cudaEventRecord(done[t], c.stream));
-			} catch (const Error& e) {
-				std::lock_guard<std::mutex> lock(err_mutex);
-				if (err.empty()) { err = e.what(); err_code = e.code; }
-			} catch (const std::exception& e) {
-				std::lock_guard<std::mutex> lock(err_mutex);
-				if (err.empty()) { err = e.what(); err_code = XB_ERR_INVALID; }
+				if (!started[w]) { XB_CUDA(cudaSetDevice(c.device)); XB_CUDA(cudaStreamWaitEvent(c.stream, start, 0)); started[w] = 1; }
+				if (pending[w].size() >= XB_PENDING_SLOTS) drain(w);
+				xb_tt* t = make(b);
+				std::vector<size_t> mr(t->d > 1 ? t->d - 1 : 1, max_rank);
+				PendingRound p;
+				const int how = round_plan_enqueue(t, mr.data(), eps, p, pending[w].size());
+				if (how == 0) round_tt(t, mr.data(), eps, nullptr, 0);
+				else if (how == 2) pending[w].push_back(std::move(p));
 			}
-		});
-	}
+			for (int w = th; w < W; w += T) {
+				if (!started[w]) continue;
+				drain(w);
+				aux_join();
+				XB_CUDA(cudaEventCreateWithFlags(&done[w], cudaEventDisableTiming));
+				XB_CUDA(cudaEventRecord(done[w], ctx().stream));
+			}
+		} catch (const Error& e) {
+			std::lock_guard<std::mutex> lock(err_mutex);
+			if (err.empty()) { err = e.what(); err_code = e.code; }
+		} catch (const std::exception& e) {
+			std::lock_guard<std::mutex> lock(err_mutex);
+			if (err.empty()) { err = e.what(); err_code = XB_ERR_INVALID; }
+		}
+	};
+	std::vector<std::thread> threads;
+	for (int th = 0; th < T; ++th) threads.emplace_back(body, th);
 	for (auto& th : threads) th.join();
-	for (int t = 0; t < nthreads; ++t) if (done[t]) { cudaStreamWaitEvent(caller.stream, done[t], 0); cudaEventDestroy(done[t]); }
+	for (int w = 0; w < W; ++w) if (done[w]) { cudaStreamWaitEvent(caller.stream, done[w], 0); cudaEventDestroy(done[w]); }
 	cudaEventDestroy(start);
 	if (!err.empty()) throw Error(err_code, err);
 }
@@ -662,10 +728,7 @@ xb_status xb_tt_round_batched(xb_tt** tts, size_t batch, size_t max_rank, double
 		XB_REQUIRE(tts || batch == 0, "null");
 		XB_REQUIRE(eps >= 0.0 && eps < 1.0, "_eps must be smaller than one.");
 		for (size_t b = 0; b < batch; ++b) require_correct_format(tts[b]);
-		run_batch(batch, [&](size_t b) {
-			std::vector<size_t> mr(tts[b]->d > 1 ? tts[b]->d - 1 : 1, max_rank);
-			if (!round_planned(tts[b], mr.data(), eps)) round_tt(tts[b], mr.data(), eps, nullptr, 0);
-		});
+		run_batch(batch, max_rank, eps, [&](size_t b) { return tts[b]; });
 	});
 }
 
@@ -677,12 +740,7 @@ xb_status xb_tt_apply_round_batched(xb_tt** out, const xb_tt* A, xb_tt* const* x
 		require_correct_format(A);
 		for (size_t b = 0; b < batch; ++b) { require_correct_format(xs[b]); out[b] = nullptr; }
 		try {
-			run_batch(batch, [&](size_t b) {
-				xb_tt* y = tt_apply(A, xs[b]);
-				out[b] = y;
-				std::vector<size_t> mr(y->d > 1 ? y->d - 1 : 1, max_rank);
-				if (!round_planned(y, mr.data(), eps)) round_tt(y, mr.data(), eps, nullptr, 0);
-			});
+			run_batch(batch, max_rank, eps, [&](size_t b) { out[b] = tt_apply(A, xs[b]); return out[b]; });
 		} catch (...) {
 			for (size_t b = 0; b < batch; ++b) { delete out[b]; out[b] = nullptr; }
 			throw;

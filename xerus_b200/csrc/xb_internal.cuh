@@ -83,6 +83,8 @@ struct Context {
 	int als_direct_max = 1536;     // local problems up to this size are solved densely (reference semantics), larger ones by CG
 	double peer_wait_spins = 268435456.0;   // bound of the polling loops of the fused bond-split exchange (2^28 polls, about a minute)
 	int small_kernels = 1;         // min(m,n) <= 32: QR and Jacobi SVD as one single-CTA launch each (small_f64.cu)
+	int batch_threads = 0;         // host threads that drive the batch workers (0: min(batch_workers, 2))
+	unsigned int* h_flags = nullptr;   // pinned flag words of round-plan replays in flight (tt.cu)
 	int batch_workers = 16;        // host threads / library workers of the batched entry points (xb_tt_round_batched, ...)
 	int round_plans = 1;           // round(): repeated shapes replay a captured CUDA graph of the whole sweep (speculative ranks, tt.cu)
 	// Speculative execution (round plans): rank decisions are not read back; every decision point assumes the outcome the
