@@ -315,6 +315,18 @@ def measured_peaks():
         return {}
 
 
+def _rows_only(parallel, L, A_cores, R, v, rank, world, out):
+    """this rank's row block without the exchange (profiled pass of the GEMM class)"""
+    import ctypes as C
+    from xerus_b200._lib import call
+    s = len(A_cores)
+    l, r = L.shape[0], R.shape[0]
+    begin, end = parallel.slab_range(l, rank, world)
+    ptrs = (C.c_void_p * s)(*[a.data_ptr() for a in A_cores])
+    dims = (C.c_size_t * (4 * s))(*[int(x) for a in A_cores for x in a.shape])
+    call("xb_env_apply_rows", out[begin:end].data_ptr(), L.data_ptr(), l, L.shape[1], ptrs, dims, s, R.data_ptr(), r, R.shape[1], v.data_ptr(), begin, end)
+
+
 def bond_split_workload(args, rank, local_rank, world):
     """--workload c4: BASELINE configs[3], the two-site DMRG local-operator application at bond rank 512 (n = 4,
     operator rank 2), contraction split along the right bond index across the GPUs + one NCCL sum all-reduce.
@@ -337,20 +349,28 @@ def bond_split_workload(args, rank, local_rank, world):
     px = parallel.PeerExchange(r * n * n, r, rank, world, dist=dist) if world > 1 else None
     state = {"y": y}
 
-    def step(fused):
+    split = getattr(args, "split", "rows")
+
+    def step(fused, mode=None):
+        mode = mode or split
         with torch.cuda.stream(stream):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            if fused:
+            if world == 1:
+                state["y"] = parallel.env_apply(L, [A1, A2], R, v, out=y)                  # nothing to split
+            elif mode == "rows":
+                state["y"] = (parallel.row_split_apply_fused(L, [A1, A2], R, v, px) if fused else
+                              parallel.row_split_apply(L, [A1, A2], R, v, rank, world, out=y))
+            elif fused:
                 state["y"] = parallel.bond_split_apply_fused(L, [A1, A2], R, v, px)
             else:
                 state["y"] = parallel.bond_split_apply(L, [A1, A2], R, v, rank, world, out=y)
             e1.record(stream)
         return e0, e1
 
-    def timed(fused):
+    def timed(fused, mode=None):
         for _ in range(args.warmup):
-            step(fused)
+            step(fused, mode)
             if dist is not None:
                 xb.synchronize(); dist.barrier()
         if dist is not None:
@@ -363,7 +383,7 @@ def bond_split_workload(args, rank, local_rank, world):
             torch.cuda.synchronize()
             if dist is not None:
                 dist.barrier()                          # the ranks enter a step together (the fused path has no collective to align them)
-            events.append(step(fused))
+            events.append(step(fused, mode))
         torch.cuda.synchronize(); xb.synchronize()
         if dist is not None:
             dist.barrier()
@@ -372,11 +392,23 @@ def bond_split_workload(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t, xb.kernel_launch_count() - l0
 
-    use_fused = world > 1 and args.collective == "fused"
-    ms_other = None
+    collective = args.collective if args.collective != "auto" else ("fused" if world <= 4 else "nccl")
+    use_fused = world > 1 and collective == "fused"
+    ms_other, variants = None, {}
     if world > 1:
-        ms_other, _ = timed(not use_fused)
+        # every exchange variant in the same run: {rows, bond} x {fused over peer memory, NCCL}; the line's value is --split/--collective
+        for mode in ("rows", "bond"):
+            for fz in (True, False):
+                if mode == split and fz == use_fused:
+                    continue
+                t_, _ = timed(fz, mode)
+                variants["%s_%s" % (mode, "fused" if fz else "nccl")] = float(t_.item())
+        ms_other = variants.get("%s_%s" % (split, "nccl" if use_fused else "fused"))
+        ms_other = torch.tensor([ms_other]) if ms_other is not None else None
     ms, launches = timed(use_fused)
+    variants["%s_%s" % (split, "fused" if use_fused else ("nccl" if world > 1 else "single"))] = float(ms.item())
+    if px is not None:
+        px.check()
     y = state["y"]
     # check against the unsplit application on this rank
     ref = parallel.env_apply(L, [A1, A2], R, v)
@@ -384,7 +416,10 @@ def bond_split_workload(args, rank, local_rank, world):
     err = float((y - ref).norm() / ref.norm())
     # time spent in the GEMM class alone (CUDA events inside the library), for the roofline of the dominant kernel
     xb.profile_enable(True)
-    parallel.env_apply(L, [A1, A2], R, v, slab=parallel.slab_range(r, rank, world))
+    if split == "rows" and world > 1:
+        _rows_only(parallel, L, [A1, A2], R, v, rank, world, y)
+    else:
+        parallel.env_apply(L, [A1, A2], R, v, slab=parallel.slab_range(r, rank, world))
     xb.synchronize()
     gsc, glaunch, gms = xb.profile_get("gemm")
     _, mlaunch, mms = xb.profile_get("mid_apply")
@@ -408,12 +443,15 @@ def bond_split_workload(args, rank, local_rank, world):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t, "higher_is_better": False, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic (i.i.d. N(0,1) environments, operator cores and vector)",
                 "config": {"workload": "two-site DMRG local apply, bond rank %d, n=4, operator rank 2 (BASELINE configs[3]); "
-                                       "environment contraction split along the right bond over %d GPU(s) + NCCL all-reduce" % (r, world),
+                                       "environment contraction split along the bond index over %d GPU(s)" % (r, world),
                            "l2": "flushed between timed iterations",
-                           "collective": ("none" if world == 1 else ("fused: GEMM epilogue writes row blocks into the peers' buffers over NVLink + reduce kernel (xb_env_apply_fused)"
-                                                                     if use_fused else "xb_env_apply + ncclAllReduce")),
-                           "exchanged_bytes_per_rank": int(y.numel() * 8 * 2 * (world - 1) / world) if world > 1 else 0},
+                           "split": ("left bond index: row blocks of the result, all-gather" if split == "rows" else "right (contracted) bond index: partial sums, reduction"),
+                           "collective": ("none" if world == 1 else (("fused: the epilogue of the last GEMM stores the rank's row block into every rank's buffer over NVLink (xb_env_apply_rows_fused)"
+                                                                      if split == "rows" else "fused: GEMM epilogue writes row blocks into the peers' buffers over NVLink + reduce kernel (xb_env_apply_fused)")
+                                                                     if use_fused else ("xb_env_apply_rows + ncclAllGather" if split == "rows" else "xb_env_apply + ncclAllReduce"))),
+                           "exchanged_bytes_per_rank": (int(y.numel() * 8 * (1 if split == "rows" else 2) * (world - 1) / world) if world > 1 else 0)},
                 "other_collective_ms": (float(ms_other.item()) if ms_other is not None else None),
+                "variants_ms": variants,
                 "gpu_launches": launches, "check": {"rel_err_vs_unsplit": err},
                 "whole_job_tflops": flops / (t * 1e-3) / 1e12,
                 "whole_job_frac_of_peak": flops / (t * 1e-3) / 1e12 / (peak * world),      # of the N GPUs' combined peak
@@ -484,7 +522,10 @@ def main():
     ap.add_argument("--impl", default="xb200", choices=["xb200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c4", "c5"])
     ap.add_argument("--bond", type=int, default=512, help="bond rank for --workload c4")
-    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"], help="--workload c4 at N > 1: reduction fused over peer memory, or NCCL all-reduce")
+    ap.add_argument("--collective", default="auto", choices=["auto", "fused", "nccl"],
+                    help="--workload c4 at N > 1: exchange fused over peer memory, or NCCL; auto = fused up to 4 GPUs, NCCL all-gather at 8 "
+                         "(measured: at 8 GPUs the 64-byte remote stores of the GEMM epilogue lose to NCCL's bulk all-gather)")
+    ap.add_argument("--split", default="rows", choices=["rows", "bond"], help="--workload c4: split the LEFT bond index (row blocks of the result, all-gather; default) or the contracted RIGHT bond index (partial sums, reduction)")
     ap.add_argument("--items", type=int, default=8, help="items per GPU per step for --workload c5")
     ap.add_argument("--workers", type=int, default=16, help="library workers (host threads + CUDA streams) per GPU for --workload c5")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -196,6 +196,17 @@ xb_status xb_env_apply(double* y, const double* L, size_t l, size_t a_left, cons
  * rank's row block of the partial result straight into that rank's buffer over NVLink, a reduce kernel sums the blocks in
  * rank order and writes the sum into every rank's result area; *y_out points at this rank's copy of the full result, valid
  * in stream order.  `epoch` counts the calls on these buffers from 1 and must agree on all ranks. */
+/* The same application split along the LEFT bond index instead (rows of the result): rank g takes the rows [l_begin, l_end) of
+ * L and does 1/world of all three stages of the chain; the row blocks of y are disjoint, so the exchange is an all-gather and
+ * nothing is summed.  xb_env_apply_rows writes the rank's row block ((l_end - l_begin) x m_1..m_s x r, contiguous) to y_rows
+ * (exchange left to the caller, e.g. ncclAllGather); xb_env_apply_rows_fused stores it into the result area of every rank's
+ * symmetric buffer from the epilogue of the last GEMM (buffers, epoch and *y_out as for xb_env_apply_fused; the two fused
+ * variants use different flag words and may share buffers). */
+xb_status xb_env_apply_rows(double* y_rows, const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims,
+                            size_t sites, const double* R, size_t r, size_t a_right, const double* v, size_t l_begin, size_t l_end);
+xb_status xb_env_apply_rows_fused(const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims, size_t sites,
+                                  const double* R, size_t r, size_t a_right, const double* v, size_t l_begin, size_t l_end,
+                                  int rank, int world, void* const* sym, unsigned int epoch, double** y_out);
 xb_status xb_peer_buffer_bytes(size_t rows, size_t cols, int world, size_t* bytes);
 xb_status xb_peer_buffer_create(size_t bytes, void** dptr, unsigned char* handle64);
 xb_status xb_peer_buffer_open(const unsigned char* handle64, void** dptr);

@@ -227,6 +227,68 @@ def test_env_apply_and_bond_split(sites):
 
 
 @pytest.mark.parametrize("world", [1, 2, 4])
+def test_fused_row_split_apply_on_one_device(world):
+    """xb_env_apply_rows / xb_env_apply_rows_fused (split along the left bond: row blocks of the result, all-gather fused into the
+    GEMM epilogue) with the "ranks" as host threads on library workers of one device: every rank ends with the full application,
+    bit-identical across ranks and equal to the unsplit one row block by row block."""
+    import threading
+    import ctypes as C
+    import torch
+    from xerus_b200 import parallel
+    from xerus_b200._lib import call
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(19)
+    r, n, a = 48, 4, 2
+    rnd = lambda *shape: torch.randn(*shape, dtype=torch.float64, generator=g).to(dev)
+    L, R, A1, A2 = rnd(r, a, r), rnd(r, a, r), rnd(a, n, n, a), rnd(a, n, n, a)
+    vs = [rnd(r, n, n, r), rnd(r, n, n, r)]
+    torch.cuda.synchronize()
+    rows, cols = r * n * n, r
+    bufs = parallel.PeerExchange.allocate_local(rows, cols, world)
+    results = [[None, None] for _ in range(world)]
+    errors = []
+    barrier = threading.Barrier(world)
+
+    def run(rank):
+        try:
+            xb.worker_select(rank + 1)
+            px = parallel.PeerExchange(rows, cols, rank, world, local_buffers=bufs)
+            for it, v in enumerate(vs):
+                y = parallel.row_split_apply_fused(L, [A1, A2], R, v, px)
+                px.check()
+                results[rank][it] = y.clone()
+                barrier.wait()
+        except Exception as ex:                             # noqa: BLE001
+            errors.append(ex)
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(k,)) for k in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    xb.worker_select(0)
+    for it, v in enumerate(vs):
+        ref = parallel.env_apply(L, [A1, A2], R, v)
+        xb.synchronize()
+        for k in range(world):
+            assert float((results[k][it] - ref).norm() / ref.norm()) < 1e-13
+            assert torch.equal(results[k][it], results[0][it])
+    # the non-fused entry point: one row block
+    out = torch.zeros(r // 2, n, n, r, dtype=torch.float64, device=dev)
+    ptrs = (C.c_void_p * 2)(A1.data_ptr(), A2.data_ptr())
+    dims = (C.c_size_t * 8)(*[int(x) for t_ in (A1, A2) for x in t_.shape])
+    call("xb_env_apply_rows", out.data_ptr(), L.data_ptr(), r, a, ptrs, dims, 2, R.data_ptr(), r, a, vs[0].data_ptr(), r // 2, r)
+    xb.synchronize()
+    ref = parallel.env_apply(L, [A1, A2], R, vs[0])
+    xb.synchronize()
+    assert float((out - ref[r // 2:]).norm() / ref.norm()) < 1e-13
+    for q in bufs:
+        call("xb_peer_buffer_destroy", q)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
 def test_fused_bond_split_apply_on_one_device(world):
     """xb_env_apply_fused with the "ranks" as host threads on library workers of one device (same kernels, same flag protocol,
     plain device pointers instead of IPC mappings): every rank ends with the full application, bit-identical across ranks, equal

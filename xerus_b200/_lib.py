@@ -73,6 +73,8 @@ _SIGS = {
     "xb_als_default_options": [P(ALSOptions), C.c_uint32, C.c_int],
     "xb_als_solve": [vp, vp, vp, P(ALSOptions), dp, szp],
     "xb_env_apply": [vp, vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz],
+    "xb_env_apply_rows": [vp, vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz],
+    "xb_env_apply_rows_fused": [vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz, C.c_int, C.c_int, P(vp), C.c_uint, P(vp)],
     "xb_peer_buffer_bytes": [sz, sz, C.c_int, szp], "xb_peer_buffer_create": [sz, P(vp), C.c_char_p],
     "xb_peer_buffer_open": [C.c_char_p, P(vp)], "xb_peer_buffer_close": [vp], "xb_peer_buffer_check": [vp], "xb_peer_buffer_destroy": [vp],
     "xb_env_apply_fused": [vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz, C.c_int, C.c_int, P(vp), C.c_uint, P(vp)],

@@ -1362,6 +1362,77 @@ xb_status xb_env_apply_fused(const double* L, size_t l, size_t a_left, const dou
 	});
 }
 
+// ---- the same application split along the LEFT bond index (rows of the result) -------------------------------------------------
+// y(l, m.., r) = sum L(l, a, l') ... : rank g takes the rows l in [l_begin, l_end) of L and with them 1/world of ALL three stages
+// (L.v, operator cores, .R) — nothing of the chain is replicated, and the row blocks of y are disjoint, so there is nothing to
+// reduce: the exchange is an all-gather.  Fused variant: the epilogue of the last GEMM stores the rank's row block into the result
+// area of EVERY rank (remote stores over NVLink while the remaining tiles are still being multiplied), one warp fences at system
+// scope and bumps flag 4 on every rank, one thread waits for world bumps.  Half the NVLink traffic of the bond split of the
+// contracted index (no partial sums travel), no reduce kernel, one wait instead of two.  v, A, R are needed in full on every rank.
+__global__ void peer_signal_all_kernel(unsigned int* const* flags, const int world, const int which) {
+	__threadfence_system();
+	if (int(threadIdx.x) < world) atomicAdd_system(flags[threadIdx.x] + which, 1u);
+}
+
+static void env_apply_rows_impl(double* y_rows, const GemmScatter* sc, const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims,
+                                size_t sites, const double* R, size_t r, size_t a_right, const double* v, size_t l_begin, size_t l_end) {
+	XB_REQUIRE(sites >= 1 && sites <= 4, "1 to 4 sites");
+	XB_REQUIRE(l_begin < l_end && l_end <= l, "illegal slab of the left bond");
+	std::vector<DT> ac;
+	std::vector<size_t> vd = {l};
+	for (size_t p = 0; p < sites; ++p) {
+		const size_t* d = A_dims + 4 * p;
+		XB_REQUIRE(d[0] == (p == 0 ? a_left : A_dims[4 * (p - 1) + 3]), "operator bond dimensions do not coincide");
+		ac.push_back(dt_view(A_cores[p], {d[0], d[1], d[2], d[3]}));
+		vd.push_back(d[2]);
+	}
+	XB_REQUIRE(A_dims[4 * (sites - 1) + 3] == a_right, "operator bond dimensions do not coincide");
+	vd.push_back(r);
+	DT Ls = dt_view(L + l_begin * a_left * l, {l_end - l_begin, a_left, l});       // rows of L are contiguous: a view, no copy
+	if (sc) { spd_env_apply(Ls, ac, dt_view(R, {r, a_right, r}), dt_view(v, vd), sc); return; }
+	DT res = spd_env_apply(Ls, ac, dt_view(R, {r, a_right, r}), dt_view(v, vd));
+	copy(y_rows, res.p, res.size());
+}
+
+xb_status xb_env_apply_rows(double* y_rows, const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims,
+                            size_t sites, const double* R, size_t r, size_t a_right, const double* v, size_t l_begin, size_t l_end) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(y_rows && L && A_cores && A_dims && R && v, "null");
+		env_apply_rows_impl(y_rows, nullptr, L, l, a_left, A_cores, A_dims, sites, R, r, a_right, v, l_begin, l_end);
+	});
+}
+
+xb_status xb_env_apply_rows_fused(const double* L, size_t l, size_t a_left, const double* const* A_cores, const size_t* A_dims, size_t sites,
+                                  const double* R, size_t r, size_t a_right, const double* v, size_t l_begin, size_t l_end,
+                                  int rank, int world, void* const* sym, unsigned int epoch, double** y_out) {
+	return guard([&] {
+		ensure_init();
+		XB_REQUIRE(L && A_cores && A_dims && R && v && sym && y_out, "null");
+		XB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world && epoch >= 1, "illegal rank / world / epoch");
+		size_t rows = l, row_len = 1;                        // result: (l, m_1..m_s, r)
+		for (size_t p = 0; p < sites; ++p) row_len *= A_dims[4 * p + 1];
+		rows *= row_len;
+		auto flags_of = [&](int p) { return reinterpret_cast<unsigned int*>(sym[p]); };
+		auto y_of = [&](int p) { return reinterpret_cast<double*>(static_cast<char*>(sym[p]) + PEER_FLAG_BYTES) + rows * r; };   // same layout as xb_env_apply_fused
+		GemmScatter sc;
+		sc.rows_per_block = 0; sc.replicate = world;
+		for (int i = 0; i < 8; ++i) sc.blk[i] = (i < world) ? y_of(i) + l_begin * row_len * r : nullptr;
+		env_apply_rows_impl(nullptr, &sc, L, l, a_left, A_cores, A_dims, sites, R, r, a_right, v, l_begin, l_end);
+		Context& c = ctx();
+		unsigned int* table_h[8];
+		for (int p = 0; p < 8; ++p) table_h[p] = (p < world) ? flags_of(p) : nullptr;
+		DBuf table(8);
+		XB_CUDA(cudaMemcpyAsync(table.p, table_h, 8 * sizeof(void*), cudaMemcpyHostToDevice, c.stream));
+		peer_signal_all_kernel<<<1, 32, 0, c.stream>>>(reinterpret_cast<unsigned int* const*>(table.p), world, 4);
+		XB_LAUNCH_CHECK();
+		const unsigned int max_spins = unsigned(std::max(1024.0, c.peer_wait_spins));
+		peer_wait_kernel<<<1, 32, 0, c.stream>>>(flags_of(rank), 4, epoch * unsigned(world), max_spins);      // every rank's row block has landed here
+		XB_LAUNCH_CHECK();
+		*y_out = y_of(rank);
+	});
+}
+
 xb_status xb_als_solve(const xb_tt* A, xb_tt* x, const xb_tt* b, const xb_als_options* opt, double* energy, size_t* local_iterations) {
 	return guard([&] {
 		ensure_init();

@@ -28,6 +28,9 @@ struct GemmArgs {
 	// receive buffer over NVLink, so the transfer runs while the remaining tiles are still being multiplied).
 	double* Cblk[8];
 	int rpb;
+	// optional replicated output (beta = 0): every element is written to Cblk[0 .. rep) — the row-split bond application stores
+	// its row block of the result into the result area of every rank (the all-gather happens in the epilogue, over NVLink)
+	int rep;
 	// tall outputs (TT unfoldings: m = prod n_i reaches millions of rows): the m tiles go on grid.x, whose limit is 2^31 - 1
 	// (grid.y stops at 65535), the n tiles on grid.y
 	int swap_xy;
@@ -136,8 +139,12 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g
 #pragma unroll
 			for (int c = 0; c < 2; ++c) {
 				if (col + c < g.n) {
-					double* p = gemm_out_row(g, C, row) + col + c;
 					double v = g.alpha * acc[i][j][c];
+					if (g.rep) {
+						for (int dst = 0; dst < g.rep; ++dst) g.Cblk[dst][(long long)row * g.ldc + col + c] = v;
+						continue;
+					}
+					double* p = gemm_out_row(g, C, row) + col + c;
 					if (g.beta != 0.0) v += g.beta * (*p);
 					*p = v;
 				}
@@ -256,6 +263,16 @@ __global__ void __launch_bounds__(BIG_THREADS, 1) gemm_f64_big_kernel(const Gemm
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
 			const int col = n0 + wn * 32 + j * 8 + tig * 2;
+			if (g.rep) {
+				const long long off = (long long)row * g.ldc + col;
+				if (vec_store && col + 1 < g.n) {
+					const double2 v = make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
+					for (int dst = 0; dst < g.rep; ++dst) *reinterpret_cast<double2*>(g.Cblk[dst] + off) = v;
+				} else {
+					for (int c = 0; c < 2; ++c) if (col + c < g.n) for (int dst = 0; dst < g.rep; ++dst) g.Cblk[dst][off + c] = g.alpha * acc[i][j][c];
+				}
+				continue;
+			}
 			double* p = gemm_out_row(g, C, row) + col;
 			if (vec_store && col + 1 < g.n) {
 				double2 v = make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
@@ -303,7 +320,7 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
 	g.strideC = (long long)strideC; g.strideA = (long long)strideA; g.strideB = (long long)strideB;
 	g.m = int(m); g.n = int(n); g.k = int(k);
 	g.transA = transA; g.transB = transB; g.alpha = alpha; g.beta = beta;
-	g.rpb = 0; g.swap_xy = 0;
+	g.rpb = 0; g.swap_xy = 0; g.rep = 0;
 	for (int i = 0; i < 8; ++i) g.Cblk[i] = nullptr;
 	auto make_grid = [&](size_t tile) {
 		const size_t tn = (n + tile - 1) / tile, tm = (m + tile - 1) / tile;
@@ -312,7 +329,12 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
 		return g.swap_xy ? dim3(unsigned(tm), unsigned(tn), unsigned(batch)) : dim3(unsigned(tn), unsigned(tm), unsigned(batch));
 	};
 	bool blocks_aligned = true;
-	if (tl_scatter) {
+	if (tl_scatter && tl_scatter->replicate > 0) {
+		XB_REQUIRE(beta == 0.0 && batch == 1 && tl_scatter->replicate <= 8, "replicated GEMM output: beta = 0, one problem, at most 8 destinations");
+		g.rep = tl_scatter->replicate;
+		for (int i = 0; i < 8; ++i) { g.Cblk[i] = tl_scatter->blk[i]; if (g.Cblk[i] && (reinterpret_cast<uintptr_t>(g.Cblk[i]) & 15)) blocks_aligned = false; }
+		C = g.Cblk[0]; g.C = C;
+	} else if (tl_scatter) {
 		XB_REQUIRE(beta == 0.0 && batch == 1 && tl_scatter->rows_per_block > 0 && (m + tl_scatter->rows_per_block - 1) / tl_scatter->rows_per_block <= 8,
 		           "scattered GEMM output: beta = 0, one problem, at most 8 row blocks");
 		g.rpb = int(tl_scatter->rows_per_block);

@@ -143,7 +143,8 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
                   double beta, size_t batch);
 
 // C row i -> blk[i / rows_per_block] + (i % rows_per_block) * ldc (beta = 0): the row blocks may be buffers of peer GPUs
-struct GemmScatter { double* blk[8]; size_t rows_per_block; };
+// replicate > 0: instead, the whole result is written to blk[0 .. replicate) (same layout in each)
+struct GemmScatter { double* blk[8]; size_t rows_per_block; int replicate = 0; };
 void gemm_scatter(const GemmScatter& sc, size_t ldc, size_t m, size_t n, double alpha, const double* A, size_t lda, bool transA, size_t k,
                   const double* B, size_t ldb, bool transB);
 

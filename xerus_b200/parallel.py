@@ -125,6 +125,56 @@ def bond_split_apply(L, A_cores, R, v, rank, world, out=None, group=None):
     return y
 
 
+def row_split_apply(L, A_cores, R, v, rank, world, out=None, group=None):
+    """The application split along the LEFT bond index (rows of the result) over `world` GPUs: every rank computes its row block
+    (1/world of all three stages), then ONE all-gather (NCCL over NVLink) assembles y on all ranks — nothing is summed.  Must run
+    with the library stream current, as bond_split_apply."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from ._lib import call
+    s = len(A_cores)
+    l, r = L.shape[0], R.shape[0]
+    if l % world:
+        raise ValueError("the left bond must split evenly over the ranks")
+    if out is None:
+        out = torch.empty((l,) + tuple(a.shape[1] for a in A_cores) + (r,), dtype=torch.float64, device=v.device)
+    begin, end = slab_range(l, rank, world)
+    ptrs = (C.c_void_p * s)(*[a.data_ptr() for a in A_cores])
+    dims = (C.c_size_t * (4 * s))(*[int(x) for a in A_cores for x in a.shape])
+    call("xb_env_apply_rows", out[begin:end].data_ptr(), L.data_ptr(), l, L.shape[1], ptrs, dims, s, R.data_ptr(), r, R.shape[1],
+         v.data_ptr(), begin, end)
+    if world > 1:
+        dist.all_gather_into_tensor(out, out[begin:end], group=group)
+    return out
+
+
+def row_split_apply_fused(L, A_cores, R, v, px):
+    """row_split_apply with the all-gather fused into the application over peer memory (xb_env_apply_rows_fused): the epilogue of the
+    last GEMM stores this rank's row block into the result area of every rank over NVLink.  Returns a torch view of this rank's copy
+    of y (valid in the library stream's order; overwritten by the next call on `px`)."""
+    import ctypes as C
+    import torch
+    from ._lib import call
+    s = len(A_cores)
+    l, r = L.shape[0], R.shape[0]
+    if l % px.world:
+        raise ValueError("the left bond must split evenly over the ranks")
+    begin, end = slab_range(l, px.rank, px.world)
+    ptrs = (C.c_void_p * s)(*[a.data_ptr() for a in A_cores])
+    dims = (C.c_size_t * (4 * s))(*[int(x) for a in A_cores for x in a.shape])
+    sym = (C.c_void_p * px.world)(*px.ptrs)
+    px.epoch_rows += 1
+    y = C.c_void_p()
+    call("xb_env_apply_rows_fused", L.data_ptr(), l, L.shape[1], ptrs, dims, s, R.data_ptr(), r, R.shape[1], v.data_ptr(), begin, end,
+         px.rank, px.world, sym, px.epoch_rows, C.byref(y))
+    shape = (l,) + tuple(a.shape[1] for a in A_cores) + (r,)
+
+    class _Arr:                                              # __cuda_array_interface__ view of the result area (no copy)
+        __cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (y.value, False), "version": 3, "strides": None}
+    return torch.as_tensor(_Arr(), device=v.device)
+
+
 class PeerExchange:
     """Symmetric peer-memory buffers for bond_split_apply_fused: every rank allocates one buffer, exports its CUDA IPC handle,
     and maps the buffers of the other ranks of the box (handles travel through torch.distributed).  With `group_size` ranks in
@@ -133,7 +183,7 @@ class PeerExchange:
     def __init__(self, rows, cols, rank, world, dist=None, local_buffers=None):
         import ctypes as C
         from ._lib import call
-        self.rank, self.world, self.epoch = rank, world, 0
+        self.rank, self.world, self.epoch, self.epoch_rows = rank, world, 0, 0
         self.rows, self.cols = rows, cols
         nbytes = C.c_size_t()
         call("xb_peer_buffer_bytes", rows, cols, world, C.byref(nbytes))
