@@ -42,7 +42,7 @@ __device__ __forceinline__ double* gemm_out_row(const GemmArgs& g, double* C, co
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_THREADS = 128;
 
-template <int WMF, int WNF>
+template <int WMF, int WNF, bool REP = false>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g) {
 	constexpr int BM = 2 * WMF * 8, BN = 2 * WNF * 8, BK = GEMM_BK;
 	constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_f64_kernel(const GemmArgs g
 			for (int c = 0; c < 2; ++c) {
 				if (col + c < g.n) {
 					double v = g.alpha * acc[i][j][c];
-					if (g.rep) {
+					if (REP) {
 						for (int dst = 0; dst < g.rep; ++dst) g.Cblk[dst][(long long)row * g.ldc + col + c] = v;
 						continue;
 					}
@@ -196,7 +196,8 @@ __device__ __forceinline__ void big_load_tile(double* __restrict__ sm, const dou
 	}
 }
 
-template <bool TA, bool TB>
+// REP: replicated output (GemmArgs::rep destinations) — a separate instantiation so that the ordinary epilogue stays as it was
+template <bool TA, bool TB, bool REP>
 __global__ void __launch_bounds__(BIG_THREADS, 1) gemm_f64_big_kernel(const GemmArgs g, const int vec_store) {
 	extern __shared__ __align__(16) double big_smem[];
 	double* As = big_smem;                               // [STAGES][BIG_TILE]
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(BIG_THREADS, 1) gemm_f64_big_kernel(const Gemm
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
 			const int col = n0 + wn * 32 + j * 8 + tig * 2;
-			if (g.rep) {
+			if (REP) {
 				const long long off = (long long)row * g.ldc + col;
 				if (vec_store && col + 1 < g.n) {
 					const double2 v = make_double2(g.alpha * acc[i][j][0], g.alpha * acc[i][j][1]);
@@ -292,15 +293,19 @@ __global__ void __launch_bounds__(BIG_THREADS, 1) gemm_f64_big_kernel(const Gemm
 	}
 }
 
-template <bool TA, bool TB>
-static void launch_big(const GemmArgs& g, const dim3 grid, const int vec_store) {
+template <bool TA, bool TB, bool REP>
+static void launch_big_impl(const GemmArgs& g, const dim3 grid, const int vec_store) {
 	constexpr size_t smem = size_t(2) * BIG_STAGES * BIG_TILE * sizeof(double);
 	static bool attr = false;
 	if (!attr) {
-		XB_CUDA(cudaFuncSetAttribute(gemm_f64_big_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+		XB_CUDA(cudaFuncSetAttribute(gemm_f64_big_kernel<TA, TB, REP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
 		attr = true;
 	}
-	gemm_f64_big_kernel<TA, TB><<<grid, BIG_THREADS, smem, ctx().stream>>>(g, vec_store);
+	gemm_f64_big_kernel<TA, TB, REP><<<grid, BIG_THREADS, smem, ctx().stream>>>(g, vec_store);
+}
+template <bool TA, bool TB>
+static void launch_big(const GemmArgs& g, const dim3 grid, const int vec_store) {
+	if (g.rep) launch_big_impl<TA, TB, true>(g, grid, vec_store); else launch_big_impl<TA, TB, false>(g, grid, vec_store);
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -358,10 +363,12 @@ void gemm_batched(double* C, size_t ldc, size_t strideC, size_t m, size_t n, dou
 	const bool small = ctx().gemm_force_small || tiles64 < size_t(ctx().num_sms);
 	if (small) {
 		const dim3 grid = make_grid(32);
-		gemm_f64_kernel<2, 2><<<grid, GEMM_THREADS, 0, ctx().stream>>>(g);
+		if (g.rep) gemm_f64_kernel<2, 2, true><<<grid, GEMM_THREADS, 0, ctx().stream>>>(g);
+		else gemm_f64_kernel<2, 2><<<grid, GEMM_THREADS, 0, ctx().stream>>>(g);
 	} else {
 		const dim3 grid = make_grid(64);
-		gemm_f64_kernel<4, 4><<<grid, GEMM_THREADS, 0, ctx().stream>>>(g);
+		if (g.rep) gemm_f64_kernel<4, 4, true><<<grid, GEMM_THREADS, 0, ctx().stream>>>(g);
+		else gemm_f64_kernel<4, 4><<<grid, GEMM_THREADS, 0, ctx().stream>>>(g);
 	}
 	XB_LAUNCH_CHECK();
 }
