@@ -56,6 +56,15 @@ xb_status   xb_set_option(const char* key, double value); /* tuning/diagnostic k
 xb_status   xb_profile_enable(int on);
 xb_status   xb_profile_get(const char* kernel_class, uint64_t* scopes, uint64_t* launches, double* milliseconds);
 
+/* (group, name, shape) call registry — the reference's XERUS_PERFORMANCE_ANALYSIS (misc/performanceAnalysis.h:30-39): every
+ * per-call entry point records (calls, microseconds of host wall time) under the reference's own group / name / shape strings
+ * (blasLapackWrapper.cpp:83-720, e.g. "Dense BLAS" / "Matrix-Matrix-Multiplication" / "512x256 * 256x256"); the sweep layer
+ * records under the group "TT sweep".  Off by default.  Strings returned by xb_perf_entry stay valid until xb_perf_reset. */
+xb_status xb_perf_enable(int on);
+xb_status xb_perf_reset(void);
+xb_status xb_perf_count(size_t* n);
+xb_status xb_perf_entry(size_t i, const char** group, const char** name, const char** shape, uint64_t* calls, double* microseconds);
+
 /* ---- memory hooks (back Tensor::denseData, reference: src/xerus/tensor.cpp:58, basic.cpp:31) ------------------ */
 xb_status xb_alloc(void** dptr, size_t bytes);
 xb_status xb_free(void* dptr);

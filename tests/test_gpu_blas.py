@@ -432,3 +432,33 @@ def test_svd_beyond_the_persistent_kernels():
     assert np.max(np.abs(S - s_ref)) < 1e-12 * s_ref[0]
     assert rel((U * S) @ Vt, A) < 1e-12
     assert np.linalg.norm(U.T @ U - np.eye(1100)) < 1e-10 and np.linalg.norm(Vt @ Vt.T - np.eye(1100)) < 1e-10
+
+
+def test_call_registry_uses_the_reference_shape_strings():
+    """xb_perf_*: the (group, name, shape) registry of the reference's XERUS_PERFORMANCE_ANALYSIS (misc/performanceAnalysis.h:30-39)
+    at the C ABI, with the strings of blasLapackWrapper.cpp:83-720."""
+    rng = np.random.default_rng(5)
+    xb.perf_reset()
+    xb.perf_enable(True)
+    try:
+        A, B = rng.standard_normal((37, 23)), rng.standard_normal((23, 19))
+        BW.matrix_matrix_product(1.0, A, False, B, False)
+        BW.matrix_matrix_product(1.0, A, False, B, False)
+        BW.svd(A)
+        BW.qr(A)
+        D = rng.standard_normal((20, 7)) @ rng.standard_normal((7, 30))
+        BW.qc(D)
+        t = xb.TTTensor.random([3, 4, 3, 4], 5, rng)
+        t.round(2)
+    finally:
+        xb.perf_enable(False)
+    ent = xb.perf_entries()
+    assert ent[("Dense BLAS", "Matrix-Matrix-Multiplication", "37x23 * 23x19")][0] == 2
+    assert ent[("Dense LAPACK", "Singular Value Decomposition", "37x23")][0] == 1
+    assert ent[("Dense LAPACK", "QR Factorisation", "37x23")][0] == 1
+    assert ("Dense LAPACK", "QRP Factorisation", "20x7 * 7x30") in ent
+    assert any(k[0] == "TT sweep" and k[1] == "round" for k in ent)
+    assert all(v[1] > 0 for v in ent.values())
+    assert "Matrix-Matrix-Multiplication" in xb.perf_analysis()
+    BW.qr(A)                                  # disabled: nothing is recorded
+    assert xb.perf_entries()[("Dense LAPACK", "QR Factorisation", "37x23")][0] == 1

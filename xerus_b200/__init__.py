@@ -66,6 +66,50 @@ def profile_get(kernel_class):
     return s.value, l.value, ms.value
 
 
+def perf_enable(on=True):
+    """The reference's XERUS_PERFORMANCE_ANALYSIS registry at the C ABI (misc/performanceAnalysis.h:30-39): every call is recorded
+    under (group, name, shape) with the reference's own strings."""
+    from ._lib import call
+    call("xb_perf_enable", int(bool(on)))
+
+
+def perf_reset():
+    from ._lib import call
+    call("xb_perf_reset")
+
+
+def perf_entries():
+    """{(group, name, shape): (calls, microseconds)} — the analogue of misc::performanceAnalysis::calls."""
+    import ctypes as C
+    from ._lib import call
+    n = C.c_size_t()
+    call("xb_perf_count", C.byref(n))
+    out = {}
+    for i in range(n.value):
+        g, nm, sh, calls, us = C.c_char_p(), C.c_char_p(), C.c_char_p(), C.c_uint64(), C.c_double()
+        call("xb_perf_entry", i, C.byref(g), C.byref(nm), C.byref(sh), C.byref(calls), C.byref(us))
+        out[(g.value.decode(), nm.value.decode(), sh.value.decode())] = (calls.value, us.value)
+    return out
+
+
+def perf_analysis():
+    """Text report in the spirit of misc::performanceAnalysis::get_analysis() (performanceAnalysis.cpp:34-82)."""
+    ent = perf_entries()
+    lines = []
+    groups = sorted({k[0] for k in ent})
+    total = sum(v[1] for v in ent.values()) or 1.0
+    for g in groups:
+        gt = sum(v[1] for k, v in ent.items() if k[0] == g)
+        lines.append("%s: %.3f ms (%.1f %%)" % (g, gt / 1e3, 100 * gt / total))
+        for nm in sorted({k[1] for k in ent if k[0] == g}):
+            nt = sum(v[1] for k, v in ent.items() if k[:2] == (g, nm))
+            nc = sum(v[0] for k, v in ent.items() if k[:2] == (g, nm))
+            lines.append("  %-32s %8d calls %12.3f ms" % (nm, nc, nt / 1e3))
+            for k, v in sorted(((k, v) for k, v in ent.items() if k[:2] == (g, nm)), key=lambda kv: -kv[1][1]):
+                lines.append("      %-40s %8d calls %12.3f ms" % (k[2], v[0], v[1] / 1e3))
+    return "\n".join(lines)
+
+
 def worker_select(worker):
     """Binds the calling host thread to a private worker (stream + scratch); see include/xb200.h."""
     from ._lib import call

@@ -75,6 +75,8 @@ _SIGS = {
     "xb_env_apply": [vp, vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz],
     "xb_env_apply_rows": [vp, vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz],
     "xb_env_apply_rows_fused": [vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz, C.c_int, C.c_int, P(vp), C.c_uint, P(vp)],
+    "xb_perf_enable": [C.c_int], "xb_perf_reset": [], "xb_perf_count": [szp],
+    "xb_perf_entry": [sz, P(C.c_char_p), P(C.c_char_p), P(C.c_char_p), P(C.c_uint64), dp],
     "xb_peer_buffer_bytes": [sz, sz, C.c_int, szp], "xb_peer_buffer_create": [sz, P(vp), C.c_char_p],
     "xb_peer_buffer_open": [C.c_char_p, P(vp)], "xb_peer_buffer_close": [vp], "xb_peer_buffer_check": [vp], "xb_peer_buffer_destroy": [vp],
     "xb_env_apply_fused": [vp, sz, sz, P(vp), szp, sz, vp, sz, sz, vp, sz, sz, C.c_int, C.c_int, P(vp), C.c_uint, P(vp)],

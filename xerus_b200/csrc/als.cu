@@ -1446,6 +1446,10 @@ xb_status xb_als_solve(const xb_tt* A, xb_tt* x, const xb_tt* b, const xb_als_op
 			for (size_t i = 0; i < x->d; ++i)
 				XB_REQUIRE(A->dim_m[i] == x->dim_m[i] && A->dim_n[i] == x->dim_m[i], "operator and tensor dimensions differ");   // :495-496
 		}
+		size_t rmax = 0, nmax = 0;
+		for (size_t i = 0; i < x->d; ++i) { rmax = std::max(rmax, x->rank[i]); nmax = std::max(nmax, x->dim_m[i]); }
+		PerfScope pa("TT sweep", opt->sites == 2 ? "DMRG" : (opt->local_solver == 1 ? "ASD" : "ALS"),
+		             "d=" + pa_str(x->d) + " n=" + pa_str(nmax) + " r=" + pa_str(rmax) + " half-sweeps=" + pa_str(opt->num_half_sweeps));
 		Als als;
 		als.A = A; als.x = x; als.b = b; als.opt = *opt;
 		*energy = als.run();

@@ -29,6 +29,7 @@ extern "C" {
 
 xb_status xb_one_norm(const double* x, size_t n, double* result) {
 	return guard([&] {
+		PerfScope pa("Dense BLAS", "One Norm", pa_str(n));
 		ensure_init(); XB_REQUIRE(result && (x || !n), "null");
 		if (!n) { *result = 0.0; return; }
 		Staged dx(x, n); DBuf r(1);
@@ -39,6 +40,7 @@ xb_status xb_one_norm(const double* x, size_t n, double* result) {
 
 xb_status xb_two_norm(const double* x, size_t n, double* result) {
 	return guard([&] {
+		PerfScope pa("Dense BLAS", "Two Norm", pa_str(n));
 		ensure_init(); XB_REQUIRE(result && (x || !n), "null");
 		if (!n) { *result = 0.0; return; }
 		Staged dx(x, n);
@@ -48,6 +50,7 @@ xb_status xb_two_norm(const double* x, size_t n, double* result) {
 
 xb_status xb_dot_product(const double* x, size_t n, const double* y, double* result) {
 	return guard([&] {
+		PerfScope pa("Dense BLAS", "Dot Product", pa_str(n) + "*" + pa_str(n));
 		ensure_init(); XB_REQUIRE(result && ((x && y) || !n), "null");
 		if (!n) { *result = 0.0; return; }
 		Staged dx(x, n), dy(y, n);
@@ -59,6 +62,7 @@ xb_status xb_matrix_vector_product(double* x, size_t m, double alpha, const doub
 	// x (m entries) = alpha * op(A) * y (n entries); A is stored m x n, or n x m when `transposed`
 	// (blasLapackWrapper.cpp:114-131: dgemv NoTrans(m, n, lda = n) resp. Trans(n, m, lda = m))
 	return guard([&] {
+		PerfScope pa("Dense BLAS", "Matrix Vector Product", pa_str(m) + "x" + pa_str(n) + " * " + pa_str(n));
 		ensure_init(); XB_REQUIRE(x && A && y, "null");
 		Staged dA(A, m * n), dy(y, n); DBuf dx(m);
 		gemm(dx, 1, m, 1, alpha, dA, transposed ? m : n, transposed != 0, n, dy, 1, false, 0.0);
@@ -68,6 +72,7 @@ xb_status xb_matrix_vector_product(double* x, size_t m, double alpha, const doub
 
 xb_status xb_dyadic_vector_product(double* A, size_t m, size_t n, double alpha, const double* x, const double* y) {
 	return guard([&] {
+		PerfScope pa("Dense BLAS", "Dyadic Vector Product", pa_str(m) + " o " + pa_str(n));
 		ensure_init(); XB_REQUIRE(A && x && y, "null");
 		Staged dx(x, m), dy(y, n); DBuf dA(m * n);
 		gemm(dA, n, m, n, alpha, dx, 1, false, 1, dy, n, false, 0.0);
@@ -78,6 +83,7 @@ xb_status xb_dyadic_vector_product(double* A, size_t m, size_t n, double alpha, 
 xb_status xb_matrix_matrix_product(double* C, size_t leftDim, size_t rightDim, double alpha, const double* A, size_t lda,
                                    int transposeA, size_t middleDim, const double* B, size_t ldb, int transposeB) {
 	return guard([&] {
+		PerfScope pa("Dense BLAS", "Matrix-Matrix-Multiplication", pa_str(leftDim) + "x" + pa_str(middleDim) + " * " + pa_str(middleDim) + "x" + pa_str(rightDim));
 		ensure_init(); XB_REQUIRE(C && A && B, "null");
 		XB_REQUIRE(leftDim <= 0x7fffffffULL && rightDim <= 0x7fffffffULL && middleDim <= 0x7fffffffULL, "Dimension to large for BLAS/Lapack");
 		const size_t a_rows = transposeA ? middleDim : leftDim, a_cols = transposeA ? leftDim : middleDim;
@@ -92,6 +98,7 @@ xb_status xb_matrix_matrix_product(double* C, size_t leftDim, size_t rightDim, d
 
 xb_status xb_svd(double* U, double* S, double* Vt, const double* A, size_t m, size_t n) {
 	return guard([&] {
+		PerfScope pa("Dense LAPACK", "Singular Value Decomposition", pa_str(m) + "x" + pa_str(n));
 		ensure_init(); XB_REQUIRE(U && S && Vt && A, "null");
 		XB_REQUIRE(m <= 0x7fffffffULL && n <= 0x7fffffffULL, "Dimension to large for BLAS/Lapack");
 		const size_t k = std::min(m, n);
@@ -109,9 +116,11 @@ xb_status xb_qc(double* Q, double* C, size_t* rank, const double* A, size_t m, s
 		XB_REQUIRE(m > 0 && n > 0, "Dimension m and n must be larger than zero");
 		const size_t k = std::min(m, n);
 		Staged dA(A, m * n); DBuf dQ(m * k), dC(k * n);
+		PerfScope pa("Dense LAPACK", "QRP Factorisation", "");
 		const size_t r = qc(dQ, dC, dA, m, n);
 		to_host(Q, dQ, m * r); to_host(C, dC, r * n); sync();
 		*rank = r;
+		pa.s = pa_str(m) + "x" + pa_str(r) + " * " + pa_str(r) + "x" + pa_str(n);      // blasLapackWrapper.cpp:302
 	});
 }
 
@@ -121,14 +130,17 @@ xb_status xb_cq(double* C, double* Q, size_t* rank, const double* A, size_t m, s
 		XB_REQUIRE(m > 0 && n > 0, "Dimension m and n must be larger than zero");
 		const size_t k = std::min(m, n);
 		Staged dA(A, m * n); DBuf dC(m * k), dQ(k * n);
+		PerfScope pa("Dense LAPACK", "QRP Factorisation", "");
 		const size_t r = cq(dC, dQ, dA, m, n);
 		to_host(C, dC, m * r); to_host(Q, dQ, r * n); sync();
 		*rank = r;
+		pa.s = pa_str(n) + "x" + pa_str(r) + " * " + pa_str(r) + "x" + pa_str(m);      // blasLapackWrapper.cpp:368
 	});
 }
 
 xb_status xb_qr(double* Q, double* R, const double* A, size_t m, size_t n) {
 	return guard([&] {
+		PerfScope pa("Dense LAPACK", "QR Factorisation", pa_str(m) + "x" + pa_str(n));
 		ensure_init(); XB_REQUIRE(Q && R && A, "QR decomposition must not be called with null pointers");
 		XB_REQUIRE(A != R, "_A and _R must be different, otherwise qr call will fail.");     // blasLapackWrapper.cpp:396
 		XB_REQUIRE(m > 0 && n > 0, "Dimension m and n must be larger than zero");
@@ -141,6 +153,7 @@ xb_status xb_qr(double* Q, double* R, const double* A, size_t m, size_t n) {
 
 xb_status xb_rq(double* R, double* Q, const double* A, size_t m, size_t n) {
 	return guard([&] {
+		PerfScope pa("Dense LAPACK", "RQ Factorisation", pa_str(m) + "x" + pa_str(n));
 		ensure_init(); XB_REQUIRE(Q && R && A, "QR decomposition must not be called with null pointers");
 		XB_REQUIRE(A != R, "_A and _R must be different, otherwise qr call will fail.");     // :463
 		XB_REQUIRE(m > 0 && n > 0, "Dimension m and n must be larger than zero");
@@ -172,6 +185,7 @@ static void least_squares(double* dX, const double* dA, size_t m, size_t n, cons
 
 xb_status xb_solve_least_squares(double* x, const double* A, size_t m, size_t n, const double* b, size_t p) {
 	return guard([&] {
+		PerfScope pa("Dense LAPACK", "Solve Least Squares", pa_str(m) + "x" + pa_str(n) + " * " + pa_str(p));
 		ensure_init(); XB_REQUIRE(x && A && b, "null");
 		Staged dA(A, m * n), dB(b, m * p); DBuf dX(n * p);
 		least_squares(dX, dA, m, n, dB, p);
@@ -183,8 +197,10 @@ xb_status xb_solve(double* x, const double* A, size_t m, size_t n, const double*
 	return guard([&] {
 		ensure_init(); XB_REQUIRE(x && A && b, "null");
 		XB_REQUIRE(m <= 0x7fffffffULL && n <= 0x7fffffffULL && nrhs <= 0x7fffffffULL, "Dimension to large for BLAS/Lapack");
+		PerfScope pa("Dense LAPACK", "Solve (PLU)", pa_str(n) + "x" + pa_str(n) + "x" + pa_str(nrhs));      // :582 / :622
 		Staged dA(A, m * n), dB(b, m * nrhs);
 		if (m != n) {                                             // :553-559
+			pa.n = "Solve Least Squares"; pa.s = pa_str(m) + "x" + pa_str(n) + " * " + pa_str(nrhs);
 			DBuf dX(n * nrhs);
 			least_squares(dX, dA, m, n, dB, nrhs);
 			to_host(x, dX, n * nrhs); sync();
@@ -196,7 +212,7 @@ xb_status xb_solve(double* x, const double* A, size_t m, size_t n, const double*
 		if (symmetric && definite) {
 			DBuf Ac(n * n), Bc(n * nrhs);
 			copy(Ac, dA, n * n); copy(Bc, dB, n * nrhs);
-			if (cholesky_solve(Ac, Bc, n, nrhs)) { to_host(x, Bc, n * nrhs); sync(); done = true; }
+			if (cholesky_solve(Ac, Bc, n, nrhs)) { to_host(x, Bc, n * nrhs); sync(); done = true; pa.n = "Solve (Cholesky)"; }
 		}
 		if (!done) {   // LU with partial pivoting: the reference's dgesv branch, also standing in for dsysv (:638)
 			lu_solve(dA, dB, n, nrhs);

@@ -1,6 +1,8 @@
 // xb200 runtime: device context, stream, stream-ordered memory pool, error state, memory hooks of the C ABI.
 #include "xb_internal.cuh"
 #include <atomic>
+#include <chrono>
+#include <map>
 #include <mutex>
 #include <cstdlib>
 
@@ -201,6 +203,37 @@ double read_scalar(const double* d_value) {
 	return c.h_scratch[0];
 }
 
+// ---- (group, name, shape) call registry -------------------------------------------------------------------------------
+// The reference brackets every blasWrapper call with XERUS_PA_START / XERUS_PA_END(group, name, shape) and keeps
+// (calls, microseconds) per shape (misc/performanceAnalysis.h:30-39, blasLapackWrapper.cpp:83-720).  The same registry at the
+// C ABI, with the reference's own group / name / shape strings for the per-call layer, so shape catalogues can be compared
+// one to one; the sweep layer adds the group "TT sweep".  Off by default (xb_perf_enable); host wall time of the call.
+static std::atomic<bool> g_perf_on{false};
+static std::mutex g_perf_mutex;
+struct PerfEntry { std::string group, name, shape; uint64_t calls = 0; double us = 0.0; };
+static std::map<std::string, size_t> g_perf_index;
+static std::vector<PerfEntry> g_perf_entries;
+
+PerfScope::PerfScope(const char* group, const char* name, const std::string& shape) {
+	if (!g_perf_on.load(std::memory_order_relaxed)) return;
+	on = true; g = group; n = name; s = shape;
+	t0 = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+PerfScope::~PerfScope() {
+	if (!on) return;
+	const double t1 = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+	std::lock_guard<std::mutex> lock(g_perf_mutex);
+	const std::string key = std::string(g) + "\x1f" + n + "\x1f" + s;
+	auto it = g_perf_index.find(key);
+	if (it == g_perf_index.end()) {
+		it = g_perf_index.emplace(key, g_perf_entries.size()).first;
+		PerfEntry e; e.group = g; e.name = n; e.shape = s;
+		g_perf_entries.push_back(e);
+	}
+	g_perf_entries[it->second].calls += 1;
+	g_perf_entries[it->second].us += t1 - t0;
+}
+
 // ---- profiling ----------------------------------------------------------------------------------------------------
 #define g_prof_pending (ctx().prof_pending)
 #define g_prof_totals (ctx().prof_totals)
@@ -334,6 +367,26 @@ xb_status xb_profile_get(const char* kernel_class, uint64_t* scopes, uint64_t* l
 		if (scopes) *scopes = t.scopes;
 		if (launches) *launches = t.launches;
 		if (milliseconds) *milliseconds = t.ms;
+	});
+}
+
+xb_status xb_perf_enable(int on) { return guard([&] { g_perf_on.store(on != 0); }); }
+xb_status xb_perf_reset(void) {
+	return guard([&] { std::lock_guard<std::mutex> lock(g_perf_mutex); g_perf_index.clear(); g_perf_entries.clear(); });
+}
+xb_status xb_perf_count(size_t* n) {
+	return guard([&] { XB_REQUIRE(n, "null"); std::lock_guard<std::mutex> lock(g_perf_mutex); *n = g_perf_entries.size(); });
+}
+xb_status xb_perf_entry(size_t i, const char** group, const char** name, const char** shape, uint64_t* calls, double* microseconds) {
+	return guard([&] {
+		std::lock_guard<std::mutex> lock(g_perf_mutex);
+		XB_REQUIRE(i < g_perf_entries.size(), "perf entry index out of range");
+		const PerfEntry& e = g_perf_entries[i];            // the strings stay valid until xb_perf_reset
+		if (group) *group = e.group.c_str();
+		if (name) *name = e.name.c_str();
+		if (shape) *shape = e.shape.c_str();
+		if (calls) *calls = e.calls;
+		if (microseconds) *microseconds = e.us;
 	});
 }
 

@@ -17,6 +17,13 @@ namespace xb {
 
 static void check_idx(const xb_tt* t, size_t idx) { XB_REQUIRE(t && idx < t->d, "Illegal component index"); }
 
+// shape string of a TT for the call registry: "d=32 n=2 r=256" (largest external dimension and bond rank)
+static std::string tt_shape(const xb_tt* t) {
+	size_t n = 0, r = 0;
+	for (size_t i = 0; i < t->d; ++i) { n = std::max(n, t->ext(i)); r = std::max(r, t->rank[i]); }
+	return "d=" + pa_str(t->d) + " n=" + pa_str(n) + " r=" + pa_str(r);
+}
+
 // TensorNetwork::transfer_core for a TT chain (tensorNetwork.cpp:821-909).
 static void transfer_core(xb_tt* t, size_t from, size_t to, bool allow_rank_reduction) {
 	if (to == from + 1) {
@@ -706,6 +713,9 @@ xb_status xb_tt_round_svals(xb_tt* tt, const size_t* max_ranks, double eps, doub
 		require_correct_format(tt);
 		XB_REQUIRE(max_ranks || tt->d == 1, "There must be exactly degree-1 maxRanks");
 		XB_REQUIRE(eps >= 0.0 && eps < 1.0, "_eps must be smaller than one.");
+		size_t cap = 0;
+		for (size_t i = 0; i + 1 < tt->d; ++i) cap = std::max(cap, max_ranks[i]);
+		PerfScope pa("TT sweep", "round", tt_shape(tt) + " -> " + (cap ? pa_str(cap) : std::string("eps")));
 		if (!svals && round_planned(tt, max_ranks, eps)) return;
 		round_tt(tt, max_ranks, eps, svals, stride);
 	});

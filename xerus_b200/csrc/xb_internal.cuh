@@ -111,6 +111,14 @@ struct ProfScope {
 	~ProfScope();
 };
 
+// (group, name, shape) registry of the C-ABI calls (runtime.cu); no-op unless xb_perf_enable(1)
+struct PerfScope {
+	bool on = false; const char* g = nullptr; const char* n = nullptr; std::string s; double t0 = 0.0;
+	PerfScope(const char* group, const char* name, const std::string& shape);
+	~PerfScope();
+};
+inline std::string pa_str(size_t v) { return std::to_string(v); }
+
 // stream-ordered device allocations from the library pool
 double* dalloc(size_t n_doubles);
 void* dalloc_bytes(size_t bytes);
