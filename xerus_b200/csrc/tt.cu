@@ -337,6 +337,7 @@ static int round_plan_enqueue(xb_tt* t, const size_t* max_ranks, double eps, Pen
 		c.count_allocs = false;
 		pl->arena_size = c.alloc_counter + in_bytes + (1u << 20);
 		pl->ranks_out = t->rank; pl->canon_out = t->canonicalized; pl->core_out = t->core_position;
+		if (pl->arena_size > (size_t(8) << 30)) pl->unplannable = true;      // sweeps that allocate more than 8 GB stay on the ordinary path
 		return 1;
 	}
 	if (!pl->exec) {
