@@ -358,3 +358,34 @@ def test_asd(golden2, tag, d, n, hs):
         e_ref = float(golden2["%s.gen_hs%d.energy" % (tag, hs)])
         assert abs(e - e_ref) < 1e-8 * abs(e_ref)
         assert O.tt_distance_rel(x, load_tt(golden2, "%s.gen_hs%d.x" % (tag, hs))) < 1e-7
+
+
+# ------------------------------------------------------------------------------------------- BASELINE sizes (reduced) ----
+# tests/golden/xerus_ref_sizes_v1.npz (oracle/make_golden_sizes.py): the reference at the reduced sizes SURVEY 8d names for the
+# configs it cannot run in full; the numpy restatement is pinned at the sizes that finish in seconds here.
+@pytest.fixture(scope="module")
+def sizes():
+    import os
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "xerus_ref_sizes_v1.npz")))
+
+
+def test_config2_rank8_sweep(sizes):
+    d, n = 16, 10
+    A, b = O.laplace_operator(d, n), O.tt_ones([n] * d)
+    x = load_tt(sizes, "c2_r8.x0")
+    e = O.ALS_SPD(A, x, b, 2)
+    e_ref = float(sizes["c2_r8.energy"])
+    assert abs(e - e_ref) < 1e-10 * abs(e_ref)
+    assert O.tt_distance_rel(x, load_tt(sizes, "c2_r8.x")) < 1e-8
+
+
+@pytest.mark.parametrize("r", [8, 16])
+def test_config4_reduced_dmrg_half_sweep(sizes, r):
+    d, n = 10, 4
+    A, b = O.laplace_operator(d, n), O.tt_ones([n] * d)
+    x = load_tt(sizes, "c4_r%d.x0" % r)
+    e = O.DMRG_SPD(A, x, b, 1)
+    e_ref = float(sizes["c4_r%d.energy" % r])
+    assert abs(e - e_ref) < 1e-10 * abs(e_ref)
+    assert x.ranks() == [int(v) for v in sizes["c4_r%d.x.ranks" % r]]
+    assert O.tt_distance_rel(x, load_tt(sizes, "c4_r%d.x" % r)) < 1e-8

@@ -126,3 +126,40 @@ def test_bond_split_allreduce_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert results[0] < 1e-13 and results[1] < 1e-13
+
+
+def _row_worker(rank, world, port, q):
+    """Row-split local apply (split along the LEFT bond: xb_env_apply_rows + all-gather) with a numpy stand-in for the device
+    kernel: the ranks' row blocks all-gather (gloo) to the full application on every rank, bit for bit."""
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(4)
+        l, r, a, n = 6, 7, 2, 3
+        L, R = rng.standard_normal((l, a, l)), rng.standard_normal((r, a, r))
+        A1, v = rng.standard_normal((a, n, n, a)), rng.standard_normal((l, n, r))
+        b, e = parallel.slab_range(l, rank, world)
+        block = np.einsum("xay,ainb,zbw,ynw->xiz", L[b:e], A1, R, v)                  # rows [b, e) of the result: nothing to sum
+        y = torch.empty(l, n, r, dtype=torch.float64)
+        dist.all_gather_into_tensor(y, torch.from_numpy(np.ascontiguousarray(block)))
+        full = np.einsum("xay,ainb,zbw,ynw->xiz", L, A1, R, v)
+        q.put((rank, float(np.linalg.norm(y.numpy() - full) / np.linalg.norm(full)), bool(np.array_equal(y.numpy()[b:e], block))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_split_allgather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_row_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = {k: (err, same) for k, err, same in (q.get(timeout=120) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for k in (0, 1):
+        assert results[k][0] < 1e-13 and results[k][1]
