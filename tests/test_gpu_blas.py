@@ -462,3 +462,43 @@ def test_call_registry_uses_the_reference_shape_strings():
     assert "Matrix-Matrix-Multiplication" in xb.perf_analysis()
     BW.qr(A)                                  # disabled: nothing is recorded
     assert xb.perf_entries()[("Dense LAPACK", "QR Factorisation", "37x23")][0] == 1
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (1, 7), (7, 1), (33, 2), (2, 33), (5, 300), (300, 5), (31, 31), (32, 64), (512, 32), (32, 512)])
+def test_single_cta_kernels_on_ragged_shapes(m, n):
+    """qr_small_kernel / svd_small_kernel (min(m, n) <= 32, csrc/small_f64.cu): odd column counts (a zero column pads the
+    tournament), one-column and one-row matrices, the largest rows the kernels take, both orientations — against the general
+    kernels (small_kernels=0) and against numpy."""
+    rng = np.random.default_rng(m * 1000 + n)
+    A = rng.standard_normal((m, n)) * 10.0 ** rng.uniform(-3, 3)
+    k = min(m, n)
+    out = {}
+    try:
+        for v in (1, 0):
+            xb.set_option("small_kernels", v)
+            U, S, Vt = BW.svd(A)
+            Q, R = BW.qr(A)
+            Rq, Qr = BW.rq(A)
+            out[v] = (S, np.abs(np.diag(R[:k, :k])))
+            assert rel((U * S) @ Vt, A) < 1e-13 and rel(Q @ R, A) < 1e-13 and rel(Rq @ Qr, A) < 1e-13
+            assert np.linalg.norm(U.T @ U - np.eye(k)) < 1e-12 and np.linalg.norm(Vt @ Vt.T - np.eye(k)) < 1e-12
+            assert np.linalg.norm(Q.T @ Q - np.eye(k)) < 1e-13
+            assert np.all(np.diff(S) <= 0)
+    finally:
+        xb.set_option("small_kernels", 1)
+    s_ref = np.linalg.svd(A, compute_uv=False)
+    assert np.max(np.abs(out[1][0] - s_ref)) < 1e-13 * s_ref[0]
+    assert np.max(np.abs(out[1][0] - out[0][0])) < 1e-13 * s_ref[0]
+    assert np.allclose(out[1][1], out[0][1], rtol=1e-10, atol=1e-13 * out[0][1].max())
+
+
+def test_single_cta_svd_of_zero_and_rank_deficient_matrices():
+    Z = np.zeros((6, 9))
+    U, S, Vt = BW.svd(Z)
+    assert np.all(S == 0) and np.all(np.isfinite(U)) and np.all(np.isfinite(Vt))
+    rng = np.random.default_rng(2)
+    D = rng.standard_normal((40, 3)) @ rng.standard_normal((3, 20))          # rank 3 of 20
+    U, S, Vt = BW.svd(D)
+    assert rel((U * S) @ Vt, D) < 1e-13 and np.all(S[3:] < 1e-13 * S[0])
+    Q, C, r = BW.qc(D)
+    assert r == 3 and rel(Q @ C, D) < 1e-12
