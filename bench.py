@@ -312,6 +312,47 @@ def batch_workload(args, rank, local_rank, world):
     return None
 
 
+def dmrg_sweep_workload(args, rank, local_rank, world):
+    """--workload c4sweep: BASELINE configs[3] as a sweep — one full two-site DMRG_SPD sweep (2 half-sweeps) at bond rank `--bond`
+    (default 512) on the Laplace-like operator of degree 24, n = 4 with a right-hand side of full TT-rank (with b = ones the
+    two-site split collapses the bond to the solution's low rank after the first site).  Local problems: 4.19 M unknowns, matrix-free
+    CG on the three-factor local operator (17.5 GFLOP per application); split: SVD of a 2048 x 2048 matrix cut to rank 512.
+    The reference cannot run this (local matrix 8.8 TB, and its two-site driver throws at the sweep turn).  Single GPU; one step."""
+    import numpy as np
+    torch, xb, dist, stream = setup(local_rank, world)
+    if rank != 0:
+        return None
+    d, n, r = args.sweep_degree, 4, args.bond
+    rng = np.random.default_rng(4)
+    A = xb.TTOperator.laplace(d, n)
+    b = xb.TTTensor.random([n] * d, r, rng); b *= 1.0 / b.frob_norm()
+    x0 = xb.TTTensor.random([n] * d, r, rng); x0 *= 1.0 / x0.frob_norm()
+    variant = xb.ALSVariant(2, 0, True, localTolerance=1e-8)
+    warm = xb.TTTensor.random([n] * 6, 8, rng)                                   # loads the kernels of the path on a toy problem
+    variant(xb.TTOperator.laplace(6, n), warm, xb.TTTensor.random([n] * 6, 8, rng), 2)
+    out = {}
+    for hs in (1, 2):
+        x = x0.copy()
+        xb.synchronize()
+        l0 = xb.kernel_launch_count()
+        t0 = time.perf_counter()
+        e = variant(A, x, b, hs)
+        xb.synchronize()
+        out[hs] = dict(seconds=time.perf_counter() - t0, energy=e, applications=variant.last_local_iterations,
+                       residual=A.apply(x).distance(b) / b.frob_norm(), ranks_max=max(x.ranks()), launches=xb.kernel_launch_count() - l0)
+    apply_flops = 2 * (r * 2) * r * (n * n * r) + 2 * 2 * (r * n * r) * (2 * n) * (n * 2) + 2 * (r * n * n) * (2 * r) * r
+    return {"metric": "two-site DMRG_SPD sweep seconds (FP64, bond %d)" % r, "value": out[2]["seconds"], "unit": "s", "n_gpus": 1, "steps": 1, "warmup": 1,
+            "ms_per_step": out[2]["seconds"] * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (Laplace-like operator, random right-hand side and start of TT-rank %d, normalised)" % r,
+            "config": {"workload": "two-site DMRG sweep, bond rank %d, degree %d, n=4 (BASELINE configs[3] as a sweep)" % (r, d),
+                       "local_problem": "%d unknowns, matrix-free CG to 1e-8, SVD split of a %d x %d matrix" % (r * n * n * r, r * n, n * r),
+                       "l2": "operands of one application (75 MB) smaller than L2; a sweep touches 24 x 8 MB of cores"},
+            "gpu_launches": out[2]["launches"], "half_sweep_1": out[1], "full_sweep": out[2],
+            "check": {"energy_monotone": out[2]["energy"] >= out[1]["energy"] - 1e-12 * abs(out[1]["energy"]), "ranks_max": out[2]["ranks_max"]},
+            "algorithmic_flops_local_applies": out[2]["applications"] * apply_flops,
+            "reference": "not runnable: densified local operator (als.cpp:44) would be 8.8 TB; two-site driver throws at the sweep turn (als.cpp:371,:376)"}
+
+
 def measured_peaks():
     """MEASURED_PEAKS.json (driver-written, HBM copy GB/s and bf16 TF/s of this pool's B200s); {} if absent."""
     try:
@@ -526,7 +567,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="xb200", choices=["xb200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + ["c4", "c5", "c4sweep"])
+    ap.add_argument("--sweep-degree", type=int, default=24, help="degree of the TT for --workload c4sweep")
     ap.add_argument("--bond", type=int, default=512, help="bond rank for --workload c4")
     ap.add_argument("--collective", default="auto", choices=["auto", "fused", "nccl"],
                     help="--workload c4 at N > 1: exchange fused over peer memory, or NCCL; auto = fused up to 4 GPUs, NCCL all-gather at 8 "
@@ -542,8 +584,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.workload in ("c4", "c5") and args.impl == "xb200":
-        line = (batch_workload if args.workload == "c5" else bond_split_workload)(args, rank, local_rank, world)
+    if args.workload in ("c4", "c5", "c4sweep") and args.impl == "xb200":
+        line = {"c5": batch_workload, "c4": bond_split_workload, "c4sweep": dmrg_sweep_workload}[args.workload](args, rank, local_rank, world)
         if line is not None:
             print(json.dumps(line))
         teardown()

@@ -154,7 +154,7 @@ xb_status xb_tt_round_svals(xb_tt* tt, const size_t* max_ranks, double eps, doub
 xb_status xb_tt_soft_threshold(xb_tt* tt, const double* taus, int prevent_zero);
 /* Batches of independent items (BASELINE config 5).  The items run concurrently on library workers (CUDA stream + memory pool +
  * plan cache each — option "batch_workers", default 16) driven asynchronously by a few library-owned host threads (option
- * "batch_threads", default 2); the call is stream-ordered with respect to the caller's worker on both sides.  xb_tt_round_batched: tts[b].round(max_rank, eps).  xb_tt_apply_round_batched: the item of
+ * "batch_threads", default 2); the call is stream-ordered with respect to the caller's worker on both sides.  The items of a batch must be distinct objects.  xb_tt_round_batched: tts[b].round(max_rank, eps).  xb_tt_apply_round_batched: the item of
  * config 5, out[b] = round(A x_b) (y(i&0) = A(i/2,j/2) * x(j&0), then TTNetwork::round); the caller destroys out[b]. */
 xb_status xb_tt_round_batched(xb_tt** tts, size_t batch, size_t max_rank, double eps);
 xb_status xb_tt_apply_round_batched(xb_tt** out, const xb_tt* A, xb_tt* const* xs, size_t batch, size_t max_rank, double eps);

@@ -233,8 +233,12 @@ static void capture_plan(RoundPlan& pl, const xb_tt* t, const size_t* max_ranks,
 	const size_t d = t->d;
 	pl.staging.resize(d);
 	for (size_t i = 0; i < d; ++i) pl.staging[i].resize(t->core_size(i));
-	XB_CUDA(cudaMalloc(reinterpret_cast<void**>(&pl.flag), 4 * sizeof(unsigned int)));
-	XB_CUDA(cudaMalloc(reinterpret_cast<void**>(&pl.arena), pl.arena_size));
+	if (cudaMalloc(reinterpret_cast<void**>(&pl.flag), 4 * sizeof(unsigned int)) != cudaSuccess ||
+	    cudaMalloc(reinterpret_cast<void**>(&pl.arena), pl.arena_size) != cudaSuccess) {
+		cudaGetLastError();                                       // no memory for the arena: this shape stays on the ordinary path
+		pl.unplannable = true; pl.staging.clear();
+		return;
+	}
 	XB_CUDA(cudaStreamSynchronize(c.stream));
 	xb_tt proto;
 	proto.d = d; proto.is_operator = t->is_operator; proto.dim_m = t->dim_m; proto.dim_n = t->dim_n; proto.rank = t->rank;
@@ -465,6 +469,7 @@ template <class F> static void run_batch(size_t batch, size_t max_rank, double e
 	std::vector<std::thread> threads;
 	for (int th = 0; th < T; ++th) threads.emplace_back(body, th);
 	for (auto& th : threads) th.join();
+	if (!err.empty()) xb_synchronize_all();      // nothing of a failed batch may still be running when the caller gets its items back
 	for (int w = 0; w < W; ++w) if (done[w]) { cudaStreamWaitEvent(caller.stream, done[w], 0); cudaEventDestroy(done[w]); }
 	cudaEventDestroy(start);
 	if (!err.empty()) throw Error(err_code, err);
