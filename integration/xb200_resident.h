@@ -1,6 +1,6 @@
 // Resident front-end: the sweeps of xerus::TTNetwork / ALSVariant carried out by the sweep layer of libxb200 (include/xb200.h)
-// behind the reference's own API.  integration/patch_reference.py inserts one call to each of these hooks into a build-time copy
-// of the reference's ttNetwork.cpp / als.cpp (the reference tree itself is never modified and none of its text is stored here):
+// behind the reference's own API.  integration/patch_reference.py inserts one call to each of these hooks into a transient build-time
+// copy of the reference's ttNetwork.cpp / als.cpp (the reference tree itself is never modified and none of its text is stored here):
 //
 //   TTNetwork<isOperator>::round(maxRanks, eps)      (src/xerus/ttNetwork.cpp:644)   -> xb200_resident::round
 //   TTNetwork<isOperator>::move_core(pos, keepRank)  (src/xerus/ttNetwork.cpp:582)   -> xb200_resident::move_core
