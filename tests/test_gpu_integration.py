@@ -51,7 +51,9 @@ def run_tests(binary, names, env=None):
                 res[n] = False
         return res
 
-    result = verdicts(list(names))
+    # the tests that need SuiteSparse abort the process (the stub throws through the runner): they get a process each
+    solo = [n for n in names if n in NEEDS_SPARSE | FAILS_ON_CPU_TOO]
+    result = verdicts([n for n in names if n not in solo])
     for n in names:
         if n not in result:
             result[n] = verdicts([n]).get(n, False)
