@@ -8,6 +8,7 @@ Inserted (each right after the reference's own argument checks, so error behavio
   ttNetwork.cpp  TTNetwork::round(maxRanks, eps)         if (xb200_resident::round(*this, _maxRanks, _eps)) return;
                  TTNetwork::move_core(position, keepRank) if (xb200_resident::move_core(*this, _position, _keepRank)) return;
                  TTNetwork::soft_threshold(taus, .)       if (xb200_resident::soft_threshold(*this, _taus)) return;
+                 TTNetwork::operator+=(other)             if (xb200_resident::add(*this, _other)) return *this;
   als.cpp        ALSVariant::solve(...)                   { double e; if (xb200_resident::als_solve(*this, _Ap, _x, _b, ..., e)) return e; }
 """
 import os
@@ -40,6 +41,8 @@ def main():
                       "require_correct_format();", "if (xb200_resident::move_core(*this, _position, _keepRank)) { return; }", "move_core")
     tt = insert_after(tt, r"void TTNetwork<isOperator>::soft_threshold\(const std::vector<double> &_taus, const bool  /\*_preventZero\*/\) \{",
                       "require_correct_format();", "if (xb200_resident::soft_threshold(*this, _taus)) { return; }", "soft_threshold")
+    tt = insert_after(tt, r"TTNetwork<isOperator>& TTNetwork<isOperator>::operator\+=\(const TTNetwork<isOperator>& _other\) \{",
+                      "require_correct_format();", "if (xb200_resident::add(*this, _other)) { return *this; }", "operator+=")
     first = tt.index("#include")
     tt = tt[:first] + inc + tt[first:]
     open(os.path.join(out, "ttNetwork_resident.cpp"), "w").write(tt)
@@ -58,7 +61,7 @@ def main():
     first = als.index("#include")
     als = als[:first] + inc + als[first:]
     open(os.path.join(out, "als_resident.cpp"), "w").write(als)
-    print("patched: ttNetwork_resident.cpp (round, move_core, soft_threshold), als_resident.cpp (ALSVariant::solve)")
+    print("patched: ttNetwork_resident.cpp (round, move_core, soft_threshold, operator+=), als_resident.cpp (ALSVariant::solve)")
 
 
 if __name__ == "__main__":

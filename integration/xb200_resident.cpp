@@ -111,6 +111,20 @@ template<bool isOperator> bool soft_threshold(xerus::TTNetwork<isOperator>& tt, 
 	return true;
 }
 
+// operator+= (:797-847): block stacking of the components and, for a canonicalised left operand, the move_core that restores
+// its core position — stacking and sweep in one device call (xb_tt_add)
+template<bool isOperator> bool add(xerus::TTNetwork<isOperator>& tt, const xerus::TTNetwork<isOperator>& other) {
+	const size_t d = tt.degree() / (isOperator ? 2 : 1);
+	if (d < 2 || !enabled(total_size(tt) + total_size(other))) return false;
+	Handle Ha, Hb, Hc;
+	to_device(Ha, tt);
+	to_device(Hb, other);
+	check(xb_tt_add(&Hc.h, Ha.h, Hb.h));
+	from_device(tt, Hc);
+	g_counters.add += 1;
+	return true;
+}
+
 bool als_solve(const xerus::ALSVariant& variant, const xerus::TTOperator* A, xerus::TTTensor& x, const xerus::TTTensor& b,
                size_t numHalfSweeps, double convergenceEpsilon, double& energy) {
 	if (x.degree() < 1 || !enabled(total_size(x))) return false;
@@ -145,5 +159,7 @@ template bool move_core<false>(xerus::TTNetwork<false>&, size_t, bool);
 template bool move_core<true>(xerus::TTNetwork<true>&, size_t, bool);
 template bool soft_threshold<false>(xerus::TTNetwork<false>&, const std::vector<double>&);
 template bool soft_threshold<true>(xerus::TTNetwork<true>&, const std::vector<double>&);
+template bool add<false>(xerus::TTNetwork<false>&, const xerus::TTNetwork<false>&);
+template bool add<true>(xerus::TTNetwork<true>&, const xerus::TTNetwork<true>&);
 
 } // namespace xb200_resident

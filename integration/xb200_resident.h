@@ -5,6 +5,7 @@
 //   TTNetwork<isOperator>::round(maxRanks, eps)      (src/xerus/ttNetwork.cpp:644)   -> xb200_resident::round
 //   TTNetwork<isOperator>::move_core(pos, keepRank)  (src/xerus/ttNetwork.cpp:582)   -> xb200_resident::move_core
 //   TTNetwork<isOperator>::soft_threshold(taus, .)   (src/xerus/ttNetwork.cpp:688)   -> xb200_resident::soft_threshold
+//   TTNetwork<isOperator>::operator+=(other)         (src/xerus/ttNetwork.cpp:797)   -> xb200_resident::add
 //   ALSVariant::solve(A, x, b, halfSweeps, eps, .)   (src/xerus/algorithms/als.cpp:483) -> xb200_resident::als_solve
 //
 // A hook returns true when it has done the work; false sends the call down the reference's own code (hooks disabled with
@@ -19,9 +20,10 @@ namespace xb200_resident {
 	template<bool isOperator> bool round(xerus::TTNetwork<isOperator>& tt, const std::vector<size_t>& maxRanks, double eps);
 	template<bool isOperator> bool move_core(xerus::TTNetwork<isOperator>& tt, size_t position, bool keepRank);
 	template<bool isOperator> bool soft_threshold(xerus::TTNetwork<isOperator>& tt, const std::vector<double>& taus);
+	template<bool isOperator> bool add(xerus::TTNetwork<isOperator>& tt, const xerus::TTNetwork<isOperator>& other);
 	bool als_solve(const xerus::ALSVariant& variant, const xerus::TTOperator* A, xerus::TTTensor& x, const xerus::TTTensor& b,
 	               size_t numHalfSweeps, double convergenceEpsilon, double& energy);
 	// statistics for the tests: how many calls each hook has served
-	struct Counters { size_t round = 0, move_core = 0, soft_threshold = 0, als = 0, h2d_bytes = 0, d2h_bytes = 0; };
+	struct Counters { size_t round = 0, move_core = 0, soft_threshold = 0, add = 0, als = 0, h2d_bytes = 0, d2h_bytes = 0; };
 	const Counters& counters();
 }
