@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import xerus_b200 as xb
-from conftest import golden_tt
+from conftest import ROOT, golden_tt
 from oracle import tt_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -407,3 +407,39 @@ def test_batched_items_match_the_single_calls():
     assert xb.apply_round_batched(A, [], r) == []
     with pytest.raises(xb.XerusError):
         xb.apply_round_batched(A, [xb.TTTensor.ones([n] * (d - 1))], r)
+
+
+def test_shutdown_releases_every_worker_and_reinit_works():
+    """xb_shutdown: streams, events, scratch, memory pools and round plans of every worker go; a second xb_init starts
+    from a clean slate.  Runs in a process of its own (the handles of this process must not outlive a shutdown)."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, threading, numpy as np
+sys.path.insert(0, %r)
+import xerus_b200 as xb
+from xerus_b200._lib import call
+rng = np.random.default_rng(3)
+def work():
+    ts = [xb.TTTensor.random([3, 4, 3, 4], 5, rng) for _ in range(6)]
+    for t in ts[:3]:
+        t.round(2)                                  # ordinary, capture, replay on worker 0
+    xb.round_batched(ts[3:], 2)                     # batch workers
+    def other():
+        xb.worker_select(3)
+        u = xb.TTTensor.random([3, 3, 3], 2, np.random.default_rng(1)); u.move_core(2); xb.synchronize()
+    th = threading.Thread(target=other); th.start(); th.join()
+    xb.synchronize_all()
+    return [t.ranks() for t in ts]
+xb.init(0)
+a = work()
+del rng
+call("xb_shutdown")
+rng = np.random.default_rng(3)
+xb.init(0)
+b = work()
+assert a == b, (a, b)
+print("reinit ok", a[0])
+""" % ROOT
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "reinit ok" in p.stdout, p.stdout + p.stderr
