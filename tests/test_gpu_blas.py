@@ -502,3 +502,108 @@ def test_single_cta_svd_of_zero_and_rank_deficient_matrices():
     assert rel((U * S) @ Vt, D) < 1e-13 and np.all(S[3:] < 1e-13 * S[0])
     Q, C, r = BW.qc(D)
     assert r == 3 and rel(Q @ C, D) < 1e-12
+
+
+@pytest.fixture
+def chol_everywhere():
+    """Cholesky-QR2 from the first row on (default: from 1024 rows, where it overtakes the cluster panel kernels)."""
+    xb.set_option("qr_chol_min_rows", 0)
+    yield
+    xb.set_option("qr_chol_min_rows", 1024)
+
+
+def _graded(m, n, cond, seed):
+    rng = np.random.default_rng(seed)
+    U, _ = np.linalg.qr(rng.standard_normal((m, n)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    return (U * np.logspace(0, -np.log10(cond), n)) @ V.T
+
+
+def _qr_paths(A):
+    """BW.qr(A) with the per-class profile on: (Q, R, taken, declined) where taken / declined count Cholesky-QR2 attempts."""
+    xb.profile_enable(True)
+    try:
+        t0, d0 = xb.profile_get("qr_chol")[0], xb.profile_get("qr_chol_declined")[0]
+        Q, R = BW.qr(A)
+        t1, d1 = xb.profile_get("qr_chol")[0], xb.profile_get("qr_chol_declined")[0]
+    finally:
+        xb.profile_enable(False)
+    return Q, R, t1 - t0, d1 - d0
+
+
+@pytest.mark.parametrize("m,n", [(64, 33), (128, 128), (512, 128), (500, 50), (4096, 16), (3000, 120), (97, 97), (20000, 100), (300, 65), (2000, 7), (509, 60)])
+@pytest.mark.parametrize("cond", [1.0, 1e2, 1e4])
+def test_cholesky_qr2_on_well_conditioned_tall_matrices(m, n, cond, chol_everywhere):
+    """Tall QRs of up to 128 columns take the Cholesky-QR2 path (csrc/qr_f64.cu: cholqr2): orthogonality and residual at the
+    level of the Householder path, R equal to LAPACK's up to row signs, and the same factors with the path switched off."""
+    A = _graded(m, n, cond, m + n) * 3.0e7
+    Q, R, taken, declined = _qr_paths(A)
+    assert taken == 1 and declined == 0
+    assert rel(Q @ R, A) < 1e-14
+    assert np.linalg.norm(Q.T @ Q - np.eye(n)) < 5e-14
+    assert np.array_equal(np.tril(R, -1), np.zeros_like(R)) and np.all(np.diag(R) > 0)
+    Qo, Ro = O.qr(A)
+    s = np.sign(np.diag(Ro))
+    assert rel(s[:, None] * Ro, R) < 1e-12 * cond
+    try:
+        xb.set_option("qr_chol", 0)
+        Qh, Rh, taken, _ = _qr_paths(A)
+    finally:
+        xb.set_option("qr_chol", 1)
+    assert taken == 0
+    sh = np.sign(np.diag(Rh))
+    assert rel(sh[:, None] * Rh, R) < 1e-12 * cond and rel(Qh * sh, Q) < 1e-11 * cond
+
+
+@pytest.mark.parametrize("case", ["cond1e7", "cond1e13", "rank_deficient", "zero_column", "huge", "tiny", "zero", "nan"])
+def test_cholesky_qr2_declines_what_it_cannot_do(case, chol_everywhere):
+    """Ill-conditioned, rank-deficient or badly scaled input is declined on the device and factored by Householder reflections:
+    the caller sees the same contract either way."""
+    m, n = 600, 80
+    rng = np.random.default_rng(5)
+    if case.startswith("cond"):
+        A = _graded(m, n, float(case[4:]), 3)
+    elif case == "rank_deficient":
+        A = rng.standard_normal((m, 20)) @ rng.standard_normal((20, n))
+    elif case == "zero_column":
+        A = rng.standard_normal((m, n)); A[:, 17] = 0.0
+    elif case == "huge":
+        A = rng.standard_normal((m, n)) * 1e140                           # A^T A overflows unscaled
+    elif case == "tiny":
+        A = rng.standard_normal((m, n)) * 1e-140
+    elif case == "zero":
+        A = np.zeros((m, n))
+    else:
+        A = rng.standard_normal((m, n)); A[5, 7] = np.nan
+    Q, R, taken, declined = _qr_paths(A)
+    assert taken == 1 and (declined == 1 or case == "cond1e7")              # 1e7 is inside what the second pass can repair
+    if case == "nan":
+        return                                                              # garbage in, garbage out — but no hang and no exception
+    assert rel(Q @ R, A) < 1e-13 if case != "zero" else np.all(R == 0)
+    assert np.linalg.norm(Q.T @ Q - np.eye(n)) < 1e-12
+    assert np.array_equal(np.tril(R, -1), np.zeros_like(R))
+
+
+def test_cholesky_qr2_backs_off_inside_a_call_and_plans_replay_its_decisions(chol_everywhere):
+    """A sweep over ill-conditioned cores stops trying after two declines in a row (and tries again 16 candidates later); a round
+    plan records which candidates were accepted and replays exactly those, so plan and ordinary path stay bit-identical."""
+    rng = np.random.default_rng(9)
+    d, n, r = 8, 4, 40
+    dims = [n] * d
+    ranks = [1] + [min(r, n ** min(i, d - i)) for i in range(1, d)] + [1]
+    cores = [rng.standard_normal((ranks[i], n, ranks[i + 1])) for i in range(d)]
+    # a graded bond in the middle: the QRs that carry it are declined, the others are not
+    cores[4] = np.einsum("a,anb->anb", np.logspace(0, -9, ranks[4]), cores[4])
+    results = []
+    for plans, repeats in ((0, 1), (1, 3)):                                  # ordinary; first sight, capture + replay, replay
+        xb.set_option("round_plans", plans)
+        for _ in range(repeats):
+            t = xb.TTTensor.from_cores(cores)
+            t.round(24)
+            results.append(t.cores())
+    for other in results[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(results[0], other))
+    ref = O.TT([c.copy() for c in cores])
+    ref.round(24)
+    got = O.TT(results[0], core_position=0)
+    assert got.ranks() == ref.ranks() and O.tt_distance_rel(got, ref) < 1e-10

@@ -524,6 +524,81 @@ static void apply_block_reflector(double* C, size_t ldc, size_t mp, size_t nc, c
 	XB_LAUNCH_CHECK();
 }
 
+// ---- Cholesky-QR2 -----------------------------------------------------------------------------------------------------------
+// Tall matrices of up to 128 columns — the first unfoldings of a TT-SVD, cores with large mode dimensions, anything with
+// thousands of rows — are where the Householder path is weakest: ~10 dependent launches per 32 columns, twice (factor, then
+// form Q), and beyond 2048 rows the panel no longer fits the cluster kernel (49 ms at 20000 x 100).  For these,
+//     G = A^T A,  R1 = chol(G),  Q1 = A R1^-1,     G2 = Q1^T Q1,  R2 = chol(G2),  Q = Q1 R2^-1,  R = R2 R1
+// is 7..9 launches of GEMM-rich work whose cost hardly depends on m (0.39 ms at 20000 x 100; table in DESIGN.md 3.2).  The
+// Gram matrices are split-K batched GEMMs over row slabs; the factorisation, its inverse and the sum of up to 4 slab results
+// are one single-CTA launch (small_f64.cu: chol_inv_kernel).  The second pass restores orthogonality to O(u) provided
+// cond(A)^2 u << 1 (Yamamoto et al., "Roundoff error analysis of the CholeskyQR2 algorithm", ETNA 44 (2015)), so the path
+// polices itself on the device: the first Cholesky must see a pivot ratio >= 1e-10 (cond(A) <~ 1e5), the second must start from
+// ||Q1^T Q1 - I||_F <= 1/2.  Anything else — ill-conditioned or rank-deficient input, entries so large or small that the Gram
+// matrix leaves the range of a double — is *declined* and the Householder path below runs instead: the decision is read back
+// on the ordinary path (the callers synchronise for the rank decision right after anyway) and speculated under a round plan
+// (reason 4), which replays the accept / decline decisions its recording run made (Context::chol_tape).  After two declines in
+// a row the next 16 candidates of the same call go straight to Householder.  R has a positive diagonal here and a mixed-sign
+// one from Householder; both are QRs of A (dgeqrf's signs are not part of the contract the reference's callers rely on:
+// blasLapackWrapper.cpp:374-437 only promises A = Q R with orthonormal Q).
+static bool cholqr2(double* Q, double* R, const double* A, const size_t m, const size_t n) {
+	Context& c = ctx();
+	if (!c.qr_chol || c.chol_off || n > m || !chol_inv_fits(n)) return false;
+	{
+		// measured crossover against the cluster panel kernels (profiles/time_qr_chol.py): ~250 us whatever m at 128 columns against
+		// 265 / 353 / 538 us at 512 / 768 / 2048 rows; 175 us against 136 / 185 / 261 us at 64 columns; beyond 2048 rows (where the
+		// panels leave the cluster kernel) 0.15 ms against 1.8 ms at 4096 x 16 and 0.39 ms against 49 ms at 20000 x 100
+		// up to 32 columns are a single panel: 90 us at 1024 x 32 — until the panel leaves the cluster kernel
+		const size_t min_rows = size_t(std::max(c.qr_chol_min_rows, 0));
+		const size_t thr = n >= 96 ? std::min<size_t>(min_rows, 640) : (n <= 32 && min_rows > 0) ? std::max<size_t>(min_rows, 2049) : min_rows;
+		if (m < thr) return false;
+	}
+	if (c.chol_tape_mode == 2) {                                       // capture of a plan: do what the recording run did
+		const bool take = c.chol_tape_pos < c.chol_tape.size() && c.chol_tape[c.chol_tape_pos] != 0;
+		c.chol_tape_pos += 1;
+		if (!take) return false;
+	} else if (c.chol_skip > 0) {                                      // back-off after repeated declines (ill-conditioned workload)
+		c.chol_skip -= 1;
+		if (c.chol_tape_mode == 1) c.chol_tape.push_back(0);
+		return false;
+	}
+	ProfScope prof("qr_chol");
+	const bool spec = c.speculate;
+	// split-K for the two Gram matrices: S row slabs as one batched GEMM (a single n x n product is one to sixteen CTAs walking
+	// all m rows); up to 4 partial sums are added up by the Cholesky kernel as it loads, more go through one summation launch
+	size_t S = std::min<size_t>(std::max<size_t>(m / 128, 1), std::min<size_t>(1024, std::max<size_t>((size_t(1) << 22) / (n * n), 64)));
+	for (size_t t = S; t > S / 2 && t >= 2; --t) if (m % t == 0) { S = t; break; }
+	const size_t slab = m / S, rest = m - S * slab;
+	DBuf P(S * n * n), R1(n * n), R2(n * n), W(n * n), Q1(m * n), fl(1);
+	unsigned int* f = spec ? c.spec_flag : reinterpret_cast<unsigned int*>(fl.p);
+	auto gram = [&](const double* X) -> size_t {
+		ProfScope ps("chol_gram");
+		gemm_batched(P, n, n * n, n, n, 1.0, X, n, slab * n, true, slab, X, n, slab * n, false, 0.0, S);
+		if (rest) gemm(P, n, n, n, 1.0, X + S * slab * n, n, true, rest, X + S * slab * n, n, false, 1.0);
+		if (S <= 4) return S;
+		sum_parts(P, P, S, n * n);
+		return 1;
+	};
+	size_t parts = gram(A);
+	{ ProfScope ps("chol_fact"); chol_inv(P, parts, n, R1, W, false, 1e-10, f, 4u, !spec); }
+	{ ProfScope ps("chol_apply"); gemm(Q1, n, m, n, 1.0, A, n, false, n, W, n, true, 0.0); }
+	parts = gram(Q1);
+	{ ProfScope ps("chol_fact"); chol_inv(P, parts, n, R2, W, true, 0.25, spec ? f : f + 1, 4u, !spec); }
+	{ ProfScope ps("chol_apply"); gemm(Q, n, m, n, 1.0, Q1, n, false, n, W, n, true, 0.0); }
+	{ ProfScope ps("chol_rr"); gemm(R, n, n, n, 1.0, R2, n, false, n, R1, n, false, 0.0); }
+	if (spec) return true;
+	XB_CUDA(cudaMemcpyAsync(c.h_scratch, fl.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaStreamSynchronize(c.stream));
+	unsigned int w[2];
+	std::memcpy(w, c.h_scratch, sizeof w);
+	const bool ok = w[0] == 0u && w[1] == 0u;
+	if (c.chol_tape_mode == 1) c.chol_tape.push_back(ok ? 1 : 0);
+	if (ok) { c.chol_declines = 0; return true; }
+	ProfScope declined("qr_chol_declined");
+	if (++c.chol_declines >= 2) c.chol_skip = 16;
+	return false;
+}
+
 void qr(double* Q, double* R, const double* A, size_t m, size_t n, bool defer_q) {
 	XB_REQUIRE(m > 0 && n > 0, "Dimension m and n must be larger than zero");    // blasLapackWrapper.cpp:392-393
 	XB_REQUIRE(m <= 0x7fffffffULL && n <= 0x7fffffffULL, "Dimension to large for QR");
@@ -533,6 +608,7 @@ void qr(double* Q, double* R, const double* A, size_t m, size_t n, bool defer_q)
 		qr_small(Q, (long long)k, 1, R, (long long)n, 1, A, (long long)n, 1, m, n);
 		return;
 	}
+	if (cholqr2(Q, R, A, m, n)) return;
 	const size_t npanels = (k + QR_NB - 1) / QR_NB;
 	DBuf W(m * n), Vall(npanels * m * QR_NB), Tall(npanels * QR_NB * QR_NB);
 	const size_t nch_max = (m + QR_CHUNK - 1) / QR_CHUNK;

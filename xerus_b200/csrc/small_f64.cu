@@ -352,4 +352,234 @@ void svd_small(const double* A, long long rs, long long cs, size_t mw, size_t nw
 	XB_LAUNCH_CHECK();
 }
 
+
+// ---- Cholesky factor and its inverse -------------------------------------------------------------------------------------------
+// G = sum of `nparts` n x n row-major slices (the split-K partial sums of a Gram matrix A^T A; symmetric, only the upper triangle
+// is used) = R^T R:  R -> Ro (upper triangular) and W^T = R^-T -> Wo (lower triangular: that is how it sits in the registers, so
+// both stores are coalesced and the GEMM that applies W reads it transposed), explicit zeros in the other triangle, n <= 128.
+// The building block of the Cholesky-QR2 path for tall matrices (qr_f64.cu: cholqr2), where the Householder route is a chain of
+// ~10 dependent panel / block-reflector launches per 32 columns and this is one launch between two GEMMs.
+//
+// The matrix lives in registers: 512 threads as a 16 x 32 grid, thread (ty, tx) owns the elements (ty + 16 a, tx + 32 b) —
+// cyclic in both directions, so the work stays balanced while the active part of the matrix moves.  One Gauss step per column
+// and one block barrier per step: the pivot row is published through a double-buffered row in shared memory, and the warp that
+// owns the *next* pivot row updates and publishes it (with the reciprocal of its pivot) before it touches its other rows, so
+// that latency hides behind everybody else's updates.  The same row operations are applied to the identity in the strict lower
+// triangle of the array (G = L D L^T: the upper triangle ends as D L^T, the lower as L^-1 without its unit diagonal), which gives
+// W^T = D^-1/2 L^-1 with no triangular solve afterwards; R = D^-1/2 (D L^T).
+// near_identity (the second pass of Cholesky-QR2, G = I + E): ||E||_F <= 1e-8 takes R = I + U, W = I - U with U = triu(E) minus
+// half its diagonal, exact to O(||E||^2) <= 1e-16 — no factorisation at all.
+// Status word: *flag = flag_value when G is not *safely* positive definite — a diagonal entry outside [1e-200, 1e200] (the caller
+// works unscaled) or NaN, a pivot <= 0, min pivot < ratio * max pivot, or (near_identity) ||G - I||_F > 1/2, which is what bounds
+// the orthogonality of the second pass.  With clear != 0 a clean run writes 0 (the ordinary path reads the word back; a speculated
+// run shares one sticky word with the other checks of its graph).
+constexpr int CH_THREADS = 512;
+
+template <int CB>
+__global__ void __launch_bounds__(CH_THREADS, 1) chol_inv_kernel(const double* __restrict__ G, const int nparts, const long long part_stride, const int n,
+                                                                 double* __restrict__ Ro, double* __restrict__ Wo, const int near_identity, const double ratio,
+                                                                 unsigned int* __restrict__ flag, const unsigned int flag_value, const int clear) {
+	constexpr int RA = 2 * CB;
+	__shared__ double rowbuf[2][32 * CB];
+	__shared__ double pv[2], pinv[2];
+	__shared__ double piv[32 * CB];
+	__shared__ double red[CH_THREADS / 32];
+	const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+	double v[RA][CB];
+#pragma unroll
+	for (int a = 0; a < RA; ++a)
+#pragma unroll
+		for (int b = 0; b < CB; ++b) v[a][b] = 0.0;
+	// slices outermost: the RA * CB loads of one slice are independent and in flight together
+	for (int s = 0; s < nparts; ++s) {
+		const double* src = G + (long long)s * part_stride;
+#pragma unroll
+		for (int a = 0; a < RA; ++a) {
+			const int i = ty + 16 * a;
+#pragma unroll
+			for (int b = 0; b < CB; ++b) {
+				const int k = tx + 32 * b;
+				// clamped address, masked value: no branch per element, so the loads of a slice issue back to back
+				const double g = __ldg(src + (size_t)min(i, n - 1) * n + min(k, n - 1));
+				v[a][b] += (i < n && k < n) ? g : 0.0;
+			}
+		}
+	}
+	double dv = 0.0;
+	int bad = 0;
+#pragma unroll
+	for (int a = 0; a < RA; ++a) {
+		const int i = ty + 16 * a;
+#pragma unroll
+		for (int b = 0; b < CB; ++b) {
+			const int k = tx + 32 * b;
+			if (i < n && k < n) {
+				const double g = v[a][b];
+				const double t = g - (i == k ? 1.0 : 0.0);
+				dv += t * t;
+				if (i == k && !(g >= 1e-200 && g <= 1e200)) bad = 1;
+			}
+		}
+	}
+	if (tid < 2 * 32 * CB) (&rowbuf[0][0])[tid] = 0.0;
+	dv = warp_sum(dv);
+	if (tx == 0) red[ty] = dv;
+	bad = __syncthreads_or(bad);
+	double dev2 = 0.0;
+#pragma unroll
+	for (int w = 0; w < CH_THREADS / 32; ++w) dev2 += red[w];
+	if (near_identity && !(dev2 <= 0.25)) bad = 1;
+	if (bad) { if (tid == 0) *flag = flag_value; return; }
+	if (near_identity && dev2 <= 1e-16) {
+#pragma unroll
+		for (int a = 0; a < RA; ++a) {
+			const int i = ty + 16 * a;
+#pragma unroll
+			for (int b = 0; b < CB; ++b) {
+				const int k = tx + 32 * b;
+				if (i >= n || k >= n) continue;
+				const double g = v[a][b];
+				const size_t e = (size_t)i * n + k;
+				if (k > i) { Ro[e] = g; Wo[e] = 0.0; }
+				else if (k == i) { Ro[e] = 0.5 * (1.0 + g); Wo[e] = 0.5 * (3.0 - g); }
+				else { Ro[e] = 0.0; Wo[e] = -g; }                  // G(i, k) = G(k, i)
+			}
+		}
+		if (tid == 0 && clear) *flag = 0u;
+		return;
+	}
+	if (ty == 0) {
+#pragma unroll
+		for (int b = 0; b < CB; ++b) rowbuf[0][tx + 32 * b] = v[0][b];
+		if (tx == 0) { pv[0] = v[0][0]; pinv[0] = __drcp_rn(v[0][0]); }
+	}
+	__syncthreads();
+	// Step j, row i > j of this thread: v(i, k) -= f_i r_k with f_i = U(j, i) / p_j and r the published pivot row, on the columns
+	// k < j (the L^-1 part), k = j (r_j = 1 implied and v(i, j) = 0 before: L^-1(i, j) = -f_i) and k >= i (the Schur complement).
+	// The columns j < k < i in between are not live yet — they pick up garbage that the step j' = k overwrites — so a row is four
+	// unconditional DFMAs; what costs instructions is decided once per step, not per element: the block of 32 columns that holds
+	// column j (switch, compile-time inside), the first live row of the warp (switch with fall-through over the register rows).
+#define CH_ROW(A, JB)                                                                               \
+	if ((A) < RA) {                                                                                 \
+		constexpr int A_ = (A) < RA ? (A) : 0, JB_ = (JB) < CB ? (JB) : 0;                          \
+		const double fa_ = f[A_] * inv;                                                             \
+		if (tx == jl) v[A_][JB_] = 0.0;                                                             \
+		_Pragma("unroll") for (int b = 0; b < CB; ++b) v[A_][b] = fma(-fa_, rk[b], v[A_][b]);       \
+	}
+#define CH_PUB(A)                                                                                   \
+	if ((A) < RA) {                                                                                 \
+		constexpr int A_ = (A) < RA ? (A) : 0;                                                      \
+		_Pragma("unroll") for (int b = 0; b < CB; ++b) rowbuf[buf ^ 1][tx + 32 * b] = v[A_][b];     \
+	}
+#define CH_STEP(JB)                                                                                 \
+	{                                                                                               \
+		if (own_next) {                                                                             \
+			switch (an) {                                                                           \
+				case 0: CH_ROW(0, JB) CH_PUB(0) break;                                              \
+				case 1: CH_ROW(1, JB) CH_PUB(1) break;                                              \
+				case 2: CH_ROW(2, JB) CH_PUB(2) break;                                              \
+				case 3: CH_ROW(3, JB) CH_PUB(3) break;                                              \
+				case 4: CH_ROW(4, JB) CH_PUB(4) break;                                              \
+				case 5: CH_ROW(5, JB) CH_PUB(5) break;                                              \
+				case 6: CH_ROW(6, JB) CH_PUB(6) break;                                              \
+				default: CH_ROW(7, JB) CH_PUB(7) break;                                             \
+			}                                                                                       \
+			__syncwarp();                                                                           \
+			if (tx == 0) { const double pc = rowbuf[buf ^ 1][jn]; pv[buf ^ 1] = pc; pinv[buf ^ 1] = __drcp_rn(pc); } \
+		}                                                                                           \
+		switch (a_start) {                                                                          \
+			case 0: CH_ROW(0, JB)                                                                   \
+			case 1: CH_ROW(1, JB)                                                                   \
+			case 2: CH_ROW(2, JB)                                                                   \
+			case 3: CH_ROW(3, JB)                                                                   \
+			case 4: CH_ROW(4, JB)                                                                   \
+			case 5: CH_ROW(5, JB)                                                                   \
+			case 6: CH_ROW(6, JB)                                                                   \
+			case 7: CH_ROW(7, JB)                                                                   \
+			default: break;                                                                         \
+		}                                                                                           \
+	}
+	for (int j = 0; j < n; ++j) {
+		const int buf = j & 1;
+		const double p = pv[buf];                        // the same word for every thread: the exit below is uniform
+		const double inv = pinv[buf];
+		double rk[CB], f[RA];
+#pragma unroll
+		for (int b = 0; b < CB; ++b) { const int k = tx + 32 * b; rk[b] = (k == j) ? 1.0 : rowbuf[buf][k]; }
+#pragma unroll
+		for (int a = 0; a < RA; ++a) f[a] = rowbuf[buf][ty + 16 * a];
+		if (!(p > 0.0)) { if (tid == 0) *flag = flag_value; return; }
+		if (tid == 0) piv[j] = p;
+		// the warp that owns the next pivot row does that row first and publishes it; its lane 0 reads the new pivot back from
+		// shared memory and adds the reciprocal, while the other warps are busy with their rows
+		const int jn = j + 1, jl = j & 31;
+		const bool own_next = jn < n && (jn & 15) == ty;
+		const int an = jn >> 4;
+		const int a0 = (j >= ty) ? ((j - ty) >> 4) + 1 : 0;          // first row of this warp below the pivot row
+		const int a_start = own_next ? an + 1 : a0;
+		switch (j >> 5) {
+			case 0: CH_STEP(0) break;
+			case 1: CH_STEP(1) break;
+			case 2: CH_STEP(2) break;
+			default: CH_STEP(3) break;
+		}
+		__syncthreads();
+	}
+#undef CH_ROW
+#undef CH_PUB
+#undef CH_STEP
+	bool flagged = false;
+	if (tid == 0) {
+		double pmin = HUGE_VAL, pmax = 0.0;
+		for (int i = 0; i < n; ++i) { pmin = fmin(pmin, piv[i]); pmax = fmax(pmax, piv[i]); }
+		flagged = !(pmin >= ratio * pmax);
+	}
+#pragma unroll
+	for (int a = 0; a < RA; ++a) {
+		const int i = ty + 16 * a;
+		if (i >= n) continue;
+		const double rs = rsqrt(piv[i]);
+#pragma unroll
+		for (int b = 0; b < CB; ++b) {
+			const int k = tx + 32 * b;
+			if (k >= n) continue;
+			const double x = v[a][b] * rs;
+			const size_t e = (size_t)i * n + k;
+			if (k > i) { Ro[e] = x; Wo[e] = 0.0; }
+			else if (k == i) { Ro[e] = x; Wo[e] = rs; }
+			else { Ro[e] = 0.0; Wo[e] = x; }
+		}
+	}
+	if (tid == 0) { if (flagged) *flag = flag_value; else if (clear) *flag = 0u; }
+}
+
+bool chol_inv_fits(size_t n) { return n >= 1 && n <= 128; }
+
+void chol_inv(const double* G, size_t nparts, size_t n, double* R, double* W, bool near_identity, double ratio, unsigned int* flag, unsigned int flag_value, bool clear) {
+	const long long ps = (long long)(n * n);
+	const int ni = near_identity ? 1 : 0, cl = clear ? 1 : 0;
+	cudaStream_t st = ctx().stream;
+	if (n <= 32) chol_inv_kernel<1><<<1, CH_THREADS, 0, st>>>(G, int(nparts), ps, int(n), R, W, ni, ratio, flag, flag_value, cl);
+	else if (n <= 64) chol_inv_kernel<2><<<1, CH_THREADS, 0, st>>>(G, int(nparts), ps, int(n), R, W, ni, ratio, flag, flag_value, cl);
+	else if (n <= 96) chol_inv_kernel<3><<<1, CH_THREADS, 0, st>>>(G, int(nparts), ps, int(n), R, W, ni, ratio, flag, flag_value, cl);
+	else chol_inv_kernel<4><<<1, CH_THREADS, 0, st>>>(G, int(nparts), ps, int(n), R, W, ni, ratio, flag, flag_value, cl);
+	XB_LAUNCH_CHECK();
+}
+
+// out[e] = sum over `parts` slices of P[q * len + e]: one block per element group, fixed summation tree (deterministic)
+__global__ void __launch_bounds__(256) sum_parts_kernel(double* __restrict__ out, const double* __restrict__ P, const int parts, const size_t len) {
+	// 8 elements per block, 32 lanes each: lane l adds the slices l, l + 32, ...; a shuffle tree finishes
+	const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+	const size_t e = (size_t)blockIdx.x * 8 + sub;
+	if (e >= len) return;
+	double s = 0.0;
+	for (int q = lane; q < parts; q += 32) s += P[(size_t)q * len + e];
+	s = warp_sum(s);
+	if (lane == 0) out[e] = s;
+}
+void sum_parts(double* out, const double* P, size_t parts, size_t len) {
+	sum_parts_kernel<<<unsigned((len + 7) / 8), 256, 0, ctx().stream>>>(out, P, int(parts), len);
+	XB_LAUNCH_CHECK();
+}
+
 } // namespace xb

@@ -136,6 +136,7 @@ static void round_edge(xb_tt* t, size_t from, size_t max_rank, double eps, doubl
 // edge from the right (:700)
 static void round_tt(xb_tt* t, const size_t* max_ranks, double eps, double* svals, size_t stride, const double* taus = nullptr) {   // ttNetwork.cpp:644-665
 	XB_REQUIRE(eps >= 0.0 && eps < 1.0, "_eps must be smaller than one.");
+	ctx().chol_skip = 0; ctx().chol_declines = 0;                        // a sweep's path is a function of its input alone
 	const size_t d = t->d;
 	const bool initial_canon = t->canonicalized;
 	const size_t initial_core = t->core_position;
@@ -200,6 +201,9 @@ struct RoundPlan {
 	char* arena = nullptr; size_t arena_size = 0;   // every temporary and result of the captured sweep (bump-allocated, never reused)
 	unsigned int* flag = nullptr;
 	uint64_t nodes = 0;
+	std::vector<char> chol_tape;                // accept / decline of every Cholesky-QR2 candidate of the recording run, in call order
+	bool no_chol = false;                       // replays kept failing on a Cholesky-QR2 check: this plan is Householder only
+	unsigned chol_failures = 0;
 	~RoundPlan() {
 		if (exec) cudaGraphExecDestroy(exec);
 		if (graph) cudaGraphDestroy(graph);
@@ -249,6 +253,7 @@ static void capture_plan(RoundPlan& pl, const xb_tt* t, const size_t* max_ranks,
 	std::string why;
 	XB_CUDA(cudaStreamBeginCapture(c.stream, cudaStreamCaptureModeThreadLocal));
 	c.speculate = true; c.spec_flag = pl.flag;
+	c.chol_tape = pl.chol_tape; c.chol_tape_pos = 0; c.chol_tape_mode = 2; c.chol_off = pl.no_chol;
 	c.arena = pl.arena; c.arena_size = pl.arena_size; c.arena_off = 0; c.arena_on = true;
 	try {
 		XB_CUDA(cudaMemsetAsync(pl.flag, 0, 4 * sizeof(unsigned int), c.stream));
@@ -266,6 +271,7 @@ static void capture_plan(RoundPlan& pl, const xb_tt* t, const size_t* max_ranks,
 	pl.out.clear();
 	for (size_t i = 0; i < d; ++i) { pl.out.push_back(proto.core[i].p); proto.core[i].p = nullptr; proto.core[i].n = 0; }
 	c.speculate = false; c.spec_flag = nullptr;
+	c.chol_tape_mode = 0; c.chol_off = false; c.chol_tape.clear();
 	c.arena_on = false; c.arena = nullptr;
 	cudaGraph_t g = nullptr;
 	const cudaError_t e_end = cudaStreamEndCapture(c.stream, &g);
@@ -297,6 +303,7 @@ struct PendingRound {
 	xb_tt* t = nullptr;
 	std::vector<size_t> ranks_out; bool canon_out = false; size_t core_out = 0;   // copied from the plan (which may be evicted meanwhile)
 	std::vector<DBuf> fresh;
+	std::string key;
 	unsigned int* h_flag = nullptr;
 	std::vector<size_t> max_ranks; double eps = 0.0;
 };
@@ -337,8 +344,11 @@ static int round_plan_enqueue(xb_tt* t, const size_t* max_ranks, double eps, Pen
 		size_t in_bytes = 0;
 		for (size_t i = 0; i < t->d; ++i) in_bytes += (t->core_size(i) * sizeof(double) + 255) / 256 * 256;
 		c.count_allocs = true; c.alloc_counter = 0;
-		try { round_tt(t, max_ranks, eps, nullptr, 0); } catch (...) { c.count_allocs = false; throw; }
+		c.chol_tape.clear(); c.chol_tape_mode = 1; c.chol_off = pl->no_chol;
+		try { round_tt(t, max_ranks, eps, nullptr, 0); } catch (...) { c.count_allocs = false; c.chol_tape_mode = 0; c.chol_off = false; throw; }
 		c.count_allocs = false;
+		c.chol_tape_mode = 0; c.chol_off = false;
+		pl->chol_tape.swap(c.chol_tape); c.chol_tape.clear();
 		pl->arena_size = c.alloc_counter + in_bytes + (1u << 20);
 		pl->ranks_out = t->rank; pl->canon_out = t->canonicalized; pl->core_out = t->core_position;
 		if (pl->arena_size > (size_t(8) << 30)) pl->unplannable = true;      // sweeps that allocate more than 8 GB stay on the ordinary path
@@ -372,7 +382,7 @@ static int round_plan_enqueue(xb_tt* t, const size_t* max_ranks, double eps, Pen
 		}
 		copy_many(src, dst, n);
 	}
-	out.t = t; out.eps = eps;
+	out.t = t; out.eps = eps; out.key = pl->key;
 	out.ranks_out = pl->ranks_out; out.canon_out = pl->canon_out; out.core_out = pl->core_out;
 	out.max_ranks.assign(max_ranks, max_ranks + (d - 1));
 	return 2;
@@ -382,6 +392,22 @@ static int round_plan_enqueue(xb_tt* t, const size_t* max_ranks, double eps, Pen
 static void round_plan_finish(PendingRound& p) {
 	if (*p.h_flag != 0) {
 		if (getenv("XB_DEBUG_PLAN")) fprintf(stderr, "[plan] speculation failed (reason %u): ordinary path\n", *p.h_flag);
+		if (*p.h_flag == 4u) {
+			// a Cholesky-QR2 step met input it had to decline.  The second time this happens the plan is dropped and recorded again
+			// without that path (the caller has synchronised the stream: nothing of the plan is in flight)
+			Context& c = ctx();
+			for (size_t i = 0; i < c.plans.size(); ++i) {
+				RoundPlan* pl = c.plans[i];
+				if (pl->key != p.key || pl->no_chol) continue;
+				if (++pl->chol_failures >= 2) {
+					RoundPlan* fresh_plan = new RoundPlan();
+					fresh_plan->key = pl->key; fresh_plan->no_chol = true; fresh_plan->stamp = pl->stamp;
+					delete pl;
+					c.plans[i] = fresh_plan;
+				}
+				break;
+			}
+		}
 		p.fresh.clear();
 		round_tt(p.t, p.max_ranks.data(), p.eps, nullptr, 0);
 		return;

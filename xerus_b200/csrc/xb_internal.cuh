@@ -66,6 +66,12 @@ struct Context {
 	int svd_flip = 1;              // Jacobi on the rows of the triangular factor after a QR reduction (pre-conditioning)
 	int svd_square_qr = 1;         // square inputs also go through the QR reduction (needed for svd_flip)
 	int qr_cluster = 1;            // QR panels of 128..2048 rows on a thread-block cluster (registers + DSMEM reduction)
+	int qr_chol = 1;               // tall QRs of up to 128 columns by Cholesky-QR2 where the input allows it (qr_f64.cu)
+	int qr_chol_min_rows = 1024;   // ... from this many rows on (below, the cluster panel kernels are as fast or faster)
+	int chol_skip = 0, chol_declines = 0;     // back-off after declined attempts (reset at every C-ABI entry)
+	bool chol_off = false;                    // the plan being recorded / captured is Householder only
+	int chol_tape_mode = 0;                   // 0 off, 1 record accept / decline per candidate, 2 replay them (plan capture)
+	std::vector<char> chol_tape; size_t chol_tape_pos = 0;
 	int qr_cluster_min_rows = 64;  // smallest panel height for the cluster panel kernel (below: one CTA, panel in shared memory)
 	int svd_fast = 1;              // specialised Jacobi kernel (compile-time row length, 128-bit accesses) up to 512 columns
 	int svd_jacc = 1;              // specialised Jacobi kernel: rotations of a block visit accumulated, applied to V once (DMMA)
@@ -137,7 +143,7 @@ struct DBuf {   // RAII device buffer
 };
 
 template <class F> xb_status guard(F&& f) {
-	try { f(); return XB_OK; }
+	try { Context& c = ctx(); c.chol_skip = 0; c.chol_declines = 0; f(); return XB_OK; }
 	catch (const Error& e) { set_last_error(e.what()); return e.code; }
 	catch (const std::exception& e) { set_last_error(e.what()); return XB_ERR_INVALID; }
 }
@@ -207,6 +213,9 @@ struct SpecUnsupported : Error { explicit SpecUnsupported(const std::string& m) 
 // single-CTA kernels for min(m, n) <= 32 (small_f64.cu); G(i, j) = A[i * ars + j * acs], outputs through strides
 bool qr_small_fits(size_t m, size_t n);
 void qr_small(double* Q, long long qrs, long long qcs, double* R, long long rrs, long long rcs, const double* A, long long ars, long long acs, size_t m, size_t n);
+bool chol_inv_fits(size_t n);
+void chol_inv(const double* G, size_t nparts, size_t n, double* R, double* W, bool near_identity, double ratio, unsigned int* flag, unsigned int flag_value, bool clear);
+void sum_parts(double* out, const double* P, size_t parts, size_t len);
 bool svd_small_fits(size_t mw, size_t nw);
 void svd_small(const double* A, long long rs, long long cs, size_t mw, size_t nw, double* GT, size_t ld, size_t voff, double* Ssorted, int* perm,
                double* scale2, unsigned int* info, double tol, double last_cos, int max_sweeps, int polish);
