@@ -545,12 +545,15 @@ static bool cholqr2(double* Q, double* R, const double* A, const size_t m, const
 	Context& c = ctx();
 	if (!c.qr_chol || c.chol_off || n > m || !chol_inv_fits(n)) return false;
 	{
-		// measured crossover against the cluster panel kernels (profiles/time_qr_chol.py): ~250 us whatever m at 128 columns against
-		// 265 / 353 / 538 us at 512 / 768 / 2048 rows; 175 us against 136 / 185 / 261 us at 64 columns; beyond 2048 rows (where the
-		// panels leave the cluster kernel) 0.15 ms against 1.8 ms at 4096 x 16 and 0.39 ms against 49 ms at 20000 x 100
-		// up to 32 columns are a single panel: 90 us at 1024 x 32 — until the panel leaves the cluster kernel
+		// measured crossover against the cluster panel kernels (profiles/r2_qr_cholqr2.txt), per call on the ordinary path: ~250 us
+		// whatever m at 128 columns against 265 / 353 / 538 us at 512 / 768 / 2048 rows; 175 us against 136 / 185 / 261 us at 64
+		// columns; beyond 2048 rows (where the panels leave the cluster kernel) 0.15 ms against 1.8 ms at 4096 x 16 and 0.39 ms
+		// against 49 ms at 20000 x 100.  Up to 32 columns are a single panel (90 us at 1024 x 32) until that limit.  Inside a round
+		// plan, where launches cost nothing and what counts is SM time, 96+ columns win from 256 rows on (config 5: 1310 -> 1535
+		// items/s), so that class starts there on both paths (240 -> 279 us at 256 x 128 on the ordinary one) and plan and
+		// ordinary path keep taking the same decisions.
 		const size_t min_rows = size_t(std::max(c.qr_chol_min_rows, 0));
-		const size_t thr = n >= 96 ? std::min<size_t>(min_rows, 640) : (n <= 32 && min_rows > 0) ? std::max<size_t>(min_rows, 2049) : min_rows;
+		const size_t thr = n >= 96 ? std::min<size_t>(min_rows, 256) : (n <= 32 && min_rows > 0) ? std::max<size_t>(min_rows, 2049) : min_rows;
 		if (m < thr) return false;
 	}
 	if (c.chol_tape_mode == 2) {                                       // capture of a plan: do what the recording run did
