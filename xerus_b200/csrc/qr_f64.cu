@@ -550,7 +550,7 @@ static bool cholqr2(double* Q, double* R, const double* A, const size_t m, const
 		// columns; beyond 2048 rows (where the panels leave the cluster kernel) 0.15 ms against 1.8 ms at 4096 x 16 and 0.39 ms
 		// against 49 ms at 20000 x 100.  Up to 32 columns are a single panel (90 us at 1024 x 32) until that limit.  Inside a round
 		// plan, where launches cost nothing and what counts is SM time, 96+ columns win from 256 rows on (config 5: 1310 -> 1535
-		// items/s), so that class starts there on both paths (240 -> 279 us at 256 x 128 on the ordinary one) and plan and
+		// items/s), so that class starts there on both paths (240 -> 225 us at 256 x 128 on the ordinary one) and plan and
 		// ordinary path keep taking the same decisions.
 		const size_t min_rows = size_t(std::max(c.qr_chol_min_rows, 0));
 		const size_t thr = n >= 96 ? std::min<size_t>(min_rows, 256) : (n <= 32 && min_rows > 0) ? std::max<size_t>(min_rows, 2049) : min_rows;

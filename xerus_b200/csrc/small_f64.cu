@@ -375,6 +375,58 @@ void svd_small(const double* A, long long rs, long long cs, size_t mw, size_t nw
 // run shares one sticky word with the other checks of its graph).
 constexpr int CH_THREADS = 512;
 
+// Steps j = 16 Q .. 16 Q + 15 of the elimination, for the thread grid of chol_inv_kernel (ty = warp = row residue mod 16,
+// tx = lane = column residue mod 32; register row a holds matrix row ty + 16 a).  Inside such a block everything that shapes the
+// code is known at compile time: the block of 32 columns that holds column j (Q / 2), the register row that may hold the pivot
+// row or rows above it (Q; rows a > Q are below the pivot for every warp), and the register row of the next pivot (Q, or Q + 1
+// after the last step) — no jump tables in the step, only warp-uniform predicates.
+// Step j, row i > j: v(i, k) -= f_i r_k with f_i = U(j, i) / p_j and r the published pivot row, on the columns k < j (the L^-1
+// part), k = j (the publisher stores r_j = 1, and v(i, j) is zeroed first: L^-1(i, j) = -f_i) and k >= i (the Schur complement).
+// The columns j < k < i in between are not live yet — they pick up garbage that the step j' = k overwrites — so a row is CB
+// unconditional DFMAs.  The warp that owns the next pivot row does that row first and publishes it; its lane 0 reads the new
+// pivot back from shared memory, adds the reciprocal and puts the 1 in its place, while the other warps are busy with their rows.
+template <int CB, int Q>
+__device__ __forceinline__ bool chol_inv_block(double (&v)[2 * CB][CB], double (*rowbuf)[32 * CB], double* pv, double* pinv, double* piv,
+                                               const int n, const int tx, const int ty, unsigned int* flag, const unsigned int flag_value) {
+	constexpr int RA = 2 * CB, JB = (Q >> 1) < CB ? (Q >> 1) : 0, QN = (Q + 1 < RA) ? Q + 1 : Q;
+	const int jend = min(n, 16 * Q + 16);
+#define CH_ROW(A)                                                                                   \
+	{                                                                                               \
+		const double fa_ = rowbuf[buf][ty + 16 * (A)] * inv;                                        \
+		if (tx == jl) v[A][JB] = 0.0;                                                               \
+		_Pragma("unroll") for (int b = 0; b < CB; ++b) v[A][b] = fma(-fa_, rk[b], v[A][b]);         \
+	}
+#define CH_PUB(A)                                                                                   \
+	{                                                                                               \
+		_Pragma("unroll") for (int b = 0; b < CB; ++b) rowbuf[buf ^ 1][tx + 32 * b] = v[A][b];      \
+	}
+	for (int j = 16 * Q; j < jend; ++j) {
+		const int buf = j & 1, t = j & 15, jl = j & 31, jn = j + 1;
+		const double p = pv[buf];                        // the same word for every thread: the exit below is uniform
+		const double inv = pinv[buf];
+		double rk[CB];
+#pragma unroll
+		for (int b = 0; b < CB; ++b) rk[b] = rowbuf[buf][tx + 32 * b];
+		if (!(p > 0.0)) { if (threadIdx.x == 0) *flag = flag_value; return false; }
+		if (threadIdx.x == 0) piv[j] = p;
+		const bool own_next = jn < n && ((t + 1) & 15) == ty;
+		if (own_next) {
+			if (t < 15) { CH_ROW(Q) CH_PUB(Q) } else { CH_ROW(QN) CH_PUB(QN) }
+			__syncwarp();
+			if (tx == 0) { const double pc = rowbuf[buf ^ 1][jn]; pv[buf ^ 1] = pc; pinv[buf ^ 1] = __drcp_rn(pc); rowbuf[buf ^ 1][jn] = 1.0; }
+		}
+		if (ty > t && !(own_next && t < 15)) CH_ROW(Q)
+#pragma unroll
+		for (int a = Q + 1; a < RA; ++a) {
+			if (!(own_next && t == 15 && a == QN)) CH_ROW(a)
+		}
+		__syncthreads();
+	}
+#undef CH_ROW
+#undef CH_PUB
+	return true;
+}
+
 template <int CB>
 __global__ void __launch_bounds__(CH_THREADS, 1) chol_inv_kernel(const double* __restrict__ G, const int nparts, const long long part_stride, const int n,
                                                                  double* __restrict__ Ro, double* __restrict__ Wo, const int near_identity, const double ratio,
@@ -451,83 +503,27 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_inv_kernel(const double* _
 	if (ty == 0) {
 #pragma unroll
 		for (int b = 0; b < CB; ++b) rowbuf[0][tx + 32 * b] = v[0][b];
-		if (tx == 0) { pv[0] = v[0][0]; pinv[0] = __drcp_rn(v[0][0]); }
+		__syncwarp();
+		if (tx == 0) { pv[0] = v[0][0]; pinv[0] = __drcp_rn(v[0][0]); rowbuf[0][0] = 1.0; }
 	}
 	__syncthreads();
-	// Step j, row i > j of this thread: v(i, k) -= f_i r_k with f_i = U(j, i) / p_j and r the published pivot row, on the columns
-	// k < j (the L^-1 part), k = j (r_j = 1 implied and v(i, j) = 0 before: L^-1(i, j) = -f_i) and k >= i (the Schur complement).
-	// The columns j < k < i in between are not live yet — they pick up garbage that the step j' = k overwrites — so a row is four
-	// unconditional DFMAs; what costs instructions is decided once per step, not per element: the block of 32 columns that holds
-	// column j (switch, compile-time inside), the first live row of the warp (switch with fall-through over the register rows).
-#define CH_ROW(A, JB)                                                                               \
-	if ((A) < RA) {                                                                                 \
-		constexpr int A_ = (A) < RA ? (A) : 0, JB_ = (JB) < CB ? (JB) : 0;                          \
-		const double fa_ = f[A_] * inv;                                                             \
-		if (tx == jl) v[A_][JB_] = 0.0;                                                             \
-		_Pragma("unroll") for (int b = 0; b < CB; ++b) v[A_][b] = fma(-fa_, rk[b], v[A_][b]);       \
-	}
-#define CH_PUB(A)                                                                                   \
-	if ((A) < RA) {                                                                                 \
-		constexpr int A_ = (A) < RA ? (A) : 0;                                                      \
-		_Pragma("unroll") for (int b = 0; b < CB; ++b) rowbuf[buf ^ 1][tx + 32 * b] = v[A_][b];     \
-	}
-#define CH_STEP(JB)                                                                                 \
-	{                                                                                               \
-		if (own_next) {                                                                             \
-			switch (an) {                                                                           \
-				case 0: CH_ROW(0, JB) CH_PUB(0) break;                                              \
-				case 1: CH_ROW(1, JB) CH_PUB(1) break;                                              \
-				case 2: CH_ROW(2, JB) CH_PUB(2) break;                                              \
-				case 3: CH_ROW(3, JB) CH_PUB(3) break;                                              \
-				case 4: CH_ROW(4, JB) CH_PUB(4) break;                                              \
-				case 5: CH_ROW(5, JB) CH_PUB(5) break;                                              \
-				case 6: CH_ROW(6, JB) CH_PUB(6) break;                                              \
-				default: CH_ROW(7, JB) CH_PUB(7) break;                                             \
-			}                                                                                       \
-			__syncwarp();                                                                           \
-			if (tx == 0) { const double pc = rowbuf[buf ^ 1][jn]; pv[buf ^ 1] = pc; pinv[buf ^ 1] = __drcp_rn(pc); } \
-		}                                                                                           \
-		switch (a_start) {                                                                          \
-			case 0: CH_ROW(0, JB)                                                                   \
-			case 1: CH_ROW(1, JB)                                                                   \
-			case 2: CH_ROW(2, JB)                                                                   \
-			case 3: CH_ROW(3, JB)                                                                   \
-			case 4: CH_ROW(4, JB)                                                                   \
-			case 5: CH_ROW(5, JB)                                                                   \
-			case 6: CH_ROW(6, JB)                                                                   \
-			case 7: CH_ROW(7, JB)                                                                   \
-			default: break;                                                                         \
-		}                                                                                           \
-	}
-	for (int j = 0; j < n; ++j) {
-		const int buf = j & 1;
-		const double p = pv[buf];                        // the same word for every thread: the exit below is uniform
-		const double inv = pinv[buf];
-		double rk[CB], f[RA];
-#pragma unroll
-		for (int b = 0; b < CB; ++b) { const int k = tx + 32 * b; rk[b] = (k == j) ? 1.0 : rowbuf[buf][k]; }
-#pragma unroll
-		for (int a = 0; a < RA; ++a) f[a] = rowbuf[buf][ty + 16 * a];
-		if (!(p > 0.0)) { if (tid == 0) *flag = flag_value; return; }
-		if (tid == 0) piv[j] = p;
-		// the warp that owns the next pivot row does that row first and publishes it; its lane 0 reads the new pivot back from
-		// shared memory and adds the reciprocal, while the other warps are busy with their rows
-		const int jn = j + 1, jl = j & 31;
-		const bool own_next = jn < n && (jn & 15) == ty;
-		const int an = jn >> 4;
-		const int a0 = (j >= ty) ? ((j - ty) >> 4) + 1 : 0;          // first row of this warp below the pivot row
-		const int a_start = own_next ? an + 1 : a0;
-		switch (j >> 5) {
-			case 0: CH_STEP(0) break;
-			case 1: CH_STEP(1) break;
-			case 2: CH_STEP(2) break;
-			default: CH_STEP(3) break;
+	{
+		bool ok = chol_inv_block<CB, 0>(v, rowbuf, pv, pinv, piv, n, tx, ty, flag, flag_value);
+		if (ok && n > 16) ok = chol_inv_block<CB, 1>(v, rowbuf, pv, pinv, piv, n, tx, ty, flag, flag_value);
+		if constexpr (CB >= 2) {
+			if (ok && n > 32) ok = chol_inv_block<CB, 2>(v, rowbuf, pv, pinv, piv, n, tx, ty, flag, flag_value);
+			if (ok && n > 48) ok = chol_inv_block<CB, 3>(v, rowbuf, pv, pinv, piv, n, tx, ty, flag, flag_value);
 		}
-		__syncthreads();
+		if constexpr (CB >= 3) {
+			if (ok && n > 64) ok = chol_inv_block<CB, 4>(v, rowbuf, pv, pinv, piv, n, tx, ty, flag, flag_value);
+			if (ok && n > 80) ok = chol_inv_block<CB, 5>(v, rowbuf, pv, pinv, piv, n, tx, ty, flag, flag_value);
+		}
+		if constexpr (CB >= 4) {
+			if (ok && n > 96) ok = chol_inv_block<CB, 6>(v, rowbuf, pv, pinv, piv, n, tx, ty, flag, flag_value);
+			if (ok && n > 112) ok = chol_inv_block<CB, 7>(v, rowbuf, pv, pinv, piv, n, tx, ty, flag, flag_value);
+		}
+		if (!ok) return;
 	}
-#undef CH_ROW
-#undef CH_PUB
-#undef CH_STEP
 	bool flagged = false;
 	if (tid == 0) {
 		double pmin = HUGE_VAL, pmax = 0.0;
