@@ -443,6 +443,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chol_inv_kernel(const double* _
 #pragma unroll
 		for (int b = 0; b < CB; ++b) v[a][b] = 0.0;
 	// slices outermost: the RA * CB loads of one slice are independent and in flight together
+	if (n == 32 * CB) {
+		// full tile (n = 32, 64, 96, 128 — the bond dimensions of config 5): no bounds, one base pointer and immediate offsets
+		const double* base = G + (size_t)ty * n + tx;
+		for (int s = 0; s < nparts; ++s, base += part_stride) {
+#pragma unroll
+			for (int a = 0; a < RA; ++a)
+#pragma unroll
+				for (int b = 0; b < CB; ++b) v[a][b] += __ldg(base + (size_t)a * 16 * (32 * CB) + 32 * b);
+		}
+	} else
 	for (int s = 0; s < nparts; ++s) {
 		const double* src = G + (long long)s * part_stride;
 #pragma unroll
