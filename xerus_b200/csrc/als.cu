@@ -956,7 +956,7 @@ struct Als {
 			if (spd_cg_persistent(*site_apply, xv.data(), rhs.p, pw.data(), sc.p, max_it, target, bnorm2, done, reason, rr, rr0)) {
 				if (reason == 4 || !(rr == rr)) throw Error(XB_ERR_NUMERIC, "local CG produced NaN (operator not positive definite?)");
 				cg_iterations += done;
-				if (getenv("XB_DEBUG_ALS")) fprintf(stderr, "[als] site %zu n=%zu cg its=%zu rel res=%.3e (start %.3e) [one launch]\n", cur, n, done, std::sqrt(rr / bnorm2), std::sqrt(rr0 / bnorm2));
+				if (getenv("XB_DEBUG_ALS")) fprintf(stderr, "[als] site %zu n=%zu cg its=%zu reason=%u rel res=%.3e (start %.3e) [one launch]\n", cur, n, done, reason, std::sqrt(rr / bnorm2), std::sqrt(rr0 / bnorm2));
 				return xv;
 			}
 		}
