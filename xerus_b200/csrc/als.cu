@@ -188,8 +188,8 @@ struct SpdSiteApply {
 //   u(m,b | r')  = A2 t1                  (shared memory)
 //   y(li, m, r)  = u(m | b,r') R(r | b,r')^T   (R stays transposed in shared memory for the whole run)
 // and the CTA also owns the matching segments of x, r, p.  Per iteration there are two reductions (p.q and r.r: per-CTA
-// partials in global memory, summed by every CTA in the same fixed order, so all CTAs take identical decisions) and three
-// grid barriers.  The stopping logic of the host loop (target, stagnation at the rounding floor, re-anchoring) runs on the
+// partials in global memory, summed by every CTA in the same fixed order, so all CTAs take identical decisions) and two
+// grid barriers (three in the textbook arrangement, SpdCgArgs::merged = 0).  The stopping logic of the host loop (target, stagnation at the rounding floor, re-anchoring) runs on the
 // device; the host reads one status record per launch.
 struct SpdCgArgs {
 	const double* L; const double* A2; const double* R;
@@ -198,6 +198,7 @@ struct SpdCgArgs {
 	int l, a, n, m, b, rr;           // L (l, a, l), A2 (m b | a n), R (rr, b, rr); vectors (l, n, rr) with m == n
 	int nsl;                         // slices per CTA (1 whenever l <= number of co-resident CTAs)
 	int max_it;
+	int merged;                      // 1: two grid barriers per iteration (q = A r + beta q, see the loop)
 	double target, bnorm2;
 };
 constexpr int CGP_THREADS = 256;
@@ -272,7 +273,8 @@ __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) 
 	double* ps = rs + (size_t)nsl * Cout;
 	double* qs = ps + (size_t)nsl * Cout;
 	double* bs = qs + (size_t)nsl * Cout;          //            ... and of the right-hand side
-	double* red = bs + (size_t)nsl * Cout;         // [32]
+	double* hs = bs + (size_t)nsl * Cout;          //            ... and of q = A p carried by recurrence (merged variant)
+	double* red = hs + (size_t)nsl * Cout;         // [32]
 	// cluster variant: weights of all slices of the cluster over this CTA's rows, staged partials, received partials
 	const int crows = (l + CSZ - 1) / CSZ + 1;
 	double* Lc = red + 32;                         // [CSZ][crows][2]
@@ -512,9 +514,57 @@ __global__ void __launch_bounds__(CGP_THREADS) spd_cg_kernel(const SpdCgArgs g) 
 		cgp_grid_barrier(g.barrier, bar_expected, G, g.info);
 		best = rr; since_best = 0; reason = 0;
 		const double rr_start = rr;
+		double beta_m = 0.0;                          // merged variant: p_{-1} = q_{-1} = 0
+		if (g.merged) for (int e = tid; e < nsl * Cout; e += CGP_THREADS) { ps[e] = 0.0; hs[e] = 0.0; }
 	for (; it < g.max_it; ++it) {
 		double* part = g.partial + (size_t)(it & 1) * 2 * G;
 		if (timing) t0 = clock64();
+		if (g.merged) {
+			// Two barriers per iteration instead of three: what the other CTAs need is r, not p — A p = A r + beta A p_old, so
+			// the operator is applied to the published residual and q, p follow by recurrence on the owned segments.
+			// Same iterates in exact arithmetic; the recurrence for q adds to the gap between recurrence and true residual,
+			// which the re-anchoring below absorbs.
+			double dummy = 0.0, pq_local = 0.0;
+			apply_owned(g.p, rs, dummy);                                  // qs = A r   (g.p holds r)
+			for (int e = tid; e < nsl * Cout; e += CGP_THREADS) {
+				if (blockIdx.x + (e / Cout) * G < l) {
+					const double h = qs[e] + beta_m * hs[e], pn = rs[e] + beta_m * ps[e];
+					hs[e] = h; ps[e] = pn;
+					pq_local += pn * h;
+				}
+			}
+			const double pq_cta = cgp_block_sum(pq_local, red);
+			if (tid == 0) __stcg(part + blockIdx.x, pq_cta);
+			if (timing) { const long long t1 = clock64(); tk[1] += t1 - t0; t0 = t1; }
+			cgp_grid_barrier(g.barrier, bar_expected, G, g.info);
+			if (timing) { const long long t1 = clock64(); tk[2] += t1 - t0; t0 = t1; }
+			const double pq = cgp_grid_sum(part, G, red);
+			const double alpha = (pq != 0.0) ? rr / pq : 0.0;
+			double rr_local = 0.0;
+			for (int e = tid; e < nsl * Cout; e += CGP_THREADS) {
+				const int li = blockIdx.x + (e / Cout) * G;
+				if (li < l) {
+					xs[e] += alpha * ps[e];
+					const double rn = rs[e] - alpha * hs[e];
+					rs[e] = rn;
+					rr_local += rn * rn;
+					__stcg(g.p + (size_t)li * Cout + (e % Cout), rn);
+				}
+			}
+			const double rr_cta = cgp_block_sum(rr_local, red);
+			if (tid == 0) __stcg(part + G + blockIdx.x, rr_cta);
+			if (timing) { const long long t1 = clock64(); tk[3] += t1 - t0; t0 = t1; }
+			cgp_grid_barrier(g.barrier, bar_expected, G, g.info);         // r.r is complete and the new r is visible to every CTA
+			if (timing) { const long long t1 = clock64(); tk[4] += t1 - t0; t0 = t1; }
+			const double rrn = cgp_grid_sum(part + G, G, red);
+			beta_m = (rr != 0.0) ? rrn / rr : 0.0;
+			rr = rrn;
+			if (!(rr == rr)) { reason = 4; ++it; break; }
+			if (rr <= g.target) { reason = 1; ++it; break; }
+			if (rr < 0.5 * best) { best = rr; since_best = 0; } else if (++since_best >= 48) { reason = 2; ++it; break; }
+			if (rr < 1e-20 * rr_start) { reason = 3; ++it; break; }
+			continue;
+		}
 		// ---- q = A p on the owned slices, and the partial of p.q
 		double pq_local = 0.0;
 		apply_owned(g.p, ps, pq_local);
@@ -582,7 +632,7 @@ bool spd_cg_persistent(const SpdSiteApply& sa, double* x, const double* b, doubl
 	auto smem_for = [&](size_t nsl, size_t csz) {
 		const size_t crows = (sa.l + csz - 1) / csz + 1;
 		const size_t cluster_part = csz > 1 ? ((csz * crows * 2 + 1) & ~size_t(1)) + 2 * csz * KA * Rp : 2;
-		return (KR * Rp + ((QA * KA + 1) & ~size_t(1)) + size_t(CGP_AMAX) * sa.l + KA * Rp + ((sa.m * KR + 1) & ~size_t(1)) + 5 * nsl * Cout + 32 +
+		return (KR * Rp + ((QA * KA + 1) & ~size_t(1)) + size_t(CGP_AMAX) * sa.l + KA * Rp + ((sa.m * KR + 1) & ~size_t(1)) + 6 * nsl * Cout + 32 +
 		        cluster_part) * sizeof(double);
 	};
 	struct Variant { const void* fn; int csz; };
@@ -595,7 +645,7 @@ bool spd_cg_persistent(const SpdSiteApply& sa, double* x, const double* b, doubl
 	SpdCgArgs g;
 	g.L = sa.L; g.A2 = sa.A2; g.R = sa.R; g.x = x; g.rhs = b; g.p = p; g.sc = sc; g.info = info; g.barrier = info + 11;
 	g.l = int(sa.l); g.a = int(sa.a); g.n = int(sa.n); g.m = int(sa.m); g.b = int(sa.b); g.rr = int(sa.r);
-	g.max_it = int(std::min<size_t>(max_it, 1u << 30)); g.target = target; g.bnorm2 = bnorm2;
+	g.max_it = int(std::min<size_t>(max_it, 1u << 30)); g.target = target; g.bnorm2 = bnorm2; g.merged = c.als_cg_merged ? 1 : 0;
 	int G = 0;
 	bool launched = false;
 	// cluster variant: one slice per CTA, operator bond <= 2, even row length, 16-byte multiples for the bulk copies, and the

@@ -38,6 +38,7 @@ static void apply_option(Context& c, const std::string& k, double value) {
 	else if (k == "als_graph") c.als_graph = int(value);
 	else if (k == "als_persistent_cg") c.als_persistent_cg = int(value);
 	else if (k == "als_cg_cluster") c.als_cg_cluster = int(value);
+	else if (k == "als_cg_merged") c.als_cg_merged = int(value);
 	else if (k == "svd_jacc") c.svd_jacc = int(value);
 	else if (k == "svd_fast") c.svd_fast = int(value);
 	else if (k == "qr_cluster") c.qr_cluster = int(value);
@@ -120,7 +121,7 @@ static void select_worker(int w) {
 		c->initialised = true; c->worker = i; c->device = g_ctx.device; c->pool = g_ctx.pool;
 		c->num_sms = g_ctx.num_sms; c->max_smem_optin = g_ctx.max_smem_optin;
 		c->svd_max_sweeps = g_ctx.svd_max_sweeps; c->gemm_force_small = g_ctx.gemm_force_small; c->gemm_big = g_ctx.gemm_big; c->qr_defer = g_ctx.qr_defer;
-		c->svd_persistent = g_ctx.svd_persistent; c->svd_polish = g_ctx.svd_polish; c->tt_svd_polish = g_ctx.tt_svd_polish; c->svd_recursive = g_ctx.svd_recursive; c->svd_flip = g_ctx.svd_flip; c->svd_split = g_ctx.svd_split; c->svd_dsmem = g_ctx.svd_dsmem; c->svd_colsort = g_ctx.svd_colsort; c->svd_last_sweep_cos = g_ctx.svd_last_sweep_cos; c->svd_gram = g_ctx.svd_gram; c->als_graph = g_ctx.als_graph; c->als_persistent_cg = g_ctx.als_persistent_cg; c->als_cg_cluster = g_ctx.als_cg_cluster; c->svd_jacc = g_ctx.svd_jacc; c->svd_fast = g_ctx.svd_fast; c->qr_cluster = g_ctx.qr_cluster; c->qr_cluster_min_rows = g_ctx.qr_cluster_min_rows; c->qr_chol = g_ctx.qr_chol; c->qr_chol_min_rows = g_ctx.qr_chol_min_rows; c->svd_square_qr = g_ctx.svd_square_qr;
+		c->svd_persistent = g_ctx.svd_persistent; c->svd_polish = g_ctx.svd_polish; c->tt_svd_polish = g_ctx.tt_svd_polish; c->svd_recursive = g_ctx.svd_recursive; c->svd_flip = g_ctx.svd_flip; c->svd_split = g_ctx.svd_split; c->svd_dsmem = g_ctx.svd_dsmem; c->svd_colsort = g_ctx.svd_colsort; c->svd_last_sweep_cos = g_ctx.svd_last_sweep_cos; c->svd_gram = g_ctx.svd_gram; c->als_graph = g_ctx.als_graph; c->als_persistent_cg = g_ctx.als_persistent_cg; c->als_cg_cluster = g_ctx.als_cg_cluster; c->als_cg_merged = g_ctx.als_cg_merged; c->svd_jacc = g_ctx.svd_jacc; c->svd_fast = g_ctx.svd_fast; c->qr_cluster = g_ctx.qr_cluster; c->qr_cluster_min_rows = g_ctx.qr_cluster_min_rows; c->qr_chol = g_ctx.qr_chol; c->qr_chol_min_rows = g_ctx.qr_chol_min_rows; c->svd_square_qr = g_ctx.svd_square_qr;
 		c->svd_max_bw = g_ctx.svd_max_bw; c->als_direct_max = g_ctx.als_direct_max; c->round_plans = g_ctx.round_plans; c->small_kernels = g_ctx.small_kernels; c->peer_wait_spins = g_ctx.peer_wait_spins; c->batch_workers = g_ctx.batch_workers; c->batch_threads = g_ctx.batch_threads;
 		XB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 		XB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_scratch), c->h_scratch_len * sizeof(double)));

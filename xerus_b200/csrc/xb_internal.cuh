@@ -75,6 +75,7 @@ struct Context {
 	int qr_cluster_min_rows = 64;  // smallest panel height for the cluster panel kernel (below: one CTA, panel in shared memory)
 	int svd_fast = 1;              // specialised Jacobi kernel (compile-time row length, 128-bit accesses) up to 512 columns
 	int svd_jacc = 1;              // specialised Jacobi kernel: rotations of a block visit accumulated, applied to V once (DMMA)
+	int als_cg_merged = 1;         // persistent CG: two grid barriers per iteration (operator applied to r, q by recurrence)
 	int als_cg_cluster = 1;        // persistent CG: step 1 shared inside thread-block clusters (partial sums exchanged through DSMEM)
 	int als_persistent_cg = 1;     // one-site SPD local problems: a whole CG run in one cooperative launch (spd_cg_kernel)
 	int als_graph = 1;             // one-site SPD CG: chunks of 8 iterations replayed as a CUDA graph
