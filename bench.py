@@ -207,7 +207,7 @@ def als_sweep_numbers(xb, np, torch, stream, args, fp64_peak=None):
                         "accounting": "operator applications x (2 x 2 r_A n r^3 + 2 r_A^2 n^2 r^2) flop (SURVEY 8d: 12 MFLOP per apply at config 2)",
                         "kernel_ms_per_sweep": solve_ms, "launches_per_sweep": solve_launches, "move_and_environment_ms_per_sweep": move_ms,
                         "traffic": None,
-                        "note": "latency bound: 50 CTAs, three grid barriers per CG iteration on 12 MFLOP of work (profiles/r1_cg.txt)"},
+                        "note": "latency bound: 50 CTAs, two grid barriers per CG iteration on 12 MFLOP of work (profiles/r1_cg.txt)"},
            "reference_cpu": "not runnable inside a bench run at r=50: ~1 h per sweep extrapolated (BASELINE.md section 2)"}
     if os.path.exists(REF_BENCH) and not args.no_cpu_baseline:
         try:
