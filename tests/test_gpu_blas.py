@@ -531,11 +531,13 @@ def _qr_paths(A):
     return Q, R, t1 - t0, d1 - d0
 
 
-@pytest.mark.parametrize("m,n", [(64, 33), (128, 128), (512, 128), (500, 50), (4096, 16), (3000, 120), (97, 97), (20000, 100), (300, 65), (2000, 7), (509, 60)])
+@pytest.mark.parametrize("m,n", [(64, 33), (128, 128), (512, 128), (500, 50), (4096, 16), (3000, 120), (97, 97), (20000, 100), (300, 65), (2000, 7), (509, 60),
+                                  (4096, 150), (3000, 200), (2500, 256), (2049, 129)])
 @pytest.mark.parametrize("cond", [1.0, 1e2, 1e4])
 def test_cholesky_qr2_on_well_conditioned_tall_matrices(m, n, cond, chol_everywhere):
-    """Tall QRs of up to 128 columns take the Cholesky-QR2 path (csrc/qr_f64.cu: cholqr2): orthogonality and residual at the
-    level of the Householder path, R equal to LAPACK's up to row signs, and the same factors with the path switched off."""
+    """Tall QRs of up to 128 columns take the Cholesky-QR2 path (csrc/qr_f64.cu: cholqr2), and so do 129..256 columns beyond 2048
+    rows (two column halves, block Gram-Schmidt in between): orthogonality and residual at the level of the Householder path,
+    R equal to LAPACK's up to row signs, and the same factors with the path switched off."""
     A = _graded(m, n, cond, m + n) * 3.0e7
     Q, R, taken, declined = _qr_paths(A)
     assert taken == 1 and declined == 0

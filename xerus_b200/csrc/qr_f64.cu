@@ -541,10 +541,45 @@ static void apply_block_reflector(double* C, size_t ldc, size_t mp, size_t nc, c
 // a row the next 16 candidates of the same call go straight to Householder.  R has a positive diagonal here and a mixed-sign
 // one from Householder; both are QRs of A (dgeqrf's signs are not part of the contract the reference's callers rely on:
 // blasLapackWrapper.cpp:374-437 only promises A = Q R with orthonormal Q).
+// split-K over row slabs: S slabs of `slab` rows plus `rest` rows that go on top of the first partial sum
+struct RowSplit { size_t S, slab, rest; };
+static RowSplit split_rows(size_t m, size_t out_elems) {
+	size_t S = std::min<size_t>(std::max<size_t>(m / 128, 1), std::min<size_t>(1024, std::max<size_t>((size_t(1) << 22) / out_elems, 64)));
+	for (size_t t = S; t > S / 2 && t >= 2; --t) if (m % t == 0) { S = t; break; }
+	return RowSplit{S, m / S, m - S * (m / S)};
+}
+// P[0 .. parts) (na x nb each) <- partial sums of X^T Y over the m rows (X: m x na, ldx; Y: m x nb, ldy) as one batched GEMM (a
+// single product would be a handful of CTAs walking all m rows).  Up to 4 partial sums are left for the consumer to add up while
+// it loads (chol_inv_kernel), more — or any number with sum_all — go through one summation launch.  Returns the parts left.
+static size_t xty_split(double* P, const double* X, size_t ldx, size_t na, const double* Y, size_t ldy, size_t nb, const RowSplit& rs, bool sum_all) {
+	ProfScope ps("chol_gram");
+	gemm_batched(P, nb, na * nb, na, nb, 1.0, X, ldx, rs.slab * ldx, true, rs.slab, Y, ldy, rs.slab * ldy, false, 0.0, rs.S);
+	if (rs.rest) gemm(P, nb, na, nb, 1.0, X + rs.S * rs.slab * ldx, ldx, true, rs.rest, Y + rs.S * rs.slab * ldy, ldy, false, 1.0);
+	if (rs.S == 1 || (rs.S <= 4 && !sum_all)) return rs.S;
+	sum_parts(P, P, rs.S, na * nb);
+	return 1;
+}
+// enqueues Q (m x n, ldq), R (n x n) of A (m x n, lda), n <= 128; the two status words f1, f2 receive 4 on a decline
+static void cholqr2_enqueue(double* Q, size_t ldq, double* R, const double* A, size_t lda, size_t m, size_t n, unsigned int* f1, unsigned int* f2, bool clear) {
+	const RowSplit rs = split_rows(m, n * n);
+	DBuf P(rs.S * n * n), R1(n * n), R2(n * n), W(n * n), Q1(m * n);
+	size_t parts = xty_split(P, A, lda, n, A, lda, n, rs, false);
+	{ ProfScope ps("chol_fact"); chol_inv(P, parts, n, R1, W, false, 1e-10, f1, 4u, clear); }
+	{ ProfScope ps("chol_apply"); gemm(Q1, n, m, n, 1.0, A, lda, false, n, W, n, true, 0.0); }
+	parts = xty_split(P, Q1, n, n, Q1, n, n, rs, false);
+	{ ProfScope ps("chol_fact"); chol_inv(P, parts, n, R2, W, true, 0.25, f2, 4u, clear); }
+	{ ProfScope ps("chol_apply"); gemm(Q, ldq, m, n, 1.0, Q1, n, false, n, W, n, true, 0.0); }
+	{ ProfScope ps("chol_rr"); gemm(R, n, n, n, 1.0, R2, n, false, n, R1, n, false, 0.0); }
+}
+
 static bool cholqr2(double* Q, double* R, const double* A, const size_t m, const size_t n) {
 	Context& c = ctx();
-	if (!c.qr_chol || c.chol_off || n > m || !chol_inv_fits(n)) return false;
-	{
+	if (!c.qr_chol || c.chol_off || n > m) return false;
+	// 129..256 columns beyond the reach of the cluster panel kernel (> 2048 rows: 15 ms at 4096 x 150): two column halves, block
+	// Gram-Schmidt between them with the projection applied twice, Cholesky-QR2 on each half
+	const bool wide = n > 128 && n <= 256 && m > 2048;
+	if (!wide) {
+		if (!chol_inv_fits(n)) return false;
 		// measured crossover against the cluster panel kernels (profiles/r2_qr_cholqr2.txt), per call on the ordinary path: ~250 us
 		// whatever m at 128 columns against 265 / 353 / 538 us at 512 / 768 / 2048 rows; 175 us against 136 / 185 / 261 us at 64
 		// columns; beyond 2048 rows (where the panels leave the cluster kernel) 0.15 ms against 1.8 ms at 4096 x 16 and 0.39 ms
@@ -567,34 +602,38 @@ static bool cholqr2(double* Q, double* R, const double* A, const size_t m, const
 	}
 	ProfScope prof("qr_chol");
 	const bool spec = c.speculate;
-	// split-K for the two Gram matrices: S row slabs as one batched GEMM (a single n x n product is one to sixteen CTAs walking
-	// all m rows); up to 4 partial sums are added up by the Cholesky kernel as it loads, more go through one summation launch
-	size_t S = std::min<size_t>(std::max<size_t>(m / 128, 1), std::min<size_t>(1024, std::max<size_t>((size_t(1) << 22) / (n * n), 64)));
-	for (size_t t = S; t > S / 2 && t >= 2; --t) if (m % t == 0) { S = t; break; }
-	const size_t slab = m / S, rest = m - S * slab;
-	DBuf P(S * n * n), R1(n * n), R2(n * n), W(n * n), Q1(m * n), fl(1);
-	unsigned int* f = spec ? c.spec_flag : reinterpret_cast<unsigned int*>(fl.p);
-	auto gram = [&](const double* X) -> size_t {
-		ProfScope ps("chol_gram");
-		gemm_batched(P, n, n * n, n, n, 1.0, X, n, slab * n, true, slab, X, n, slab * n, false, 0.0, S);
-		if (rest) gemm(P, n, n, n, 1.0, X + S * slab * n, n, true, rest, X + S * slab * n, n, false, 1.0);
-		if (S <= 4) return S;
-		sum_parts(P, P, S, n * n);
-		return 1;
-	};
-	size_t parts = gram(A);
-	{ ProfScope ps("chol_fact"); chol_inv(P, parts, n, R1, W, false, 1e-10, f, 4u, !spec); }
-	{ ProfScope ps("chol_apply"); gemm(Q1, n, m, n, 1.0, A, n, false, n, W, n, true, 0.0); }
-	parts = gram(Q1);
-	{ ProfScope ps("chol_fact"); chol_inv(P, parts, n, R2, W, true, 0.25, spec ? f : f + 1, 4u, !spec); }
-	{ ProfScope ps("chol_apply"); gemm(Q, n, m, n, 1.0, Q1, n, false, n, W, n, true, 0.0); }
-	{ ProfScope ps("chol_rr"); gemm(R, n, n, n, 1.0, R2, n, false, n, R1, n, false, 0.0); }
+	DBuf fl(2);
+	unsigned int* fw = reinterpret_cast<unsigned int*>(fl.p);
+	auto word = [&](int i) { return spec ? c.spec_flag : fw + i; };
+	const int nwords = wide ? 4 : 2;
+	if (!wide) {
+		cholqr2_enqueue(Q, n, R, A, n, m, n, word(0), word(1), !spec);
+	} else {
+		const size_t n1 = (n + 1) / 2, n2 = n - n1;
+		const RowSplit rs = split_rows(m, n1 * n2);
+		DBuf R11(n1 * n1), R22(n2 * n2), R12(n1 * n2), Rb(n1 * n2), T(m * n2), P(rs.S * n1 * n2);
+		cholqr2_enqueue(Q, n, R11, A, n, m, n1, word(0), word(1), !spec);                  // Q1 = Q(:, :n1)
+		copy2d(T, n2, A + n1, n, m, n2);
+		for (int pass = 0; pass < 2; ++pass) {                                              // T -= Q1 (Q1^T T), twice
+			double* Rx = pass ? Rb.p : R12.p;
+			xty_split(P, Q, n, n1, T, n2, n2, rs, true);
+			copy(Rx, P, n1 * n2);
+			gemm(T, n2, m, n2, -1.0, Q, n, false, n1, Rx, n2, false, 1.0);
+		}
+		axpy(R12, 1.0, Rb, n1 * n2);
+		cholqr2_enqueue(Q + n1, n, R22, T, n2, m, n2, word(2), word(3), !spec);             // Q2 = Q(:, n1:)
+		fill(R, 0.0, n * n);
+		copy2d(R, n, R11, n1, n1, n1);
+		copy2d(R + n1, n, R12, n2, n1, n2);
+		copy2d(R + n1 * n + n1, n, R22, n2, n2, n2);
+	}
 	if (spec) return true;
-	XB_CUDA(cudaMemcpyAsync(c.h_scratch, fl.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+	XB_CUDA(cudaMemcpyAsync(c.h_scratch, fl.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
 	XB_CUDA(cudaStreamSynchronize(c.stream));
-	unsigned int w[2];
+	unsigned int w[4];
 	std::memcpy(w, c.h_scratch, sizeof w);
-	const bool ok = w[0] == 0u && w[1] == 0u;
+	bool ok = true;
+	for (int i = 0; i < nwords; ++i) ok = ok && w[i] == 0u;
 	if (c.chol_tape_mode == 1) c.chol_tape.push_back(ok ? 1 : 0);
 	if (ok) { c.chol_declines = 0; return true; }
 	ProfScope declined("qr_chol_declined");
