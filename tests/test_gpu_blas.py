@@ -609,3 +609,29 @@ def test_cholesky_qr2_backs_off_inside_a_call_and_plans_replay_its_decisions(cho
     ref.round(24)
     got = O.TT(results[0], core_position=0)
     assert got.ranks() == ref.ranks() and O.tt_distance_rel(got, ref) < 1e-10
+
+
+def test_round_plan_drops_cholesky_qr2_after_repeated_declines(chol_everywhere):
+    """A plan recorded on well-conditioned cores speculates that its Cholesky-QR2 candidates are accepted.  TTs of the same shape
+    with a graded bond fail that check on replay (reason 4): the call falls back to the ordinary path, and after the second
+    failure the plan is recorded again Householder-only.  Every result along the way must be right."""
+    rng = np.random.default_rng(21)
+    d, n, r = 6, 4, 40
+    ranks = [1] + [min(r, n ** min(i, d - i)) for i in range(1, d)] + [1]
+
+    def cores(graded):
+        cs = [rng.standard_normal((ranks[i], n, ranks[i + 1])) for i in range(d)]
+        if graded:
+            cs[3] = np.einsum("a,anb->anb", np.logspace(0, -9, ranks[3]), cs[3])
+        return cs
+
+    xb.set_option("round_plans", 1)                       # new option epoch: no plan for this shape yet
+    for graded in (False, False, True, True, True, True, False, True):
+        cs = cores(graded)
+        t = xb.TTTensor.from_cores(cs)
+        t.round(24)
+        ref = O.TT([c.copy() for c in cs])
+        ref.round(24)
+        got = O.TT(t.cores(), core_position=0)
+        assert got.ranks() == ref.ranks()
+        assert O.tt_distance_rel(got, ref) < 1e-10, graded
